@@ -1,0 +1,161 @@
+/*
+ * qarbom_b200 -- C ABI of the B200-native classical RBM training hot path
+ * (CD-k / PCD Gibbs chains, positive/negative-phase gradient, parameter update,
+ * reconstruction-error and free-energy evaluation) of NITeQ/QARBoM.jl.
+ *
+ * The reference has NO FFI for this path: it is reached through Julia multiple dispatch
+ * only.  Each entry point below therefore cites the reference *function* it replaces
+ * (paths relative to the reference repository); INTEGRATION.md shows the `ccall` stubs
+ * a maintainer adds on the Julia side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative QB_E_* code on failure; the
+ *     message is available (per calling thread) from qb_last_error();
+ *   - host buffers are borrowed for the duration of the call only; all calls on one
+ *     handle must be serialised by the caller; calls block until the device is done;
+ *   - parameter arrays use the Julia layout: W is column-major V x H (W[i + V*j]),
+ *     U is column-major L x H; datasets are N rows of V (resp. L) contiguous elements
+ *     (Vector{Vector{T}} flattened), element type selected by a QB_DT_* code;
+ *   - there is no CPU fallback: every entry point that computes fails with
+ *     QB_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef QARBOM_B200_H
+#define QARBOM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB_VERSION 100
+
+/* status codes */
+#define QB_OK 0
+#define QB_E_ARG (-1)      /* invalid argument / shape */
+#define QB_E_CUDA (-2)     /* CUDA runtime / driver failure, or no usable device */
+#define QB_E_STATE (-3)    /* call sequence error (no data, no chains, ...) */
+#define QB_E_NCCL (-4)     /* NCCL unavailable or failed */
+#define QB_E_UNSUPPORTED (-5)
+
+/* visible unit kind: RBM / RBMClassifier vs GRBM / GRBMClassifier (src/rbm.jl:2-39) */
+#define QB_VISIBLE_BERNOULLI 0
+#define QB_VISIBLE_GAUSSIAN 1
+
+/* arithmetic mode */
+#define QB_PREC_FP32 0  /* fp32 CUDA-core kernels: validation mode (1e-5 rel. vs Float64) */
+#define QB_PREC_BF16 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate: production */
+
+/* host element types for datasets */
+#define QB_DT_F64 0
+#define QB_DT_I64 1
+#define QB_DT_F32 2
+#define QB_DT_U8 3
+
+typedef struct qb_handle qb_handle;
+
+typedef struct qb_config {
+    int64_t n_visible;     /* V */
+    int64_t n_hidden;      /* H */
+    int64_t n_classifiers; /* L, 0 for RBM / GRBM */
+    int32_t visible_kind;  /* QB_VISIBLE_* */
+    int32_t precision;     /* QB_PREC_* */
+    int64_t max_batch;     /* largest number of LOCAL rows (mini-batch rows == chains) per step */
+    int32_t device;        /* CUDA device ordinal */
+    int32_t rank;          /* data-parallel rank of this handle (0 on one GPU) */
+    int32_t world;         /* number of data-parallel ranks (1 on one GPU) */
+    int32_t reserved;
+} qb_config;
+
+int32_t qb_version(void);
+int32_t qb_device_count(int32_t *count);
+const char *qb_last_error(void);
+
+/* RBM(...) / GRBM(...) / RBMClassifier(...) constructors own the host arrays
+ * (src/rbm.jl:43-99); the handle owns their device mirror. */
+int32_t qb_create(qb_handle **out, const qb_config *cfg);
+int32_t qb_destroy(qb_handle *h);
+
+/* rbm.W / rbm.a / rbm.b / rbm.U / rbm.c upload and download (fields of src/rbm.jl:2-39;
+ * the download is what copy_rbm / copy_rbm! snapshot, src/rbm.jl:231-255).
+ * U and c are NULL when n_classifiers == 0. */
+int32_t qb_set_params(qb_handle *h, const double *W, const double *a, const double *b, const double *U, const double *c);
+int32_t qb_get_params(qb_handle *h, double *W, double *a, double *b, double *U, double *c);
+
+/* Extension (absent from update_rbm!, src/rbm.jl:152-163): both default to 0, which
+ * reproduces the reference update exactly. */
+int32_t qb_set_optimizer(qb_handle *h, double momentum, double weight_decay);
+
+/* x_train [, label_train] of train! (src/training/train_cd.jl:45-59,
+ * src/training/train_pcd.jl:133-148): the LOCAL rows of the dataset become resident in HBM.
+ * With world > 1 the caller passes, for every global mini-batch, this rank's contiguous
+ * slice of rows, concatenated in mini-batch order. Y may be NULL when n_classifiers == 0. */
+int32_t qb_set_data(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype, int64_t n_rows);
+
+/* _init_fantasy_data (src/fantasy_data.jl:66-86): n_chains LOCAL persistent chains.  Host
+ * arrays (n_chains rows of V / H / L doubles: the reference's rand(V), rand(H), rand(L))
+ * or NULL to draw the same U[0,1) floats from the device Philox stream. */
+int32_t qb_init_chains(qb_handle *h, int64_t n_chains, const double *v, const double *hid, const double *y);
+int32_t qb_get_chains(qb_handle *h, double *v, double *hid, double *y);
+
+/* Production RNG: Philox4x32-10 keyed by `seed`, counters keyed by (draw, global row,
+ * unit) so results do not depend on the number of GPUs. */
+int32_t qb_seed(qb_handle *h, uint64_t seed);
+
+/* Validation mode: replace the random stream of the NEXT step call by injected values,
+ * dense per Gibbs step: U_h[k][B][H], U_v[k][B][V] (Bernoulli visibles) or Z_v[k][B][V]
+ * (standard normals, Gaussian visibles), U_y[k][B][L].  This is the de-interleaved form
+ * of the serial rand()/randn() order of src/gibbs.jl:57-72 and src/fantasy_data.jl:12-29
+ * (SURVEY.md section 8(a)).  B = local rows. Unused arrays are NULL. */
+int32_t qb_inject_streams(qb_handle *h, const double *U_h, const double *U_v, const double *U_y, const double *Z_v,
+                          int64_t k, int64_t B);
+
+/* One mini-batch of persistent_contrastive_divergence! (src/training/train_pcd.jl:11-40;
+ * classifier :57-92) on resident mini-batch `batch_index` with B local rows. */
+int32_t qb_pcd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, double lr, double llr);
+/* One mini-batch of contrastive_divergence! (src/training/train_cd.jl:4-19, :25-41).
+ * B == 1 is the reference (online); B > 1 is the declared mini-batch extension. */
+int32_t qb_cd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, double lr, double llr);
+
+/* persistent_contrastive_divergence! / contrastive_divergence! for a whole epoch over the
+ * resident data (`_set_mini_batches` semantics, src/utils.jl:13-26: trailing remainder
+ * dropped).  times[3] = seconds in (sample, gibbs, update), the triple the reference
+ * returns to train! (src/training/train_pcd.jl:42), measured with CUDA events. */
+int32_t qb_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]);
+int32_t qb_cd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]);
+
+/* Same step, but the mini-batch comes from HOST memory on every call (end-to-end path:
+ * upload, step, and a device->host read of the batch reconstruction error sum). */
+int32_t qb_pcd_step_host(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype, int64_t B,
+                         int64_t k, double lr, double llr, double *recon_sq_err);
+int32_t qb_cd_step_host(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype, int64_t B,
+                        int64_t k, double lr, double llr, double *recon_sq_err);
+
+/* evaluate + _evaluate(MeanSquaredError) + reconstruct (src/evaluation.jl:16-20,52-70;
+ * src/rbm.jl:220-224): sum over samples of sum_units (x - reconstruct(x))^2 / n_rows.
+ * X == NULL evaluates the resident dataset. Z (n_rows x V standard normals) optionally
+ * injects the noise the GRBM reconstruct draws (src/rbm.jl:187). */
+int32_t qb_eval_mse(qb_handle *h, const void *X, int32_t x_dtype, int64_t n_rows, const double *Z, double *out);
+/* New metric: mean free energy, sign convention of the QUBO objective (src/qubo.jl:43-55). */
+int32_t qb_eval_free_energy(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype,
+                            int64_t n_rows, double *out);
+/* reconstruct(rbm, v) for n_rows rows (src/rbm.jl:220-224). */
+int32_t qb_reconstruct(qb_handle *h, const double *v, int64_t n_rows, const double *Z, double *out);
+/* conditional_prob_h (src/rbm.jl:165,170-171) for n_rows rows; y may be NULL (2-arg form). */
+int32_t qb_conditional_prob_h(qb_handle *h, const double *v, const double *y, int64_t n_rows, double *out);
+
+/* Data-parallel gradient allreduce over NCCL (new; the reference is single-process).
+ * Rank 0 creates the id, the caller ships the 128 bytes to the other ranks. */
+int32_t qb_comm_unique_id(void *id128);
+int32_t qb_comm_init(qb_handle *h, const void *id128);
+
+/* Introspection for benchmarks: kernels launched by this library on this handle, and
+ * CUDA-event time of the dominant (GEMM) kernels since the last reset. */
+int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_launches, double *gemm_ms);
+int32_t qb_reset_counters(qb_handle *h);
+int32_t qb_set_option(qb_handle *h, const char *key, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QARBOM_B200_H */

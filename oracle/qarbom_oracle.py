@@ -64,6 +64,38 @@ class Stream:
         self.zpos += n
         return out
 
+    def bernoulli(self, p: np.ndarray) -> np.ndarray:
+        """``[rand() < p_i ? 1 : 0 for p_i in p]`` (src/gibbs.jl:5,15,31,48)."""
+        return (self.rand(len(p)) < p).astype(np.int64)
+
+
+class GuardedStream(Stream):
+    """Test helper: an injected stream whose near-ties are pushed away from the decision
+    boundary.  Any uniform with |u - p| < guard is replaced IN PLACE by p -/+ 2*guard on the
+    same side (rounded to fp32), so the sampled trajectory is unchanged while an fp32
+    device evaluation of p (|dp| ~ 1e-6) cannot flip a state."""
+
+    def __init__(self, uniforms=None, normals=None, guard: float = 1e-4):
+        super().__init__(uniforms, normals)
+        self.u = self.u.copy()
+        self.guard = guard
+        self.nudged = 0
+
+    def bernoulli(self, p: np.ndarray) -> np.ndarray:
+        n = len(p)
+        lo = self.upos
+        u = self.rand(n)
+        out = u < p
+        near = np.abs(u - p) < self.guard
+        if near.any():
+            tgt = np.where(out, p - 2 * self.guard, p + 2 * self.guard)
+            tgt = np.clip(tgt, 0.0, 1.0 - 2.0 ** -24).astype(np.float32).astype(np.float64)
+            ok = (tgt < p) == out  # clipping may fail at p ~ 0 or 1: leave those, tests guard-band them
+            idx = np.nonzero(near & ok)[0]
+            self.u[lo + idx] = tgt[idx]
+            self.nudged += idx.size
+        return out.astype(np.int64)
+
 
 class NumpyStream(Stream):
     """Free-running stream for statistical runs (not for bit parity)."""
@@ -77,6 +109,9 @@ class NumpyStream(Stream):
 
     def randn(self, n: int) -> np.ndarray:
         return self.g.standard_normal(n)
+
+    def bernoulli(self, p: np.ndarray) -> np.ndarray:
+        return (self.g.random(len(p)) < p).astype(np.int64)
 
 
 # --------------------------------------------------------------------------- model
@@ -203,7 +238,7 @@ def classify(m: Model, v: np.ndarray) -> np.ndarray:
 def gibbs_sample_hidden(m: Model, v, stream: Stream, y=None) -> np.ndarray:
     """src/gibbs.jl:3-6 / :29-32: H uniforms in unit order, strict ``rand() < p``."""
     p = conditional_prob_h(m, v, y)
-    return (stream.rand(m.n_hidden) < p).astype(np.int64)
+    return stream.bernoulli(p)
 
 
 def gibbs_sample_visible(m: Model, h, stream: Stream) -> np.ndarray:
@@ -211,13 +246,13 @@ def gibbs_sample_visible(m: Model, h, stream: Stream) -> np.ndarray:
     if m.gaussian:
         return conditional_prob_v(m, h, stream)
     p = conditional_prob_v(m, h)
-    return (stream.rand(m.n_visible) < p).astype(np.int64)
+    return stream.bernoulli(p)
 
 
 def gibbs_sample_label(m: Model, h, stream: Stream) -> np.ndarray:
     """src/gibbs.jl:46-49: softmax probabilities, then INDEPENDENT Bernoulli per unit."""
     p = conditional_prob_y_given_h(m, h)
-    return (stream.rand(m.n_classifiers) < p).astype(np.int64)
+    return stream.bernoulli(p)
 
 
 def _get_v_model(m: Model, v, n_gibbs: int, stream: Stream):

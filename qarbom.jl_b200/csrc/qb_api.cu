@@ -1,0 +1,1039 @@
+// C ABI (include/qarbom_b200.h): handle, HBM layout, and the host-side orchestration of the
+// CD-k / PCD mini-batch step on top of the kernels in simt_kernels.cuh (QB_PREC_FP32) and
+// sm100_gemm.cuh (QB_PREC_BF16).  No CPU compute path exists in this library.
+#include "../../include/qarbom_b200.h"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+#include "simt_kernels.cuh"
+#include "sm100_gemm.cuh"
+
+using namespace qb;
+
+static thread_local std::string g_last_error;
+
+// ----------------------------------------------------------------------------- NCCL (dlopen'ed, optional)
+namespace {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct Nccl {
+    void *lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+Nccl &nccl() {
+    static Nccl n;
+    if (!n.lib) {
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (n.lib) break;
+        }
+        QB_CHECK(n.lib != nullptr, QB_E_NCCL, "libnccl.so.2 not found (dlopen)");
+        n.GetUniqueId = (decltype(n.GetUniqueId))dlsym(n.lib, "ncclGetUniqueId");
+        n.CommInitRank = (decltype(n.CommInitRank))dlsym(n.lib, "ncclCommInitRank");
+        n.AllReduce = (decltype(n.AllReduce))dlsym(n.lib, "ncclAllReduce");
+        n.CommDestroy = (decltype(n.CommDestroy))dlsym(n.lib, "ncclCommDestroy");
+        n.GetErrorString = (decltype(n.GetErrorString))dlsym(n.lib, "ncclGetErrorString");
+        QB_CHECK(n.GetUniqueId && n.CommInitRank && n.AllReduce && n.CommDestroy, QB_E_NCCL, "NCCL symbols missing");
+    }
+    return n;
+}
+#define QB_NCCL(expr)                                                                          \
+    do {                                                                                       \
+        int _r = (expr);                                                                       \
+        if (_r != 0) throw qb::Error(QB_E_NCCL, std::string(#expr) + " failed: " +             \
+                                     (nccl().GetErrorString ? nccl().GetErrorString(_r) : "?")); \
+    } while (0)
+}  // namespace
+
+// ----------------------------------------------------------------------------- device matrices
+struct Mat {
+    float *f = nullptr;  // fp32 [rows][ld]        (QB_PREC_FP32)
+    bf16 *b = nullptr;   // bf16 [rows][ld]        (QB_PREC_BF16)
+    bf16 *bT = nullptr;  // bf16 [units][ldT]      (QB_PREC_BF16, gradient operand)
+    int64_t ld = 0, ldT = 0, rows = 0, units = 0;
+    Mat row_slice(int64_t r0, int64_t n) const {  // rows [r0, r0+n); the transposed view is not sliceable
+        Mat m = *this;
+        if (m.f) m.f += r0 * ld;
+        if (m.b) m.b += r0 * ld;
+        m.bT = nullptr;
+        m.rows = n;
+        return m;
+    }
+};
+
+struct Rng {  // how a sampling half-step gets its random numbers
+    const float *inj = nullptr; int64_t ld_inj = 0;  // injected [rows][units]
+    RngKey key{}; int use_rng = 0;
+};
+
+struct qb_handle {
+    qb_config cfg{};
+    int64_t V = 0, H = 0, L = 0, VL = 0, ldv = 0, ldh = 0, Bmax = 0, ldb = 0;
+    bool bf = false, gaussian = false;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    // flat parameter / gradient / velocity vectors: [W (H x ldv) | acat (ldv) | b (ldh)]
+    float *P = nullptr, *G = nullptr, *Vel = nullptr;
+    int64_t nW = 0, nP = 0;
+    bf16 *Wb = nullptr, *WbT = nullptr;
+    double momentum = 0.0, weight_decay = 0.0;
+    // resident dataset
+    Mat data; int64_t N = 0;
+    bf16 *dataT = nullptr; int64_t dataT_B = 0, dataT_nb = 0, dataT_ld = 0;
+    // persistent chains and work buffers (Bmax rows)
+    Mat cv, ch; int64_t n_chains = 0; bool chains_binary = false;
+    Mat phd, hs, vm, phm, hb;  // pos-phase probs, sampled hidden, CD model visible, CD final probs, host-batch staging
+    float *pre_h = nullptr, *pre_v = nullptr, *lab_pre = nullptr, *softplus_rows = nullptr;
+    float *out_f32 = nullptr;  // fp32 [Bmax][max(ldv, ldh)] API output staging
+    float *znoise = nullptr;   // fp32 [Bmax][V] injected reconstruct noise (Gaussian visibles)
+    double *dscal = nullptr;   // device scalar accumulators [4]
+    void *staging = nullptr; size_t staging_bytes = 0;
+    // injected streams for the next step
+    float *injUh = nullptr, *injUv = nullptr, *injZv = nullptr; int64_t inj_k = 0, inj_B = 0; bool inj_active = false;
+    size_t injUh_cap = 0, injUv_cap = 0, injZv_cap = 0;
+    uint64_t seed = 0, draw = 0;
+    ncclComm_t comm = nullptr;
+    int64_t launches = 0, gemm_launches = 0;
+    int force_bn = 0;
+};
+
+namespace {
+
+template <typename T>
+T *dalloc(size_t n) {
+    T *p = nullptr;
+    QB_CUDA(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+    QB_CUDA(cudaMemset(p, 0, (n ? n : 1) * sizeof(T)));
+    return p;
+}
+
+Mat alloc_mat(const qb_handle *h, int64_t rows, int64_t units, bool want_T) {
+    Mat m;
+    m.rows = rows; m.units = units;
+    m.ld = round_up(units, 8);
+    m.ldT = round_up(rows, 8);
+    if (h->bf) {
+        m.b = dalloc<bf16>(rows * m.ld);
+        if (want_T) m.bT = dalloc<bf16>(units * m.ldT);
+    } else {
+        m.f = dalloc<float>(rows * m.ld);
+    }
+    return m;
+}
+void free_mat(Mat &m) {
+    cudaFree(m.f); cudaFree(m.b); cudaFree(m.bT);
+    m = Mat();
+}
+
+inline dim3 grid1d(int64_t n, int block = 256) { return dim3((unsigned)ceil_div(n, block)); }
+
+float *Wf(qb_handle *h) { return h->P; }
+float *acat(qb_handle *h) { return h->P + h->nW; }
+float *bh(qb_handle *h) { return h->P + h->nW + h->ldv; }
+float *G_W(qb_handle *h) { return h->G; }
+float *G_a(qb_handle *h) { return h->G + h->nW; }
+float *G_b(qb_handle *h) { return h->G + h->nW + h->ldv; }
+
+void ensure_staging(qb_handle *h, size_t bytes) {
+    if (h->staging_bytes >= bytes) return;
+    cudaFree(h->staging);
+    h->staging = nullptr; h->staging_bytes = 0;
+    QB_CUDA(cudaMalloc(&h->staging, bytes));
+    h->staging_bytes = bytes;
+}
+
+size_t dt_size(int dt) {
+    switch (dt) {
+        case QB_DT_F64: return 8;
+        case QB_DT_I64: return 8;
+        case QB_DT_F32: return 4;
+        case QB_DT_U8: return 1;
+    }
+    throw Error(QB_E_ARG, "unknown element type code");
+}
+
+// host rows (n x cols of dtype) -> device matrix columns [col0, col0+cols) of dst rows [r0, r0+n)
+void upload_rows(qb_handle *h, const void *src, int dt, int64_t n, int64_t cols, Mat &dst, int64_t r0, int64_t col0) {
+    if (n == 0 || cols == 0) return;
+    const size_t es = dt_size(dt);
+    const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)((64u << 20) / (cols * es)));
+    for (int64_t r = 0; r < n; r += chunk_rows) {
+        const int64_t nr = std::min(chunk_rows, n - r);
+        ensure_staging(h, (size_t)nr * cols * es);
+        QB_CUDA(cudaMemcpyAsync(h->staging, (const char *)src + (size_t)r * cols * es, (size_t)nr * cols * es,
+                                cudaMemcpyHostToDevice, h->stream));
+        float *df = dst.f ? dst.f + (r0 + r) * dst.ld : nullptr;
+        bf16 *db = dst.b ? dst.b + (r0 + r) * dst.ld : nullptr;
+        const int64_t tot = nr * cols;
+        switch (dt) {
+            case QB_DT_F64: convert_rows_kernel<double><<<grid1d(tot), 256, 0, h->stream>>>((const double *)h->staging, cols, nr, df, db, dst.ld, col0); break;
+            case QB_DT_I64: convert_rows_kernel<long long><<<grid1d(tot), 256, 0, h->stream>>>((const long long *)h->staging, cols, nr, df, db, dst.ld, col0); break;
+            case QB_DT_F32: convert_rows_kernel<float><<<grid1d(tot), 256, 0, h->stream>>>((const float *)h->staging, cols, nr, df, db, dst.ld, col0); break;
+            default: convert_rows_kernel<unsigned char><<<grid1d(tot), 256, 0, h->stream>>>((const unsigned char *)h->staging, cols, nr, df, db, dst.ld, col0); break;
+        }
+        QB_CUDA(cudaGetLastError());
+        h->launches++;
+        QB_CUDA(cudaStreamSynchronize(h->stream));  // staging buffer is reused
+    }
+}
+
+// device matrix columns -> host doubles (n x cols)
+void download_rows(qb_handle *h, const Mat &src, int64_t r0, int64_t col0, int64_t n, int64_t cols, double *dst) {
+    if (!dst || n == 0 || cols == 0) return;
+    ensure_staging(h, (size_t)n * cols * sizeof(double));
+    if (src.f) export_rows_kernel<float><<<grid1d(n * cols), 256, 0, h->stream>>>(src.f + r0 * src.ld, src.ld, col0, n, cols, (double *)h->staging);
+    else export_rows_kernel<bf16><<<grid1d(n * cols), 256, 0, h->stream>>>(src.b + r0 * src.ld, src.ld, col0, n, cols, (double *)h->staging);
+    QB_CUDA(cudaGetLastError());
+    h->launches++;
+    QB_CUDA(cudaMemcpyAsync(dst, h->staging, (size_t)n * cols * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QB_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+void transpose_into(qb_handle *h, const bf16 *src, int64_t lds, int64_t rows, int64_t cols, bf16 *dst, int64_t ldd) {
+    dim3 g((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+    transpose_bf16_kernel<<<g, 256, 0, h->stream>>>(src, lds, (int)rows, (int)cols, dst, ldd);
+    QB_CUDA(cudaGetLastError());
+    h->launches++;
+}
+
+RngKey make_key(qb_handle *h) {
+    RngKey k;
+    k.seed_lo = (uint32_t)h->seed; k.seed_hi = (uint32_t)(h->seed >> 32);
+    k.draw_lo = (uint32_t)h->draw; k.draw_hi = (uint32_t)(h->draw >> 32) & 0x7FFFFFFFu;
+    h->draw++;
+    return k;
+}
+Rng philox_rng(qb_handle *h) { Rng r; r.key = make_key(h); r.use_rng = 1; return r; }
+Rng injected_rng(const float *p, int64_t ld) { Rng r; r.inj = p; r.ld_inj = ld; return r; }
+
+int64_t row0_of(const qb_handle *h, int64_t B) { return (int64_t)h->cfg.rank * B; }
+
+void simt_gemm(qb_handle *h, const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbk, int64_t sbn, float *C,
+               int64_t ldc, int64_t M, int64_t N, int64_t K, float alpha, float beta, const float *bias) {
+    dim3 g((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
+    simt_gemm_kernel<<<g, 256, 0, h->stream>>>(A, sam, sak, B, sbk, sbn, C, ldc, (int)M, (int)N, (int)K, alpha, beta, bias);
+    QB_CUDA(cudaGetLastError());
+    h->launches++; h->gemm_launches++;
+}
+
+// ----------------------------------------------------------------------------- the three ops
+struct HiddenOut {
+    Mat *prob = nullptr;   // probabilities (fp32 path: .f; bf16 path: .b and/or .bT per flags)
+    Mat *state = nullptr;  // sampled binary states
+    bool prob_rm = false, prob_T = false, state_rm = false, state_T = false;
+    float *prob_f32 = nullptr; int64_t ld_pf = 0;  // bf16 path only: extra fp32 copy of the probabilities
+    int bg_what = 0; float bg_sign = 0.f;          // bf16 path: fold the hidden bias gradient
+    float *softplus_rows = nullptr;                // free-energy mode (no other outputs)
+};
+
+// conditional_prob_h (+ gibbs_sample_hidden): in = visible-side rows [rows][kdim] (kdim = V or V+L)
+void op_hidden(qb_handle *h, const Mat &in, int64_t rows, int64_t kdim, const HiddenOut &o, const Rng &rng, int64_t row0) {
+    if (!h->bf) {
+        simt_gemm(h, in.f, in.ld, 1, Wf(h), 1, h->ldv, h->pre_h, h->ldh, rows, h->H, kdim, 1.f, 0.f, bh(h));
+        if (o.softplus_rows) return;  // fp32 path reads pre_h directly
+        act_sample_kernel<<<grid1d(rows * h->H), 256, 0, h->stream>>>(
+            h->pre_h, h->ldh, (int)rows, (int)h->H, 0, o.prob ? o.prob->f : nullptr, o.prob ? o.prob->ld : 0,
+            o.state ? o.state->f : nullptr, o.state ? o.state->ld : 0, rng.inj, rng.ld_inj, rng.key, row0, rng.use_rng);
+        QB_CUDA(cudaGetLastError());
+        h->launches++;
+        return;
+    }
+    sm100::Operand A{h->Wb, h->H, kdim, h->ldv}, B{in.b, rows, kdim, in.ld};
+    sm100::EpiParams ep{};
+    ep.mode = sm100::EPI_SAMPLE; ep.M = (int)h->H; ep.N = (int)rows;
+    ep.bias = bh(h); ep.split = (int)h->H;
+    ep.act = o.softplus_rows ? sm100::ACT_GAUSSIAN : sm100::ACT_SIGMOID;
+    ep.sample = (o.state != nullptr);
+    if (o.state) {
+        if (o.state_rm) { ep.state_rm = o.state->b; ep.ld_srm = o.state->ld; }
+        if (o.state_T) { ep.state_T = o.state->bT; ep.ld_sT = o.state->ldT; }
+    }
+    if (o.prob) {
+        if (o.prob_rm) { ep.prob_rm = o.prob->b; ep.ld_prm = o.prob->ld; }
+        if (o.prob_T) { ep.prob_T = o.prob->bT; ep.ld_pT = o.prob->ldT; }
+    }
+    ep.prob_f32 = o.prob_f32; ep.ld_pf = o.ld_pf;
+    ep.inj = rng.inj; ep.ld_inj = rng.ld_inj; ep.key = rng.key; ep.use_rng = rng.use_rng; ep.row0 = row0;
+    ep.bg_what = o.bg_what; ep.bg_sign = o.bg_sign; ep.bias_grad = G_b(h);
+    ep.softplus_rows = o.softplus_rows;
+    sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn);
+    h->launches++; h->gemm_launches++;
+}
+
+struct VisibleOut {
+    Mat *state = nullptr;  // sampled visible (+label) state, or mean-field values when sample == false
+    bool sample = true;
+    bool state_rm = true, state_T = false;
+    float *prob_f32 = nullptr; int64_t ld_pf = 0;  // fp32 copy of probabilities / means [rows][ldv]
+    bool f32_from_state = false;                    // bf16 path: prob_f32 receives the (noisy) value
+    int bg_sign_neg = 0;                            // bf16 path: G_a -= column sums of the state
+    const Mat *ref = nullptr; double *sqerr = nullptr;  // reconstruction error vs ref rows (visible units only)
+};
+
+// conditional_prob_v / gibbs_sample_visible (+ gibbs_sample_label): in = hidden rows [rows][H]
+void op_visible(qb_handle *h, const Mat &in, int64_t rows, const VisibleOut &o, const Rng &rng, int64_t row0) {
+    const int act = h->gaussian ? 1 : 0;
+    if (!h->bf) {
+        simt_gemm(h, in.f, in.ld, 1, Wf(h), h->ldv, 1, h->pre_v, h->ldv, rows, h->VL, h->H, 1.f, 0.f, acat(h));
+        // value written for each visible unit: sampled state (sample), probability (Bernoulli
+        // mean-field) or mean + noise (Gaussian; noise only if the caller supplied a stream)
+        float *st = o.state ? o.state->f : nullptr;
+        int64_t lds = o.state ? o.state->ld : 0;
+        float *prob_dst = o.prob_f32;
+        int64_t ldp = o.ld_pf;
+        if (act == 0 && !o.sample) {
+            if (!prob_dst) { prob_dst = st; ldp = lds; }
+            st = nullptr;
+        }
+        act_sample_kernel<<<grid1d(rows * h->V), 256, 0, h->stream>>>(h->pre_v, h->ldv, (int)rows, (int)h->V, act, prob_dst, ldp, st,
+                                                                      lds, rng.inj, rng.ld_inj, rng.key, row0, rng.use_rng);
+        QB_CUDA(cudaGetLastError());
+        h->launches++;
+        if (h->L > 0 && o.sample) {
+            label_kernel<<<grid1d(rows, 128), 128, 0, h->stream>>>(h->pre_v, h->ldv, (int)rows, (int)h->V, (int)h->L, nullptr, 0,
+                                                                   o.state->f, o.state->ld, rng.inj, rng.ld_inj, rng.key, row0);
+            QB_CUDA(cudaGetLastError());
+            h->launches++;
+        }
+        if (o.sqerr) {
+            const float *recon = (act == 0) ? prob_dst : o.state->f;
+            int64_t ldr = (act == 0) ? ldp : o.state->ld;
+            sqerr_kernel<float><<<std::min<int64_t>(1184, ceil_div(rows * h->V, 256)), 256, 0, h->stream>>>(
+                o.ref->f, o.ref->ld, recon, ldr, (int)rows, (int)h->V, o.sqerr);
+            QB_CUDA(cudaGetLastError());
+            h->launches++;
+        }
+        return;
+    }
+    sm100::Operand A{h->WbT, h->VL, h->H, h->ldh}, B{in.b, rows, h->H, in.ld};
+    sm100::EpiParams ep{};
+    ep.mode = sm100::EPI_SAMPLE; ep.M = (int)h->VL; ep.N = (int)rows;
+    ep.bias = acat(h); ep.split = (int)h->V; ep.lab_pre = h->lab_pre; ep.ld_lab = h->L > 0 ? h->L : 1;
+    ep.act = act ? sm100::ACT_GAUSSIAN : sm100::ACT_SIGMOID;
+    ep.sample = o.sample || (act == 1 && (rng.inj || rng.use_rng));
+    if (o.state) {
+        if (o.state_rm) { ep.state_rm = o.state->b; ep.ld_srm = o.state->ld; }
+        if (o.state_T) { ep.state_T = o.state->bT; ep.ld_sT = o.state->ldT; }
+    }
+    ep.prob_f32 = o.prob_f32; ep.ld_pf = o.ld_pf; ep.f32_from_state = o.f32_from_state ? 1 : 0;
+    ep.inj = rng.inj; ep.ld_inj = rng.ld_inj; ep.key = rng.key; ep.use_rng = rng.use_rng; ep.row0 = row0;
+    if (o.bg_sign_neg) { ep.bg_what = 2; ep.bg_sign = -1.f; ep.bias_grad = G_a(h); }
+    if (o.sqerr) { ep.sqerr = o.sqerr; ep.ref_rm = o.ref->b; ep.ld_ref = o.ref->ld; }
+    sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn);
+    h->launches++; h->gemm_launches++;
+    if (h->L > 0 && o.sample && o.state) {
+        label_bf16_kernel<<<grid1d(rows, 128), 128, 0, h->stream>>>(
+            h->lab_pre, h->L, (int)rows, (int)h->V, (int)h->L, o.state_rm ? o.state->b : nullptr, o.state->ld,
+            o.state_T ? o.state->bT : nullptr, o.state->ldT, rng.inj, rng.ld_inj, rng.key, row0,
+            o.bg_sign_neg ? G_a(h) : nullptr);
+        QB_CUDA(cudaGetLastError());
+        h->launches++;
+    }
+}
+
+template <typename T>
+void colsum(qb_handle *h, const T *A, int64_t lda, int64_t rows, int64_t cols, float sign, float *out) {
+    dim3 g((unsigned)ceil_div(cols, 32), (unsigned)std::min<int64_t>(64, ceil_div(rows, 8)));
+    colsum_kernel<T><<<g, 256, 0, h->stream>>>(A, lda, (int)rows, (int)cols, sign, out);
+    QB_CUDA(cudaGetLastError());
+    h->launches++;
+}
+
+// G = posH' posV - negH' negV   (and the bias gradients that were not folded into epilogues)
+void op_grad(qb_handle *h, const Mat &posH, const Mat &posV, const bf16 *posV_T, int64_t posV_ldT, const Mat &negH,
+             const Mat &negV, int64_t rows) {
+    if (!h->bf) {
+        simt_gemm(h, posH.f, 1, posH.ld, posV.f, posV.ld, 1, G_W(h), h->ldv, h->H, h->VL, rows, 1.f, 0.f, nullptr);
+        simt_gemm(h, negH.f, 1, negH.ld, negV.f, negV.ld, 1, G_W(h), h->ldv, h->H, h->VL, rows, -1.f, 1.f, nullptr);
+        colsum<float>(h, posV.f, posV.ld, rows, h->VL, 1.f, G_a(h));
+        colsum<float>(h, negV.f, negV.ld, rows, h->VL, -1.f, G_a(h));
+        colsum<float>(h, posH.f, posH.ld, rows, h->H, 1.f, G_b(h));
+        colsum<float>(h, negH.f, negH.ld, rows, h->H, -1.f, G_b(h));
+        return;
+    }
+    sm100::Operand A{posH.bT, h->H, rows, posH.ldT}, B{posV_T, h->VL, rows, posV_ldT};
+    sm100::Operand A2{negH.bT, h->H, rows, negH.ldT}, B2{negV.bT, h->VL, rows, negV.ldT};
+    sm100::EpiParams ep{};
+    ep.mode = sm100::EPI_GRAD; ep.M = (int)h->H; ep.N = (int)h->VL;
+    ep.out_f32 = G_W(h); ep.ld_out = h->ldv;
+    sm100::launch(h->stream, A, B, &A2, &B2, ep, h->num_sms, h->force_bn);
+    h->launches++; h->gemm_launches++;
+    colsum<bf16>(h, posV.b, posV.ld, rows, h->VL, 1.f, G_a(h));  // data-side visible sums; the rest is folded
+}
+
+void zero_bias_grads(qb_handle *h) { QB_CUDA(cudaMemsetAsync(G_a(h), 0, (h->ldv + h->ldh) * sizeof(float), h->stream)); }
+
+// update_rbm!(rbm, dW, [dU,] da, db, [dc,] lr/B [, llr/B]) after the data-parallel sum of G
+void op_update(qb_handle *h, double lr, double llr, int64_t B_local) {
+    if (h->comm) {
+        QB_NCCL(nccl().AllReduce(h->G, h->G, (size_t)h->nP, /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->comm, h->stream));
+    }
+    const double Bg = (double)B_local * (double)h->cfg.world;
+    const float lr_e = (float)(lr / Bg), llr_e = (float)(llr / Bg);
+    const bool use_vel = (h->momentum != 0.0 || h->weight_decay != 0.0);
+    if (use_vel && !h->Vel) h->Vel = dalloc<float>(h->nP);
+    dim3 g((unsigned)ceil_div(h->VL, 64), (unsigned)ceil_div(h->H, 64));
+    update_w_kernel<<<g, 256, 0, h->stream>>>(Wf(h), G_W(h), use_vel ? h->Vel : nullptr, (int)h->H, (int)h->VL, (int)h->V, h->ldv,
+                                              lr_e, llr_e, (float)h->momentum, (float)h->weight_decay, h->Wb, h->WbT, h->ldh);
+    QB_CUDA(cudaGetLastError());
+    const int nb = (int)(h->ldv + h->ldh);
+    update_bias_kernel<<<grid1d(nb), 256, 0, h->stream>>>(acat(h), G_a(h), use_vel ? h->Vel + h->nW : nullptr, (int)h->ldv,
+                                                          (int)h->V, nb, lr_e, llr_e, (float)h->momentum);
+    QB_CUDA(cudaGetLastError());
+    h->launches += 2;
+}
+
+void refresh_shadows(qb_handle *h) {
+    if (!h->bf) return;
+    dim3 g((unsigned)ceil_div(h->VL, 64), (unsigned)ceil_div(h->H, 64));
+    shadow_kernel<<<g, 256, 0, h->stream>>>(Wf(h), (int)h->H, (int)h->VL, h->ldv, h->Wb, h->WbT, h->ldh);
+    QB_CUDA(cudaGetLastError());
+    h->launches++;
+}
+
+// transposed copies of every resident mini-batch for batch size B (gradient GEMM operand), built lazily
+void ensure_dataT(qb_handle *h, int64_t B) {
+    if (!h->bf || h->dataT_B == B) return;
+    cudaFree(h->dataT);
+    h->dataT = nullptr;
+    const int64_t nb = h->N / B;
+    h->dataT_ld = round_up(B, 8);
+    h->dataT = dalloc<bf16>((size_t)std::max<int64_t>(nb, 1) * h->VL * h->dataT_ld);
+    for (int64_t m = 0; m < nb; m++)
+        transpose_into(h, h->data.b + m * B * h->data.ld, h->data.ld, B, h->VL, h->dataT + m * h->VL * h->dataT_ld, h->dataT_ld);
+    h->dataT_B = B; h->dataT_nb = nb;
+}
+
+struct StepRng {  // per Gibbs step s: hidden uniforms, visible uniforms / normals (labels ride on the visible draw)
+    qb_handle *h; int64_t B; bool inj;
+    Rng hidden(int64_t s) { return inj ? injected_rng(h->injUh + s * B * h->H, h->H) : philox_rng(h); }
+    Rng visible(int64_t s) {
+        if (!inj) return philox_rng(h);
+        if (h->gaussian && h->L == 0) return injected_rng(h->injZv + s * B * h->V, h->V);
+        // Gaussian classifier: normals for visibles and uniforms for labels live in one [B][VL] array
+        return injected_rng(h->injUv + s * B * h->VL, h->VL);
+    }
+};
+
+void check_step_args(qb_handle *h, int64_t B, int64_t k) {
+    QB_CHECK(B >= 1 && B <= h->Bmax, QB_E_ARG, "batch rows must be in [1, max_batch]");
+    QB_CHECK(k >= 1, QB_E_ARG, "gibbs steps must be >= 1");
+    QB_CHECK(h->cfg.world == 1 || (B % 4) == 0, QB_E_ARG, "multi-GPU requires local batch rows % 4 == 0");
+    if (h->inj_active) QB_CHECK(h->inj_k >= k && h->inj_B == B, QB_E_ARG, "injected streams do not match (k, B) of the step");
+}
+
+// k Gibbs steps on the persistent chains (_update_fantasy_data!, src/fantasy_data.jl:12-29)
+void advance_chains(qb_handle *h, int64_t B, int64_t k, StepRng &sr, bool fold_bias) {
+    const int64_t row0 = row0_of(h, B);
+    for (int64_t s = 0; s < k; s++) {
+        const bool last = (s == k - 1);
+        HiddenOut ho; ho.state = &h->ch; ho.state_rm = true; ho.state_T = last;
+        if (last && fold_bias) { ho.bg_what = 2; ho.bg_sign = -1.f; }
+        op_hidden(h, h->cv, B, h->VL, ho, sr.hidden(s), row0);
+        VisibleOut vo; vo.state = &h->cv; vo.sample = true; vo.state_rm = true; vo.state_T = last;
+        vo.bg_sign_neg = (last && fold_bias) ? 1 : 0;
+        op_visible(h, h->ch, B, vo, sr.visible(s), row0);
+    }
+    h->chains_binary = true;
+}
+
+// bf16 path, classifier PCD before the first chain update: chains still hold the raw U[0,1) floats of
+// _init_fantasy_data, whose column sums were never folded by an epilogue.
+void fold_chain_bias_explicit(qb_handle *h, int64_t B) {
+    colsum<bf16>(h, h->cv.b, h->cv.ld, B, h->VL, -1.f, G_a(h));
+    colsum<bf16>(h, h->ch.b, h->ch.ld, B, h->H, -1.f, G_b(h));
+}
+
+void pcd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr,
+                   cudaEvent_t *ev) {
+    QB_CHECK(h->n_chains >= B, QB_E_STATE, "qb_init_chains must provide at least B chains");
+    StepRng sr{h, B, h->inj_active};
+    const int64_t row0 = row0_of(h, B);
+    zero_bias_grads(h);
+    const bool clf = h->L > 0;
+    if (ev) QB_CUDA(cudaEventRecord(ev[0], h->stream));
+    if (!clf) advance_chains(h, B, k, sr, h->bf);  // chains FIRST: train_pcd.jl:14-16
+    else if (h->bf) {
+        // classifier: gradient uses the chains as they are (train_pcd.jl:57-86); their transposes and
+        // column sums come from the previous step's epilogues, except before the very first update
+        if (!h->chains_binary) {
+            transpose_into(h, h->cv.b, h->cv.ld, B, h->VL, h->cv.bT, h->cv.ldT);
+            transpose_into(h, h->ch.b, h->ch.ld, B, h->H, h->ch.bT, h->ch.ldT);
+        }
+        fold_chain_bias_explicit(h, B);
+    }
+    if (ev) QB_CUDA(cudaEventRecord(ev[1], h->stream));
+    HiddenOut ho; ho.prob = &h->phd; ho.prob_T = true; ho.bg_what = 1; ho.bg_sign = 1.f;  // conditional_prob_h(v_data[, y_data])
+    op_hidden(h, xb, B, h->VL, ho, Rng(), row0);
+    if (ev) QB_CUDA(cudaEventRecord(ev[2], h->stream));
+    op_grad(h, h->phd, xb, xbT, xb_ldT, h->ch, h->cv, B);
+    op_update(h, lr, llr, B);
+    if (ev) QB_CUDA(cudaEventRecord(ev[3], h->stream));
+    if (clf) advance_chains(h, B, k, sr, false);  // classifier: chains AFTER the update, train_pcd.jl:89-92
+    if (ev) QB_CUDA(cudaEventRecord(ev[4], h->stream));
+    h->inj_active = false;
+}
+
+void cd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr,
+                  cudaEvent_t *ev) {
+    StepRng sr{h, B, h->inj_active};
+    const int64_t row0 = row0_of(h, B);
+    zero_bias_grads(h);
+    if (ev) QB_CUDA(cudaEventRecord(ev[0], h->stream));
+    // positive phase fused with the first hidden sample of the chain (same p(h | v_data[, y_data]))
+    HiddenOut h0; h0.prob = &h->phd; h0.prob_T = true; h0.bg_what = 1; h0.bg_sign = 1.f; h0.state = &h->hs; h0.state_rm = true;
+    op_hidden(h, xb, B, h->VL, h0, sr.hidden(0), row0);
+    if (ev) QB_CUDA(cudaEventRecord(ev[1], h->stream));
+    for (int64_t s = 0; s < k; s++) {
+        const bool last = (s == k - 1);
+        if (s > 0) {
+            HiddenOut hs; hs.state = &h->hs; hs.state_rm = true;
+            op_hidden(h, h->vm, B, h->VL, hs, sr.hidden(s), row0);
+        }
+        VisibleOut vo; vo.state = &h->vm; vo.sample = true; vo.state_rm = true; vo.state_T = last; vo.bg_sign_neg = (last && h->bf) ? 1 : 0;
+        op_visible(h, h->hs, B, vo, sr.visible(s), row0);
+    }
+    // h_model = conditional_prob_h(rbm, v_model): probabilities, 2-arg form (ignores y_model, train_cd.jl:34)
+    HiddenOut hm; hm.prob = &h->phm; hm.prob_T = true; hm.bg_what = 1; hm.bg_sign = -1.f;
+    op_hidden(h, h->vm, B, h->V, hm, Rng(), row0);
+    if (ev) QB_CUDA(cudaEventRecord(ev[2], h->stream));
+    op_grad(h, h->phd, xb, xbT, xb_ldT, h->phm, h->vm, B);
+    op_update(h, lr, llr, B);
+    if (ev) QB_CUDA(cudaEventRecord(ev[3], h->stream));
+    h->inj_active = false;
+}
+
+// resident mini-batch `m` of B rows as (row-major view, transposed pointer)
+void batch_view(qb_handle *h, int64_t m, int64_t B, Mat &xb, const bf16 *&xbT, int64_t &ldT) {
+    QB_CHECK(h->N > 0, QB_E_STATE, "qb_set_data has not been called");
+    QB_CHECK(m >= 0 && (m + 1) * B <= h->N, QB_E_ARG, "mini-batch index out of range");
+    xb = h->data.row_slice(m * B, B);
+    xbT = nullptr; ldT = 0;
+    if (h->bf) {
+        ensure_dataT(h, B);
+        xbT = h->dataT + m * h->VL * h->dataT_ld;
+        ldT = h->dataT_ld;
+    }
+}
+
+void stage_host_batch(qb_handle *h, const void *X, int xdt, const void *Y, int ydt, int64_t B) {
+    QB_CHECK(X != nullptr, QB_E_ARG, "X is NULL");
+    QB_CHECK(h->L == 0 || Y != nullptr, QB_E_ARG, "labels required for classifier models");
+    upload_rows(h, X, xdt, B, h->V, h->hb, 0, 0);
+    if (h->L > 0) upload_rows(h, Y, ydt, B, h->L, h->hb, 0, h->V);
+    if (h->bf) transpose_into(h, h->hb.b, h->hb.ld, B, h->VL, h->hb.bT, h->hb.ldT);
+}
+
+// sum over rows of sum_units (x - reconstruct(x))^2 for rows of `x` (chunked by Bmax), accumulated into dscal[0]
+void recon_sqerr(qb_handle *h, const Mat &x, int64_t n, const double *Z_host, int64_t global_row0) {
+    for (int64_t r = 0; r < n; r += h->Bmax) {
+        const int64_t nr = std::min(h->Bmax, n - r);
+        Mat xs = x.row_slice(r, nr);
+        HiddenOut ho; ho.prob = &h->phd; ho.prob_rm = true;
+        op_hidden(h, xs, nr, h->V, ho, Rng(), 0);
+        Rng rng;
+        if (h->gaussian) {  // reconstruct on a GRBM draws N(0,1) noise per unit (src/rbm.jl:187)
+            if (Z_host) {
+                Mat zf; zf.f = h->znoise; zf.ld = h->V; zf.rows = nr; zf.units = h->V;
+                upload_rows(h, Z_host + (size_t)r * h->V, QB_DT_F64, nr, h->V, zf, 0, 0);
+                rng = injected_rng(h->znoise, h->V);
+            } else {
+                rng = philox_rng(h);
+            }
+        }
+        VisibleOut vo; vo.state = &h->vm; vo.sample = false; vo.state_rm = !h->bf; vo.ref = &xs; vo.sqerr = h->dscal;
+        op_visible(h, h->phd, nr, vo, rng, global_row0 + r);
+    }
+}
+
+double read_scalar(qb_handle *h, int i) {
+    double v = 0.0;
+    QB_CUDA(cudaMemcpyAsync(&v, h->dscal + i, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QB_CUDA(cudaStreamSynchronize(h->stream));
+    return v;
+}
+
+template <typename F>
+int32_t guarded(F &&fn) {
+    try {
+        fn();
+        return QB_OK;
+    } catch (const qb::Error &e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return QB_E_CUDA;
+    }
+}
+#define QB_H(h) QB_CHECK((h) != nullptr, QB_E_ARG, "handle is NULL"); QB_CUDA(cudaSetDevice((h)->cfg.device))
+
+}  // namespace
+
+// ============================================================================= C ABI
+extern "C" {
+
+int32_t qb_version(void) { return QB_VERSION; }
+const char *qb_last_error(void) { return g_last_error.c_str(); }
+
+int32_t qb_device_count(int32_t *count) {
+    return guarded([&] {
+        QB_CHECK(count != nullptr, QB_E_ARG, "count is NULL");
+        int n = 0;
+        QB_CUDA(cudaGetDeviceCount(&n));
+        *count = n;
+    });
+}
+
+int32_t qb_create(qb_handle **out, const qb_config *cfg) {
+    return guarded([&] {
+        QB_CHECK(out && cfg, QB_E_ARG, "NULL argument");
+        QB_CHECK(cfg->n_visible > 0 && cfg->n_hidden > 0 && cfg->n_classifiers >= 0, QB_E_ARG, "V, H must be > 0 and L >= 0");
+        QB_CHECK(cfg->max_batch > 0, QB_E_ARG, "max_batch must be > 0");
+        QB_CHECK(cfg->precision == QB_PREC_FP32 || cfg->precision == QB_PREC_BF16, QB_E_ARG, "unknown precision");
+        QB_CHECK(cfg->visible_kind == QB_VISIBLE_BERNOULLI || cfg->visible_kind == QB_VISIBLE_GAUSSIAN, QB_E_ARG, "unknown visible kind");
+        QB_CHECK(cfg->world >= 1 && cfg->rank >= 0 && cfg->rank < cfg->world, QB_E_ARG, "bad rank/world");
+        int ndev = 0;
+        QB_CUDA(cudaGetDeviceCount(&ndev));
+        QB_CHECK(ndev > 0, QB_E_CUDA, "no CUDA device visible: qarbom_b200 has no CPU path");
+        QB_CHECK(cfg->device >= 0 && cfg->device < ndev, QB_E_ARG, "device ordinal out of range");
+        QB_CUDA(cudaSetDevice(cfg->device));
+        cudaDeviceProp prop;
+        QB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+        QB_CHECK(prop.major == 10, QB_E_CUDA,
+                 std::string("qarbom_b200 is built for sm_100a only; device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor));
+        std::unique_ptr<qb_handle> h(new qb_handle());
+        h->cfg = *cfg;
+        h->V = cfg->n_visible; h->H = cfg->n_hidden; h->L = cfg->n_classifiers; h->VL = h->V + h->L;
+        h->ldv = round_up(h->VL, 8); h->ldh = round_up(h->H, 8);
+        h->Bmax = cfg->max_batch; h->ldb = round_up(h->Bmax, 8);
+        h->bf = cfg->precision == QB_PREC_BF16;
+        h->gaussian = cfg->visible_kind == QB_VISIBLE_GAUSSIAN;
+        h->num_sms = prop.multiProcessorCount;
+        QB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        QB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : h->ev) QB_CUDA(cudaEventCreate(&e));
+        h->nW = h->H * h->ldv; h->nP = h->nW + h->ldv + h->ldh;
+        h->P = dalloc<float>(h->nP); h->G = dalloc<float>(h->nP);
+        if (h->bf) {
+            sm100::init_device();
+            h->Wb = dalloc<bf16>(h->H * h->ldv);
+            h->WbT = dalloc<bf16>(h->VL * h->ldh);
+        }
+        h->cv = alloc_mat(h.get(), h->Bmax, h->VL, true);
+        h->ch = alloc_mat(h.get(), h->Bmax, h->H, true);
+        h->phd = alloc_mat(h.get(), h->Bmax, h->H, true);
+        h->hs = alloc_mat(h.get(), h->Bmax, h->H, false);
+        h->vm = alloc_mat(h.get(), h->Bmax, h->VL, true);
+        h->phm = alloc_mat(h.get(), h->Bmax, h->H, true);
+        h->hb = alloc_mat(h.get(), h->Bmax, h->VL, true);
+        h->pre_h = dalloc<float>(h->Bmax * h->ldh);
+        h->pre_v = dalloc<float>(h->Bmax * h->ldv);
+        h->lab_pre = dalloc<float>(h->Bmax * std::max<int64_t>(h->L, 1));
+        h->softplus_rows = dalloc<float>(h->Bmax);
+        h->out_f32 = dalloc<float>(h->Bmax * std::max(h->ldv, h->ldh));
+        h->dscal = dalloc<double>(4);
+        if (h->gaussian) h->znoise = dalloc<float>(h->Bmax * h->V);
+        QB_CUDA(cudaDeviceSynchronize());
+        *out = h.release();
+    });
+}
+
+int32_t qb_destroy(qb_handle *h) {
+    return guarded([&] {
+        if (!h) return;
+        cudaSetDevice(h->cfg.device);
+        cudaDeviceSynchronize();
+        if (h->comm) nccl().CommDestroy(h->comm);
+        cudaFree(h->P); cudaFree(h->G); cudaFree(h->Vel); cudaFree(h->Wb); cudaFree(h->WbT);
+        free_mat(h->data); cudaFree(h->dataT);
+        free_mat(h->cv); free_mat(h->ch); free_mat(h->phd); free_mat(h->hs); free_mat(h->vm); free_mat(h->phm); free_mat(h->hb);
+        cudaFree(h->pre_h); cudaFree(h->pre_v); cudaFree(h->lab_pre); cudaFree(h->softplus_rows); cudaFree(h->out_f32);
+        cudaFree(h->dscal); cudaFree(h->znoise); cudaFree(h->staging); cudaFree(h->injUh); cudaFree(h->injUv); cudaFree(h->injZv);
+        for (auto &e : h->ev) cudaEventDestroy(e);
+        cudaStreamDestroy(h->stream); cudaStreamDestroy(h->copy_stream);
+        delete h;
+    });
+}
+
+int32_t qb_set_params(qb_handle *h, const double *W, const double *a, const double *b, const double *U, const double *c) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(W && a && b, QB_E_ARG, "W, a, b must not be NULL");
+        QB_CHECK(h->L == 0 || (U && c), QB_E_ARG, "U, c required for classifier models");
+        // Julia column-major V x H == row-major [H][V]; U (L x H) == [H][L]
+        std::vector<float> p((size_t)h->nP, 0.f);
+        for (int64_t j = 0; j < h->H; j++) {
+            for (int64_t i = 0; i < h->V; i++) p[j * h->ldv + i] = (float)W[i + h->V * j];
+            for (int64_t l = 0; l < h->L; l++) p[j * h->ldv + h->V + l] = (float)U[l + h->L * j];
+        }
+        for (int64_t i = 0; i < h->V; i++) p[h->nW + i] = (float)a[i];
+        for (int64_t l = 0; l < h->L; l++) p[h->nW + h->V + l] = (float)c[l];
+        for (int64_t j = 0; j < h->H; j++) p[h->nW + h->ldv + j] = (float)b[j];
+        QB_CUDA(cudaMemcpyAsync(h->P, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        if (h->Vel) QB_CUDA(cudaMemsetAsync(h->Vel, 0, h->nP * sizeof(float), h->stream));
+        refresh_shadows(h);
+        QB_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int32_t qb_get_params(qb_handle *h, double *W, double *a, double *b, double *U, double *c) {
+    return guarded([&] {
+        QB_H(h);
+        std::vector<float> p((size_t)h->nP);
+        QB_CUDA(cudaMemcpyAsync(p.data(), h->P, p.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        QB_CUDA(cudaStreamSynchronize(h->stream));
+        for (int64_t j = 0; j < h->H; j++) {
+            if (W) for (int64_t i = 0; i < h->V; i++) W[i + h->V * j] = (double)p[j * h->ldv + i];
+            if (U) for (int64_t l = 0; l < h->L; l++) U[l + h->L * j] = (double)p[j * h->ldv + h->V + l];
+        }
+        if (a) for (int64_t i = 0; i < h->V; i++) a[i] = (double)p[h->nW + i];
+        if (c) for (int64_t l = 0; l < h->L; l++) c[l] = (double)p[h->nW + h->V + l];
+        if (b) for (int64_t j = 0; j < h->H; j++) b[j] = (double)p[h->nW + h->ldv + j];
+    });
+}
+
+int32_t qb_set_optimizer(qb_handle *h, double momentum, double weight_decay) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(momentum >= 0.0 && momentum < 1.0 && weight_decay >= 0.0, QB_E_ARG, "momentum in [0,1), weight_decay >= 0");
+        h->momentum = momentum; h->weight_decay = weight_decay;
+    });
+}
+
+int32_t qb_set_data(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype, int64_t n_rows) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(X != nullptr && n_rows > 0, QB_E_ARG, "X is NULL or n_rows <= 0");
+        QB_CHECK(h->L == 0 || Y != nullptr, QB_E_ARG, "labels required for classifier models");
+        free_mat(h->data);
+        cudaFree(h->dataT); h->dataT = nullptr; h->dataT_B = 0;
+        h->data = alloc_mat(h, n_rows, h->VL, false);
+        h->N = n_rows;
+        upload_rows(h, X, x_dtype, n_rows, h->V, h->data, 0, 0);
+        if (h->L > 0) upload_rows(h, Y, y_dtype, n_rows, h->L, h->data, 0, h->V);
+        QB_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int32_t qb_init_chains(qb_handle *h, int64_t n_chains, const double *v, const double *hid, const double *y) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(n_chains >= 1 && n_chains <= h->Bmax, QB_E_ARG, "n_chains must be in [1, max_batch]");
+        h->n_chains = n_chains; h->chains_binary = false;
+        if (v) {
+            QB_CHECK(hid != nullptr && (h->L == 0 || y != nullptr), QB_E_ARG, "v, h (and y) must all be given");
+            upload_rows(h, v, QB_DT_F64, n_chains, h->V, h->cv, 0, 0);
+            if (h->L > 0) upload_rows(h, y, QB_DT_F64, n_chains, h->L, h->cv, 0, h->V);
+            upload_rows(h, hid, QB_DT_F64, n_chains, h->H, h->ch, 0, 0);
+        } else {
+            // rand(V), rand(H)[, rand(L)] per chain (src/fantasy_data.jl:66-86) from the Philox stream
+            const int64_t row0 = row0_of(h, n_chains);
+            RngKey kv = make_key(h), kh = make_key(h);
+            uniform_fill_kernel<<<grid1d(n_chains * h->VL), 256, 0, h->stream>>>(h->cv.f, h->cv.b, h->cv.ld, n_chains, h->VL, kv, row0);
+            uniform_fill_kernel<<<grid1d(n_chains * h->H), 256, 0, h->stream>>>(h->ch.f, h->ch.b, h->ch.ld, n_chains, h->H, kh, row0);
+            QB_CUDA(cudaGetLastError());
+            h->launches += 2;
+        }
+        QB_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int32_t qb_get_chains(qb_handle *h, double *v, double *hid, double *y) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(h->n_chains > 0, QB_E_STATE, "no chains");
+        download_rows(h, h->cv, 0, 0, h->n_chains, h->V, v);
+        download_rows(h, h->ch, 0, 0, h->n_chains, h->H, hid);
+        if (h->L > 0) download_rows(h, h->cv, 0, h->V, h->n_chains, h->L, y);
+    });
+}
+
+int32_t qb_seed(qb_handle *h, uint64_t seed) {
+    return guarded([&] { QB_H(h); h->seed = seed; h->draw = 0; });
+}
+
+int32_t qb_inject_streams(qb_handle *h, const double *U_h, const double *U_v, const double *U_y, const double *Z_v, int64_t k,
+                          int64_t B) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(U_h != nullptr && k >= 1 && B >= 1 && B <= h->Bmax, QB_E_ARG, "U_h required, k >= 1, 1 <= B <= max_batch");
+        QB_CHECK(h->gaussian ? (Z_v != nullptr) : (U_v != nullptr), QB_E_ARG, "U_v (Bernoulli) or Z_v (Gaussian) required");
+        QB_CHECK(h->L == 0 || U_y != nullptr, QB_E_ARG, "U_y required for classifier models");
+        auto put = [&](float *&buf, size_t &cap, const std::vector<float> &src) {
+            if (cap < src.size()) { cudaFree(buf); buf = nullptr; QB_CUDA(cudaMalloc(&buf, src.size() * sizeof(float))); cap = src.size(); }
+            QB_CUDA(cudaMemcpyAsync(buf, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+            QB_CUDA(cudaStreamSynchronize(h->stream));
+        };
+        std::vector<float> uh((size_t)k * B * h->H);
+        for (size_t i = 0; i < uh.size(); i++) uh[i] = (float)U_h[i];
+        put(h->injUh, h->injUh_cap, uh);
+        if (h->gaussian && h->L == 0) {
+            std::vector<float> z((size_t)k * B * h->V);
+            for (size_t i = 0; i < z.size(); i++) z[i] = (float)Z_v[i];
+            put(h->injZv, h->injZv_cap, z);
+        } else {
+            // one [k][B][VL] array: visible columns hold uniforms (Bernoulli) or normals (Gaussian), label columns uniforms
+            std::vector<float> uv((size_t)k * B * h->VL);
+            const double *vis = h->gaussian ? Z_v : U_v;
+            for (int64_t s = 0; s < k; s++)
+                for (int64_t r = 0; r < B; r++) {
+                    float *dst = uv.data() + ((size_t)s * B + r) * h->VL;
+                    for (int64_t i = 0; i < h->V; i++) dst[i] = (float)vis[((size_t)s * B + r) * h->V + i];
+                    for (int64_t l = 0; l < h->L; l++) dst[h->V + l] = (float)U_y[((size_t)s * B + r) * h->L + l];
+                }
+            put(h->injUv, h->injUv_cap, uv);
+        }
+        h->inj_k = k; h->inj_B = B; h->inj_active = true;
+    });
+}
+
+int32_t qb_pcd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, double lr, double llr) {
+    return guarded([&] {
+        QB_H(h);
+        check_step_args(h, B, k);
+        Mat xb; const bf16 *xbT; int64_t ldT;
+        batch_view(h, batch_index, B, xb, xbT, ldT);
+        pcd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, nullptr);
+        QB_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int32_t qb_cd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, double lr, double llr) {
+    return guarded([&] {
+        QB_H(h);
+        check_step_args(h, B, k);
+        Mat xb; const bf16 *xbT; int64_t ldT;
+        batch_view(h, batch_index, B, xb, xbT, ldT);
+        cd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, nullptr);
+        QB_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+static void epoch_impl(qb_handle *h, bool pcd, int64_t B, int64_t k, double lr, double llr, double times[3]) {
+    check_step_args(h, B, k);
+    QB_CHECK(!h->inj_active, QB_E_STATE, "injected streams are per step; use qb_pcd_step / qb_cd_step");
+    QB_CHECK(h->N >= B, QB_E_ARG, "dataset smaller than one mini-batch");
+    const int64_t nb = h->N / B;  // _set_mini_batches: trailing remainder dropped (src/utils.jl:13-26)
+    double t[3] = {0, 0, 0};
+    for (int64_t m = 0; m < nb; m++) {
+        Mat xb; const bf16 *xbT; int64_t ldT;
+        batch_view(h, m, B, xb, xbT, ldT);
+        const bool timed = (times != nullptr);
+        if (pcd) pcd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, timed ? h->ev : nullptr);
+        else cd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, timed ? h->ev : nullptr);
+        if (timed) {
+            QB_CUDA(cudaStreamSynchronize(h->stream));
+            float a = 0, b = 0, c = 0, d = 0;
+            QB_CUDA(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+            QB_CUDA(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+            QB_CUDA(cudaEventElapsedTime(&c, h->ev[2], h->ev[3]));
+            if (pcd) {
+                QB_CUDA(cudaEventElapsedTime(&d, h->ev[3], h->ev[4]));
+                t[1] += (a + d) * 1e-3; t[0] += b * 1e-3; t[2] += c * 1e-3;  // gibbs, sample, update
+            } else {
+                t[0] += a * 1e-3; t[1] += b * 1e-3; t[2] += c * 1e-3;
+            }
+        }
+    }
+    QB_CUDA(cudaStreamSynchronize(h->stream));
+    if (times) { times[0] = t[0]; times[1] = t[1]; times[2] = t[2]; }
+}
+
+int32_t qb_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]) {
+    return guarded([&] { QB_H(h); epoch_impl(h, true, B, k, lr, llr, times); });
+}
+int32_t qb_cd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]) {
+    return guarded([&] { QB_H(h); epoch_impl(h, false, B, k, lr, llr, times); });
+}
+
+static void step_host_impl(qb_handle *h, bool pcd, const void *X, int xdt, const void *Y, int ydt, int64_t B, int64_t k,
+                           double lr, double llr, double *recon) {
+    check_step_args(h, B, k);
+    stage_host_batch(h, X, xdt, Y, ydt, B);
+    if (pcd) pcd_step_impl(h, h->hb, h->hb.bT, h->hb.ldT, B, k, lr, llr, nullptr);
+    else cd_step_impl(h, h->hb, h->hb.bT, h->hb.ldT, B, k, lr, llr, nullptr);
+    if (recon) {
+        QB_CUDA(cudaMemsetAsync(h->dscal, 0, sizeof(double), h->stream));
+        recon_sqerr(h, h->hb, B, nullptr, row0_of(h, B));
+        *recon = read_scalar(h, 0);
+    } else {
+        QB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+}
+
+int32_t qb_pcd_step_host(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype, int64_t B, int64_t k,
+                         double lr, double llr, double *recon_sq_err) {
+    return guarded([&] { QB_H(h); step_host_impl(h, true, X, x_dtype, Y, y_dtype, B, k, lr, llr, recon_sq_err); });
+}
+int32_t qb_cd_step_host(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype, int64_t B, int64_t k,
+                        double lr, double llr, double *recon_sq_err) {
+    return guarded([&] { QB_H(h); step_host_impl(h, false, X, x_dtype, Y, y_dtype, B, k, lr, llr, recon_sq_err); });
+}
+
+int32_t qb_eval_mse(qb_handle *h, const void *X, int32_t x_dtype, int64_t n_rows, const double *Z, double *out) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(out != nullptr, QB_E_ARG, "out is NULL");
+        QB_CUDA(cudaMemsetAsync(h->dscal, 0, sizeof(double), h->stream));
+        if (X == nullptr) {
+            QB_CHECK(h->N > 0, QB_E_STATE, "no resident dataset");
+            n_rows = h->N;
+            recon_sqerr(h, h->data, h->N, Z, (int64_t)h->cfg.rank * h->N);
+        } else {
+            QB_CHECK(n_rows > 0, QB_E_ARG, "n_rows <= 0");
+            for (int64_t r = 0; r < n_rows; r += h->Bmax) {
+                const int64_t nr = std::min(h->Bmax, n_rows - r);
+                upload_rows(h, (const char *)X + (size_t)r * h->V * dt_size(x_dtype), x_dtype, nr, h->V, h->hb, 0, 0);
+                recon_sqerr(h, h->hb, nr, Z ? Z + (size_t)r * h->V : nullptr, r);
+            }
+        }
+        *out = read_scalar(h, 0) / (double)n_rows;  // _evaluate(MeanSquaredError): sum over units, / dataset_size
+    });
+}
+
+int32_t qb_eval_free_energy(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype, int64_t n_rows,
+                            double *out) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(out != nullptr, QB_E_ARG, "out is NULL");
+        QB_CUDA(cudaMemsetAsync(h->dscal, 0, 2 * sizeof(double), h->stream));
+        const bool resident = (X == nullptr);
+        if (resident) { QB_CHECK(h->N > 0, QB_E_STATE, "no resident dataset"); n_rows = h->N; }
+        QB_CHECK(n_rows > 0, QB_E_ARG, "n_rows <= 0");
+        const bool with_y = h->L > 0 && (resident || Y != nullptr);
+        const int64_t kdim = with_y ? h->VL : h->V;
+        for (int64_t r = 0; r < n_rows; r += h->Bmax) {
+            const int64_t nr = std::min(h->Bmax, n_rows - r);
+            Mat xs;
+            if (resident) xs = h->data.row_slice(r, nr);
+            else {
+                upload_rows(h, (const char *)X + (size_t)r * h->V * dt_size(x_dtype), x_dtype, nr, h->V, h->hb, 0, 0);
+                if (with_y) upload_rows(h, (const char *)Y + (size_t)r * h->L * dt_size(y_dtype), y_dtype, nr, h->L, h->hb, 0, h->V);
+                xs = h->hb.row_slice(0, nr);
+            }
+            HiddenOut ho;
+            if (h->bf) {
+                QB_CUDA(cudaMemsetAsync(h->softplus_rows, 0, nr * sizeof(float), h->stream));
+                ho.softplus_rows = h->softplus_rows;
+            } else {
+                ho.softplus_rows = h->pre_h;  // marker: fp32 path keeps the pre-activations in pre_h
+            }
+            op_hidden(h, xs, nr, kdim, ho, Rng(), 0);
+            const int threads = 256, warps_per_block = threads / 32;
+            dim3 g((unsigned)ceil_div(nr, warps_per_block));
+            if (h->bf) free_energy_kernel<bf16><<<g, threads, 0, h->stream>>>(xs.b, xs.ld, nullptr, 0, h->softplus_rows, acat(h), (int)nr, (int)h->V, (int)kdim, (int)h->H, h->gaussian ? 1 : 0, h->dscal);
+            else free_energy_kernel<float><<<g, threads, 0, h->stream>>>(xs.f, xs.ld, h->pre_h, h->ldh, nullptr, acat(h), (int)nr, (int)h->V, (int)kdim, (int)h->H, h->gaussian ? 1 : 0, h->dscal);
+            QB_CUDA(cudaGetLastError());
+            h->launches++;
+        }
+        *out = read_scalar(h, 0) / (double)n_rows;
+    });
+}
+
+int32_t qb_reconstruct(qb_handle *h, const double *v, int64_t n_rows, const double *Z, double *out) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(v && out && n_rows > 0, QB_E_ARG, "NULL argument or n_rows <= 0");
+        for (int64_t r = 0; r < n_rows; r += h->Bmax) {
+            const int64_t nr = std::min(h->Bmax, n_rows - r);
+            upload_rows(h, v + (size_t)r * h->V, QB_DT_F64, nr, h->V, h->hb, 0, 0);
+            HiddenOut ho; ho.prob = &h->phd; ho.prob_rm = true;
+            op_hidden(h, h->hb, nr, h->V, ho, Rng(), 0);
+            Rng rng;
+            if (h->gaussian) {
+                if (Z) {
+                    Mat zf; zf.f = h->znoise; zf.ld = h->V; zf.rows = nr; zf.units = h->V;
+                    upload_rows(h, Z + (size_t)r * h->V, QB_DT_F64, nr, h->V, zf, 0, 0);
+                    rng = injected_rng(h->znoise, h->V);
+                } else {
+                    rng = philox_rng(h);
+                }
+            }
+            Mat of; of.f = h->out_f32; of.ld = h->ldv; of.rows = nr; of.units = h->VL;
+            VisibleOut vo; vo.sample = false;
+            if (h->bf) { vo.state = nullptr; vo.prob_f32 = h->out_f32; vo.ld_pf = h->ldv; vo.f32_from_state = h->gaussian; }
+            else vo.state = &of;
+            op_visible(h, h->phd, nr, vo, rng, r);
+            download_rows(h, of, 0, 0, nr, h->V, out + (size_t)r * h->V);
+        }
+    });
+}
+
+int32_t qb_conditional_prob_h(qb_handle *h, const double *v, const double *y, int64_t n_rows, double *out) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(v && out && n_rows > 0, QB_E_ARG, "NULL argument or n_rows <= 0");
+        QB_CHECK(y == nullptr || h->L > 0, QB_E_ARG, "y given for a model without label units");
+        for (int64_t r = 0; r < n_rows; r += h->Bmax) {
+            const int64_t nr = std::min(h->Bmax, n_rows - r);
+            upload_rows(h, v + (size_t)r * h->V, QB_DT_F64, nr, h->V, h->hb, 0, 0);
+            if (y) upload_rows(h, y + (size_t)r * h->L, QB_DT_F64, nr, h->L, h->hb, 0, h->V);
+            Mat of; of.f = h->out_f32; of.ld = h->ldh; of.rows = nr; of.units = h->H;
+            HiddenOut ho;
+            if (h->bf) { ho.prob_f32 = h->out_f32; ho.ld_pf = h->ldh; }
+            else ho.prob = &of;
+            op_hidden(h, h->hb, nr, y ? h->VL : h->V, ho, Rng(), 0);
+            download_rows(h, of, 0, 0, nr, h->H, out + (size_t)r * h->H);
+        }
+    });
+}
+
+int32_t qb_comm_unique_id(void *id128) {
+    return guarded([&] {
+        QB_CHECK(id128 != nullptr, QB_E_ARG, "id buffer is NULL");
+        ncclUniqueId id;
+        QB_NCCL(nccl().GetUniqueId(&id));
+        memcpy(id128, &id, sizeof(id));
+    });
+}
+
+int32_t qb_comm_init(qb_handle *h, const void *id128) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(id128 != nullptr, QB_E_ARG, "id buffer is NULL");
+        QB_CHECK(h->cfg.world > 1, QB_E_ARG, "world == 1 needs no communicator");
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof(id));
+        QB_NCCL(nccl().CommInitRank(&h->comm, h->cfg.world, id, h->cfg.rank));
+    });
+}
+
+int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_launches, double *gemm_ms) {
+    return guarded([&] {
+        QB_H(h);
+        if (kernel_launches) *kernel_launches = h->launches;
+        if (gemm_launches) *gemm_launches = h->gemm_launches;
+        if (gemm_ms) *gemm_ms = 0.0;
+    });
+}
+int32_t qb_reset_counters(qb_handle *h) {
+    return guarded([&] { QB_H(h); h->launches = 0; h->gemm_launches = 0; });
+}
+int32_t qb_set_option(qb_handle *h, const char *key, double value) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(key != nullptr, QB_E_ARG, "key is NULL");
+        if (!strcmp(key, "force_bn")) {
+            int bn = (int)value;
+            QB_CHECK(bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 256, QB_E_ARG, "force_bn must be 0/32/64/128/256");
+            h->force_bn = bn;
+        } else {
+            throw Error(QB_E_ARG, std::string("unknown option ") + key);
+        }
+    });
+}
+
+}  // extern "C"

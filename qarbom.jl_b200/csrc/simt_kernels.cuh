@@ -1,0 +1,355 @@
+// fp32 CUDA-core kernels: the validation-precision path (QB_PREC_FP32) and the
+// bandwidth-bound helper kernels shared with the tensor-core path (update, column sums,
+// conversions, transposes, metric reductions).
+#pragma once
+#include "common.cuh"
+
+namespace qb {
+
+// ----------------------------------------------------------------------------- fp32 GEMM
+// C[m*ldc + n] = alpha * sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] + beta * C + bias_n[n]
+// 64x64 tile, 16-deep k slices, 256 threads, 4x4 register micro-tile, sequential-k fp32 FMA.
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const float *__restrict__ A, int64_t sam, int64_t sak,
+                                                        const float *__restrict__ B, int64_t sbk, int64_t sbn,
+                                                        float *__restrict__ C, int64_t ldc, int M, int N, int K,
+                                                        float alpha, float beta, const float *__restrict__ bias_n) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int t = threadIdx.x;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int tm = (t / 16) * 4, tn = (t % 16) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int idx = t + i * 256;
+            int m, k;
+            if (sak == 1) { m = idx / 16; k = idx % 16; } else { m = idx % 64; k = idx / 64; }
+            float v = 0.f;
+            if (m0 + m < M && k0 + k < K) v = A[(int64_t)(m0 + m) * sam + (int64_t)(k0 + k) * sak];
+            As[k][m] = v;
+            int n, kb;
+            if (sbn == 1) { n = idx % 64; kb = idx / 64; } else { kb = idx % 16; n = idx / 16; }
+            float w = 0.f;
+            if (n0 + n < N && k0 + kb < K) w = B[(int64_t)(k0 + kb) * sbk + (int64_t)(n0 + n) * sbn];
+            Bs[kb][n] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[k][tm + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[k][tn + j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int m = m0 + tm + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int n = n0 + tn + j;
+            if (n >= N) continue;
+            float v = alpha * acc[i][j];
+            if (beta != 0.f) v += beta * C[(int64_t)m * ldc + n];
+            if (bias_n) v += bias_n[n];
+            C[(int64_t)m * ldc + n] = v;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- activation + sampling
+// act: 0 = sigmoid (+ Bernoulli sample when `state`), 1 = Gaussian visible (value = pre [+ z])
+// Units in [0, n_units) of every row; label units are finished by label_kernel instead.
+__global__ void act_sample_kernel(const float *__restrict__ pre, int64_t ld, int rows, int n_units, int act,
+                                  float *__restrict__ prob, int64_t ldp, float *__restrict__ state, int64_t lds,
+                                  const float *__restrict__ inj, int64_t ldi, RngKey key, int64_t row0, int use_rng) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows * n_units) return;
+    int r = (int)(i / n_units), u = (int)(i % n_units);
+    float x = pre[(int64_t)r * ld + u];
+    if (act == 0) {
+        float p = sigmoid_exact(x);
+        if (prob) prob[(int64_t)r * ldp + u] = p;
+        if (state) {
+            float rn = inj ? inj[(int64_t)r * ldi + u] : rng_uniform(key, (uint32_t)u, (uint64_t)(row0 + r));
+            state[(int64_t)r * lds + u] = (rn < p) ? 1.f : 0.f;
+        }
+    } else {
+        if (prob) prob[(int64_t)r * ldp + u] = x;
+        if (state) {
+            float z = 0.f;
+            if (inj) z = inj[(int64_t)r * ldi + u];
+            else if (use_rng) z = rng_normal(key, (uint32_t)u, (uint64_t)(row0 + r));
+            state[(int64_t)r * lds + u] = x + z;
+        }
+    }
+}
+
+// gibbs_sample_label (src/gibbs.jl:46-49 + src/rbm.jl:196-205): softmax over the L label
+// pre-activations of a row, then independent Bernoulli per label unit.  One thread per row.
+__global__ void label_kernel(const float *__restrict__ pre, int64_t ld, int rows, int V, int L, float *__restrict__ prob,
+                             int64_t ldp, float *__restrict__ state, int64_t lds, const float *__restrict__ inj,
+                             int64_t ldi, RngKey key, int64_t row0) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float *p = pre + (int64_t)r * ld + V;
+    float mx = -INFINITY;
+    for (int l = 0; l < L; l++) mx = fmaxf(mx, p[l]);
+    float s = 0.f;
+    for (int l = 0; l < L; l++) s += expf(p[l] - mx);
+    float lden = mx + logf(s);
+    for (int l = 0; l < L; l++) {
+        float q = expf(p[l] - lden);
+        if (prob) prob[(int64_t)r * ldp + V + l] = q;
+        if (state) {
+            float rn = inj ? inj[(int64_t)r * ldi + V + l] : rng_uniform(key, (uint32_t)(V + l), (uint64_t)(row0 + r));
+            state[(int64_t)r * lds + V + l] = (rn < q) ? 1.f : 0.f;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- column sums (bias gradients)
+// out[c] (+)= sign * sum_r A[r*lda + c]; 32 columns x 8 row-lanes per block, rows strided by gridDim.y*8.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T *__restrict__ A, int64_t lda, int rows, int cols,
+                                                     float sign, float *__restrict__ out) {
+    __shared__ float red[8][33];
+    int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    int rl = threadIdx.x >> 5;
+    float acc = 0.f;
+    if (c < cols)
+        for (int r = blockIdx.y * 8 + rl; r < rows; r += gridDim.y * 8) acc += (float)A[(int64_t)r * lda + c];
+    red[rl][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (rl == 0 && c < cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) s += red[i][threadIdx.x & 31];
+        atomicAdd(out + c, sign * s);
+    }
+}
+
+// ----------------------------------------------------------------------------- parameter update (K5)
+// W region: tile [64 h][64 c] per block; fp32 read-modify-write of theta (+ velocity),
+// refresh of the bf16 shadows Wb[h][c] and (through a shared-memory transpose) WbT[c][h].
+//   vel = momentum*vel + lr_c*g - lr_c*wd*w ;  w += vel     (momentum = wd = 0: w += lr_c*g,
+//   i.e. update_rbm!, src/rbm.jl:152-163 / :120-136 with lr_c = lr/B for c < V, llr/B for labels)
+__global__ void __launch_bounds__(256) update_w_kernel(float *__restrict__ W, const float *__restrict__ G,
+                                                       float *__restrict__ Vel, int H, int VL, int V, int64_t ldv,
+                                                       float lr, float llr, float momentum, float wd,
+                                                       bf16 *__restrict__ Wb, bf16 *__restrict__ WbT, int64_t ldh) {
+    __shared__ bf16 tile[64][64 + 2];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int c = blockIdx.x * 64 + tx;
+    const int h0 = blockIdx.y * 64;
+    const float lr_c = (c < V) ? lr : llr;
+#pragma unroll 4
+    for (int i = ty; i < 64; i += 4) {
+        int h = h0 + i;
+        float w = 0.f;
+        if (h < H && c < VL) {
+            int64_t o = (int64_t)h * ldv + c;
+            w = W[o];
+            float g = G[o];
+            if (Vel) {
+                float v = momentum * Vel[o] + lr_c * g - lr_c * wd * w;
+                Vel[o] = v;
+                w += v;
+            } else {
+                w += lr_c * g;
+            }
+            W[o] = w;
+            if (Wb) Wb[o] = __float2bfloat16(w);
+        }
+        if (WbT) tile[i][tx] = __float2bfloat16(w);
+    }
+    if (!WbT) return;
+    __syncthreads();
+    const int h = h0 + tx;
+#pragma unroll 4
+    for (int i = ty; i < 64; i += 4) {
+        int cc = blockIdx.x * 64 + i;
+        if (cc < VL && h < H) WbT[(int64_t)cc * ldh + h] = tile[tx][i];
+    }
+}
+
+// bias region: [acat (VL) | b (H)] stored contiguously after W with the same treatment (no weight decay)
+__global__ void update_bias_kernel(float *__restrict__ P, const float *__restrict__ G, float *__restrict__ Vel, int n_vis,
+                                   int V, int n_total, float lr, float llr, float momentum) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    float lr_c = (i < n_vis && i >= V) ? llr : lr;  // label biases c use llr; a and b use lr
+    float g = G[i];
+    if (Vel) {
+        float v = momentum * Vel[i] + lr_c * g;
+        Vel[i] = v;
+        P[i] += v;
+    } else {
+        P[i] += lr_c * g;
+    }
+}
+
+// refresh both bf16 shadows from fp32 W (after qb_set_params)
+__global__ void __launch_bounds__(256) shadow_kernel(const float *__restrict__ W, int H, int VL, int64_t ldv,
+                                                     bf16 *__restrict__ Wb, bf16 *__restrict__ WbT, int64_t ldh) {
+    __shared__ bf16 tile[64][64 + 2];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int c = blockIdx.x * 64 + tx, h0 = blockIdx.y * 64;
+    for (int i = ty; i < 64; i += 4) {
+        int h = h0 + i;
+        float w = (h < H && c < VL) ? W[(int64_t)h * ldv + c] : 0.f;
+        if (h < H && c < VL) Wb[(int64_t)h * ldv + c] = __float2bfloat16(w);
+        tile[i][tx] = __float2bfloat16(w);
+    }
+    __syncthreads();
+    const int h = h0 + tx;
+    for (int i = ty; i < 64; i += 4) {
+        int cc = blockIdx.x * 64 + i;
+        if (cc < VL && h < H) WbT[(int64_t)cc * ldh + h] = tile[tx][i];
+    }
+}
+
+// ----------------------------------------------------------------------------- conversions / transposes
+template <typename T>
+__global__ void convert_rows_kernel(const T *__restrict__ src, int64_t src_cols, int64_t rows, float *__restrict__ dstf,
+                                    bf16 *__restrict__ dstb, int64_t ld, int64_t col0) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * src_cols) return;
+    int64_t r = i / src_cols, c = i % src_cols;
+    float v = (float)src[i];
+    if (dstf) dstf[r * ld + col0 + c] = v;
+    if (dstb) dstb[r * ld + col0 + c] = __float2bfloat16(v);
+}
+
+template <typename T>
+__global__ void export_rows_kernel(const T *__restrict__ src, int64_t ld, int64_t col0, int64_t rows, int64_t cols,
+                                   double *__restrict__ dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    int64_t r = i / cols, c = i % cols;
+    dst[i] = (double)(float)src[r * ld + col0 + c];
+}
+
+// dst[c*ldd + r] = src[r*lds + c]   (bf16; 32x32 tiles)
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16 *__restrict__ src, int64_t lds, int rows, int cols,
+                                                             bf16 *__restrict__ dst, int64_t ldd) {
+    __shared__ bf16 tile[32][33];
+    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = ty; i < 32; i += 8) {
+        int r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < rows && c < cols) ? src[(int64_t)r * lds + c] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        int c = c0 + i, r = r0 + tx;
+        if (c < cols && r < rows) dst[(int64_t)c * ldd + r] = tile[tx][i];
+    }
+}
+
+__global__ void f32_to_bf16_kernel(const float *__restrict__ src, bf16 *__restrict__ dst, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2bfloat16(src[i]);
+}
+__global__ void bf16_to_f32_kernel(const bf16 *__restrict__ src, float *__restrict__ dst, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __bfloat162float(src[i]);
+}
+
+// ----------------------------------------------------------------------------- metric reductions
+// sum over rows x cols of (X - R)^2 -> double accumulator (block reduce, one atomic per block)
+template <typename TX>
+__global__ void __launch_bounds__(256) sqerr_kernel(const TX *__restrict__ X, int64_t ldx, const float *__restrict__ R,
+                                                    int64_t ldr, int rows, int cols, double *__restrict__ out) {
+    __shared__ float red[8];
+    float acc = 0.f;
+    int64_t n = (int64_t)rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / cols, c = i % cols;
+        float d = (float)X[r * ldx + c] - R[r * ldr + c];
+        acc = fmaf(d, d, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; i++) s += red[i];
+        atomicAdd(out, (double)s);
+    }
+}
+
+// free energy of each row: F = vis_term - sum_j softplus(pre_h[r][j]);  vis_term = -a.v - c.y (Bernoulli)
+// or 0.5*||v - a||^2 - c.y (Gaussian).  The softplus sum comes either from fp32 pre-activations
+// (fp32 path) or from per-row sums accumulated by the tensor-core epilogue.  One warp per row.
+template <typename TX>
+__global__ void __launch_bounds__(256) free_energy_kernel(const TX *__restrict__ X, int64_t ldx, const float *__restrict__ preh,
+                                                          int64_t ldp, const float *__restrict__ softplus_rows,
+                                                          const float *__restrict__ acat, int rows, int V, int ncols, int H,
+                                                          int gaussian, double *__restrict__ out) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    float f = 0.f;
+    for (int c = lane; c < ncols; c += 32) {
+        float x = (float)X[(int64_t)warp * ldx + c], a = acat[c];
+        if (gaussian && c < V) f += 0.5f * (x - a) * (x - a);
+        else f -= a * x;
+    }
+    if (preh)
+        for (int j = lane; j < H; j += 32) f -= softplus_f(preh[(int64_t)warp * ldp + j]);
+    f = warp_sum(f);
+    if (lane == 0) {
+        if (softplus_rows) f -= softplus_rows[warp];
+        atomicAdd(out, (double)f);
+    }
+}
+
+// bf16-path label sampling: softmax over the L raw label pre-activations written by the visible
+// GEMM epilogue, independent Bernoulli per unit, stores into both state orientations and folds
+// the (negative) label bias gradient.
+__global__ void label_bf16_kernel(const float *__restrict__ lab_pre, int64_t ld_lab, int rows, int V, int L,
+                                  bf16 *__restrict__ state_rm, int64_t ld, bf16 *__restrict__ state_T, int64_t ldT,
+                                  const float *__restrict__ inj, int64_t ldi, RngKey key, int64_t row0,
+                                  float *__restrict__ bias_grad) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float *p = lab_pre + (int64_t)r * ld_lab;
+    float mx = -INFINITY;
+    for (int l = 0; l < L; l++) mx = fmaxf(mx, p[l]);
+    float s = 0.f;
+    for (int l = 0; l < L; l++) s += expf(p[l] - mx);
+    float lden = mx + logf(s);
+    for (int l = 0; l < L; l++) {
+        float q = expf(p[l] - lden);
+        float rn = inj ? inj[(int64_t)r * ldi + V + l] : rng_uniform(key, (uint32_t)(V + l), (uint64_t)(row0 + r));
+        float st = (rn < q) ? 1.f : 0.f;
+        if (state_rm) state_rm[(int64_t)r * ld + V + l] = __float2bfloat16(st);
+        if (state_T) state_T[(int64_t)(V + l) * ldT + r] = __float2bfloat16(st);
+        if (bias_grad && st != 0.f) atomicAdd(bias_grad + V + l, -st);
+    }
+}
+
+// _init_fantasy_data with the device stream: U[0,1) floats (src/fantasy_data.jl:66-86)
+__global__ void uniform_fill_kernel(float *__restrict__ f, bf16 *__restrict__ b, int64_t ld, int64_t rows, int64_t units,
+                                    RngKey key, int64_t row0) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * units) return;
+    int64_t r = i / units, u = i % units;
+    float v = rng_uniform(key, (uint32_t)u, (uint64_t)(row0 + r));
+    if (f) f[r * ld + u] = v;
+    if (b) b[r * ld + u] = __float2bfloat16(v);
+}
+
+}  // namespace qb

@@ -1,0 +1,529 @@
+// tcgen05 / TMEM / TMA fused Gibbs-step GEMM for sm_100a (QB_PREC_BF16 path).
+//
+//   D[m][n] = sum_k A[m][k] * B[n][k]  ( - sum_k A2[m][k] * B2[n][k] )      bf16 x bf16 -> fp32 in TMEM
+//
+// Both operands are K-major (row = m or n, contiguous k), staged by TMA into 128B-swizzled
+// shared memory, multiplied by single-thread tcgen05.mma (cta_group::1, M=128, N=BN, K=16)
+// into one of two TMEM accumulator stages, and drained by two epilogue warpgroups while the
+// MMA warp already works on the next tile (persistent CTAs, static tile schedule).
+//
+// Orientation for the Gibbs half-steps: UNITS are on M (TMEM lanes, one thread per unit),
+// batch ROWS are on N (TMEM columns).  So the weight matrix is the A operand and the state
+// matrix the B operand; bias and bias-gradient sums are thread-local, row-major state
+// stores are lane-coalesced and transposed state stores are per-thread contiguous.
+//
+// Epilogues (all fused, nothing but the requested outputs ever reaches HBM):
+//   EPI_SAMPLE: x = acc + bias[unit];  p = sigmoid(x) | x (Gaussian mean / raw)
+//               s = (u < p) | x + z;   u,z from Philox4x32-10 or injected arrays
+//               optional stores: state row-major / transposed (bf16), prob row-major /
+//               transposed (bf16), prob fp32; optional reductions: bias gradient
+//               (thread-local), squared reconstruction error, softplus row sums.
+//   EPI_GRAD:   fp32 store of the accumulator (the phase-2 product is negated in the MMA).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace qb {
+namespace sm100 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 384;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
+constexpr int EPI_WARP0 = 4;
+constexpr int SMEM_AB_BUDGET = 192 * 1024;
+
+enum { EPI_SAMPLE = 0, EPI_GRAD = 1 };
+enum { ACT_SIGMOID = 0, ACT_GAUSSIAN = 1 };
+
+struct EpiParams {
+    int mode;
+    int M, N;  // valid extents of D (M: units or H; N: batch rows or VL)
+    // ---- EPI_SAMPLE
+    const float *bias;
+    int act;
+    int sample;  // draw a state (Bernoulli / Gaussian noise); 0 = probabilities / mean only
+    int split;   // units >= split are label units: raw pre-activation goes to lab_pre only
+    float *lab_pre; long long ld_lab;
+    bf16 *state_rm; long long ld_srm;  // [rows][units]
+    bf16 *state_T; long long ld_sT;    // [units][rows]
+    bf16 *prob_rm; long long ld_prm;
+    bf16 *prob_T; long long ld_pT;
+    float *prob_f32; long long ld_pf;  // [rows][units]
+    int f32_from_state;                // prob_f32 receives the sampled / noisy value instead of p
+    const float *inj; long long ld_inj;  // [rows][units] injected uniforms (Bernoulli) or normals (Gaussian)
+    RngKey key; long long row0; int use_rng;
+    float *bias_grad; float bg_sign; int bg_what;  // 1: probabilities/mean, 2: sampled state
+    const bf16 *ref_rm; long long ld_ref; double *sqerr;
+    float *softplus_rows;
+    // ---- EPI_GRAD
+    float *out_f32; long long ld_out;
+};
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[16]) {
+    // the registers are listed as in/out so no consumer can be scheduled above the wait
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused: one swizzle atom along K) | SBO>>4 [32,46) = 1024 B
+// (8 rows x 128 B) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1,
+// b=BF16 [10,13)=1, a_negate bit 13, a/b K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool negate_a) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((negate_a ? 1u : 0u) << 13) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+template <int BN>
+struct Cfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (SMEM_AB_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_AB_BUDGET / STAGE_BYTES);
+    static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;  // two accumulator stages
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ----------------------------------------------------------------------------- epilogues
+template <int BN>
+__device__ __forceinline__ void epilogue_sample(const EpiParams &ep, uint32_t tmem_acc, int m_blk, int n_blk, int quarter,
+                                                int wg, int lane) {
+    const int unit = m_blk * BM + quarter * 32 + lane;
+    const bool uvalid = unit < ep.M;
+    const bool is_label = uvalid && unit >= ep.split;
+    const float bias = uvalid ? ep.bias[unit] : 0.f;
+    float bg_acc = 0.f, sq_acc = 0.f;
+    constexpr int COLS_PER_WG = BN / 2;
+#pragma unroll 1
+    for (int c0 = wg * COLS_PER_WG; c0 < (wg + 1) * COLS_PER_WG; c0 += 16) {
+        uint32_t r[16];
+        __syncwarp();  // re-converge lanes that skipped stores before the .aligned TMEM load
+        tmem_ld16(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        tmem_wait_ld(r);
+        const int row_base = n_blk * BN + c0;
+        if (row_base >= ep.N) continue;  // warp-uniform
+        const bool full = (row_base + 16 <= ep.N);
+        float pv[16], sv[16];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            uint32_t rnd[4] = {0, 0, 0, 0};
+            float zn[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ep.sample && !ep.inj && ep.use_rng) {
+                const unsigned long long grow = (unsigned long long)(ep.row0 + row_base + 4 * g);
+                if (ep.act == ACT_SIGMOID) {
+                    Philox4 ph = rng_uniform4(ep.key, (uint32_t)unit, (uint32_t)(grow >> 2));
+                    rnd[0] = ph.x; rnd[1] = ph.y; rnd[2] = ph.z; rnd[3] = ph.w;
+                } else {
+                    rng_normal2(ep.key, (uint32_t)unit, (uint32_t)(grow >> 1), zn[0], zn[1]);
+                    rng_normal2(ep.key, (uint32_t)unit, (uint32_t)(grow >> 1) + 1u, zn[2], zn[3]);
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int j = 4 * g + jj;
+                const int row = row_base + j;
+                const float x = __uint_as_float(r[j]) + bias;
+                float p, s;
+                if (ep.act == ACT_SIGMOID && !is_label) {
+                    p = sigmoid_fast(x);
+                    s = p;
+                    if (ep.sample) {
+                        float u;
+                        if (ep.inj) u = (uvalid && row < ep.N) ? ep.inj[(long long)row * ep.ld_inj + unit] : 1.f;
+                        else u = u24(rnd[jj]);
+                        s = (u < p) ? 1.f : 0.f;
+                    }
+                } else {
+                    p = x;
+                    s = x;
+                    if (ep.sample && !is_label) {
+                        float z = zn[jj];
+                        if (ep.inj) z = (uvalid && row < ep.N) ? ep.inj[(long long)row * ep.ld_inj + unit] : 0.f;
+                        s = x + z;
+                    }
+                }
+                pv[j] = p;
+                sv[j] = s;
+            }
+        }
+        if (ep.softplus_rows) {  // free energy: sum over units of softplus(pre) per batch row
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                float sp = (uvalid && !is_label) ? softplus_f(pv[j]) : 0.f;  // act must be raw (pv == pre)
+                sp = warp_sum(sp);
+                if (lane == 0 && row_base + j < ep.N) atomicAdd(ep.softplus_rows + row_base + j, sp);
+            }
+            continue;
+        }
+        if (!uvalid) continue;
+        if (is_label) {  // label units: raw pre-activations, finished by label_kernel
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (row_base + j < ep.N) ep.lab_pre[(long long)(row_base + j) * ep.ld_lab + (unit - ep.split)] = pv[j];
+            continue;
+        }
+        if (ep.bg_what) {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (full || row_base + j < ep.N) bg_acc += (ep.bg_what == 1) ? pv[j] : sv[j];
+        }
+        if (ep.sqerr) {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (full || row_base + j < ep.N) {
+                    float d = __bfloat162float(ep.ref_rm[(long long)(row_base + j) * ep.ld_ref + unit]) - sv[j];
+                    sq_acc = fmaf(d, d, sq_acc);
+                }
+        }
+        if (ep.state_rm) {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (full || row_base + j < ep.N)
+                    ep.state_rm[(long long)(row_base + j) * ep.ld_srm + unit] = __float2bfloat16(sv[j]);
+        }
+        if (ep.prob_rm) {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (full || row_base + j < ep.N)
+                    ep.prob_rm[(long long)(row_base + j) * ep.ld_prm + unit] = __float2bfloat16(pv[j]);
+        }
+        if (ep.prob_f32) {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (full || row_base + j < ep.N) ep.prob_f32[(long long)(row_base + j) * ep.ld_pf + unit] = ep.f32_from_state ? sv[j] : pv[j];
+        }
+        if (ep.state_T) {
+            bf16 *dst = ep.state_T + (long long)unit * ep.ld_sT + row_base;
+            if (full) {
+                uint4 v0 = make_uint4(pack_bf16x2(sv[0], sv[1]), pack_bf16x2(sv[2], sv[3]), pack_bf16x2(sv[4], sv[5]),
+                                      pack_bf16x2(sv[6], sv[7]));
+                uint4 v1 = make_uint4(pack_bf16x2(sv[8], sv[9]), pack_bf16x2(sv[10], sv[11]), pack_bf16x2(sv[12], sv[13]),
+                                      pack_bf16x2(sv[14], sv[15]));
+                reinterpret_cast<uint4 *>(dst)[0] = v0;
+                reinterpret_cast<uint4 *>(dst)[1] = v1;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (row_base + j < ep.N) dst[j] = __float2bfloat16(sv[j]);
+            }
+        }
+        if (ep.prob_T) {
+            bf16 *dst = ep.prob_T + (long long)unit * ep.ld_pT + row_base;
+            if (full) {
+                uint4 v0 = make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]),
+                                      pack_bf16x2(pv[6], pv[7]));
+                uint4 v1 = make_uint4(pack_bf16x2(pv[8], pv[9]), pack_bf16x2(pv[10], pv[11]), pack_bf16x2(pv[12], pv[13]),
+                                      pack_bf16x2(pv[14], pv[15]));
+                reinterpret_cast<uint4 *>(dst)[0] = v0;
+                reinterpret_cast<uint4 *>(dst)[1] = v1;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (row_base + j < ep.N) dst[j] = __float2bfloat16(pv[j]);
+            }
+        }
+    }
+    if (ep.bg_what && uvalid && !is_label) atomicAdd(ep.bias_grad + unit, ep.bg_sign * bg_acc);
+    if (ep.sqerr) {
+        sq_acc = warp_sum(sq_acc);
+        if (lane == 0) atomicAdd(ep.sqerr, (double)sq_acc);
+    }
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_grad(const EpiParams &ep, uint32_t tmem_acc, int m_blk, int n_blk, int quarter, int wg,
+                                              int lane) {
+    const int m = m_blk * BM + quarter * 32 + lane;
+    constexpr int COLS_PER_WG = BN / 2;
+#pragma unroll 1
+    for (int c0 = wg * COLS_PER_WG; c0 < (wg + 1) * COLS_PER_WG; c0 += 16) {
+        uint32_t r[16];
+        __syncwarp();  // re-converge lanes that skipped stores before the .aligned TMEM load
+        tmem_ld16(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        tmem_wait_ld(r);
+        const int n0 = n_blk * BN + c0;
+        if (n0 >= ep.N || m >= ep.M) continue;
+        float *dst = ep.out_f32 + (long long)m * ep.ld_out + n0;
+        if (n0 + 16 <= ep.N) {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                reinterpret_cast<uint4 *>(dst)[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (n0 + j < ep.N) dst[j] = __uint_as_float(r[j]);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- the kernel
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gibbs_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, int K1, int K2,
+                  const EpiParams ep) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+    // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base word
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (ep.M + BM - 1) / BM, tiles_n = (ep.N + BN - 1) / BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int kb1 = (K1 + BK - 1) / BK, kb2 = (K2 + BK - 1) / BK, kb_total = kb1 + kb2;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapA);
+        prefetch_tmap(&mapB);
+        if (kb2) { prefetch_tmap(&mapA2); prefetch_tmap(&mapB2); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===== TMA producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
+                for (int kb = 0; kb < kb_total; kb++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+                    mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    if (kb < kb1) {
+                        tma_load_2d(sa, &mapA, full_bar(stage), kb * BK, m_blk * BM);
+                        tma_load_2d(sb, &mapB, full_bar(stage), kb * BK, n_blk * BN);
+                    } else {
+                        tma_load_2d(sa, &mapA2, full_bar(stage), (kb - kb1) * BK, m_blk * BM);
+                        tma_load_2d(sb, &mapB2, full_bar(stage), (kb - kb1) * BK, n_blk * BN);
+                    }
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc_pos = make_idesc(BN, false), idesc_neg = make_idesc(BN, true);
+            int stage = 0; uint32_t phase = 0;
+            int iter = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, iter++) {
+                const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+                mbar_wait(tempty_bar(as), aphase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < kb_total; kb++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+                    const uint64_t adesc = make_kmajor_sw128_desc(sa), bdesc = make_kmajor_sw128_desc(sb);
+                    const uint32_t idesc = (kb < kb1) ? idesc_pos : idesc_neg;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                        umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    }
+                    umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+                    if (kb == kb_total - 1) umma_commit(tfull_bar(as));
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===== epilogue: 2 warpgroups x 4 warps; warp (w % 4) owns TMEM lanes [32*(w%4), +32)
+        const int quarter = warp & 3, wg = (warp - EPI_WARP0) >> 2;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, iter++) {
+            const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
+            const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+            mbar_wait(tfull_bar(as), aphase);
+            tcgen05_fence_after();
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
+            if (ep.mode == EPI_SAMPLE) epilogue_sample<BN>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else epilogue_grad<BN>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ----------------------------------------------------------------------------- host side
+struct Operand {
+    const bf16 *ptr;
+    long long rows, k, ld;  // [rows][k] with row stride ld (elements); ld % 8 == 0, ptr 16 B aligned
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        QB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        QB_CHECK(p != nullptr && q == cudaDriverEntryPointSuccess, -2, "cuTensorMapEncodeTiled not available from the driver");
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+inline CUtensorMap make_tmap(const Operand &o, int box_rows) {
+    QB_CHECK(o.ld % 8 == 0 && ((uintptr_t)o.ptr % 16) == 0, -1, "TMA operand must be 16-byte aligned with ld % 8 == 0");
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)o.k, (cuuint64_t)o.rows};
+    cuuint64_t strides[1] = {(cuuint64_t)o.ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)o.ptr, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    QB_CHECK(r == CUDA_SUCCESS, -2, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
+template <int BN>
+inline void launch_bn(cudaStream_t st, const Operand &A, const Operand &B, const Operand *A2, const Operand *B2,
+                      const EpiParams &ep, int num_sms) {
+    using C = Cfg<BN>;
+    CUtensorMap ma = make_tmap(A, BM), mb = make_tmap(B, BN);
+    CUtensorMap ma2 = A2 ? make_tmap(*A2, BM) : ma, mb2 = B2 ? make_tmap(*B2, BN) : mb;
+    const int tiles = (int)(ceil_div(ep.M, BM) * ceil_div(ep.N, BN));
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    gibbs_gemm_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, ma2, mb2, (int)A.k, A2 ? (int)A2->k : 0, ep);
+    QB_CUDA(cudaGetLastError());
+}
+
+// once per device (qb_create): opt in to the large dynamic shared-memory carve-out
+inline void init_device() {
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::SMEM_BYTES));
+}
+
+// D[M][N]: picks the widest N tile that still yields at least one tile per SM.
+inline void launch(cudaStream_t st, const Operand &A, const Operand &B, const Operand *A2, const Operand *B2, const EpiParams &ep,
+                   int num_sms, int force_bn = 0) {
+    QB_CHECK(A.k == B.k && A.k > 0, -1, "GEMM operands disagree on K");
+    QB_CHECK((A2 == nullptr) == (B2 == nullptr), -1, "phase-2 operands must come in pairs");
+    const long long tm = ceil_div(ep.M, BM);
+    int bn = 32;
+    const int cands[4] = {256, 128, 64, 32};
+    for (int i = 0; i < 4; i++) {
+        if (tm * ceil_div(ep.N, cands[i]) >= num_sms || cands[i] == 32) { bn = cands[i]; break; }
+    }
+    if (force_bn) bn = force_bn;
+    switch (bn) {
+        case 256: launch_bn<256>(st, A, B, A2, B2, ep, num_sms); break;
+        case 128: launch_bn<128>(st, A, B, A2, B2, ep, num_sms); break;
+        case 64: launch_bn<64>(st, A, B, A2, B2, ep, num_sms); break;
+        default: launch_bn<32>(st, A, B, A2, B2, ep, num_sms); break;
+    }
+}
+
+}  // namespace sm100
+}  // namespace qb

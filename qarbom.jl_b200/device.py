@@ -1,0 +1,182 @@
+"""`DeviceRBM`: one C-ABI handle bound to one host-side model (the Python stand-in for the
+Julia shim, which cannot be executed in this image -- see INTEGRATION.md)."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import QbConfig, as_rows, check, lib, ptr
+
+
+class DeviceRBM:
+    def __init__(self, rbm, max_batch: int, precision: str = "bf16", device: int = 0, rank: int = 0, world: int = 1,
+                 seed: int = 0):
+        self.rbm = rbm
+        self.V, self.H, self.L = rbm.n_visible, rbm.n_hidden, getattr(rbm, "n_classifiers", 0)
+        cfg = QbConfig(self.V, self.H, self.L,
+                       _ffi.QB_VISIBLE_GAUSSIAN if rbm.gaussian else _ffi.QB_VISIBLE_BERNOULLI,
+                       {"fp32": _ffi.QB_PREC_FP32, "bf16": _ffi.QB_PREC_BF16}[precision], int(max_batch), device, rank,
+                       world, 0)
+        self._h = ctypes.c_void_p()
+        check(lib().qb_create(ctypes.byref(self._h), ctypes.byref(cfg)))
+        self.world, self.rank = world, rank
+        self.push_params()
+        self.seed(seed)
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().qb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ------------------------------------------------------------------ parameters
+    def push_params(self):
+        r = self.rbm
+        W = np.asfortranarray(r.W, dtype=np.float64)  # Julia Matrix{Float64}: column-major V x H
+        U = np.asfortranarray(r.U, dtype=np.float64) if self.L else None
+        c = np.ascontiguousarray(r.c, dtype=np.float64) if self.L else None
+        a = np.ascontiguousarray(r.a, dtype=np.float64)
+        b = np.ascontiguousarray(r.b, dtype=np.float64)
+        check(lib().qb_set_params(self._h, ptr(W), ptr(a), ptr(b), ptr(U), ptr(c)))
+
+    def pull_params(self):
+        r = self.rbm
+        W = np.zeros((self.V, self.H), order="F")
+        a, b = np.zeros(self.V), np.zeros(self.H)
+        U = np.zeros((self.L, self.H), order="F") if self.L else None
+        c = np.zeros(self.L) if self.L else None
+        check(lib().qb_get_params(self._h, ptr(W), ptr(a), ptr(b), ptr(U), ptr(c)))
+        r.W[...] = W
+        r.a[...] = a
+        r.b[...] = b
+        if self.L:
+            r.U[...] = U
+            r.c[...] = c
+
+    def set_optimizer(self, momentum: float = 0.0, weight_decay: float = 0.0):
+        check(lib().qb_set_optimizer(self._h, momentum, weight_decay))
+
+    def seed(self, seed: int):
+        check(lib().qb_seed(self._h, ctypes.c_uint64(seed)))
+
+    def set_option(self, key: str, value: float):
+        check(lib().qb_set_option(self._h, key.encode(), float(value)))
+
+    # ------------------------------------------------------------------ data / chains
+    def set_data(self, x, y=None):
+        X, xdt = as_rows(x, self.V)
+        Y, ydt = as_rows(y, self.L) if self.L else (None, 0)
+        check(lib().qb_set_data(self._h, ptr(X), xdt, ptr(Y), ydt, X.shape[0]))
+        self.n_rows = X.shape[0]
+
+    def init_chains(self, n: int, v=None, h=None, y=None):
+        v = None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+        h = None if h is None else np.ascontiguousarray(h, dtype=np.float64)
+        y = None if y is None else np.ascontiguousarray(y, dtype=np.float64)
+        check(lib().qb_init_chains(self._h, n, ptr(v), ptr(h), ptr(y)))
+        self.n_chains = n
+
+    def get_chains(self):
+        n = self.n_chains
+        v, h = np.zeros((n, self.V)), np.zeros((n, self.H))
+        y = np.zeros((n, self.L)) if self.L else None
+        check(lib().qb_get_chains(self._h, ptr(v), ptr(h), ptr(y)))
+        return v, h, y
+
+    def inject_streams(self, U_h, U_v=None, U_y=None, Z_v=None):
+        U_h = np.ascontiguousarray(U_h, dtype=np.float64)
+        k, B = U_h.shape[0], U_h.shape[1]
+        U_v = None if U_v is None else np.ascontiguousarray(U_v, dtype=np.float64)
+        U_y = None if U_y is None else np.ascontiguousarray(U_y, dtype=np.float64)
+        Z_v = None if Z_v is None else np.ascontiguousarray(Z_v, dtype=np.float64)
+        check(lib().qb_inject_streams(self._h, ptr(U_h), ptr(U_v), ptr(U_y), ptr(Z_v), k, B))
+
+    # ------------------------------------------------------------------ training steps
+    def pcd_step(self, batch_index: int, B: int, k: int, lr: float, llr: float = 0.0):
+        check(lib().qb_pcd_step(self._h, batch_index, B, k, lr, llr))
+
+    def cd_step(self, batch_index: int, B: int, k: int, lr: float, llr: float = 0.0):
+        check(lib().qb_cd_step(self._h, batch_index, B, k, lr, llr))
+
+    def pcd_epoch(self, B: int, k: int, lr: float, llr: float = 0.0, timed: bool = True):
+        t = (ctypes.c_double * 3)()
+        check(lib().qb_pcd_epoch(self._h, B, k, lr, llr, t if timed else None))
+        return tuple(t)
+
+    def cd_epoch(self, B: int, k: int, lr: float, llr: float = 0.0, timed: bool = True):
+        t = (ctypes.c_double * 3)()
+        check(lib().qb_cd_epoch(self._h, B, k, lr, llr, t if timed else None))
+        return tuple(t)
+
+    def step_host(self, method: str, x, y, k: int, lr: float, llr: float = 0.0, want_recon: bool = True) -> float:
+        X, xdt = as_rows(x, self.V)
+        Y, ydt = as_rows(y, self.L) if self.L else (None, 0)
+        out = ctypes.c_double(0.0)
+        fn = lib().qb_pcd_step_host if method.upper() == "PCD" else lib().qb_cd_step_host
+        check(fn(self._h, ptr(X), xdt, ptr(Y), ydt, X.shape[0], k, lr, llr, ctypes.byref(out) if want_recon else None))
+        return out.value
+
+    # ------------------------------------------------------------------ evaluation
+    def eval_mse(self, x=None, Z=None) -> float:
+        out = ctypes.c_double(0.0)
+        Z = None if Z is None else np.ascontiguousarray(Z, dtype=np.float64)
+        if x is None:
+            check(lib().qb_eval_mse(self._h, None, 0, 0, ptr(Z), ctypes.byref(out)))
+        else:
+            X, xdt = as_rows(x, self.V)
+            check(lib().qb_eval_mse(self._h, ptr(X), xdt, X.shape[0], ptr(Z), ctypes.byref(out)))
+        return out.value
+
+    def eval_free_energy(self, x=None, y=None) -> float:
+        out = ctypes.c_double(0.0)
+        if x is None:
+            check(lib().qb_eval_free_energy(self._h, None, 0, None, 0, 0, ctypes.byref(out)))
+        else:
+            X, xdt = as_rows(x, self.V)
+            Y, ydt = as_rows(y, self.L) if (self.L and y is not None) else (None, 0)
+            check(lib().qb_eval_free_energy(self._h, ptr(X), xdt, ptr(Y), ydt, X.shape[0], ctypes.byref(out)))
+        return out.value
+
+    def reconstruct(self, v, Z=None) -> np.ndarray:
+        v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1, self.V))
+        Z = None if Z is None else np.ascontiguousarray(Z, dtype=np.float64)
+        out = np.zeros_like(v)
+        check(lib().qb_reconstruct(self._h, ptr(v), v.shape[0], ptr(Z), ptr(out)))
+        return out
+
+    def conditional_prob_h(self, v, y=None) -> np.ndarray:
+        v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1, self.V))
+        y = None if y is None else np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1, self.L))
+        out = np.zeros((v.shape[0], self.H))
+        check(lib().qb_conditional_prob_h(self._h, ptr(v), ptr(y), v.shape[0], ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ multi-GPU / counters
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        check(lib().qb_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, uid: bytes):
+        buf = ctypes.create_string_buffer(uid, 128)
+        check(lib().qb_comm_init(self._h, buf))
+
+    def counters(self):
+        a, b, c = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_double(0)
+        check(lib().qb_get_counters(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value
+
+    def reset_counters(self):
+        check(lib().qb_reset_counters(self._h))

@@ -1,0 +1,48 @@
+"""numpy restatement of the library's Philox4x32-10 stream contract (csrc/common.cuh):
+
+  uniform(draw, row, unit) = (philox(ctr=(unit, row>>2, draw_lo, draw_hi), key=seed)[row & 3] >> 8) * 2^-24
+  normal (draw, row, unit) = box_muller(philox(ctr=(unit, row>>1, draw_lo, draw_hi | 2^31), key=seed)[2*(row&1) : +2])
+"""
+import numpy as np
+
+M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+W0, W1 = 0x9E3779B9, 0xBB67AE85
+MASK = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & MASK for c in (c0, c1, c2, c3))
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def uniforms(seed: int, draw: int, rows: int, units: int, row0: int = 0) -> np.ndarray:
+    """[rows][units] float64 array of the uniforms the device uses for one sampling half-step."""
+    r = (np.arange(rows, dtype=np.uint64) + np.uint64(row0))[:, None]
+    u = np.arange(units, dtype=np.uint64)[None, :]
+    r, u = np.broadcast_arrays(r, u)
+    out = philox4x32_10(u, r >> np.uint64(2), draw & 0xFFFFFFFF, (draw >> 32) & 0x7FFFFFFF, seed & 0xFFFFFFFF, seed >> 32)
+    sel = (r & np.uint64(3)).astype(np.int64)
+    x = np.choose(sel, out)
+    return (x >> np.uint64(8)).astype(np.float64) / float(1 << 24)
+
+
+def normals(seed: int, draw: int, rows: int, units: int, row0: int = 0) -> np.ndarray:
+    r = (np.arange(rows, dtype=np.uint64) + np.uint64(row0))[:, None]
+    u = np.arange(units, dtype=np.uint64)[None, :]
+    r, u = np.broadcast_arrays(r, u)
+    out = philox4x32_10(u, r >> np.uint64(1), draw & 0xFFFFFFFF, ((draw >> 32) & 0x7FFFFFFF) | 0x80000000,
+                        seed & 0xFFFFFFFF, seed >> 32)
+    odd = (r & np.uint64(1)).astype(bool)
+    a = np.where(odd, out[2], out[0])
+    b = np.where(odd, out[3], out[1])
+    u1 = ((a >> np.uint64(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -24)
+    u2 = (b >> np.uint64(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    z = np.sqrt(np.float32(-2.0) * np.log(u1)) * np.cos(np.float32(2.0 * np.pi) * u2.astype(np.float64)).astype(np.float32)
+    return z.astype(np.float64)

@@ -1,0 +1,350 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Run with -m gpu on a B200.
+
+Validation mode (fp32 kernels, injected streams): sampled states must match the Float64
+oracle bit-exactly (streams are guard-banded by 1e-4 so an fp32 evaluation of p cannot flip
+a draw) and W/a/b must agree within 1e-5 relative.
+bf16 mode (tcgen05 path): the oracle runs on the bf16-rounded weights the tensor cores see
+and is re-synchronised with the device's fp32 masters after every step; states must again
+match exactly, parameter *increments* within the looser 2e-2 relative (the gradient GEMM
+consumes bf16-rounded probabilities).
+"""
+import numpy as np
+import pytest
+
+from oracle import qarbom_oracle as qo
+from tests import philox_ref
+from tests.helpers import (DenseStreams, bf16_round, chains_from_arrays, chains_to_arrays, f32_round, make_oracle_model,
+                           rel_err, to_host_rbm, u24)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def q():
+    import qarbom_b200
+    qarbom_b200.build()
+    return qarbom_b200
+
+
+TOL = {"fp32": dict(w=1e-5, dw=2e-4, p=2e-6), "bf16": dict(w=None, dw=2e-2, p=2e-6)}
+
+
+def _resync(m, dev, prec):
+    """bf16 mode: continue the oracle from the device's masters (weights as the tensor cores see them)."""
+    dev.pull_params()
+    r = dev.rbm
+    m.W[...] = bf16_round(r.W) if prec == "bf16" else r.W
+    m.a[...] = r.a
+    m.b[...] = r.b
+    if m.is_classifier:
+        m.U[...] = bf16_round(r.U) if prec == "bf16" else r.U
+        m.c[...] = r.c
+
+
+def _data(rng, n, V, L, gaussian, bf16):
+    X = rng.standard_normal((n, V)) if gaussian else rng.integers(0, 2, (n, V)).astype(np.float64)
+    X = bf16_round(X) if bf16 else f32_round(X)
+    Y = np.eye(L)[rng.integers(0, L, n)] if L else None
+    return X, Y
+
+
+# ------------------------------------------------------------------------------ conditionals
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("V,H,L", [(3, 2, 0), (16, 8, 0), (70, 33, 5), (784, 500, 10)])
+def test_conditional_prob_h_and_reconstruct(q, prec, V, H, L):
+    rng = np.random.default_rng(V * 1000 + H)
+    m = make_oracle_model(rng, V, H, L, bf16=(prec == "bf16"), scale=0.2)
+    X, Y = _data(rng, 37, V, L, False, prec == "bf16")
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=64, precision=prec) as dev:
+        ph = dev.conditional_prob_h(X)
+        ref = np.stack([qo.conditional_prob_h(m, x) for x in X])
+        assert np.max(np.abs(ph - ref)) < TOL[prec]["p"]
+        if L:
+            ph3 = dev.conditional_prob_h(X, Y)
+            ref3 = np.stack([qo.conditional_prob_h(m, x, y) for x, y in zip(X, Y)])
+            assert np.max(np.abs(ph3 - ref3)) < TOL[prec]["p"]
+        rec = dev.reconstruct(X)
+        if prec == "bf16":  # hidden probabilities are rounded to bf16 before the second GEMM
+            refr = np.stack([qo.conditional_prob_v(m, bf16_round(qo.conditional_prob_h(m, x))) for x in X])
+        else:
+            refr = np.stack([qo.reconstruct(m, x) for x in X])
+        assert np.max(np.abs(rec - refr)) < 5e-6
+
+
+# ------------------------------------------------------------------------------ PCD
+PCD_CASES = [  # V, H, L, gaussian, B, k, steps
+    (3, 2, 0, False, 2, 1, 3),        # the reference's own test scenario shape (test/generative.jl:22-38)
+    (16, 8, 0, False, 8, 2, 3),
+    (64, 32, 0, False, 16, 3, 2),
+    (70, 33, 0, False, 13, 2, 2),     # ragged: nothing is a multiple of the tile sizes
+    (784, 500, 0, False, 64, 1, 2),   # cfg-shaped
+    (3, 2, 1, False, 2, 1, 3),        # test/classification.jl shape
+    (40, 24, 5, False, 12, 2, 3),
+    (24, 16, 0, True, 8, 2, 2),       # GRBM
+    (24, 16, 3, True, 8, 1, 2),       # GRBMClassifier
+]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("V,H,L,gaussian,B,k,steps", PCD_CASES)
+def test_pcd_steps_match_oracle(q, prec, V, H, L, gaussian, B, k, steps):
+    if prec == "bf16" and gaussian:
+        pytest.skip("bf16 Gaussian visibles are covered by the single-step tolerance test below")
+    bf = prec == "bf16"
+    rng = np.random.default_rng(7 + V + 13 * H + L)
+    m = make_oracle_model(rng, V, H, L, gaussian, bf16=bf)
+    X, Y = _data(rng, steps * B, V, L, gaussian, bf)
+    cv0, ch0 = u24(rng, B, V), u24(rng, B, H)
+    cy0 = u24(rng, B, L) if L else None
+    if bf:
+        cv0, ch0 = bf16_round(cv0), bf16_round(ch0)
+        cy0 = bf16_round(cy0) if L else None
+    chains = chains_from_arrays(cv0, ch0, cy0)
+    lr, llr = 0.05, 0.02
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=B, precision=prec) as dev:
+        dev.set_data(X, Y)
+        dev.init_chains(B, cv0, ch0, cy0)
+        for t in range(steps):
+            ds = DenseStreams(rng, k, B, V, H, L, gaussian)
+            su, sz = ds.serial("pcd")
+            st = qo.GuardedStream(su, sz)
+            W0, a0, b0 = m.W.copy(), m.a.copy(), m.b.copy()
+            qo.persistent_contrastive_divergence(m, X, [range(t * B, (t + 1) * B)], chains, steps=k, learning_rate=lr,
+                                                 stream=st, y=Y, label_learning_rate=llr)
+            assert st.upos == su.size
+            ds.absorb(st.u, "pcd")
+            dev.rbm.W[...] = 0  # make sure pull_params really reads the device
+            dev.inject_streams(ds.U_h, ds.U_v, ds.U_y, ds.Z_v)
+            dev.pcd_step(t, B, k, lr, llr)
+            dv, dh, dy = dev.get_chains()
+            ov, oh, oy = chains_to_arrays(chains)
+            assert np.array_equal(dh, oh), f"hidden chain states differ at step {t}"
+            if gaussian:
+                assert np.max(np.abs(dv - ov)) < 1e-5
+            else:
+                assert np.array_equal(dv, ov), f"visible chain states differ at step {t}"
+            if L:
+                assert np.array_equal(dy, oy), f"label chain states differ at step {t}"
+            dev.pull_params()
+            r = dev.rbm
+            if bf:
+                # increments (device master is fp32; oracle started from the same rounded weights)
+                assert rel_err(r.a - a0, m.a - a0) < TOL[prec]["dw"] or np.linalg.norm(m.a - a0) < 1e-12
+                dW_o = m.W - W0
+                Wdev_before = dev_prev_W if t > 0 else W0
+                assert rel_err(r.W - Wdev_before, dW_o) < TOL[prec]["dw"]
+                dev_prev_W = r.W.copy()
+                _resync(m, dev, prec)
+            else:
+                assert rel_err(r.W, m.W) < TOL[prec]["w"]
+                assert rel_err(r.W - W0, m.W - W0) < TOL[prec]["dw"]
+                assert np.max(np.abs(r.a - m.a)) < 1e-6 and np.max(np.abs(r.b - m.b)) < 1e-6
+                if L:
+                    assert rel_err(r.U, m.U) < TOL[prec]["w"] and np.max(np.abs(r.c - m.c)) < 1e-6
+                dev_prev_W = r.W.copy()
+
+
+# ------------------------------------------------------------------------------ CD
+CD_CASES = [  # V, H, L, gaussian, B, k, n_batches
+    (3, 2, 0, False, 1, 3, 6),         # reference scenario: online CD-3 (test/generative.jl:4-20)
+    (16, 8, 0, False, 1, 2, 5),
+    (64, 32, 0, False, 16, 2, 2),      # mini-batch extension
+    (784, 500, 0, False, 32, 1, 2),    # cfg1-shaped
+    (3, 2, 1, False, 1, 3, 6),
+    (50, 20, 10, False, 16, 1, 2),     # cfg4-shaped (small)
+    (24, 16, 0, True, 8, 3, 2),        # GRBM CD-3
+]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("V,H,L,gaussian,B,k,nb", CD_CASES)
+def test_cd_steps_match_oracle(q, prec, V, H, L, gaussian, B, k, nb):
+    if prec == "bf16" and gaussian:
+        pytest.skip("bf16 Gaussian visibles are covered by the single-step tolerance test below")
+    bf = prec == "bf16"
+    rng = np.random.default_rng(11 + V + 13 * H + L + B)
+    m = make_oracle_model(rng, V, H, L, gaussian, bf16=bf)
+    X, Y = _data(rng, nb * B, V, L, gaussian, bf)
+    lr, llr = 0.05, 0.02
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=B, precision=prec) as dev:
+        dev.set_data(X, Y)
+        for t in range(nb):
+            ds = DenseStreams(rng, k, B, V, H, L, gaussian)
+            su, sz = ds.serial("cd")
+            st = qo.GuardedStream(su, sz)
+            W0 = m.W.copy()
+            tr = []
+            sl = slice(t * B, (t + 1) * B)
+            qo.contrastive_divergence(m, X[sl], steps=k, learning_rate=lr, stream=st, y=None if Y is None else Y[sl],
+                                      label_learning_rate=llr, batch_size=B, trace=tr)
+            ds.absorb(st.u, "cd")
+            dev.inject_streams(ds.U_h, ds.U_v, ds.U_y, ds.Z_v)
+            Wd0 = dev.rbm.W.copy() if t == 0 else Wd_prev
+            dev.cd_step(t, B, k, lr, llr)
+            dev.pull_params()
+            r = dev.rbm
+            if bf:
+                assert rel_err(r.W - Wd0, m.W - W0) < TOL[prec]["dw"]
+                Wd_prev = r.W.copy()
+                _resync(m, dev, prec)
+            else:
+                assert rel_err(r.W, m.W) < TOL[prec]["w"]
+                assert rel_err(r.W - W0, m.W - W0) < TOL[prec]["dw"]
+                assert np.max(np.abs(r.a - m.a)) < 1e-6 and np.max(np.abs(r.b - m.b)) < 1e-6
+                if L:
+                    assert rel_err(r.U, m.U) < TOL[prec]["w"]
+                Wd_prev = r.W.copy()
+
+
+# ------------------------------------------------------------------------------ bf16 Gaussian visibles (tolerance)
+def test_bf16_grbm_single_step_tolerance(q):
+    rng = np.random.default_rng(99)
+    V, H, B, k = 48, 32, 16, 1
+    m0 = make_oracle_model(rng, V, H, 0, True, bf16=True)
+    m = qo.copy_rbm(m0)
+    X, _ = _data(rng, B, V, 0, True, True)
+    ds = DenseStreams(rng, k, B, V, H, 0, True)
+    su, sz = ds.serial("cd")
+    st = qo.GuardedStream(su, sz)
+    qo.contrastive_divergence(m, X, steps=k, learning_rate=0.01, stream=st, batch_size=B)
+    ds.absorb(st.u, "cd")
+    with q.DeviceRBM(to_host_rbm(q, m0), max_batch=B, precision="bf16") as dev:
+        dev.set_data(X)
+        dev.inject_streams(ds.U_h, None, None, ds.Z_v)
+        dev.cd_step(0, B, k, 0.01)
+        dev.pull_params()
+        # visible samples are rounded to bf16 on the device: 2^-8 relative on v -> looser tolerance on dW
+        assert rel_err(dev.rbm.W - m0.W, m.W - m0.W) < 5e-2
+
+
+# ------------------------------------------------------------------------------ production RNG (Philox)
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_philox_mode_matches_oracle_fed_with_the_same_stream(q, prec):
+    """Device Philox == numpy Philox: the oracle, fed the uniforms the stream contract
+    defines, must reproduce the device's chain states (outside a 1e-4 guard band)."""
+    bf = prec == "bf16"
+    rng = np.random.default_rng(5)
+    V, H, B, k, seed = 96, 40, 24, 2, 0xC0FFEE1234
+    m = make_oracle_model(rng, V, H, bf16=bf)
+    X, _ = _data(rng, B, V, 0, False, bf)
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=B, precision=prec, seed=seed) as dev:
+        dev.set_data(X)
+        dev.init_chains(B)  # draws 0 (v) and 1 (h)
+        cv0, ch0, _ = dev.get_chains()
+        ev, eh = philox_ref.uniforms(seed, 0, B, V), philox_ref.uniforms(seed, 1, B, H)
+        if bf:
+            ev, eh = bf16_round(ev), bf16_round(eh)
+        assert np.array_equal(cv0, ev) and np.array_equal(ch0, eh)
+        dev.pcd_step(0, B, k, 0.05)
+        dv, dh, _ = dev.get_chains()
+    chains = chains_from_arrays(cv0, ch0)
+    U_h = np.stack([philox_ref.uniforms(seed, 2 + 2 * s, B, H) for s in range(k)])
+    U_v = np.stack([philox_ref.uniforms(seed, 3 + 2 * s, B, V) for s in range(k)])
+    # replay step by step so that near-ties can be excluded from the comparison
+    near = 0
+    for s in range(k):
+        for i, c in enumerate(chains):
+            p = qo.conditional_prob_h(m, c.v)
+            c.h = (U_h[s, i] < p).astype(np.float64)
+            near += int(np.sum(np.abs(U_h[s, i] - p) < 1e-5))
+            pv = qo.conditional_prob_v(m, c.h)
+            c.v = (U_v[s, i] < pv).astype(np.float64)
+            near += int(np.sum(np.abs(U_v[s, i] - pv) < 1e-5))
+    ov, oh, _ = chains_to_arrays(chains)
+    if near == 0:
+        assert np.array_equal(dv, ov) and np.array_equal(dh, oh)
+    else:  # extremely unlikely with these sizes; still require near-total agreement
+        assert np.mean(dv != ov) < 1e-3 and np.mean(dh != oh) < 1e-3
+
+
+def test_philox_bernoulli_frequencies(q):
+    """Statistical check of fused sampling: with W = 0 the hidden units fire with sigma(b)."""
+    V, H, B = 32, 64, 4096
+    m = qo.make_model(V, H, W=np.zeros((V, H)))
+    m.b[:] = np.linspace(-2, 2, H)
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=B, precision="bf16", seed=77) as dev:
+        dev.set_data(np.zeros((B, V)))
+        dev.init_chains(B)
+        dev.pcd_step(0, B, 1, 0.0)
+        _, h, _ = dev.get_chains()
+    p = 1 / (1 + np.exp(-m.b))
+    z = (h.mean(0) - p) / np.sqrt(p * (1 - p) / B)
+    assert np.max(np.abs(z)) < 4.5
+
+
+# ------------------------------------------------------------------------------ evaluation
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("V,H,L,gaussian", [(3, 2, 0, False), (70, 33, 0, False), (70, 33, 4, False), (40, 24, 0, True)])
+def test_eval_mse_and_free_energy(q, prec, V, H, L, gaussian):
+    bf = prec == "bf16"
+    rng = np.random.default_rng(3 + V)
+    m = make_oracle_model(rng, V, H, L, gaussian, bf16=bf, scale=0.2)
+    n = 150  # > max_batch: exercises chunking
+    X, Y = _data(rng, n, V, L, gaussian, bf)
+    Z = f32_round(rng.standard_normal((n, V))) if gaussian else None
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=64, precision=prec) as dev:
+        dev.set_data(X, Y)
+        mse_res = dev.eval_mse(None, Z)
+        mse_host = dev.eval_mse(X, Z)
+        fe = dev.eval_free_energy()
+    ref_mse = qo.evaluate_mse(m, X, qo.Stream(normals=Z))
+    tol = 2e-3 if bf else 1e-5
+    assert abs(mse_res - ref_mse) / ref_mse < tol and abs(mse_host - ref_mse) / ref_mse < tol
+    ref_fe = qo.mean_free_energy(m, X, Y)
+    assert abs(fe - ref_fe) / abs(ref_fe) < (1e-3 if bf else 1e-5)
+
+
+# ------------------------------------------------------------------------------ epoch driver / train!
+def test_epoch_equals_steps_and_drops_remainder(q):
+    rng = np.random.default_rng(8)
+    V, H, B, k, n = 20, 12, 8, 1, 27  # 3 batches + 3 dropped rows (src/utils.jl:13-26)
+    m = make_oracle_model(rng, V, H)
+    X, _ = _data(rng, n, V, 0, False, False)
+    out = []
+    for mode in ("epoch", "steps"):
+        with q.DeviceRBM(to_host_rbm(q, m), max_batch=B, precision="fp32", seed=9) as dev:
+            dev.set_data(X)
+            dev.init_chains(B)
+            if mode == "epoch":
+                t = dev.pcd_epoch(B, k, 0.05)
+                assert all(x >= 0 for x in t) and sum(t) > 0
+            else:
+                for i in range(n // B):
+                    dev.pcd_step(i, B, k, 0.05)
+            dev.pull_params()
+            out.append(dev.rbm.W.copy())
+    assert np.array_equal(out[0], out[1])
+
+
+@pytest.mark.parametrize("method", ["CD", "PCD"])
+def test_train_reference_scenario(q, method, tmp_path):
+    """test/generative.jl:4-38: RBM(3,2) on [1,0,0] x 1000, lr = 0.01/j^0.8, early stopping.
+    The reference asserts nothing; we assert what its docs promise: unit 1 is reconstructed."""
+    x = [[1, 0, 0] for _ in range(1000)]
+    rbm = q.RBM(3, 2, rng=np.random.default_rng(1))
+    kw = dict(n_epochs=20, learning_rate=[0.05 / (j ** 0.8) for j in range(1, 1001)], early_stopping=True,
+              file_path=str(tmp_path / "m.csv"), precision="fp32", verbose=False)
+    if method == "CD":
+        hist = q.train(rbm, x, q.CD, gibbs_steps=3, **kw)
+    else:
+        hist = q.train(rbm, x, q.PCD, batch_size=2, **kw)
+    rec = q.reconstruct(rbm, [1, 0, 0])
+    assert rec[0] > 0.5 > max(rec[1], rec[2])
+    assert len(hist["mse"]) >= 2 and min(hist["mse"]) <= hist["mse"][0]
+    assert (tmp_path / "m.csv").read_text().splitlines()[0] == "mse"
+
+
+def test_argument_errors(q):
+    rbm = q.RBM(4, 3)
+    with q.DeviceRBM(rbm, max_batch=4, precision="fp32") as dev:
+        with pytest.raises(q.QbError):
+            dev.pcd_step(0, 4, 1, 0.1)          # no data
+        dev.set_data(np.zeros((8, 4)))
+        with pytest.raises(q.QbError):
+            dev.pcd_step(0, 4, 1, 0.1)          # no chains
+        dev.init_chains(4)
+        with pytest.raises(q.QbError):
+            dev.pcd_step(2, 4, 1, 0.1)          # batch index out of range
+        with pytest.raises(q.QbError):
+            dev.pcd_step(0, 8, 1, 0.1)          # B > max_batch
+        dev.pcd_step(1, 4, 1, 0.1)
