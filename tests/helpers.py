@@ -104,6 +104,11 @@ def chains_to_arrays(chains):
     return v, h, y
 
 
-def rel_err(a, b):
+def rel_err(a, b, atol=2e-7):
+    """||a - b|| / ||b||, with an fp32-rounding floor (atol per element) so that exactly-zero
+    increments (e.g. v_model == v_data on a 3x2 model) compare as equal."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+    d = float(np.linalg.norm(a - b))
+    if d <= atol * np.sqrt(a.size):
+        return 0.0
+    return d / max(float(np.linalg.norm(b)), 1e-300)
