@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the RBM training hot path (CD-k / PCD) on B200, one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5] [--impl ours|reference]
+
+A "step" is one mini-batch step of the hot path (k Gibbs steps on the persistent chains,
+positive phase, gradient, allreduce, update).  The default workload is BASELINE.json's
+configs[4] -- Binary RBM 4096x4096, PCD k=10, global batch 8192 -- the configuration the
+headline metric ("... at 1/2/4/8 B200; % of roofline") and the north-star targets are
+quoted on; it fits one GPU.  With N > 1 the global batch is sharded by rows/chains over the
+ranks (strong scaling, as the config says) with one NCCL gradient allreduce per step.
+
+`value`   : samples/s with the dataset already resident in HBM (device-timed, CUDA events on
+            the library's stream, max over ranks).
+`e2e`     : the same metric through qb_pcd_step_host: every step uploads its mini-batch from
+            pinned host memory and reads the batch reconstruction error back.
+`roofline`: algorithmic GEMM flops / CUDA-event time of the GEMM launches inside the timed
+            region, against MEASURED_PEAKS.json (sustained bf16: the kernel runs inside a long step).
+`cpu_baseline` / `--impl reference`: the C restatement of the reference's per-sample Float64
+            algorithm (oracle/, Julia is not installable here) on the host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: V, H, L, gaussian, global batch, k, algo, n_batches, data density
+    "cfg1": dict(V=784, H=500, L=0, gaussian=False, B=100, k=1, algo="CD", nb=600, density=0.1307,
+                 desc="Binary RBM 784x500, CD-1, batch 100"),
+    "cfg2": dict(V=784, H=500, L=0, gaussian=False, B=256, k=1, algo="PCD", nb=234, density=0.1307,
+                 desc="Binary RBM 784x500, PCD k=1, batch 256 (chains = batch, reference semantics)"),
+    "cfg3": dict(V=1024, H=2048, L=0, gaussian=True, B=1024, k=5, algo="CD", nb=64, density=None,
+                 desc="Gaussian-Bernoulli RBM 1024x2048, CD-5, batch 1024"),
+    "cfg4": dict(V=784, H=1000, L=10, gaussian=False, B=512, k=1, algo="CD", nb=117, density=0.1307,
+                 desc="RBMClassifier 784+10 x 1000, CD-1, batch 512"),
+    "cfg5": dict(V=4096, H=4096, L=0, gaussian=False, B=8192, k=10, algo="PCD", nb=8, density=0.5,
+                 desc="Binary RBM 4096x4096, PCD k=10, batch 8192"),
+}
+METRIC = "PCD/CD-k training samples/sec"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tf=float(d["bf16_tflops_sustained"]), tf_burst=float(d["bf16_tflops"]), hbm=float(d["hbm_gbs"]),
+                    src="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tf=1400.0, tf_burst=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_data(w, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = w["B"] * w["nb"]
+    if w["gaussian"]:
+        X = rng.standard_normal((n, w["V"]), dtype=np.float32)
+    else:
+        X = (rng.random((n, w["V"]), dtype=np.float32) < w["density"]).astype(np.uint8)
+    Y = None
+    if w["L"]:
+        Y = np.zeros((n, w["L"]), dtype=np.uint8)
+        Y[np.arange(n), np.arange(n) % w["L"]] = 1
+    W0 = 0.01 * rng.standard_normal((w["V"], w["H"]))
+    U0 = 0.01 * rng.standard_normal((w["L"], w["H"])) if w["L"] else None
+    return X, Y, W0, U0
+
+
+def shard_rows(A, B, nb, rank, world):
+    """Rank's contiguous slice of every global mini-batch, concatenated in mini-batch order."""
+    if A is None:
+        return None
+    Bl = B // world
+    A = A.reshape(nb, B, -1)[:, rank * Bl:(rank + 1) * Bl]
+    return np.ascontiguousarray(A.reshape(nb * Bl, -1))
+
+
+def flops_per_step(w):
+    """(2k+3) * 2 * B * (V+L) * H (de-duplicated forward + 2 gradient contractions)."""
+    return (2 * w["k"] + 3) * 2.0 * w["B"] * (w["V"] + w["L"]) * w["H"]
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference(w, seconds_target, steps, warmup, threads=None):
+    """Times the C restatement of the reference on a bounded sample: `rows` rows of one
+    mini-batch per step (per-sample cost of the reference does not depend on the batch size)."""
+    from oracle import c_oracle
+    threads = threads or c_oracle.max_threads()
+    V, H, L, k = w["V"], w["H"], w["L"], w["k"]
+    rng = np.random.Generator(np.random.PCG64(7))
+    W0 = 0.01 * rng.standard_normal((V, H))
+    U0 = 0.01 * rng.standard_normal((L, H)) if L else None
+
+    def run(rows, n_steps):
+        m = c_oracle.CModel(W0, np.zeros(V), np.zeros(H), U0, np.zeros(L) if L else None, w["gaussian"])
+        X = rng.standard_normal((rows, V)) if w["gaussian"] else (rng.random((rows, V)) < w["density"]).astype(np.float64)
+        Y = np.eye(L)[np.arange(rows) % L] if L else None
+        chv, chh = rng.random((rows, V)), rng.random((rows, H))
+        chy = rng.random((rows, L)) if L else None
+        ts = []
+        for _ in range(n_steps):
+            t0 = time.perf_counter()
+            if w["algo"] == "PCD":
+                c_oracle.pcd_epoch(m, X, Y, rows, k, 0.01, 0.01, chv, chh, chy, seed=1, threads=threads)
+            else:
+                c_oracle.cd_epoch(m, X, Y, rows, k, 0.01, 0.01, seed=1, threads=threads)
+            ts.append(time.perf_counter() - t0)
+        return ts
+
+    t_probe = run(2, 2)[1] / 2  # seconds per row (second call: thread pool and pages are warm)
+    per_step = max(seconds_target / max(steps + warmup, 1), 0.05)
+    rows = int(max(2, min(w["B"], per_step / max(t_probe, 1e-9))))
+    ts = run(rows, warmup + steps)[warmup:]
+    sps = rows * len(ts) / sum(ts)
+    return dict(value=sps, rows=rows, threads=threads, ms_per_step=1e3 * sum(ts) / len(ts),
+                sample=f"{rows} rows of one {w['B']}-row mini-batch per step (k={k}), {len(ts)} timed steps; "
+                       f"per-sample cost of the reference is independent of the batch size")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = dict(WORKLOADS[args.workload])
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = {"workload": f"{args.workload}: {w['desc']}", "V": w["V"], "H": w["H"], "L": w["L"], "global_batch": w["B"],
+           "gibbs_steps": w["k"], "algorithm": w["algo"], "rng": "philox4x32-10",
+           "parallelism": f"dp{world} (rows/chains sharded, NCCL gradient allreduce)" if world > 1 else "single GPU"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_reference(w, 60.0, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["threads"], "kind": "port",
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gibbs_steps_per_s": r["value"] * w["k"],
+                "note": "CPU restatement of QARBoM.jl (C, Float64, per-sample GEMV + outer products; Julia not installable here)"}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import qarbom_b200 as q
+
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B, k, nb = w["B"], w["k"], w["nb"]
+    assert B % world == 0 and (B // world) % 4 == 0
+    Bl = B // world
+    X, Y, W0, U0 = make_data(w, 1000 + int(args.workload[3:]))
+    Xl, Yl = shard_rows(X, B, nb, rank, world), shard_rows(Y, B, nb, rank, world)
+    if w["L"]:
+        rbm = (q.GRBMClassifier if w["gaussian"] else q.RBMClassifier)(w["V"], w["H"], w["L"], W=W0, U=U0)
+        if w["gaussian"]:
+            rbm.a[:] = 0; rbm.b[:] = 0; rbm.c[:] = 0
+    else:
+        rbm = (q.GRBM if w["gaussian"] else q.RBM)(w["V"], w["H"], W=W0)
+    dev = q.DeviceRBM(rbm, max_batch=Bl, precision=args.precision, device=local_rank, rank=rank, world=world, seed=1234)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(q.DeviceRBM.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        dev.comm_init(bytes(uid.cpu().numpy().tobytes()))
+    dev.set_data(Xl, Yl)
+    pcd = w["algo"] == "PCD"
+    if pcd:
+        dev.init_chains(Bl)
+    lr = 0.01
+    step = (lambda i: dev.pcd_step(i % nb, Bl, k, lr, lr)) if pcd else (lambda i: dev.cd_step(i % nb, Bl, k, lr, lr))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        dev.sync()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---------------- device-resident leg
+    dev.set_option("async_steps", 1)
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    dev.reset_counters()
+    dev.set_option("time_gemms", 1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    dev.timer_start()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ms = dev.timer_stop()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms)
+    launches, gemms, gflops, timed, gemm_ms, timed_flops = dev.counters_full()
+    dev.set_option("time_gemms", 0)
+    value = B * args.steps / (ms * 1e-3)
+
+    # ---------------- end-to-end leg: host mini-batches in pinned memory, recon error read back
+    e2e = None
+    if not args.no_e2e:
+        nbuf = min(nb, 4)
+        xs = [torch.from_numpy(Xl[j * Bl:(j + 1) * Bl]).pin_memory() for j in range(nbuf)]
+        ys = [torch.from_numpy(Yl[j * Bl:(j + 1) * Bl]).pin_memory() for j in range(nbuf)] if Yl is not None else None
+        dev.set_option("async_steps", 0)
+        for i in range(args.warmup):
+            dev.step_host(w["algo"], xs[i % nbuf], ys[i % nbuf] if ys else None, k, lr, lr)
+        barrier()
+        dev.timer_start()
+        for i in range(args.steps):
+            dev.step_host(w["algo"], xs[i % nbuf], ys[i % nbuf] if ys else None, k, lr, lr)
+        ms2 = max_over_ranks(dev.timer_stop())
+        barrier()
+        h2d = int(xs[0].numel() * xs[0].element_size() + (ys[0].numel() * ys[0].element_size() if ys else 0))
+        e2e = {"value": B * args.steps / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": 8 * world, "ms_per_step": ms2 / args.steps,
+               "api": f"qb_{'pcd' if pcd else 'cd'}_step_host (upload + step + reconstruction error readback)"}
+
+    if rank != 0:
+        dev.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    pk = peaks()
+    F = flops_per_step(w) / world  # per GPU per step
+    achieved = (timed_flops / 1e12) / (gemm_ms * 1e-3) if gemm_ms > 0 else None
+    roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
+            "frac": (achieved / pk["tf"]) if achieved else None, "traffic": None,
+            "kernel": "qb::sm100::gibbs_gemm_kernel (fused Gibbs half-step / gradient GEMMs)" if args.precision == "bf16"
+            else "qb::simt_gemm_kernel (fp32 validation path)",
+            "gemm_launches_timed": timed, "avg_launch_ms": gemm_ms / max(timed, 1),
+            "gemm_share_of_step": gemm_ms / ms if ms > 0 else None,
+            "algorithmic_flops_per_step_per_gpu": F, "issued_flops_per_step_per_gpu": gflops / args.steps,
+            "peak_source": pk["src"], "whole_step_tflops": F * args.steps / (ms * 1e-3) / 1e12}
+    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": dict(cfg, l2="inputs cycle over %d resident mini-batches (%.2f GB incl. transposed copies) > 126 MB L2"
+                                    % (nb, 2 * nb * Bl * w["V"] * 2 / 1e9)),
+            "gibbs_steps_per_s": value * k, "gpu_launches": launches, "roofline": roof, "clocks": clocks, "e2e": e2e}
+    if not args.no_cpu_baseline:
+        r = cpu_reference(w, args.cpu_seconds, 3, 1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["threads"], "kind": "port",
+                                "sample": r["sample"]}
+    print(json.dumps(line))
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -149,11 +149,20 @@ int32_t qb_conditional_prob_h(qb_handle *h, const double *v, const double *y, in
 int32_t qb_comm_unique_id(void *id128);
 int32_t qb_comm_init(qb_handle *h, const void *id128);
 
-/* Introspection for benchmarks: kernels launched by this library on this handle, and
- * CUDA-event time of the dominant (GEMM) kernels since the last reset. */
-int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_launches, double *gemm_ms);
+/* Introspection for benchmarks.  Counters since the last reset: kernels launched by this
+ * library on this handle, GEMM launches and their algorithmic flops; with option
+ * "time_gemms" = 1 every GEMM launch is bracketed by CUDA events on the launching stream and
+ * timed_* report the number of launches timed, their summed duration and flops. */
+int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_launches, double *gemm_flops,
+                        int64_t *timed_gemms, double *timed_gemm_ms, double *timed_gemm_flops);
 int32_t qb_reset_counters(qb_handle *h);
+/* Options: "async_steps" (qb_pcd_step / qb_cd_step return without waiting; use qb_sync),
+ * "time_gemms", "force_bn" (tile width override for experiments). */
 int32_t qb_set_option(qb_handle *h, const char *key, double value);
+int32_t qb_sync(qb_handle *h);
+/* CUDA-event stopwatch on the handle's stream (the stream every kernel is launched on). */
+int32_t qb_timer_start(qb_handle *h);
+int32_t qb_timer_stop(qb_handle *h, double *elapsed_ms);
 
 #ifdef __cplusplus
 }

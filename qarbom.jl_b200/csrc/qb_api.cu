@@ -106,7 +106,12 @@ struct qb_handle {
     uint64_t seed = 0, draw = 0;
     ncclComm_t comm = nullptr;
     int64_t launches = 0, gemm_launches = 0;
+    double gemm_flops = 0.0;
     int force_bn = 0;
+    bool async_steps = false;   // step calls return without a stream sync (qb_sync to wait)
+    bool time_gemms = false;    // bracket every GEMM launch with CUDA events on the launching stream
+    std::vector<cudaEvent_t> gemm_ev; size_t gemm_ev_used = 0; int64_t gemm_timed = 0; double gemm_timed_flops = 0.0;
+    cudaEvent_t timer_ev[2] = {};
 };
 
 namespace {
@@ -220,12 +225,29 @@ Rng injected_rng(const float *p, int64_t ld) { Rng r; r.inj = p; r.ld_inj = ld; 
 
 int64_t row0_of(const qb_handle *h, int64_t B) { return (int64_t)h->cfg.rank * B; }
 
+// GEMM bookkeeping: algorithmic flops and (optionally) CUDA-event timing of every GEMM launch
+struct GemmScope {
+    qb_handle *h; bool timed = false; size_t i = 0;
+    GemmScope(qb_handle *h_, double flops) : h(h_) {
+        h->launches++; h->gemm_launches++; h->gemm_flops += flops;
+        if (h->time_gemms && h->gemm_ev_used + 2 <= 16384) {
+            while (h->gemm_ev.size() < h->gemm_ev_used + 2) {
+                cudaEvent_t e; QB_CUDA(cudaEventCreate(&e)); h->gemm_ev.push_back(e);
+            }
+            i = h->gemm_ev_used; h->gemm_ev_used += 2; timed = true;
+            h->gemm_timed++; h->gemm_timed_flops += flops;
+            QB_CUDA(cudaEventRecord(h->gemm_ev[i], h->stream));
+        }
+    }
+    ~GemmScope() { if (timed) cudaEventRecord(h->gemm_ev[i + 1], h->stream); }
+};
+
 void simt_gemm(qb_handle *h, const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbk, int64_t sbn, float *C,
                int64_t ldc, int64_t M, int64_t N, int64_t K, float alpha, float beta, const float *bias) {
+    GemmScope gs(h, 2.0 * (double)M * (double)N * (double)K);
     dim3 g((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
     simt_gemm_kernel<<<g, 256, 0, h->stream>>>(A, sam, sak, B, sbk, sbn, C, ldc, (int)M, (int)N, (int)K, alpha, beta, bias);
     QB_CUDA(cudaGetLastError());
-    h->launches++; h->gemm_launches++;
 }
 
 // ----------------------------------------------------------------------------- the three ops
@@ -268,8 +290,8 @@ void op_hidden(qb_handle *h, const Mat &in, int64_t rows, int64_t kdim, const Hi
     ep.inj = rng.inj; ep.ld_inj = rng.ld_inj; ep.key = rng.key; ep.use_rng = rng.use_rng; ep.row0 = row0;
     ep.bg_what = o.bg_what; ep.bg_sign = o.bg_sign; ep.bias_grad = G_b(h);
     ep.softplus_rows = o.softplus_rows;
+    GemmScope gs(h, 2.0 * (double)h->H * (double)rows * (double)kdim);
     sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn);
-    h->launches++; h->gemm_launches++;
 }
 
 struct VisibleOut {
@@ -331,8 +353,10 @@ void op_visible(qb_handle *h, const Mat &in, int64_t rows, const VisibleOut &o, 
     ep.inj = rng.inj; ep.ld_inj = rng.ld_inj; ep.key = rng.key; ep.use_rng = rng.use_rng; ep.row0 = row0;
     if (o.bg_sign_neg) { ep.bg_what = 2; ep.bg_sign = -1.f; ep.bias_grad = G_a(h); }
     if (o.sqerr) { ep.sqerr = o.sqerr; ep.ref_rm = o.ref->b; ep.ld_ref = o.ref->ld; }
-    sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn);
-    h->launches++; h->gemm_launches++;
+    {
+        GemmScope gs(h, 2.0 * (double)h->VL * (double)rows * (double)h->H);
+        sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn);
+    }
     if (h->L > 0 && o.sample && o.state) {
         label_bf16_kernel<<<grid1d(rows, 128), 128, 0, h->stream>>>(
             h->lab_pre, h->L, (int)rows, (int)h->V, (int)h->L, o.state_rm ? o.state->b : nullptr, o.state->ld,
@@ -368,8 +392,10 @@ void op_grad(qb_handle *h, const Mat &posH, const Mat &posV, const bf16 *posV_T,
     sm100::EpiParams ep{};
     ep.mode = sm100::EPI_GRAD; ep.M = (int)h->H; ep.N = (int)h->VL;
     ep.out_f32 = G_W(h); ep.ld_out = h->ldv;
-    sm100::launch(h->stream, A, B, &A2, &B2, ep, h->num_sms, h->force_bn);
-    h->launches++; h->gemm_launches++;
+    {
+        GemmScope gs(h, 4.0 * (double)h->H * (double)h->VL * (double)rows);
+        sm100::launch(h->stream, A, B, &A2, &B2, ep, h->num_sms, h->force_bn);
+    }
     colsum<bf16>(h, posV.b, posV.ld, rows, h->VL, 1.f, G_a(h));  // data-side visible sums; the rest is folded
 }
 
@@ -625,6 +651,7 @@ int32_t qb_create(qb_handle **out, const qb_config *cfg) {
         QB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         QB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         for (auto &e : h->ev) QB_CUDA(cudaEventCreate(&e));
+        for (auto &e : h->timer_ev) QB_CUDA(cudaEventCreate(&e));
         h->nW = h->H * h->ldv; h->nP = h->nW + h->ldv + h->ldh;
         h->P = dalloc<float>(h->nP); h->G = dalloc<float>(h->nP);
         if (h->bf) {
@@ -663,6 +690,8 @@ int32_t qb_destroy(qb_handle *h) {
         cudaFree(h->pre_h); cudaFree(h->pre_v); cudaFree(h->lab_pre); cudaFree(h->softplus_rows); cudaFree(h->out_f32);
         cudaFree(h->dscal); cudaFree(h->znoise); cudaFree(h->staging); cudaFree(h->injUh); cudaFree(h->injUv); cudaFree(h->injZv);
         for (auto &e : h->ev) cudaEventDestroy(e);
+        for (auto &e : h->timer_ev) cudaEventDestroy(e);
+        for (auto &e : h->gemm_ev) cudaEventDestroy(e);
         cudaStreamDestroy(h->stream); cudaStreamDestroy(h->copy_stream);
         delete h;
     });
@@ -807,7 +836,7 @@ int32_t qb_pcd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, dou
         Mat xb; const bf16 *xbT; int64_t ldT;
         batch_view(h, batch_index, B, xb, xbT, ldT);
         pcd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, nullptr);
-        QB_CUDA(cudaStreamSynchronize(h->stream));
+        if (!h->async_steps) QB_CUDA(cudaStreamSynchronize(h->stream));
     });
 }
 
@@ -818,7 +847,7 @@ int32_t qb_cd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, doub
         Mat xb; const bf16 *xbT; int64_t ldT;
         batch_view(h, batch_index, B, xb, xbT, ldT);
         cd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, nullptr);
-        QB_CUDA(cudaStreamSynchronize(h->stream));
+        if (!h->async_steps) QB_CUDA(cudaStreamSynchronize(h->stream));
     });
 }
 
@@ -1011,16 +1040,33 @@ int32_t qb_comm_init(qb_handle *h, const void *id128) {
     });
 }
 
-int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_launches, double *gemm_ms) {
+int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_launches, double *gemm_flops, int64_t *timed_gemms,
+                        double *timed_gemm_ms, double *timed_gemm_flops) {
     return guarded([&] {
         QB_H(h);
         if (kernel_launches) *kernel_launches = h->launches;
         if (gemm_launches) *gemm_launches = h->gemm_launches;
-        if (gemm_ms) *gemm_ms = 0.0;
+        if (gemm_flops) *gemm_flops = h->gemm_flops;
+        double ms = 0.0;
+        if (h->gemm_ev_used) {
+            QB_CUDA(cudaStreamSynchronize(h->stream));
+            for (size_t i = 0; i + 1 < h->gemm_ev_used; i += 2) {
+                float t = 0.f;
+                QB_CUDA(cudaEventElapsedTime(&t, h->gemm_ev[i], h->gemm_ev[i + 1]));
+                ms += t;
+            }
+        }
+        if (timed_gemms) *timed_gemms = h->gemm_timed;
+        if (timed_gemm_ms) *timed_gemm_ms = ms;
+        if (timed_gemm_flops) *timed_gemm_flops = h->gemm_timed_flops;
     });
 }
 int32_t qb_reset_counters(qb_handle *h) {
-    return guarded([&] { QB_H(h); h->launches = 0; h->gemm_launches = 0; });
+    return guarded([&] {
+        QB_H(h);
+        h->launches = 0; h->gemm_launches = 0; h->gemm_flops = 0.0;
+        h->gemm_ev_used = 0; h->gemm_timed = 0; h->gemm_timed_flops = 0.0;
+    });
 }
 int32_t qb_set_option(qb_handle *h, const char *key, double value) {
     return guarded([&] {
@@ -1030,9 +1076,30 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
             int bn = (int)value;
             QB_CHECK(bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 256, QB_E_ARG, "force_bn must be 0/32/64/128/256");
             h->force_bn = bn;
+        } else if (!strcmp(key, "async_steps")) {
+            h->async_steps = value != 0.0;
+        } else if (!strcmp(key, "time_gemms")) {
+            h->time_gemms = value != 0.0;
         } else {
             throw Error(QB_E_ARG, std::string("unknown option ") + key);
         }
+    });
+}
+int32_t qb_sync(qb_handle *h) {
+    return guarded([&] { QB_H(h); QB_CUDA(cudaStreamSynchronize(h->stream)); });
+}
+int32_t qb_timer_start(qb_handle *h) {
+    return guarded([&] { QB_H(h); QB_CUDA(cudaEventRecord(h->timer_ev[0], h->stream)); });
+}
+int32_t qb_timer_stop(qb_handle *h, double *elapsed_ms) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(elapsed_ms != nullptr, QB_E_ARG, "elapsed_ms is NULL");
+        QB_CUDA(cudaEventRecord(h->timer_ev[1], h->stream));
+        QB_CUDA(cudaEventSynchronize(h->timer_ev[1]));
+        float t = 0.f;
+        QB_CUDA(cudaEventElapsedTime(&t, h->timer_ev[0], h->timer_ev[1]));
+        *elapsed_ms = t;
     });
 }
 

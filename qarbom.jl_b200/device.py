@@ -174,9 +174,26 @@ class DeviceRBM:
         check(lib().qb_comm_init(self._h, buf))
 
     def counters(self):
-        a, b, c = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_double(0)
-        check(lib().qb_get_counters(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
-        return a.value, b.value
+        """(kernel launches, GEMM launches) since the last reset."""
+        return self.counters_full()[:2]
+
+    def counters_full(self):
+        a, b, t = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        f, ms, tf = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
+        check(lib().qb_get_counters(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(f), ctypes.byref(t),
+                                    ctypes.byref(ms), ctypes.byref(tf)))
+        return a.value, b.value, f.value, t.value, ms.value, tf.value
 
     def reset_counters(self):
         check(lib().qb_reset_counters(self._h))
+
+    def sync(self):
+        check(lib().qb_sync(self._h))
+
+    def timer_start(self):
+        check(lib().qb_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = ctypes.c_double(0)
+        check(lib().qb_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
