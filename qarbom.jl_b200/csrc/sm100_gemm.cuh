@@ -35,6 +35,8 @@ constexpr int EPI_WARP0 = 4;
 constexpr int SMEM_AB_BUDGET = 192 * 1024;
 
 enum { EPI_SAMPLE = 0, EPI_GRAD = 1 };
+// kernel specialisations: generic epilogue, gradient store, and the two compile-time fast paths
+enum { K_GENERIC = 0, K_GRAD = 1, K_FAST_SAMPLE = 2, K_FAST_PROB = 3 };
 enum { ACT_SIGMOID = 0, ACT_GAUSSIAN = 1 };
 
 struct EpiParams {
@@ -310,6 +312,93 @@ __device__ __forceinline__ void epilogue_sample(const EpiParams &ep, uint32_t tm
     }
 }
 
+// Compile-time-specialised epilogue for the hot Gibbs half-steps (Bernoulli units, Philox or no
+// sampling, no label units, no metric reductions): a fraction of the generic epilogue's
+// instruction count and code size, so it hides completely behind the next tile's MMAs.
+//   SAMPLE = true : s = (u < sigmoid(x)); stores state_rm (required), state_T (optional);
+//                   optional prob_T; bias gradient of s (bg_what == 2) or p (bg_what == 1)
+//   SAMPLE = false: p = sigmoid(x); stores prob_T / prob_rm (optional); bias gradient of p
+template <int BN, bool SAMPLE>
+__device__ __forceinline__ void epilogue_fast(const EpiParams &ep, uint32_t tmem_acc, int m_blk, int n_blk, int quarter, int wg,
+                                              int lane) {
+    const int unit = m_blk * BM + quarter * 32 + lane;
+    const bool uvalid = unit < ep.M;
+    const float bias = uvalid ? ep.bias[unit] : 0.f;
+    const bool want_sT = SAMPLE && ep.state_T != nullptr, want_pT = ep.prob_T != nullptr, want_prm = ep.prob_rm != nullptr;
+    float bg_p = 0.f;
+    int bg_s = 0;
+    constexpr int COLS_PER_WG = BN / 2;
+#pragma unroll 1
+    for (int c0 = wg * COLS_PER_WG; c0 < (wg + 1) * COLS_PER_WG; c0 += 16) {
+        uint32_t r[16];
+        __syncwarp();
+        tmem_ld16(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        tmem_wait_ld(r);
+        const int row_base = n_blk * BN + c0;
+        int nvalid = ep.N - row_base;  // rows of this chunk inside the matrix (warp-uniform)
+        if (nvalid <= 0) continue;
+        nvalid = nvalid > 16 ? 16 : nvalid;
+        const int nv = uvalid ? nvalid : 0;
+        uint32_t sb[16], pb[16];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            uint32_t rnd[4];
+            if (SAMPLE) {
+                const unsigned long long grow = (unsigned long long)(ep.row0 + row_base + 4 * g);
+                Philox4 ph = rng_uniform4(ep.key, (uint32_t)unit, (uint32_t)(grow >> 2));
+                rnd[0] = ph.x; rnd[1] = ph.y; rnd[2] = ph.z; rnd[3] = ph.w;
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int j = 4 * g + jj;
+                const float p = sigmoid_fast(__uint_as_float(r[j]) + bias);
+                if (j < nv) bg_p += p;
+                pb[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(p));
+                if (SAMPLE) {
+                    const bool on = u24(rnd[jj]) < p;
+                    sb[j] = on ? 0x3F80u : 0u;  // bf16(1.0) / bf16(0.0)
+                    bg_s += (on && j < nv) ? 1 : 0;
+                }
+            }
+        }
+        if (SAMPLE) {
+            unsigned short *dst = reinterpret_cast<unsigned short *>(ep.state_rm) + (long long)row_base * ep.ld_srm + unit;
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (j < nv) dst[(long long)j * ep.ld_srm] = (unsigned short)sb[j];
+        }
+        if (want_prm) {
+            unsigned short *dst = reinterpret_cast<unsigned short *>(ep.prob_rm) + (long long)row_base * ep.ld_prm + unit;
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (j < nv) dst[(long long)j * ep.ld_prm] = (unsigned short)pb[j];
+        }
+        if (want_sT) {
+            unsigned short *dst = reinterpret_cast<unsigned short *>(ep.state_T) + (long long)unit * ep.ld_sT + row_base;
+            if (nv == 16) {
+                reinterpret_cast<uint4 *>(dst)[0] = make_uint4(sb[0] | (sb[1] << 16), sb[2] | (sb[3] << 16), sb[4] | (sb[5] << 16), sb[6] | (sb[7] << 16));
+                reinterpret_cast<uint4 *>(dst)[1] = make_uint4(sb[8] | (sb[9] << 16), sb[10] | (sb[11] << 16), sb[12] | (sb[13] << 16), sb[14] | (sb[15] << 16));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (j < nv) dst[j] = (unsigned short)sb[j];
+            }
+        }
+        if (want_pT) {
+            unsigned short *dst = reinterpret_cast<unsigned short *>(ep.prob_T) + (long long)unit * ep.ld_pT + row_base;
+            if (nv == 16) {
+                reinterpret_cast<uint4 *>(dst)[0] = make_uint4(pb[0] | (pb[1] << 16), pb[2] | (pb[3] << 16), pb[4] | (pb[5] << 16), pb[6] | (pb[7] << 16));
+                reinterpret_cast<uint4 *>(dst)[1] = make_uint4(pb[8] | (pb[9] << 16), pb[10] | (pb[11] << 16), pb[12] | (pb[13] << 16), pb[14] | (pb[15] << 16));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (j < nv) dst[j] = (unsigned short)pb[j];
+            }
+        }
+    }
+    if (ep.bg_what && uvalid) atomicAdd(ep.bias_grad + unit, ep.bg_sign * (ep.bg_what == 1 ? bg_p : (float)bg_s));
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_grad(const EpiParams &ep, uint32_t tmem_acc, int m_blk, int n_blk, int quarter, int wg,
                                               int lane) {
@@ -337,7 +426,7 @@ __device__ __forceinline__ void epilogue_grad(const EpiParams &ep, uint32_t tmem
 }
 
 // ----------------------------------------------------------------------------- the kernel
-template <int BN>
+template <int BN, int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gibbs_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, int K1, int K2,
@@ -434,8 +523,10 @@ gibbs_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             mbar_wait(tfull_bar(as), aphase);
             tcgen05_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
-            if (ep.mode == EPI_SAMPLE) epilogue_sample<BN>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
-            else epilogue_grad<BN>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            if (KIND == K_GENERIC) epilogue_sample<BN>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_GRAD) epilogue_grad<BN>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_FAST_SAMPLE) epilogue_fast<BN, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else epilogue_fast<BN, false>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -485,24 +576,50 @@ inline CUtensorMap make_tmap(const Operand &o, int box_rows) {
     return m;
 }
 
+// which specialisation serves these epilogue parameters
+inline int pick_kind(const EpiParams &ep) {
+    if (ep.mode == EPI_GRAD) return K_GRAD;
+    const bool plain = ep.act == ACT_SIGMOID && ep.split >= ep.M && !ep.inj && !ep.sqerr && !ep.softplus_rows && !ep.prob_f32;
+    if (plain && ep.sample && ep.use_rng && ep.state_rm && !ep.prob_rm) return K_FAST_SAMPLE;
+    if (plain && !ep.sample && !ep.state_rm && !ep.state_T) return K_FAST_PROB;
+    return K_GENERIC;
+}
+
+template <int BN, int KIND>
+inline void launch_bn_kind(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &ma2,
+                           const CUtensorMap &mb2, int K1, int K2, const EpiParams &ep, int grid) {
+    using C = Cfg<BN>;
+    gibbs_gemm_kernel<BN, KIND><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, ma2, mb2, K1, K2, ep);
+}
+
 template <int BN>
 inline void launch_bn(cudaStream_t st, const Operand &A, const Operand &B, const Operand *A2, const Operand *B2,
                       const EpiParams &ep, int num_sms) {
-    using C = Cfg<BN>;
     CUtensorMap ma = make_tmap(A, BM), mb = make_tmap(B, BN);
     CUtensorMap ma2 = A2 ? make_tmap(*A2, BM) : ma, mb2 = B2 ? make_tmap(*B2, BN) : mb;
     const int tiles = (int)(ceil_div(ep.M, BM) * ceil_div(ep.N, BN));
     const int grid = tiles < num_sms ? tiles : num_sms;
-    gibbs_gemm_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, ma2, mb2, (int)A.k, A2 ? (int)A2->k : 0, ep);
+    const int K1 = (int)A.k, K2 = A2 ? (int)A2->k : 0;
+    switch (pick_kind(ep)) {
+        case K_GRAD: launch_bn_kind<BN, K_GRAD>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
+        case K_FAST_SAMPLE: launch_bn_kind<BN, K_FAST_SAMPLE>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
+        case K_FAST_PROB: launch_bn_kind<BN, K_FAST_PROB>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
+        default: launch_bn_kind<BN, K_GENERIC>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
+    }
     QB_CUDA(cudaGetLastError());
 }
 
+template <int BN>
+inline void init_bn() {
+    const int b = Cfg<BN>::SMEM_BYTES;
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+}
 // once per device (qb_create): opt in to the large dynamic shared-memory carve-out
 inline void init_device() {
-    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
-    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
-    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES));
-    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<32>::SMEM_BYTES));
+    init_bn<256>(); init_bn<128>(); init_bn<64>(); init_bn<32>();
 }
 
 // D[M][N]: picks the widest N tile that still yields at least one tile per SM.
