@@ -1,0 +1,65 @@
+"""torchrun worker for the data-parallel parity check (tests/test_multi_gpu.py):
+G ranks, each with B/G rows and chains of every mini-batch and one NCCL gradient allreduce
+per step, must reproduce the single-GPU run (Philox is keyed by the GLOBAL row)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import qarbom_b200 as q  # noqa: E402
+from bench import shard_rows  # noqa: E402
+
+
+def main():
+    prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+    rank, world, lr_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr_)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr_))
+    V, H, B, k, nb, steps = 320, 192, 64 * world, 2, 3, 3
+    rng = np.random.default_rng(0)
+    X = rng.integers(0, 2, (nb * B, V)).astype(np.uint8)
+    W0 = 0.1 * rng.standard_normal((V, H))
+    Bl = B // world
+
+    def run(rk, wd, Xs, Brows, comm):
+        rbm = q.RBM(V, H, W=W0)
+        dev = q.DeviceRBM(rbm, max_batch=Brows, precision=prec, device=lr_, rank=rk, world=wd, seed=99)
+        if comm:
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(q.DeviceRBM.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            dev.comm_init(uid.cpu().numpy().tobytes())
+        dev.set_data(Xs)
+        dev.init_chains(Brows)
+        for t in range(steps):
+            dev.pcd_step(t % nb, Brows, k, 0.05)
+        dev.pull_params()
+        v, h, _ = dev.get_chains()
+        dev.close()
+        return rbm.W.copy(), rbm.a.copy(), rbm.b.copy(), v, h
+
+    Wm, am, bm, vm, hm = run(rank, world, shard_rows(X, B, nb, rank, world), Bl, True)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (Wm, vm, hm))
+    ok = True
+    if rank == 0:
+        Ws, as_, bs, vs, hs = run(0, 1, X, B, False)
+        for r, (Wr, _, _) in enumerate(gathered):
+            assert np.array_equal(Wr, gathered[0][0]), f"replica {r} diverged from replica 0"
+        rel = np.linalg.norm(Wm - Ws) / np.linalg.norm(Ws)
+        drel = np.linalg.norm((Wm - W0) - (Ws - W0)) / np.linalg.norm(Ws - W0)
+        vcat = np.concatenate([g[1] for g in gathered]); hcat = np.concatenate([g[2] for g in gathered])
+        mis = float(np.mean(vcat != vs)), float(np.mean(hcat != hs))
+        print(f"MGPU world={world} prec={prec} relW={rel:.3e} rel_dW={drel:.3e} state_mismatch={mis}")
+        ok = rel < 1e-5 and drel < (2e-2 if prec == "bf16" else 1e-4) and max(mis) < 1e-3
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

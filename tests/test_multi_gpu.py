@@ -1,0 +1,24 @@
+"""Data-parallel parity on real GPUs (needs >= 2 devices; the 1-GPU round-end run skips it).
+Run by hand with: gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_two_rank_pcd_matches_single_gpu(prec):
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_worker.py"), prec]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "MGPU" in out.stdout
