@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -167,7 +167,7 @@ def cpu_reference(w, seconds_target, steps, warmup, threads=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
@@ -265,6 +265,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
     launches, gemms, gflops, timed, gemm_ms, timed_flops = dev.counters_full()
+    upd_n, upd_ms = dev.update_timing()
     dev.set_option("time_gemms", 0)
     value = B * args.steps / (ms * 1e-3)
 
@@ -305,12 +306,19 @@ def main():
             "gemm_share_of_step": gemm_ms / ms if ms > 0 else None,
             "algorithmic_flops_per_step_per_gpu": F, "issued_flops_per_step_per_gpu": gflops / args.steps,
             "peak_source": pk["src"], "whole_step_tflops": F * args.steps / (ms * 1e-3) / 1e12}
+    # update kernel (HBM-bound): 12 B/param fp32 read-modify-write + 4 B/param for the two bf16 shadows
+    P_w = (w["V"] + w["L"]) * w["H"]
+    upd_bytes = (16.0 if args.precision == "bf16" else 12.0) * P_w
+    upd_gbs = (upd_bytes * upd_n / 1e9) / (upd_ms * 1e-3) if upd_ms > 0 else None
+    roof_upd = {"bound": "hbm", "achieved": upd_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": (upd_gbs / pk["hbm"]) if upd_gbs else None, "traffic": None, "kernel": "qb::update_w_kernel",
+                "bytes_per_launch": upd_bytes, "avg_launch_ms": upd_ms / max(upd_n, 1), "launches_timed": upd_n}
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": dict(cfg, l2="inputs cycle over %d resident mini-batches (%.2f GB incl. transposed copies) > 126 MB L2"
                                     % (nb, 2 * nb * Bl * w["V"] * 2 / 1e9)),
-            "gibbs_steps_per_s": value * k, "gpu_launches": launches, "roofline": roof, "clocks": clocks, "e2e": e2e}
+            "gibbs_steps_per_s": value * k, "gpu_launches": launches, "roofline": roof, "roofline_update": roof_upd, "clocks": clocks, "e2e": e2e}
     if not args.no_cpu_baseline:
         r = cpu_reference(w, args.cpu_seconds, 3, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["threads"], "kind": "port",

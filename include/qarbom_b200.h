@@ -155,6 +155,8 @@ int32_t qb_comm_init(qb_handle *h, const void *id128);
  * timed_* report the number of launches timed, their summed duration and flops. */
 int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_launches, double *gemm_flops,
                         int64_t *timed_gemms, double *timed_gemm_ms, double *timed_gemm_flops);
+/* with "time_gemms": number and summed CUDA-event duration of the update_w kernel launches */
+int32_t qb_get_update_timing(qb_handle *h, int64_t *timed_updates, double *timed_update_ms);
 int32_t qb_reset_counters(qb_handle *h);
 /* Options: "async_steps" (qb_pcd_step / qb_cd_step return without waiting; use qb_sync),
  * "time_gemms", "force_bn" (tile width override for experiments). */

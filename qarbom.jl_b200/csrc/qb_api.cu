@@ -92,6 +92,8 @@ struct qb_handle {
     // resident dataset
     Mat data; int64_t N = 0;
     bf16 *dataT = nullptr; int64_t dataT_B = 0, dataT_nb = 0, dataT_ld = 0;
+    float *datasum = nullptr;          // [nb][ldv] column sums of every resident mini-batch (data side of delta_a)
+    const float *cur_datasum = nullptr;  // sums of the mini-batch being processed (nullptr: compute them)
     // persistent chains and work buffers (Bmax rows)
     Mat cv, ch; int64_t n_chains = 0; bool chains_binary = false;
     Mat phd, hs, vm, phm, hb;  // pos-phase probs, sampled hidden, CD model visible, CD final probs, host-batch staging
@@ -112,6 +114,7 @@ struct qb_handle {
     bool time_gemms = false;    // bracket every GEMM launch with CUDA events on the launching stream
     std::vector<cudaEvent_t> gemm_ev; size_t gemm_ev_used = 0; int64_t gemm_timed = 0; double gemm_timed_flops = 0.0;
     cudaEvent_t timer_ev[2] = {};
+    std::vector<cudaEvent_t> upd_ev; size_t upd_ev_used = 0; int64_t upd_timed = 0;
 };
 
 namespace {
@@ -374,6 +377,14 @@ void colsum(qb_handle *h, const T *A, int64_t lda, int64_t rows, int64_t cols, f
     QB_CUDA(cudaGetLastError());
     h->launches++;
 }
+template <>
+void colsum<bf16>(qb_handle *h, const bf16 *A, int64_t lda, int64_t rows, int64_t cols, float sign, float *out) {
+    const int64_t gx = ceil_div(cols, 256);
+    dim3 g((unsigned)gx, (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, 8), ceil_div(4 * h->num_sms, gx))));
+    colsum_bf16x8_kernel<<<g, 256, 0, h->stream>>>(A, lda, (int)rows, (int)cols, sign, out);
+    QB_CUDA(cudaGetLastError());
+    h->launches++;
+}
 
 // G = posH' posV - negH' negV   (and the bias gradients that were not folded into epilogues)
 void op_grad(qb_handle *h, const Mat &posH, const Mat &posV, const bf16 *posV_T, int64_t posV_ldT, const Mat &negH,
@@ -396,10 +407,18 @@ void op_grad(qb_handle *h, const Mat &posH, const Mat &posV, const bf16 *posV_T,
         GemmScope gs(h, 4.0 * (double)h->H * (double)h->VL * (double)rows);
         sm100::launch(h->stream, A, B, &A2, &B2, ep, h->num_sms, h->force_bn);
     }
-    colsum<bf16>(h, posV.b, posV.ld, rows, h->VL, 1.f, G_a(h));  // data-side visible sums; the rest is folded
+    if (!h->cur_datasum) colsum<bf16>(h, posV.b, posV.ld, rows, h->VL, 1.f, G_a(h));  // data-side visible sums; the rest is folded
 }
 
-void zero_bias_grads(qb_handle *h) { QB_CUDA(cudaMemsetAsync(G_a(h), 0, (h->ldv + h->ldh) * sizeof(float), h->stream)); }
+// bias-gradient accumulators start at the data-side visible sums when those are cached
+void zero_bias_grads(qb_handle *h) {
+    if (h->bf && h->cur_datasum) {
+        QB_CUDA(cudaMemcpyAsync(G_a(h), h->cur_datasum, h->ldv * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        QB_CUDA(cudaMemsetAsync(G_b(h), 0, h->ldh * sizeof(float), h->stream));
+    } else {
+        QB_CUDA(cudaMemsetAsync(G_a(h), 0, (h->ldv + h->ldh) * sizeof(float), h->stream));
+    }
+}
 
 // update_rbm!(rbm, dW, [dU,] da, db, [dc,] lr/B [, llr/B]) after the data-parallel sum of G
 void op_update(qb_handle *h, double lr, double llr, int64_t B_local) {
@@ -410,9 +429,16 @@ void op_update(qb_handle *h, double lr, double llr, int64_t B_local) {
     const float lr_e = (float)(lr / Bg), llr_e = (float)(llr / Bg);
     const bool use_vel = (h->momentum != 0.0 || h->weight_decay != 0.0);
     if (use_vel && !h->Vel) h->Vel = dalloc<float>(h->nP);
-    dim3 g((unsigned)ceil_div(h->VL, 64), (unsigned)ceil_div(h->H, 64));
+    dim3 g((unsigned)ceil_div(h->VL, 128), (unsigned)ceil_div(h->H, 64));
+    size_t ei = 0; bool timed = false;
+    if (h->time_gemms && h->upd_ev_used + 2 <= 4096) {
+        while (h->upd_ev.size() < h->upd_ev_used + 2) { cudaEvent_t e; QB_CUDA(cudaEventCreate(&e)); h->upd_ev.push_back(e); }
+        ei = h->upd_ev_used; h->upd_ev_used += 2; h->upd_timed++; timed = true;
+        QB_CUDA(cudaEventRecord(h->upd_ev[ei], h->stream));
+    }
     update_w_kernel<<<g, 256, 0, h->stream>>>(Wf(h), G_W(h), use_vel ? h->Vel : nullptr, (int)h->H, (int)h->VL, (int)h->V, h->ldv,
                                               lr_e, llr_e, (float)h->momentum, (float)h->weight_decay, h->Wb, h->WbT, h->ldh);
+    if (timed) QB_CUDA(cudaEventRecord(h->upd_ev[ei + 1], h->stream));
     QB_CUDA(cudaGetLastError());
     const int nb = (int)(h->ldv + h->ldh);
     update_bias_kernel<<<grid1d(nb), 256, 0, h->stream>>>(acat(h), G_a(h), use_vel ? h->Vel + h->nW : nullptr, (int)h->ldv,
@@ -437,8 +463,12 @@ void ensure_dataT(qb_handle *h, int64_t B) {
     const int64_t nb = h->N / B;
     h->dataT_ld = round_up(B, 8);
     h->dataT = dalloc<bf16>((size_t)std::max<int64_t>(nb, 1) * h->VL * h->dataT_ld);
-    for (int64_t m = 0; m < nb; m++)
+    cudaFree(h->datasum);
+    h->datasum = dalloc<float>((size_t)std::max<int64_t>(nb, 1) * h->ldv);
+    for (int64_t m = 0; m < nb; m++) {
         transpose_into(h, h->data.b + m * B * h->data.ld, h->data.ld, B, h->VL, h->dataT + m * h->VL * h->dataT_ld, h->dataT_ld);
+        colsum<bf16>(h, h->data.b + m * B * h->data.ld, h->data.ld, B, h->VL, 1.f, h->datasum + m * h->ldv);
+    }
     h->dataT_B = B; h->dataT_nb = nb;
 }
 
@@ -546,11 +576,12 @@ void batch_view(qb_handle *h, int64_t m, int64_t B, Mat &xb, const bf16 *&xbT, i
     QB_CHECK(h->N > 0, QB_E_STATE, "qb_set_data has not been called");
     QB_CHECK(m >= 0 && (m + 1) * B <= h->N, QB_E_ARG, "mini-batch index out of range");
     xb = h->data.row_slice(m * B, B);
-    xbT = nullptr; ldT = 0;
+    xbT = nullptr; ldT = 0; h->cur_datasum = nullptr;
     if (h->bf) {
         ensure_dataT(h, B);
         xbT = h->dataT + m * h->VL * h->dataT_ld;
         ldT = h->dataT_ld;
+        h->cur_datasum = h->datasum + m * h->ldv;
     }
 }
 
@@ -685,13 +716,14 @@ int32_t qb_destroy(qb_handle *h) {
         cudaDeviceSynchronize();
         if (h->comm) nccl().CommDestroy(h->comm);
         cudaFree(h->P); cudaFree(h->G); cudaFree(h->Vel); cudaFree(h->Wb); cudaFree(h->WbT);
-        free_mat(h->data); cudaFree(h->dataT);
+        free_mat(h->data); cudaFree(h->dataT); cudaFree(h->datasum);
         free_mat(h->cv); free_mat(h->ch); free_mat(h->phd); free_mat(h->hs); free_mat(h->vm); free_mat(h->phm); free_mat(h->hb);
         cudaFree(h->pre_h); cudaFree(h->pre_v); cudaFree(h->lab_pre); cudaFree(h->softplus_rows); cudaFree(h->out_f32);
         cudaFree(h->dscal); cudaFree(h->znoise); cudaFree(h->staging); cudaFree(h->injUh); cudaFree(h->injUv); cudaFree(h->injZv);
         for (auto &e : h->ev) cudaEventDestroy(e);
         for (auto &e : h->timer_ev) cudaEventDestroy(e);
         for (auto &e : h->gemm_ev) cudaEventDestroy(e);
+        for (auto &e : h->upd_ev) cudaEventDestroy(e);
         cudaStreamDestroy(h->stream); cudaStreamDestroy(h->copy_stream);
         delete h;
     });
@@ -749,6 +781,7 @@ int32_t qb_set_data(qb_handle *h, const void *X, int32_t x_dtype, const void *Y,
         QB_CHECK(h->L == 0 || Y != nullptr, QB_E_ARG, "labels required for classifier models");
         free_mat(h->data);
         cudaFree(h->dataT); h->dataT = nullptr; h->dataT_B = 0;
+        cudaFree(h->datasum); h->datasum = nullptr; h->cur_datasum = nullptr;
         h->data = alloc_mat(h, n_rows, h->VL, false);
         h->N = n_rows;
         upload_rows(h, X, x_dtype, n_rows, h->V, h->data, 0, 0);
@@ -891,6 +924,7 @@ int32_t qb_cd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, d
 static void step_host_impl(qb_handle *h, bool pcd, const void *X, int xdt, const void *Y, int ydt, int64_t B, int64_t k,
                            double lr, double llr, double *recon) {
     check_step_args(h, B, k);
+    h->cur_datasum = nullptr;
     stage_host_batch(h, X, xdt, Y, ydt, B);
     if (pcd) pcd_step_impl(h, h->hb, h->hb.bT, h->hb.ldT, B, k, lr, llr, nullptr);
     else cd_step_impl(h, h->hb, h->hb.bT, h->hb.ldT, B, k, lr, llr, nullptr);
@@ -1066,6 +1100,7 @@ int32_t qb_reset_counters(qb_handle *h) {
         QB_H(h);
         h->launches = 0; h->gemm_launches = 0; h->gemm_flops = 0.0;
         h->gemm_ev_used = 0; h->gemm_timed = 0; h->gemm_timed_flops = 0.0;
+        h->upd_ev_used = 0; h->upd_timed = 0;
     });
 }
 int32_t qb_set_option(qb_handle *h, const char *key, double value) {
@@ -1083,6 +1118,22 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
         } else {
             throw Error(QB_E_ARG, std::string("unknown option ") + key);
         }
+    });
+}
+int32_t qb_get_update_timing(qb_handle *h, int64_t *timed_updates, double *timed_update_ms) {
+    return guarded([&] {
+        QB_H(h);
+        double ms = 0.0;
+        if (h->upd_ev_used) {
+            QB_CUDA(cudaStreamSynchronize(h->stream));
+            for (size_t i = 0; i + 1 < h->upd_ev_used; i += 2) {
+                float t = 0.f;
+                QB_CUDA(cudaEventElapsedTime(&t, h->upd_ev[i], h->upd_ev[i + 1]));
+                ms += t;
+            }
+        }
+        if (timed_updates) *timed_updates = h->upd_timed;
+        if (timed_update_ms) *timed_update_ms = ms;
     });
 }
 int32_t qb_sync(qb_handle *h) {

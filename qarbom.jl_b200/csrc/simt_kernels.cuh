@@ -142,46 +142,119 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T *__restrict__ A, in
 }
 
 // ----------------------------------------------------------------------------- parameter update (K5)
-// W region: tile [64 h][64 c] per block; fp32 read-modify-write of theta (+ velocity),
-// refresh of the bf16 shadows Wb[h][c] and (through a shared-memory transpose) WbT[c][h].
+// W region: tile [64 h][128 c] per block, 128-bit loads/stores (4 columns per thread, 8 rows in
+// flight per thread); fp32 read-modify-write of theta (+ velocity), refresh of the bf16 shadows
+// Wb[h][c] (8-byte stores) and, through a shared-memory tile, WbT[c][h] (32 B per thread).
 //   vel = momentum*vel + lr_c*g - lr_c*wd*w ;  w += vel     (momentum = wd = 0: w += lr_c*g,
 //   i.e. update_rbm!, src/rbm.jl:152-163 / :120-136 with lr_c = lr/B for c < V, llr/B for labels)
+// Algorithmic bytes per parameter: 12 (read w, read g, write w) + 4 (two bf16 shadows); +8 with velocity.
 __global__ void __launch_bounds__(256) update_w_kernel(float *__restrict__ W, const float *__restrict__ G,
                                                        float *__restrict__ Vel, int H, int VL, int V, int64_t ldv,
                                                        float lr, float llr, float momentum, float wd,
                                                        bf16 *__restrict__ Wb, bf16 *__restrict__ WbT, int64_t ldh) {
-    __shared__ bf16 tile[64][64 + 2];
-    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-    const int c = blockIdx.x * 64 + tx;
-    const int h0 = blockIdx.y * 64;
-    const float lr_c = (c < V) ? lr : llr;
-#pragma unroll 4
-    for (int i = ty; i < 64; i += 4) {
-        int h = h0 + i;
-        float w = 0.f;
-        if (h < H && c < VL) {
-            int64_t o = (int64_t)h * ldv + c;
-            w = W[o];
-            float g = G[o];
-            if (Vel) {
-                float v = momentum * Vel[o] + lr_c * g - lr_c * wd * w;
-                Vel[o] = v;
-                w += v;
+    constexpr int TH = 64, TC = 128, PITCH = TC + 8;
+    __shared__ __align__(16) unsigned short tile[TH][PITCH];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * TC + 4 * tx;
+    const int h0 = blockIdx.y * TH;
+    const bool vec = (c + 3 < VL);
+    float lrc[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) lrc[i] = (c + i < V) ? lr : llr;
+    float4 w[8], g[8], v[8];
+#pragma unroll
+    for (int it = 0; it < 8; it++) {  // all loads first: 16-24 independent 128-bit requests per thread
+        const int h = h0 + ty + 8 * it;
+        w[it] = make_float4(0.f, 0.f, 0.f, 0.f); g[it] = w[it]; v[it] = w[it];
+        if (h < H) {
+            const int64_t o = (int64_t)h * ldv + c;
+            if (vec) {
+                w[it] = *reinterpret_cast<const float4 *>(W + o);
+                g[it] = *reinterpret_cast<const float4 *>(G + o);
+                if (Vel) v[it] = *reinterpret_cast<const float4 *>(Vel + o);
             } else {
-                w += lr_c * g;
+                float *wp = reinterpret_cast<float *>(&w[it]), *gp = reinterpret_cast<float *>(&g[it]), *vp = reinterpret_cast<float *>(&v[it]);
+                for (int i = 0; i < 4; i++)
+                    if (c + i < VL) { wp[i] = W[o + i]; gp[i] = G[o + i]; if (Vel) vp[i] = Vel[o + i]; }
             }
-            W[o] = w;
-            if (Wb) Wb[o] = __float2bfloat16(w);
         }
-        if (WbT) tile[i][tx] = __float2bfloat16(w);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int hl = ty + 8 * it, h = h0 + hl;
+        float *wp = reinterpret_cast<float *>(&w[it]), *gp = reinterpret_cast<float *>(&g[it]), *vp = reinterpret_cast<float *>(&v[it]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (Vel) { vp[i] = momentum * vp[i] + lrc[i] * gp[i] - lrc[i] * wd * wp[i]; wp[i] += vp[i]; }
+            else wp[i] += lrc[i] * gp[i];
+        }
+        __nv_bfloat162 b01 = __floats2bfloat162_rn(wp[0], wp[1]), b23 = __floats2bfloat162_rn(wp[2], wp[3]);
+        const uint2 packed = make_uint2(*reinterpret_cast<uint32_t *>(&b01), *reinterpret_cast<uint32_t *>(&b23));
+        *reinterpret_cast<uint2 *>(&tile[hl][4 * tx]) = packed;
+        if (h < H) {
+            const int64_t o = (int64_t)h * ldv + c;
+            if (vec) {
+                *reinterpret_cast<float4 *>(W + o) = w[it];
+                if (Vel) *reinterpret_cast<float4 *>(Vel + o) = v[it];
+                if (Wb) *reinterpret_cast<uint2 *>(Wb + o) = packed;
+            } else {
+                for (int i = 0; i < 4; i++)
+                    if (c + i < VL) { W[o + i] = wp[i]; if (Vel) Vel[o + i] = vp[i]; if (Wb) Wb[o + i] = __float2bfloat16(wp[i]); }
+            }
+        }
     }
     if (!WbT) return;
     __syncthreads();
-    const int h = h0 + tx;
-#pragma unroll 4
-    for (int i = ty; i < 64; i += 4) {
-        int cc = blockIdx.x * 64 + i;
-        if (cc < VL && h < H) WbT[(int64_t)cc * ldh + h] = tile[tx][i];
+    // transposed shadow: task = (column, 16-row chunk); consecutive lanes take consecutive columns
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int task = threadIdx.x + 256 * q;
+        const int cl = task & (TC - 1), hc = task >> 7;
+        const int cc = blockIdx.x * TC + cl, hb = h0 + 16 * hc;
+        if (cc >= VL || hb >= H) continue;
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) pk[i] = (uint32_t)tile[16 * hc + 2 * i][cl] | ((uint32_t)tile[16 * hc + 2 * i + 1][cl] << 16);
+        unsigned short *dst = reinterpret_cast<unsigned short *>(WbT) + (int64_t)cc * ldh + hb;
+        if (hb + 16 <= H) {
+            reinterpret_cast<uint4 *>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            reinterpret_cast<uint4 *>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+            for (int i = 0; i < 16; i++)
+                if (hb + i < H) dst[i] = tile[16 * hc + i][cl];
+        }
+    }
+}
+
+// vectorised column sums of a bf16 matrix: out[c] += sign * sum_r A[r][c]; 8 columns (16 B) per thread
+__global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16 *__restrict__ A, int64_t lda, int rows, int cols,
+                                                            float sign, float *__restrict__ out) {
+    __shared__ float red[8][32][9];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + tx) * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c < cols) {  // lda % 8 == 0 and padding columns are zero, so the 16-byte load is always in bounds
+        for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(A + (int64_t)r * lda + c);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                acc[2 * i] += __uint_as_float(w[i] << 16);
+                acc[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) red[ty][tx][i] = acc[i];
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float s2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) s2 += red[j][tx][i];
+            if (c + i < cols) atomicAdd(out + c + i, sign * s2);
+        }
     }
 }
 

@@ -184,6 +184,11 @@ class DeviceRBM:
                                     ctypes.byref(ms), ctypes.byref(tf)))
         return a.value, b.value, f.value, t.value, ms.value, tf.value
 
+    def update_timing(self):
+        n, ms = ctypes.c_int64(0), ctypes.c_double(0)
+        check(lib().qb_get_update_timing(self._h, ctypes.byref(n), ctypes.byref(ms)))
+        return n.value, ms.value
+
     def reset_counters(self):
         check(lib().qb_reset_counters(self._h))
 
