@@ -193,7 +193,8 @@ void upload_rows(qb_handle *h, const void *src, int dt, int64_t n, int64_t cols,
         }
         QB_CUDA(cudaGetLastError());
         h->launches++;
-        QB_CUDA(cudaStreamSynchronize(h->stream));  // staging buffer is reused
+        // no sync: the next copy into the staging buffer is stream-ordered after this kernel, and
+        // cudaMemcpyAsync from pageable memory returns only once the source has been staged
     }
 }
 
@@ -412,12 +413,10 @@ void op_grad(qb_handle *h, const Mat &posH, const Mat &posV, const bf16 *posV_T,
 
 // bias-gradient accumulators start at the data-side visible sums when those are cached
 void zero_bias_grads(qb_handle *h) {
-    if (h->bf && h->cur_datasum) {
-        QB_CUDA(cudaMemcpyAsync(G_a(h), h->cur_datasum, h->ldv * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-        QB_CUDA(cudaMemsetAsync(G_b(h), 0, h->ldh * sizeof(float), h->stream));
-    } else {
-        QB_CUDA(cudaMemsetAsync(G_a(h), 0, (h->ldv + h->ldh) * sizeof(float), h->stream));
-    }
+    const int n = (int)(h->ldv + h->ldh);
+    init_bias_grads_kernel<<<grid1d(n), 256, 0, h->stream>>>(G_a(h), h->bf ? h->cur_datasum : nullptr, (int)h->ldv, n);
+    QB_CUDA(cudaGetLastError());
+    h->launches++;
 }
 
 // update_rbm!(rbm, dW, [dU,] da, db, [dc,] lr/B [, llr/B]) after the data-parallel sum of G
@@ -436,8 +435,12 @@ void op_update(qb_handle *h, double lr, double llr, int64_t B_local) {
         ei = h->upd_ev_used; h->upd_ev_used += 2; h->upd_timed++; timed = true;
         QB_CUDA(cudaEventRecord(h->upd_ev[ei], h->stream));
     }
-    update_w_kernel<<<g, 256, 0, h->stream>>>(Wf(h), G_W(h), use_vel ? h->Vel : nullptr, (int)h->H, (int)h->VL, (int)h->V, h->ldv,
-                                              lr_e, llr_e, (float)h->momentum, (float)h->weight_decay, h->Wb, h->WbT, h->ldh);
+    if (use_vel)
+        update_w_kernel<true><<<g, 256, 0, h->stream>>>(Wf(h), G_W(h), h->Vel, (int)h->H, (int)h->VL, (int)h->V, h->ldv, lr_e, llr_e,
+                                                        (float)h->momentum, (float)h->weight_decay, h->Wb, h->WbT, h->ldh);
+    else
+        update_w_kernel<false><<<g, 256, 0, h->stream>>>(Wf(h), G_W(h), nullptr, (int)h->H, (int)h->VL, (int)h->V, h->ldv, lr_e, llr_e,
+                                                         0.f, 0.f, h->Wb, h->WbT, h->ldh);
     if (timed) QB_CUDA(cudaEventRecord(h->upd_ev[ei + 1], h->stream));
     QB_CUDA(cudaGetLastError());
     const int nb = (int)(h->ldv + h->ldh);

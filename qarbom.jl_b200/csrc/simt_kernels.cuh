@@ -148,11 +148,12 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T *__restrict__ A, in
 //   vel = momentum*vel + lr_c*g - lr_c*wd*w ;  w += vel     (momentum = wd = 0: w += lr_c*g,
 //   i.e. update_rbm!, src/rbm.jl:152-163 / :120-136 with lr_c = lr/B for c < V, llr/B for labels)
 // Algorithmic bytes per parameter: 12 (read w, read g, write w) + 4 (two bf16 shadows); +8 with velocity.
-__global__ void __launch_bounds__(256) update_w_kernel(float *__restrict__ W, const float *__restrict__ G,
-                                                       float *__restrict__ Vel, int H, int VL, int V, int64_t ldv,
-                                                       float lr, float llr, float momentum, float wd,
-                                                       bf16 *__restrict__ Wb, bf16 *__restrict__ WbT, int64_t ldh) {
-    constexpr int TH = 64, TC = 128, PITCH = TC + 8;
+template <bool VEL>
+__global__ void __launch_bounds__(256, 3) update_w_kernel(float *__restrict__ W, const float *__restrict__ G,
+                                                          float *__restrict__ Vel, int H, int VL, int V, int64_t ldv,
+                                                          float lr, float llr, float momentum, float wd,
+                                                          bf16 *__restrict__ Wb, bf16 *__restrict__ WbT, int64_t ldh) {
+    constexpr int TH = 64, TC = 128, PITCH = TC + 8, ROWS = 4;  // ROWS rows in flight per thread
     __shared__ __align__(16) unsigned short tile[TH][PITCH];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * TC + 4 * tx;
@@ -161,45 +162,58 @@ __global__ void __launch_bounds__(256) update_w_kernel(float *__restrict__ W, co
     float lrc[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) lrc[i] = (c + i < V) ? lr : llr;
-    float4 w[8], g[8], v[8];
+#pragma unroll 1
+    for (int pass = 0; pass < TH / (8 * ROWS); pass++) {
+        float4 w[ROWS], g[ROWS], v[ROWS];
 #pragma unroll
-    for (int it = 0; it < 8; it++) {  // all loads first: 16-24 independent 128-bit requests per thread
-        const int h = h0 + ty + 8 * it;
-        w[it] = make_float4(0.f, 0.f, 0.f, 0.f); g[it] = w[it]; v[it] = w[it];
-        if (h < H) {
-            const int64_t o = (int64_t)h * ldv + c;
-            if (vec) {
-                w[it] = *reinterpret_cast<const float4 *>(W + o);
-                g[it] = *reinterpret_cast<const float4 *>(G + o);
-                if (Vel) v[it] = *reinterpret_cast<const float4 *>(Vel + o);
-            } else {
-                float *wp = reinterpret_cast<float *>(&w[it]), *gp = reinterpret_cast<float *>(&g[it]), *vp = reinterpret_cast<float *>(&v[it]);
-                for (int i = 0; i < 4; i++)
-                    if (c + i < VL) { wp[i] = W[o + i]; gp[i] = G[o + i]; if (Vel) vp[i] = Vel[o + i]; }
+        for (int it = 0; it < ROWS; it++) {  // all loads first: independent 128-bit requests
+            const int h = h0 + ty + 8 * (pass * ROWS + it);
+            w[it] = make_float4(0.f, 0.f, 0.f, 0.f); g[it] = w[it];
+            if (VEL) v[it] = w[it];
+            if (h < H) {
+                const int64_t o = (int64_t)h * ldv + c;
+                if (vec) {
+                    w[it] = *reinterpret_cast<const float4 *>(W + o);
+                    g[it] = *reinterpret_cast<const float4 *>(G + o);
+                    if (VEL) v[it] = *reinterpret_cast<const float4 *>(Vel + o);
+                } else {
+                    float *wp = reinterpret_cast<float *>(&w[it]), *gp = reinterpret_cast<float *>(&g[it]);
+                    for (int i = 0; i < 4; i++)
+                        if (c + i < VL) { wp[i] = W[o + i]; gp[i] = G[o + i]; if (VEL) reinterpret_cast<float *>(&v[it])[i] = Vel[o + i]; }
+                }
             }
         }
-    }
 #pragma unroll
-    for (int it = 0; it < 8; it++) {
-        const int hl = ty + 8 * it, h = h0 + hl;
-        float *wp = reinterpret_cast<float *>(&w[it]), *gp = reinterpret_cast<float *>(&g[it]), *vp = reinterpret_cast<float *>(&v[it]);
+        for (int it = 0; it < ROWS; it++) {
+            const int hl = ty + 8 * (pass * ROWS + it), h = h0 + hl;
+            float *wp = reinterpret_cast<float *>(&w[it]), *gp = reinterpret_cast<float *>(&g[it]);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (Vel) { vp[i] = momentum * vp[i] + lrc[i] * gp[i] - lrc[i] * wd * wp[i]; wp[i] += vp[i]; }
-            else wp[i] += lrc[i] * gp[i];
-        }
-        __nv_bfloat162 b01 = __floats2bfloat162_rn(wp[0], wp[1]), b23 = __floats2bfloat162_rn(wp[2], wp[3]);
-        const uint2 packed = make_uint2(*reinterpret_cast<uint32_t *>(&b01), *reinterpret_cast<uint32_t *>(&b23));
-        *reinterpret_cast<uint2 *>(&tile[hl][4 * tx]) = packed;
-        if (h < H) {
-            const int64_t o = (int64_t)h * ldv + c;
-            if (vec) {
-                *reinterpret_cast<float4 *>(W + o) = w[it];
-                if (Vel) *reinterpret_cast<float4 *>(Vel + o) = v[it];
-                if (Wb) *reinterpret_cast<uint2 *>(Wb + o) = packed;
-            } else {
-                for (int i = 0; i < 4; i++)
-                    if (c + i < VL) { W[o + i] = wp[i]; if (Vel) Vel[o + i] = vp[i]; if (Wb) Wb[o + i] = __float2bfloat16(wp[i]); }
+            for (int i = 0; i < 4; i++) {
+                if (VEL) {
+                    float *vp = reinterpret_cast<float *>(&v[it]);
+                    vp[i] = momentum * vp[i] + lrc[i] * gp[i] - lrc[i] * wd * wp[i];
+                    wp[i] += vp[i];
+                } else {
+                    wp[i] += lrc[i] * gp[i];
+                }
+            }
+            __nv_bfloat162 b01 = __floats2bfloat162_rn(wp[0], wp[1]), b23 = __floats2bfloat162_rn(wp[2], wp[3]);
+            const uint2 packed = make_uint2(*reinterpret_cast<uint32_t *>(&b01), *reinterpret_cast<uint32_t *>(&b23));
+            *reinterpret_cast<uint2 *>(&tile[hl][4 * tx]) = packed;
+            if (h < H) {
+                const int64_t o = (int64_t)h * ldv + c;
+                if (vec) {
+                    *reinterpret_cast<float4 *>(W + o) = w[it];
+                    if (VEL) *reinterpret_cast<float4 *>(Vel + o) = v[it];
+                    if (Wb) *reinterpret_cast<uint2 *>(Wb + o) = packed;
+                } else {
+                    for (int i = 0; i < 4; i++)
+                        if (c + i < VL) {
+                            W[o + i] = wp[i];
+                            if (VEL) Vel[o + i] = reinterpret_cast<float *>(&v[it])[i];
+                            if (Wb) Wb[o + i] = __float2bfloat16(wp[i]);
+                        }
+                }
             }
         }
     }
@@ -272,6 +286,12 @@ __global__ void update_bias_kernel(float *__restrict__ P, const float *__restric
     } else {
         P[i] += lr_c * g;
     }
+}
+
+// start of a step: G_a = cached data-side visible sums (or 0), G_b = 0 -- one launch instead of memcpy + memset
+__global__ void init_bias_grads_kernel(float *__restrict__ Ga, const float *__restrict__ datasum, int n_vis, int n_total) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_total) Ga[i] = (datasum && i < n_vis) ? datasum[i] : 0.f;
 }
 
 // refresh both bf16 shadows from fp32 W (after qb_set_params)

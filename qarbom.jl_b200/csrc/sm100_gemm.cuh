@@ -463,6 +463,10 @@ gibbs_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     tcgen05_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+    // prefetch) overlapped the previous kernel's tail; global memory is only touched below.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ===== TMA producer
@@ -589,7 +593,13 @@ template <int BN, int KIND>
 inline void launch_bn_kind(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &ma2,
                            const CUtensorMap &mb2, int K1, int K2, const EpiParams &ep, int grid) {
     using C = Cfg<BN>;
-    gibbs_gemm_kernel<BN, KIND><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, ma2, mb2, K1, K2, ep);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    QB_CUDA(cudaLaunchKernelEx(&cfg, gibbs_gemm_kernel<BN, KIND>, ma, mb, ma2, mb2, K1, K2, ep));
 }
 
 template <int BN>

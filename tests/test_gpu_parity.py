@@ -348,3 +348,36 @@ def test_argument_errors(q):
         with pytest.raises(q.QbError):
             dev.pcd_step(0, 8, 1, 0.1)          # B > max_batch
         dev.pcd_step(1, 4, 1, 0.1)
+
+
+# ------------------------------------------------------------------------------ optimizer extension
+@pytest.mark.parametrize("V,H,L", [(40, 24, 0), (130, 70, 5)])
+def test_momentum_and_weight_decay_extension(q, V, H, L):
+    """momentum / weight decay are extensions (absent from update_rbm!, src/rbm.jl:152-163); the
+    oracle defines them (apply_update) and momentum = wd = 0 is covered by every other test."""
+    rng = np.random.default_rng(21 + V)
+    B, k, steps = 16, 1, 4
+    m = make_oracle_model(rng, V, H, L)
+    X, Y = _data(rng, steps * B, V, L, False, False)
+    cv0, ch0 = u24(rng, B, V), u24(rng, B, H)
+    cy0 = u24(rng, B, L) if L else None
+    chains = chains_from_arrays(cv0, ch0, cy0)
+    opt = qo.OptState()
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=B, precision="fp32") as dev:
+        dev.set_optimizer(0.5, 1e-3)
+        dev.set_data(X, Y)
+        dev.init_chains(B, cv0, ch0, cy0)
+        for t in range(steps):
+            ds = DenseStreams(rng, k, B, V, H, L, False)
+            su, sz = ds.serial("pcd")
+            st = qo.GuardedStream(su, sz)
+            qo.persistent_contrastive_divergence(m, X, [range(t * B, (t + 1) * B)], chains, steps=k, learning_rate=0.05,
+                                                 stream=st, y=Y, label_learning_rate=0.02, momentum=0.5, weight_decay=1e-3,
+                                                 opt=opt)
+            ds.absorb(st.u, "pcd")
+            dev.inject_streams(ds.U_h, ds.U_v, ds.U_y, ds.Z_v)
+            dev.pcd_step(t, B, k, 0.05, 0.02)
+        dev.pull_params()
+        assert rel_err(dev.rbm.W, m.W) < 1e-5 and np.max(np.abs(dev.rbm.b - m.b)) < 1e-6
+        if L:
+            assert rel_err(dev.rbm.U, m.U) < 1e-5 and np.max(np.abs(dev.rbm.c - m.c)) < 1e-6
