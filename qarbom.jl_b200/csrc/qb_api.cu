@@ -109,7 +109,7 @@ struct qb_handle {
     ncclComm_t comm = nullptr;
     int64_t launches = 0, gemm_launches = 0;
     double gemm_flops = 0.0;
-    int force_bn = 0;
+    int force_bn = 0, use_2cta = 1;
     bool async_steps = false;   // step calls return without a stream sync (qb_sync to wait)
     bool time_gemms = false;    // bracket every GEMM launch with CUDA events on the launching stream
     std::vector<cudaEvent_t> gemm_ev; size_t gemm_ev_used = 0; int64_t gemm_timed = 0; double gemm_timed_flops = 0.0;
@@ -295,7 +295,7 @@ void op_hidden(qb_handle *h, const Mat &in, int64_t rows, int64_t kdim, const Hi
     ep.bg_what = o.bg_what; ep.bg_sign = o.bg_sign; ep.bias_grad = G_b(h);
     ep.softplus_rows = o.softplus_rows;
     GemmScope gs(h, 2.0 * (double)h->H * (double)rows * (double)kdim);
-    sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn);
+    sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn, h->use_2cta);
 }
 
 struct VisibleOut {
@@ -359,7 +359,7 @@ void op_visible(qb_handle *h, const Mat &in, int64_t rows, const VisibleOut &o, 
     if (o.sqerr) { ep.sqerr = o.sqerr; ep.ref_rm = o.ref->b; ep.ld_ref = o.ref->ld; }
     {
         GemmScope gs(h, 2.0 * (double)h->VL * (double)rows * (double)h->H);
-        sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn);
+        sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn, h->use_2cta);
     }
     if (h->L > 0 && o.sample && o.state) {
         label_bf16_kernel<<<grid1d(rows, 128), 128, 0, h->stream>>>(
@@ -406,7 +406,7 @@ void op_grad(qb_handle *h, const Mat &posH, const Mat &posV, const bf16 *posV_T,
     ep.out_f32 = G_W(h); ep.ld_out = h->ldv;
     {
         GemmScope gs(h, 4.0 * (double)h->H * (double)h->VL * (double)rows);
-        sm100::launch(h->stream, A, B, &A2, &B2, ep, h->num_sms, h->force_bn);
+        sm100::launch(h->stream, A, B, &A2, &B2, ep, h->num_sms, h->force_bn, h->use_2cta);
     }
     if (!h->cur_datasum) colsum<bf16>(h, posV.b, posV.ld, rows, h->VL, 1.f, G_a(h));  // data-side visible sums; the rest is folded
 }
@@ -1114,6 +1114,9 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
             int bn = (int)value;
             QB_CHECK(bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 256, QB_E_ARG, "force_bn must be 0/32/64/128/256");
             h->force_bn = bn;
+        } else if (!strcmp(key, "use_2cta")) {
+            QB_CHECK(value == 0.0 || value == 1.0 || value == 2.0, QB_E_ARG, "use_2cta must be 0, 1 or 2");
+            h->use_2cta = (int)value;
         } else if (!strcmp(key, "async_steps")) {
             h->async_steps = value != 0.0;
         } else if (!strcmp(key, "time_gemms")) {

@@ -536,11 +536,201 @@ gibbs_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             if (lane == 0) mbar_arrive(tempty_bar(as));
         }
     }
+    __syncwarp();
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 2) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+
+// ----------------------------------------------------------------------------- 2-CTA (cta_group::2) variant
+// A CTA pair (cluster of 2 on one TPC) computes one 256 x BN tile: each CTA stages its own 128 rows
+// of A and HALF of the B tile, the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) which reads
+// both CTAs' shared memory and writes each CTA's 128 accumulator rows into its own TMEM.  Per CTA
+// and k-block this loads 16 KB + BN/2 x 128 B instead of 16 KB + BN x 128 B: a third less L2->SM
+// traffic at BN = 256 and 6 pipeline stages instead of 4.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    // executed by both CTAs; the peer bit of the barrier address is cleared so the bytes are
+    // accounted on the leader CTA's barrier (cute::SM100_TMA_2SM_LOAD_2D)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {  // arrives on the same barrier offset in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_m256(int n, bool negate_a) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((negate_a ? 1u : 0u) << 13) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN>
+struct Cfg2 {
+    static constexpr int A_BYTES = BM * BK * 2;            // this CTA's 128 rows of A
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;      // this CTA's half of the B tile
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (SMEM_AB_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_AB_BUDGET / STAGE_BYTES);
+    static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN, int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gibbs_gemm_kernel_2cta(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                       const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, int K1, int K2,
+                       const EpiParams ep) {
+    using C = Cfg2<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int tiles_m = (ep.M + 2 * BM - 1) / (2 * BM), tiles_n = (ep.N + BN - 1) / BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int kb1 = (K1 + BK - 1) / BK, kb2 = (K2 + BK - 1) / BK, kb_total = kb1 + kb2;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapA);
+        prefetch_tmap(&mapB);
+        if (kb2) { prefetch_tmap(&mapA2); prefetch_tmap(&mapB2); }
+    }
+    if (warp == 1 && lane == 0) {
+        // full: leader's arrive.expect_tx + the peer producer's remote arrive; tmem_empty: 8 epilogue warps per CTA
+        for (int s = 0; s < C::STAGES; s++) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 16); }
+        fence_barrier_init();
+    }
+    cluster_sync_all();  // both CTAs are resident before the pair-wide TMEM allocation
+    if (warp == 2) tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+    tcgen05_fence_before();
+    cluster_sync_all();  // barriers initialised and TMEM allocated in both CTAs
+    tcgen05_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs: own A rows, own half of B; bytes land on the leader's barrier)
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
+                const int m0 = m_blk * 2 * BM + (int)rank * BM, n0 = n_blk * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < kb_total; kb++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+                    if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+                    else mbar_arrive_remote(full_bar(stage), 0);
+                    if (kb < kb1) {
+                        tma_load_2d_2sm(sa, &mapA, full_bar(stage), kb * BK, m0);
+                        tma_load_2d_2sm(sb, &mapB, full_bar(stage), kb * BK, n0);
+                    } else {
+                        tma_load_2d_2sm(sa, &mapA2, full_bar(stage), (kb - kb1) * BK, m0);
+                        tma_load_2d_2sm(sb, &mapB2, full_bar(stage), (kb - kb1) * BK, n0);
+                    }
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA drives both tensor cores
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc_pos = make_idesc_m256(BN, false), idesc_neg = make_idesc_m256(BN, true);
+            int stage = 0; uint32_t phase = 0;
+            int iter = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, iter++) {
+                const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+                mbar_wait(tempty_bar(as), aphase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < kb_total; kb++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+                    const uint64_t adesc = make_kmajor_sw128_desc(sa), bdesc = make_kmajor_sw128_desc(sb);
+                    const uint32_t idesc = (kb < kb1) ? idesc_pos : idesc_neg;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++)
+                        umma_bf16_2sm(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    umma_commit_2sm(empty_bar(stage));
+                    if (kb == kb_total - 1) umma_commit_2sm(tfull_bar(as));
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===== epilogue: each CTA drains its own 128 accumulator rows
+        const int quarter = warp & 3, wg = (warp - EPI_WARP0) >> 2;
+        int iter = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, iter++) {
+            const int m_blk = (tile % tiles_m) * 2 + (int)rank, n_blk = tile / tiles_m;  // in units of 128 rows
+            const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+            mbar_wait(tfull_bar(as), aphase);
+            tcgen05_fence_after();
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
+            if (KIND == K_GENERIC) epilogue_sample<BN>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_GRAD) epilogue_grad<BN>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_FAST_SAMPLE) epilogue_fast<BN, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else epilogue_fast<BN, false>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) mbar_arrive(tempty_bar(as));
+                else mbar_arrive_remote(tempty_bar(as), 0);
+            }
+        }
+    }
+    __syncwarp();  // single-lane roles rejoin their warp before the .aligned cluster barrier
+    tcgen05_fence_before();
+    cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still signal it
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -602,6 +792,36 @@ inline void launch_bn_kind(cudaStream_t st, const CUtensorMap &ma, const CUtenso
     QB_CUDA(cudaLaunchKernelEx(&cfg, gibbs_gemm_kernel<BN, KIND>, ma, mb, ma2, mb2, K1, K2, ep));
 }
 
+template <int BN, int KIND>
+inline void launch_bn_kind_2cta(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &ma2,
+                                const CUtensorMap &mb2, int K1, int K2, const EpiParams &ep, int clusters) {
+    using C = Cfg2<BN>;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    QB_CUDA(cudaLaunchKernelEx(&cfg, gibbs_gemm_kernel_2cta<BN, KIND>, ma, mb, ma2, mb2, K1, K2, ep));
+}
+
+template <int BN>
+inline void launch_bn_2cta(cudaStream_t st, const Operand &A, const Operand &B, const Operand *A2, const Operand *B2,
+                           const EpiParams &ep, int num_sms) {
+    CUtensorMap ma = make_tmap(A, BM), mb = make_tmap(B, BN / 2);
+    CUtensorMap ma2 = A2 ? make_tmap(*A2, BM) : ma, mb2 = B2 ? make_tmap(*B2, BN / 2) : mb;
+    const int tiles = (int)(ceil_div(ep.M, 2 * BM) * ceil_div(ep.N, BN));
+    const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
+    const int K1 = (int)A.k, K2 = A2 ? (int)A2->k : 0;
+    switch (pick_kind(ep)) {
+        case K_GRAD: launch_bn_kind_2cta<BN, K_GRAD>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
+        case K_FAST_SAMPLE: launch_bn_kind_2cta<BN, K_FAST_SAMPLE>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
+        case K_FAST_PROB: launch_bn_kind_2cta<BN, K_FAST_PROB>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
+        default: launch_bn_kind_2cta<BN, K_GENERIC>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
+    }
+    QB_CUDA(cudaGetLastError());
+}
+
 template <int BN>
 inline void launch_bn(cudaStream_t st, const Operand &A, const Operand &B, const Operand *A2, const Operand *B2,
                       const EpiParams &ep, int num_sms) {
@@ -627,14 +847,24 @@ inline void init_bn() {
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
 }
+template <int BN>
+inline void init_bn_2cta() {
+    const int b = Cfg2<BN>::SMEM_BYTES;
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+}
 // once per device (qb_create): opt in to the large dynamic shared-memory carve-out
 inline void init_device() {
     init_bn<256>(); init_bn<128>(); init_bn<64>(); init_bn<32>();
+    init_bn_2cta<256>(); init_bn_2cta<128>();
 }
 
 // D[M][N]: picks the widest N tile that still yields at least one tile per SM.
+// use_2cta: 0 = never, 1 = when the problem fills the machine with 256-row tiles, 2 = always (tests)
 inline void launch(cudaStream_t st, const Operand &A, const Operand &B, const Operand *A2, const Operand *B2, const EpiParams &ep,
-                   int num_sms, int force_bn = 0) {
+                   int num_sms, int force_bn = 0, int use_2cta = 1) {
     QB_CHECK(A.k == B.k && A.k > 0, -1, "GEMM operands disagree on K");
     QB_CHECK((A2 == nullptr) == (B2 == nullptr), -1, "phase-2 operands must come in pairs");
     const long long tm = ceil_div(ep.M, BM);
@@ -644,6 +874,14 @@ inline void launch(cudaStream_t st, const Operand &A, const Operand &B, const Op
         if (tm * ceil_div(ep.N, cands[i]) >= num_sms || cands[i] == 32) { bn = cands[i]; break; }
     }
     if (force_bn) bn = force_bn;
+    if (use_2cta && (bn == 256 || bn == 128)) {
+        const long long t2 = ceil_div(ep.M, 2 * BM) * ceil_div(ep.N, bn);
+        if (use_2cta == 2 || t2 >= num_sms / 2) {
+            if (bn == 256) launch_bn_2cta<256>(st, A, B, A2, B2, ep, num_sms);
+            else launch_bn_2cta<128>(st, A, B, A2, B2, ep, num_sms);
+            return;
+        }
+    }
     switch (bn) {
         case 256: launch_bn<256>(st, A, B, A2, B2, ep, num_sms); break;
         case 128: launch_bn<128>(st, A, B, A2, B2, ep, num_sms); break;

@@ -381,3 +381,50 @@ def test_momentum_and_weight_decay_extension(q, V, H, L):
         assert rel_err(dev.rbm.W, m.W) < 1e-5 and np.max(np.abs(dev.rbm.b - m.b)) < 1e-6
         if L:
             assert rel_err(dev.rbm.U, m.U) < 1e-5 and np.max(np.abs(dev.rbm.c - m.c)) < 1e-6
+
+
+# ------------------------------------------------------------------------------ 2-CTA (cta_group::2) kernel variant
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("V,H,B", [(300, 260, 200), (512, 512, 256), (70, 33, 13)])
+def test_2cta_variant_matches_oracle(q, bn, V, H, B):
+    """Forces the cta_group::2 kernel (normally used only when 256-row tiles fill the machine) on
+    small and ragged shapes: injected streams (generic epilogue) and Philox (fast epilogue)."""
+    rng = np.random.default_rng(1234 + V + bn)
+    k = 2
+    m = make_oracle_model(rng, V, H, bf16=True)
+    X, _ = _data(rng, B, V, 0, False, True)
+    cv0, ch0 = bf16_round(u24(rng, B, V)), bf16_round(u24(rng, B, H))
+    chains = chains_from_arrays(cv0, ch0)
+    ds = DenseStreams(rng, k, B, V, H)
+    st = qo.GuardedStream(ds.serial("pcd")[0])
+    m_o = qo.copy_rbm(m)
+    qo.persistent_contrastive_divergence(m_o, X, [range(0, B)], chains, steps=k, learning_rate=0.05, stream=st)
+    ds.absorb(st.u, "pcd")
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=B, precision="bf16", seed=5) as dev:
+        dev.set_option("use_2cta", 2)
+        dev.set_option("force_bn", bn)
+        dev.set_data(X)
+        dev.init_chains(B, cv0, ch0)
+        dev.inject_streams(ds.U_h, ds.U_v)
+        dev.pcd_step(0, B, k, 0.05)
+        dv, dh, _ = dev.get_chains()
+        ov, oh, _ = chains_to_arrays(chains)
+        assert np.array_equal(dh, oh) and np.array_equal(dv, ov)
+        dev.pull_params()
+        assert rel_err(dev.rbm.W - m.W, m_o.W - m.W) < 2e-2
+    # Philox / fast epilogue: 2-CTA result must equal the 1-CTA result
+    outs = []
+    for two in (0, 2):
+        with q.DeviceRBM(to_host_rbm(q, m), max_batch=B, precision="bf16", seed=5) as dev:
+            dev.set_option("use_2cta", two)
+            dev.set_option("force_bn", bn)
+            dev.set_data(X)
+            dev.init_chains(B, cv0, ch0)
+            dev.pcd_step(0, B, k, 0.05)
+            v, h, _ = dev.get_chains()
+            dev.pull_params()
+            outs.append((v, h, dev.rbm.W.copy(), dev.rbm.a.copy(), dev.rbm.b.copy()))
+    for a, b in zip(outs[0][:3], outs[1][:3]):  # states and W (same MMA order) are bit-identical
+        assert np.array_equal(a, b)
+    for a, b in zip(outs[0][3:], outs[1][3:]):  # bias sums are float atomics: order-dependent last bits
+        assert np.max(np.abs(a - b)) < 1e-6
