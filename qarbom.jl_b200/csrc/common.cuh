@@ -34,7 +34,7 @@ static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
 
 // ----------------------------------------------------------------------------- Philox4x32-10
 // Counter-based RNG (Salmon et al., SC'11).  The stream contract of this library:
-//   uniform (draw, row, unit)  = u24( philox(ctr = (unit, row >> 2, draw_lo, draw_hi), key = seed)[row & 3] )
+//   uniform (draw, row, unit)  = u23( philox(ctr = (unit, row >> 2, draw_lo, draw_hi), key = seed)[row & 3] )
 //   normal  (draw, row, unit)  = box_muller( philox(ctr = (unit, row >> 1, draw_lo, draw_hi | 1<<31), key)[2*(row&1) .. +1] )
 // with `row` the GLOBAL row (chain / mini-batch row) so results do not depend on the
 // number of GPUs.  tests/philox_ref.py restates this in numpy.
@@ -65,8 +65,11 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     return o;
 }
 
-// 24-bit uniform in [0,1): exactly representable in fp32 and fp64.
+// 24-bit uniform in [0,1): exactly representable in fp32 and fp64 (Box-Muller inputs).
 __host__ __device__ __forceinline__ float u24(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+// 23-bit uniform in [0,1) = (x >> 9) * 2^-23, built from the mantissa bits: no int->float conversion
+// (I2F shares the quarter-rate XU pipe with the sigmoid's ex2/rcp in the GEMM epilogue).
+__device__ __forceinline__ float u23(uint32_t x) { return __uint_as_float(0x3F800000u | (x >> 9)) - 1.0f; }
 
 struct RngKey {
     uint32_t seed_lo, seed_hi;
@@ -81,7 +84,7 @@ __device__ __forceinline__ float rng_uniform(const RngKey &k, uint32_t unit, uin
     Philox4 p = rng_uniform4(k, unit, (uint32_t)(row >> 2));
     uint32_t r = (uint32_t)(row & 3);
     uint32_t v = r == 0 ? p.x : (r == 1 ? p.y : (r == 2 ? p.z : p.w));
-    return u24(v);
+    return u23(v);
 }
 __device__ __forceinline__ float box_muller(uint32_t a, uint32_t b) {
     float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)

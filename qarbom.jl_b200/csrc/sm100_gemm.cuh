@@ -30,13 +30,20 @@ namespace sm100 {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 384;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
-constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARP0 = 4;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4.. epilogue
 constexpr int SMEM_AB_BUDGET = 192 * 1024;
 
 enum { EPI_SAMPLE = 0, EPI_GRAD = 1 };
 // kernel specialisations: generic epilogue, gradient store, and the two compile-time fast paths
-enum { K_GENERIC = 0, K_GRAD = 1, K_FAST_SAMPLE = 2, K_FAST_PROB = 3 };
+enum { K_GENERIC = 0, K_GRAD = 1, K_FAST_SAMPLE = 2, K_FAST_PROB = 3, K_FAST_SAMPLE_PROB = 4 };
+// Epilogue warpgroups per CTA: the lean epilogues are latency-bound with 2 warps per scheduler
+// (ncu: IPC 0.3, epilogue time ~ MMA time), so they run 4 warpgroups (16 warps, 64 columns each at
+// BN = 256); the register-hungry generic epilogue keeps 2.
+template <int BN, int KIND>
+struct Shape {
+    static constexpr int WGS = (KIND != K_GENERIC && BN >= 64) ? 4 : 2;
+    static constexpr int THREADS = 128 + 128 * WGS;
+};
 enum { ACT_SIGMOID = 0, ACT_GAUSSIAN = 1 };
 
 struct EpiParams {
@@ -61,6 +68,7 @@ struct EpiParams {
     float *softplus_rows;
     // ---- EPI_GRAD
     float *out_f32; long long ld_out;
+    int dbg;  // experiment switches (0 in production): 1 = skip row-major stores, 2 = skip Philox, 4 = skip sigmoid
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -167,7 +175,7 @@ struct Cfg {
 };
 
 // ----------------------------------------------------------------------------- epilogues
-template <int BN>
+template <int BN, int WGS>
 __device__ __forceinline__ void epilogue_sample(const EpiParams &ep, uint32_t tmem_acc, int m_blk, int n_blk, int quarter,
                                                 int wg, int lane) {
     const int unit = m_blk * BM + quarter * 32 + lane;
@@ -175,7 +183,7 @@ __device__ __forceinline__ void epilogue_sample(const EpiParams &ep, uint32_t tm
     const bool is_label = uvalid && unit >= ep.split;
     const float bias = uvalid ? ep.bias[unit] : 0.f;
     float bg_acc = 0.f, sq_acc = 0.f;
-    constexpr int COLS_PER_WG = BN / 2;
+    constexpr int COLS_PER_WG = BN / WGS;
 #pragma unroll 1
     for (int c0 = wg * COLS_PER_WG; c0 < (wg + 1) * COLS_PER_WG; c0 += 16) {
         uint32_t r[16];
@@ -212,7 +220,7 @@ __device__ __forceinline__ void epilogue_sample(const EpiParams &ep, uint32_t tm
                     if (ep.sample) {
                         float u;
                         if (ep.inj) u = (uvalid && row < ep.N) ? ep.inj[(long long)row * ep.ld_inj + unit] : 1.f;
-                        else u = u24(rnd[jj]);
+                        else u = u23(rnd[jj]);
                         s = (u < p) ? 1.f : 0.f;
                     }
                 } else {
@@ -318,16 +326,98 @@ __device__ __forceinline__ void epilogue_sample(const EpiParams &ep, uint32_t tm
 //   SAMPLE = true : s = (u < sigmoid(x)); stores state_rm (required), state_T (optional);
 //                   optional prob_T; bias gradient of s (bg_what == 2) or p (bg_what == 1)
 //   SAMPLE = false: p = sigmoid(x); stores prob_T / prob_rm (optional); bias gradient of p
-template <int BN, bool SAMPLE>
+// sigmoid with exactly two MUFU ops and no range fix-ups: x -> -inf gives ex2 = +inf, rcp(inf) = 0
+__device__ __forceinline__ float sigmoid_mufu(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
+
+// one 16-column chunk of the fast epilogue; FULL = all 16 rows and the unit are in range (the common
+// case: no per-element predicates at all)
+template <bool SAMPLE, bool PROB, bool FULL>
+__device__ __forceinline__ void fast_chunk(const EpiParams &ep, const uint32_t (&r)[16], int unit, int row_base, int nv, float bias,
+                                           bool want_sT, bool want_pT, bool want_prm, float &bg_p, int &bg_s) {
+    uint32_t sb[16], pb[16];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        uint32_t rnd[4];
+        if (SAMPLE) {
+            const unsigned long long grow = (unsigned long long)(ep.row0 + row_base + 4 * g);
+            Philox4 ph = rng_uniform4(ep.key, (uint32_t)unit, (uint32_t)(grow >> 2));
+            rnd[0] = ph.x; rnd[1] = ph.y; rnd[2] = ph.z; rnd[3] = ph.w;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            const int j = 4 * g + jj;
+            const float p = sigmoid_mufu(__uint_as_float(r[j]) + bias);
+            if (PROB) {
+                if (FULL || j < nv) bg_p += p;
+                pb[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(p));
+            }
+            if (SAMPLE) {
+                const bool on = u23(rnd[jj]) < p;
+                sb[j] = on ? 0x3F80u : 0u;  // bf16(1.0) / bf16(0.0)
+                bg_s += (on && (FULL || j < nv)) ? 1 : 0;
+            }
+        }
+    }
+    if (SAMPLE) {
+        unsigned short *dst = reinterpret_cast<unsigned short *>(ep.state_rm) + (long long)row_base * ep.ld_srm + unit;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if (FULL || j < nv) *dst = (unsigned short)sb[j];
+            dst += ep.ld_srm;
+        }
+    }
+    if (PROB && want_prm) {
+        unsigned short *dst = reinterpret_cast<unsigned short *>(ep.prob_rm) + (long long)row_base * ep.ld_prm + unit;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if (FULL || j < nv) *dst = (unsigned short)pb[j];
+            dst += ep.ld_prm;
+        }
+    }
+    if (SAMPLE && want_sT) {
+        unsigned short *dst = reinterpret_cast<unsigned short *>(ep.state_T) + (long long)unit * ep.ld_sT + row_base;
+        if (FULL) {
+            reinterpret_cast<uint4 *>(dst)[0] = make_uint4(sb[0] | (sb[1] << 16), sb[2] | (sb[3] << 16), sb[4] | (sb[5] << 16), sb[6] | (sb[7] << 16));
+            reinterpret_cast<uint4 *>(dst)[1] = make_uint4(sb[8] | (sb[9] << 16), sb[10] | (sb[11] << 16), sb[12] | (sb[13] << 16), sb[14] | (sb[15] << 16));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (j < nv) dst[j] = (unsigned short)sb[j];
+        }
+    }
+    if (PROB && want_pT) {
+        unsigned short *dst = reinterpret_cast<unsigned short *>(ep.prob_T) + (long long)unit * ep.ld_pT + row_base;
+        if (FULL) {
+            reinterpret_cast<uint4 *>(dst)[0] = make_uint4(pb[0] | (pb[1] << 16), pb[2] | (pb[3] << 16), pb[4] | (pb[5] << 16), pb[6] | (pb[7] << 16));
+            reinterpret_cast<uint4 *>(dst)[1] = make_uint4(pb[8] | (pb[9] << 16), pb[10] | (pb[11] << 16), pb[12] | (pb[13] << 16), pb[14] | (pb[15] << 16));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (j < nv) dst[j] = (unsigned short)pb[j];
+        }
+    }
+}
+
+// Compile-time-specialised epilogue for the hot Gibbs half-steps (Bernoulli units, Philox or no
+// sampling, no label units, no metric reductions): a fraction of the generic epilogue's
+// instruction count and code size, so it hides completely behind the next tile's MMAs.
+//   SAMPLE: s = (u < sigmoid(x)); stores state_rm (required), state_T (optional); bias gradient of s
+//   PROB  : p = sigmoid(x); stores prob_T / prob_rm (optional); bias gradient of p (bg_what == 1)
+template <int BN, int WGS, bool SAMPLE, bool PROB>
 __device__ __forceinline__ void epilogue_fast(const EpiParams &ep, uint32_t tmem_acc, int m_blk, int n_blk, int quarter, int wg,
                                               int lane) {
     const int unit = m_blk * BM + quarter * 32 + lane;
     const bool uvalid = unit < ep.M;
     const float bias = uvalid ? ep.bias[unit] : 0.f;
-    const bool want_sT = SAMPLE && ep.state_T != nullptr, want_pT = ep.prob_T != nullptr, want_prm = ep.prob_rm != nullptr;
+    const bool want_sT = SAMPLE && ep.state_T != nullptr, want_pT = PROB && ep.prob_T != nullptr, want_prm = PROB && ep.prob_rm != nullptr;
     float bg_p = 0.f;
     int bg_s = 0;
-    constexpr int COLS_PER_WG = BN / 2;
+    constexpr int COLS_PER_WG = BN / WGS;
 #pragma unroll 1
     for (int c0 = wg * COLS_PER_WG; c0 < (wg + 1) * COLS_PER_WG; c0 += 16) {
         uint32_t r[16];
@@ -339,71 +429,17 @@ __device__ __forceinline__ void epilogue_fast(const EpiParams &ep, uint32_t tmem
         if (nvalid <= 0) continue;
         nvalid = nvalid > 16 ? 16 : nvalid;
         const int nv = uvalid ? nvalid : 0;
-        uint32_t sb[16], pb[16];
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-            uint32_t rnd[4];
-            if (SAMPLE) {
-                const unsigned long long grow = (unsigned long long)(ep.row0 + row_base + 4 * g);
-                Philox4 ph = rng_uniform4(ep.key, (uint32_t)unit, (uint32_t)(grow >> 2));
-                rnd[0] = ph.x; rnd[1] = ph.y; rnd[2] = ph.z; rnd[3] = ph.w;
-            }
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-                const int j = 4 * g + jj;
-                const float p = sigmoid_fast(__uint_as_float(r[j]) + bias);
-                if (j < nv) bg_p += p;
-                pb[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(p));
-                if (SAMPLE) {
-                    const bool on = u24(rnd[jj]) < p;
-                    sb[j] = on ? 0x3F80u : 0u;  // bf16(1.0) / bf16(0.0)
-                    bg_s += (on && j < nv) ? 1 : 0;
-                }
-            }
-        }
-        if (SAMPLE) {
-            unsigned short *dst = reinterpret_cast<unsigned short *>(ep.state_rm) + (long long)row_base * ep.ld_srm + unit;
-#pragma unroll
-            for (int j = 0; j < 16; j++)
-                if (j < nv) dst[(long long)j * ep.ld_srm] = (unsigned short)sb[j];
-        }
-        if (want_prm) {
-            unsigned short *dst = reinterpret_cast<unsigned short *>(ep.prob_rm) + (long long)row_base * ep.ld_prm + unit;
-#pragma unroll
-            for (int j = 0; j < 16; j++)
-                if (j < nv) dst[(long long)j * ep.ld_prm] = (unsigned short)pb[j];
-        }
-        if (want_sT) {
-            unsigned short *dst = reinterpret_cast<unsigned short *>(ep.state_T) + (long long)unit * ep.ld_sT + row_base;
-            if (nv == 16) {
-                reinterpret_cast<uint4 *>(dst)[0] = make_uint4(sb[0] | (sb[1] << 16), sb[2] | (sb[3] << 16), sb[4] | (sb[5] << 16), sb[6] | (sb[7] << 16));
-                reinterpret_cast<uint4 *>(dst)[1] = make_uint4(sb[8] | (sb[9] << 16), sb[10] | (sb[11] << 16), sb[12] | (sb[13] << 16), sb[14] | (sb[15] << 16));
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; j++)
-                    if (j < nv) dst[j] = (unsigned short)sb[j];
-            }
-        }
-        if (want_pT) {
-            unsigned short *dst = reinterpret_cast<unsigned short *>(ep.prob_T) + (long long)unit * ep.ld_pT + row_base;
-            if (nv == 16) {
-                reinterpret_cast<uint4 *>(dst)[0] = make_uint4(pb[0] | (pb[1] << 16), pb[2] | (pb[3] << 16), pb[4] | (pb[5] << 16), pb[6] | (pb[7] << 16));
-                reinterpret_cast<uint4 *>(dst)[1] = make_uint4(pb[8] | (pb[9] << 16), pb[10] | (pb[11] << 16), pb[12] | (pb[13] << 16), pb[14] | (pb[15] << 16));
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; j++)
-                    if (j < nv) dst[j] = (unsigned short)pb[j];
-            }
-        }
+        if (nv == 16) fast_chunk<SAMPLE, PROB, true>(ep, r, unit, row_base, nv, bias, want_sT, want_pT, want_prm, bg_p, bg_s);
+        else if (nv > 0) fast_chunk<SAMPLE, PROB, false>(ep, r, unit, row_base, nv, bias, want_sT, want_pT, want_prm, bg_p, bg_s);
     }
-    if (ep.bg_what && uvalid) atomicAdd(ep.bias_grad + unit, ep.bg_sign * (ep.bg_what == 1 ? bg_p : (float)bg_s));
+    if (ep.bg_what && uvalid) atomicAdd(ep.bias_grad + unit, ep.bg_sign * ((PROB && ep.bg_what == 1) ? bg_p : (float)bg_s));
 }
 
-template <int BN>
+template <int BN, int WGS>
 __device__ __forceinline__ void epilogue_grad(const EpiParams &ep, uint32_t tmem_acc, int m_blk, int n_blk, int quarter, int wg,
                                               int lane) {
     const int m = m_blk * BM + quarter * 32 + lane;
-    constexpr int COLS_PER_WG = BN / 2;
+    constexpr int COLS_PER_WG = BN / WGS;
 #pragma unroll 1
     for (int c0 = wg * COLS_PER_WG; c0 < (wg + 1) * COLS_PER_WG; c0 += 16) {
         uint32_t r[16];
@@ -427,11 +463,12 @@ __device__ __forceinline__ void epilogue_grad(const EpiParams &ep, uint32_t tmem
 
 // ----------------------------------------------------------------------------- the kernel
 template <int BN, int KIND>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__((Shape<BN, KIND>::THREADS), 1)
 gibbs_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, int K1, int K2,
                   const EpiParams ep) {
     using C = Cfg<BN>;
+    constexpr int WGS = Shape<BN, KIND>::WGS;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
@@ -454,7 +491,7 @@ gibbs_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * WGS); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -527,10 +564,11 @@ gibbs_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             mbar_wait(tfull_bar(as), aphase);
             tcgen05_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
-            if (KIND == K_GENERIC) epilogue_sample<BN>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
-            else if (KIND == K_GRAD) epilogue_grad<BN>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
-            else if (KIND == K_FAST_SAMPLE) epilogue_fast<BN, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
-            else epilogue_fast<BN, false>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            if (KIND == K_GENERIC) epilogue_sample<BN, WGS>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_GRAD) epilogue_grad<BN, WGS>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_FAST_SAMPLE) epilogue_fast<BN, WGS, true, false>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_FAST_SAMPLE_PROB) epilogue_fast<BN, WGS, true, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else epilogue_fast<BN, WGS, false, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -611,11 +649,12 @@ struct Cfg2 {
 };
 
 template <int BN, int KIND>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Shape<BN, KIND>::THREADS), 1)
 gibbs_gemm_kernel_2cta(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                        const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, int K1, int K2,
                        const EpiParams ep) {
     using C = Cfg2<BN>;
+    constexpr int WGS = Shape<BN, KIND>::WGS;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
@@ -641,7 +680,7 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ CUtensorMap mapA, const __grid_co
     if (warp == 1 && lane == 0) {
         // full: leader's arrive.expect_tx + the peer producer's remote arrive; tmem_empty: 8 epilogue warps per CTA
         for (int s = 0; s < C::STAGES; s++) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 16); }
+        for (int s = 0; s < 2; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8 * WGS); }
         fence_barrier_init();
     }
     cluster_sync_all();  // both CTAs are resident before the pair-wide TMEM allocation
@@ -713,10 +752,11 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ CUtensorMap mapA, const __grid_co
             mbar_wait(tfull_bar(as), aphase);
             tcgen05_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
-            if (KIND == K_GENERIC) epilogue_sample<BN>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
-            else if (KIND == K_GRAD) epilogue_grad<BN>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
-            else if (KIND == K_FAST_SAMPLE) epilogue_fast<BN, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
-            else epilogue_fast<BN, false>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            if (KIND == K_GENERIC) epilogue_sample<BN, WGS>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_GRAD) epilogue_grad<BN, WGS>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_FAST_SAMPLE) epilogue_fast<BN, WGS, true, false>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_FAST_SAMPLE_PROB) epilogue_fast<BN, WGS, true, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else epilogue_fast<BN, WGS, false, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -774,7 +814,8 @@ inline CUtensorMap make_tmap(const Operand &o, int box_rows) {
 inline int pick_kind(const EpiParams &ep) {
     if (ep.mode == EPI_GRAD) return K_GRAD;
     const bool plain = ep.act == ACT_SIGMOID && ep.split >= ep.M && !ep.inj && !ep.sqerr && !ep.softplus_rows && !ep.prob_f32;
-    if (plain && ep.sample && ep.use_rng && ep.state_rm && !ep.prob_rm) return K_FAST_SAMPLE;
+    if (plain && ep.sample && ep.use_rng && ep.state_rm && !ep.prob_rm)
+        return (ep.prob_T || ep.bg_what == 1) ? K_FAST_SAMPLE_PROB : K_FAST_SAMPLE;
     if (plain && !ep.sample && !ep.state_rm && !ep.state_T) return K_FAST_PROB;
     return K_GENERIC;
 }
@@ -784,7 +825,7 @@ inline void launch_bn_kind(cudaStream_t st, const CUtensorMap &ma, const CUtenso
                            const CUtensorMap &mb2, int K1, int K2, const EpiParams &ep, int grid) {
     using C = Cfg<BN>;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(Shape<BN, KIND>::THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -797,7 +838,7 @@ inline void launch_bn_kind_2cta(cudaStream_t st, const CUtensorMap &ma, const CU
                                 const CUtensorMap &mb2, int K1, int K2, const EpiParams &ep, int clusters) {
     using C = Cfg2<BN>;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(Shape<BN, KIND>::THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -817,6 +858,7 @@ inline void launch_bn_2cta(cudaStream_t st, const Operand &A, const Operand &B, 
         case K_GRAD: launch_bn_kind_2cta<BN, K_GRAD>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
         case K_FAST_SAMPLE: launch_bn_kind_2cta<BN, K_FAST_SAMPLE>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
         case K_FAST_PROB: launch_bn_kind_2cta<BN, K_FAST_PROB>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
+        case K_FAST_SAMPLE_PROB: launch_bn_kind_2cta<BN, K_FAST_SAMPLE_PROB>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
         default: launch_bn_kind_2cta<BN, K_GENERIC>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
     }
     QB_CUDA(cudaGetLastError());
@@ -834,6 +876,7 @@ inline void launch_bn(cudaStream_t st, const Operand &A, const Operand &B, const
         case K_GRAD: launch_bn_kind<BN, K_GRAD>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
         case K_FAST_SAMPLE: launch_bn_kind<BN, K_FAST_SAMPLE>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
         case K_FAST_PROB: launch_bn_kind<BN, K_FAST_PROB>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
+        case K_FAST_SAMPLE_PROB: launch_bn_kind<BN, K_FAST_SAMPLE_PROB>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
         default: launch_bn_kind<BN, K_GENERIC>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
     }
     QB_CUDA(cudaGetLastError());
@@ -846,6 +889,7 @@ inline void init_bn() {
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_SAMPLE_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
 }
 template <int BN>
 inline void init_bn_2cta() {
@@ -854,6 +898,7 @@ inline void init_bn_2cta() {
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_SAMPLE_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
 }
 // once per device (qb_create): opt in to the large dynamic shared-memory carve-out
 inline void init_device() {

@@ -1,6 +1,6 @@
 """numpy restatement of the library's Philox4x32-10 stream contract (csrc/common.cuh):
 
-  uniform(draw, row, unit) = (philox(ctr=(unit, row>>2, draw_lo, draw_hi), key=seed)[row & 3] >> 8) * 2^-24
+  uniform(draw, row, unit) = (philox(ctr=(unit, row>>2, draw_lo, draw_hi), key=seed)[row & 3] >> 9) * 2^-23
   normal (draw, row, unit) = box_muller(philox(ctr=(unit, row>>1, draw_lo, draw_hi | 2^31), key=seed)[2*(row&1) : +2])
 """
 import numpy as np
@@ -30,7 +30,7 @@ def uniforms(seed: int, draw: int, rows: int, units: int, row0: int = 0) -> np.n
     out = philox4x32_10(u, r >> np.uint64(2), draw & 0xFFFFFFFF, (draw >> 32) & 0x7FFFFFFF, seed & 0xFFFFFFFF, seed >> 32)
     sel = (r & np.uint64(3)).astype(np.int64)
     x = np.choose(sel, out)
-    return (x >> np.uint64(8)).astype(np.float64) / float(1 << 24)
+    return (x >> np.uint64(9)).astype(np.float64) / float(1 << 23)
 
 
 def normals(seed: int, draw: int, rows: int, units: int, row0: int = 0) -> np.ndarray:
