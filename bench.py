@@ -164,7 +164,15 @@ def cpu_reference(w, seconds_target, steps, warmup, threads=None):
                        f"per-sample cost of the reference is independent of the batch size")
 
 
+def emit(line: dict, fd: int) -> None:
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # stdout carries exactly ONE JSON line: libraries (NCCL prints its version banner) get stderr instead
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -197,7 +205,7 @@ def main():
                 "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gibbs_steps_per_s": r["value"] * w["k"],
                 "note": "CPU restatement of QARBoM.jl (C, Float64, per-sample GEMV + outer products; Julia not installable here)"}
-        print(json.dumps(line))
+        emit(line, out_fd)
         return 0
 
     import torch
@@ -333,7 +341,7 @@ def main():
         r = cpu_reference(w, args.cpu_seconds, 3, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["threads"], "kind": "port",
                                 "sample": r["sample"]}
-    print(json.dumps(line))
+    emit(line, out_fd)
     dev.close()
     if world > 1:
         dist.destroy_process_group()

@@ -796,7 +796,27 @@ inline EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+inline CUtensorMap encode_tmap(const Operand &o, int box_rows);
+
+// Descriptors are pure functions of (pointer, extents, stride, box): cache them, the training loop
+// re-launches the same few dozen operand views every step.
 inline CUtensorMap make_tmap(const Operand &o, int box_rows) {
+    struct Key {
+        const void *p; long long rows, k, ld; int box;
+        bool operator==(const Key &b) const { return p == b.p && rows == b.rows && k == b.k && ld == b.ld && box == b.box; }
+    };
+    struct Slot { Key key; CUtensorMap map; bool used = false; };
+    static thread_local Slot cache[256];
+    const Key key{o.ptr, o.rows, o.k, o.ld, box_rows};
+    size_t hsh = ((uintptr_t)o.ptr >> 4) * 0x9E3779B97F4A7C15ull + (size_t)o.rows * 1315423911u + (size_t)o.k * 2654435761u + (size_t)box_rows;
+    Slot &sl = cache[(hsh >> 20) & 255];
+    if (sl.used && sl.key == key) return sl.map;
+    sl.map = encode_tmap(o, box_rows);
+    sl.key = key; sl.used = true;
+    return sl.map;
+}
+
+inline CUtensorMap encode_tmap(const Operand &o, int box_rows) {
     QB_CHECK(o.ld % 8 == 0 && ((uintptr_t)o.ptr % 16) == 0, -1, "TMA operand must be 16-byte aligned with ld % 8 == 0");
     CUtensorMap m;
     cuuint64_t dims[2] = {(cuuint64_t)o.k, (cuuint64_t)o.rows};
@@ -907,25 +927,39 @@ inline void init_device() {
 }
 
 // D[M][N]: picks the widest N tile that still yields at least one tile per SM.
-// use_2cta: 0 = never, 1 = when the problem fills the machine with 256-row tiles, 2 = always (tests)
+// Tile shape selection: estimated time = waves x relative tile cost.  A 128 x BN tile on one SM and a
+// 256 x BN tile on a CTA pair take the same time; narrower tiles cost more than proportionally
+// (lower arithmetic intensity against L2).  Ties prefer the pair (a third less L2->SM traffic).
+// use_2cta: 0 = never, 1 = automatic, 2 = always when BN >= 128 (tests)
+inline void pick_shape(long long M, long long N, int num_sms, int force_bn, int use_2cta, int &bn, bool &pair) {
+    const int bns[4] = {256, 128, 64, 32};
+    const double cost[4] = {1.0, 0.85, 0.75, 0.70};  // measured: at K = 4096 a 256 x 128 pair tile takes ~as long as 256 x 256 (L2-bound)
+    double best = 1e30;
+    bn = 256; pair = false;
+    for (int two = 1; two >= 0; two--) {
+        if (two && use_2cta == 0) continue;
+        for (int i = 0; i < 4; i++) {
+            if (force_bn && bns[i] != force_bn) continue;
+            if (two && bns[i] < 128) continue;
+            if (!two && use_2cta == 2 && bns[i] >= 128) continue;
+            const long long tiles = ceil_div(M, two ? 2 * BM : BM) * ceil_div(N, bns[i]);
+            const long long slots = two ? num_sms / 2 : num_sms;
+            const double est = (double)ceil_div(tiles, slots) * cost[i] * (two ? 0.97 : 1.0);
+            if (est < best - 1e-9) { best = est; bn = bns[i]; pair = two != 0; }
+        }
+    }
+}
+
 inline void launch(cudaStream_t st, const Operand &A, const Operand &B, const Operand *A2, const Operand *B2, const EpiParams &ep,
                    int num_sms, int force_bn = 0, int use_2cta = 1) {
     QB_CHECK(A.k == B.k && A.k > 0, -1, "GEMM operands disagree on K");
     QB_CHECK((A2 == nullptr) == (B2 == nullptr), -1, "phase-2 operands must come in pairs");
-    const long long tm = ceil_div(ep.M, BM);
-    int bn = 32;
-    const int cands[4] = {256, 128, 64, 32};
-    for (int i = 0; i < 4; i++) {
-        if (tm * ceil_div(ep.N, cands[i]) >= num_sms || cands[i] == 32) { bn = cands[i]; break; }
-    }
-    if (force_bn) bn = force_bn;
-    if (use_2cta && (bn == 256 || bn == 128)) {
-        const long long t2 = ceil_div(ep.M, 2 * BM) * ceil_div(ep.N, bn);
-        if (use_2cta == 2 || t2 >= num_sms / 2) {
-            if (bn == 256) launch_bn_2cta<256>(st, A, B, A2, B2, ep, num_sms);
-            else launch_bn_2cta<128>(st, A, B, A2, B2, ep, num_sms);
-            return;
-        }
+    int bn; bool pair;
+    pick_shape(ep.M, ep.N, num_sms, force_bn, use_2cta, bn, pair);
+    if (pair) {
+        if (bn == 256) launch_bn_2cta<256>(st, A, B, A2, B2, ep, num_sms);
+        else launch_bn_2cta<128>(st, A, B, A2, B2, ep, num_sms);
+        return;
     }
     switch (bn) {
         case 256: launch_bn<256>(st, A, B, A2, B2, ep, num_sms); break;
