@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--stale-chains", action="store_true", help="also time the stale-1 chains mode on one GPU")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -286,6 +287,24 @@ def main():
     upd_n, upd_ms = dev.update_timing()
     dev.set_option("time_gemms", 0)
 
+    # ---------------- optional leg: declared stale-1 chains mode (allreduce + update overlapped with the next
+    # step's chain advance; statistical parity only)
+    overlap = None
+    if pcd and args.precision == "bf16" and w["L"] == 0 and (world > 1 or args.stale_chains):
+        dev.set_option("stale_chains", 1)
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        dev.timer_start()
+        for i in range(args.steps):
+            step(args.warmup + i)
+        ms_st = max_over_ranks(dev.timer_stop())
+        barrier()
+        dev.set_option("stale_chains", 0)
+        overlap = {"mode": "stale-1 chains: allreduce+update of step t overlap the chain advance of step t+1",
+                   "value": B * args.steps / (ms_st * 1e-3), "unit": "samples/s", "ms_per_step": ms_st / args.steps,
+                   "semantics": "declared extension, not used for `value`"}
+
     # ---------------- end-to-end leg: host mini-batches in pinned memory, recon error read back
     e2e = None
     if not args.no_e2e:
@@ -337,6 +356,8 @@ def main():
             "config": dict(cfg, l2="inputs cycle over %d resident mini-batches (%.2f GB incl. transposed copies) > 126 MB L2"
                                     % (nb, 2 * nb * Bl * w["V"] * 2 / 1e9)),
             "gibbs_steps_per_s": value * k, "gpu_launches": launches, "roofline": roof, "roofline_update": roof_upd, "clocks": clocks, "e2e": e2e}
+    if overlap:
+        line["overlap"] = overlap
     if not args.no_cpu_baseline:
         r = cpu_reference(w, args.cpu_seconds, 3, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["threads"], "kind": "port",

@@ -89,6 +89,16 @@ struct qb_handle {
     int64_t nW = 0, nP = 0;
     bf16 *Wb = nullptr, *WbT = nullptr;
     double momentum = 0.0, weight_decay = 0.0;
+    // "stale_chains" mode (declared extension, bf16 PCD only): the allreduce + update of step t run on
+    // comm_stream while the chains of step t+1 advance with the previous weight version.  Second
+    // shadow / bias / gradient buffers make the two versions coexist.
+    bool stale_chains = false, pending_update = false;
+    bf16 *Wb_alt = nullptr, *WbT_alt = nullptr;
+    float *G_alt = nullptr, *bias_buf[2] = {nullptr, nullptr};
+    float *bias_rd = nullptr;  // [acat | b] as read by the GEMM epilogues (P's own bias region unless stale mode)
+    int bias_cur = 0;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_grad = nullptr, ev_upd = nullptr;
     // resident dataset
     Mat data; int64_t N = 0;
     bf16 *dataT = nullptr; int64_t dataT_B = 0, dataT_nb = 0, dataT_ld = 0;
@@ -150,6 +160,8 @@ inline dim3 grid1d(int64_t n, int block = 256) { return dim3((unsigned)ceil_div(
 float *Wf(qb_handle *h) { return h->P; }
 float *acat(qb_handle *h) { return h->P + h->nW; }
 float *bh(qb_handle *h) { return h->P + h->nW + h->ldv; }
+float *bias_a(qb_handle *h) { return h->bias_rd ? h->bias_rd : acat(h); }
+float *bias_b(qb_handle *h) { return h->bias_rd ? h->bias_rd + h->ldv : bh(h); }
 float *G_W(qb_handle *h) { return h->G; }
 float *G_a(qb_handle *h) { return h->G + h->nW; }
 float *G_b(qb_handle *h) { return h->G + h->nW + h->ldv; }
@@ -279,7 +291,7 @@ void op_hidden(qb_handle *h, const Mat &in, int64_t rows, int64_t kdim, const Hi
     sm100::Operand A{h->Wb, h->H, kdim, h->ldv}, B{in.b, rows, kdim, in.ld};
     sm100::EpiParams ep{};
     ep.mode = sm100::EPI_SAMPLE; ep.M = (int)h->H; ep.N = (int)rows;
-    ep.bias = bh(h); ep.split = (int)h->H;
+    ep.bias = bias_b(h); ep.split = (int)h->H;
     ep.act = o.softplus_rows ? sm100::ACT_GAUSSIAN : sm100::ACT_SIGMOID;
     ep.sample = (o.state != nullptr);
     if (o.state) {
@@ -347,7 +359,7 @@ void op_visible(qb_handle *h, const Mat &in, int64_t rows, const VisibleOut &o, 
     sm100::Operand A{h->WbT, h->VL, h->H, h->ldh}, B{in.b, rows, h->H, in.ld};
     sm100::EpiParams ep{};
     ep.mode = sm100::EPI_SAMPLE; ep.M = (int)h->VL; ep.N = (int)rows;
-    ep.bias = acat(h); ep.split = (int)h->V; ep.lab_pre = h->lab_pre; ep.ld_lab = h->L > 0 ? h->L : 1;
+    ep.bias = bias_a(h); ep.split = (int)h->V; ep.lab_pre = h->lab_pre; ep.ld_lab = h->L > 0 ? h->L : 1;
     ep.act = act ? sm100::ACT_GAUSSIAN : sm100::ACT_SIGMOID;
     ep.sample = o.sample || (act == 1 && (rng.inj || rng.use_rng));
     if (o.state) {
@@ -421,10 +433,12 @@ void zero_bias_grads(qb_handle *h) {
     h->launches++;
 }
 
-// update_rbm!(rbm, dW, [dU,] da, db, [dc,] lr/B [, llr/B]) after the data-parallel sum of G
-void op_update(qb_handle *h, double lr, double llr, int64_t B_local) {
+// update_rbm!(rbm, dW, [dU,] da, db, [dc,] lr/B [, llr/B]) after the data-parallel sum of G.
+// `st` is the stream it runs on; (Wb_out, WbT_out, bias_out) the shadow set it refreshes.
+void op_update_on(qb_handle *h, double lr, double llr, int64_t B_local, cudaStream_t st, float *G, bf16 *Wb_out, bf16 *WbT_out,
+                  float *bias_out) {
     if (h->comm) {
-        QB_NCCL(nccl().AllReduce(h->G, h->G, (size_t)h->nP, /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->comm, h->stream));
+        QB_NCCL(nccl().AllReduce(G, G, (size_t)h->nP, /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->comm, st));
     }
     const double Bg = (double)B_local * (double)h->cfg.world;
     const float lr_e = (float)(lr / Bg), llr_e = (float)(llr / Bg);
@@ -435,21 +449,66 @@ void op_update(qb_handle *h, double lr, double llr, int64_t B_local) {
     if (h->time_gemms && h->upd_ev_used + 2 <= 4096) {
         while (h->upd_ev.size() < h->upd_ev_used + 2) { cudaEvent_t e; QB_CUDA(cudaEventCreate(&e)); h->upd_ev.push_back(e); }
         ei = h->upd_ev_used; h->upd_ev_used += 2; h->upd_timed++; timed = true;
-        QB_CUDA(cudaEventRecord(h->upd_ev[ei], h->stream));
+        QB_CUDA(cudaEventRecord(h->upd_ev[ei], st));
     }
     if (use_vel)
-        update_w_kernel<true><<<g, 256, 0, h->stream>>>(Wf(h), G_W(h), h->Vel, (int)h->H, (int)h->VL, (int)h->V, h->ldv, lr_e, llr_e,
-                                                        (float)h->momentum, (float)h->weight_decay, h->Wb, h->WbT, h->ldh);
+        update_w_kernel<true><<<g, 256, 0, st>>>(Wf(h), G, h->Vel, (int)h->H, (int)h->VL, (int)h->V, h->ldv, lr_e, llr_e,
+                                                 (float)h->momentum, (float)h->weight_decay, Wb_out, WbT_out, h->ldh);
     else
-        update_w_kernel<false><<<g, 256, 0, h->stream>>>(Wf(h), G_W(h), nullptr, (int)h->H, (int)h->VL, (int)h->V, h->ldv, lr_e, llr_e,
-                                                         0.f, 0.f, h->Wb, h->WbT, h->ldh);
-    if (timed) QB_CUDA(cudaEventRecord(h->upd_ev[ei + 1], h->stream));
+        update_w_kernel<false><<<g, 256, 0, st>>>(Wf(h), G, nullptr, (int)h->H, (int)h->VL, (int)h->V, h->ldv, lr_e, llr_e, 0.f, 0.f,
+                                                  Wb_out, WbT_out, h->ldh);
+    if (timed) QB_CUDA(cudaEventRecord(h->upd_ev[ei + 1], st));
     QB_CUDA(cudaGetLastError());
     const int nb = (int)(h->ldv + h->ldh);
-    update_bias_kernel<<<grid1d(nb), 256, 0, h->stream>>>(acat(h), G_a(h), use_vel ? h->Vel + h->nW : nullptr, (int)h->ldv,
-                                                          (int)h->V, nb, lr_e, llr_e, (float)h->momentum);
+    update_bias_kernel<<<grid1d(nb), 256, 0, st>>>(acat(h), G + h->nW, use_vel ? h->Vel + h->nW : nullptr, (int)h->ldv, (int)h->V, nb,
+                                                   lr_e, llr_e, (float)h->momentum, bias_out);
     QB_CUDA(cudaGetLastError());
     h->launches += 2;
+}
+void op_update(qb_handle *h, double lr, double llr, int64_t B_local) {
+    op_update_on(h, lr, llr, B_local, h->stream, h->G, h->Wb, h->WbT, h->bias_rd);
+}
+
+// stale-chains mode: make the asynchronously updated weight version the current one
+void adopt_pending_update(qb_handle *h) {
+    if (!h->pending_update) return;
+    QB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_upd, 0));
+    std::swap(h->Wb, h->Wb_alt);
+    std::swap(h->WbT, h->WbT_alt);
+    h->bias_cur ^= 1;
+    h->bias_rd = h->bias_buf[h->bias_cur];
+    h->pending_update = false;
+}
+
+// ... or only order the compute stream after it (reads of the fp32 masters, timers), keeping the
+// chains one version behind
+void wait_pending_update(qb_handle *h) {
+    if (h->pending_update) QB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_upd, 0));
+}
+
+void set_stale_mode(qb_handle *h, bool on) {
+    QB_CHECK(!on || (h->bf && h->L == 0), QB_E_UNSUPPORTED, "stale_chains needs bf16 precision and a model without label units");
+    adopt_pending_update(h);
+    QB_CUDA(cudaStreamSynchronize(h->stream));
+    if (on && !h->Wb_alt) {
+        h->Wb_alt = dalloc<bf16>(h->H * h->ldv);
+        h->WbT_alt = dalloc<bf16>(h->VL * h->ldh);
+        h->G_alt = dalloc<float>(h->nP);
+        h->bias_buf[0] = dalloc<float>(h->ldv + h->ldh);
+        h->bias_buf[1] = dalloc<float>(h->ldv + h->ldh);
+        QB_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        QB_CUDA(cudaEventCreateWithFlags(&h->ev_grad, cudaEventDisableTiming));
+        QB_CUDA(cudaEventCreateWithFlags(&h->ev_upd, cudaEventDisableTiming));
+    }
+    if (on) {
+        h->bias_cur = 0;
+        QB_CUDA(cudaMemcpyAsync(h->bias_buf[0], acat(h), (h->ldv + h->ldh) * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        QB_CUDA(cudaStreamSynchronize(h->stream));
+        h->bias_rd = h->bias_buf[0];
+    } else {
+        h->bias_rd = nullptr;
+    }
+    h->stale_chains = on;
 }
 
 void refresh_shadows(qb_handle *h) {
@@ -517,9 +576,29 @@ void fold_chain_bias_explicit(qb_handle *h, int64_t B) {
     colsum<bf16>(h, h->ch.b, h->ch.ld, B, h->H, -1.f, G_b(h));
 }
 
+// stale-chains variant of the PCD step (see qb_handle::stale_chains)
+void pcd_step_stale(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr) {
+    StepRng sr{h, B, h->inj_active};
+    const int64_t row0 = row0_of(h, B);
+    zero_bias_grads(h);
+    advance_chains(h, B, k, sr, true);  // previous weight version; overlaps the in-flight allreduce + update
+    adopt_pending_update(h);            // from here on: the latest weights
+    HiddenOut ho; ho.prob = &h->phd; ho.prob_T = true; ho.bg_what = 1; ho.bg_sign = 1.f;
+    op_hidden(h, xb, B, h->VL, ho, Rng(), row0);
+    op_grad(h, h->phd, xb, xbT, xb_ldT, h->ch, h->cv, B);
+    QB_CUDA(cudaEventRecord(h->ev_grad, h->stream));
+    QB_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_grad, 0));
+    op_update_on(h, lr, llr, B, h->comm_stream, h->G, h->Wb_alt, h->WbT_alt, h->bias_buf[h->bias_cur ^ 1]);
+    QB_CUDA(cudaEventRecord(h->ev_upd, h->comm_stream));
+    h->pending_update = true;
+    std::swap(h->G, h->G_alt);  // the next step accumulates into the other gradient buffer
+    h->inj_active = false;
+}
+
 void pcd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr,
                    cudaEvent_t *ev) {
     QB_CHECK(h->n_chains >= B, QB_E_STATE, "qb_init_chains must provide at least B chains");
+    if (h->stale_chains) { pcd_step_stale(h, xb, xbT, xb_ldT, B, k, lr, llr); return; }
     StepRng sr{h, B, h->inj_active};
     const int64_t row0 = row0_of(h, B);
     zero_bias_grads(h);
@@ -640,7 +719,8 @@ int32_t guarded(F &&fn) {
         return QB_E_CUDA;
     }
 }
-#define QB_H(h) QB_CHECK((h) != nullptr, QB_E_ARG, "handle is NULL"); QB_CUDA(cudaSetDevice((h)->cfg.device))
+#define QB_H_KEEP(h) QB_CHECK((h) != nullptr, QB_E_ARG, "handle is NULL"); QB_CUDA(cudaSetDevice((h)->cfg.device))
+#define QB_H(h) QB_H_KEEP(h); adopt_pending_update(h)
 
 }  // namespace
 
@@ -721,6 +801,10 @@ int32_t qb_destroy(qb_handle *h) {
         cudaDeviceSynchronize();
         if (h->comm) nccl().CommDestroy(h->comm);
         cudaFree(h->P); cudaFree(h->G); cudaFree(h->Vel); cudaFree(h->Wb); cudaFree(h->WbT);
+        cudaFree(h->Wb_alt); cudaFree(h->WbT_alt); cudaFree(h->G_alt); cudaFree(h->bias_buf[0]); cudaFree(h->bias_buf[1]);
+        if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+        if (h->ev_grad) cudaEventDestroy(h->ev_grad);
+        if (h->ev_upd) cudaEventDestroy(h->ev_upd);
         free_mat(h->data); cudaFree(h->dataT); cudaFree(h->datasum);
         free_mat(h->cv); free_mat(h->ch); free_mat(h->phd); free_mat(h->hs); free_mat(h->vm); free_mat(h->phm); free_mat(h->hb);
         cudaFree(h->pre_h); cudaFree(h->pre_v); cudaFree(h->lab_pre); cudaFree(h->softplus_rows); cudaFree(h->out_f32);
@@ -751,13 +835,14 @@ int32_t qb_set_params(qb_handle *h, const double *W, const double *a, const doub
         QB_CUDA(cudaMemcpyAsync(h->P, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         if (h->Vel) QB_CUDA(cudaMemsetAsync(h->Vel, 0, h->nP * sizeof(float), h->stream));
         refresh_shadows(h);
+        if (h->bias_rd) QB_CUDA(cudaMemcpyAsync(h->bias_rd, acat(h), (h->ldv + h->ldh) * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
         QB_CUDA(cudaStreamSynchronize(h->stream));
     });
 }
 
 int32_t qb_get_params(qb_handle *h, double *W, double *a, double *b, double *U, double *c) {
     return guarded([&] {
-        QB_H(h);
+        QB_H_KEEP(h); wait_pending_update(h);
         std::vector<float> p((size_t)h->nP);
         QB_CUDA(cudaMemcpyAsync(p.data(), h->P, p.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         QB_CUDA(cudaStreamSynchronize(h->stream));
@@ -820,7 +905,7 @@ int32_t qb_init_chains(qb_handle *h, int64_t n_chains, const double *v, const do
 
 int32_t qb_get_chains(qb_handle *h, double *v, double *hid, double *y) {
     return guarded([&] {
-        QB_H(h);
+        QB_H_KEEP(h);
         QB_CHECK(h->n_chains > 0, QB_E_STATE, "no chains");
         download_rows(h, h->cv, 0, 0, h->n_chains, h->V, v);
         download_rows(h, h->ch, 0, 0, h->n_chains, h->H, hid);
@@ -835,7 +920,7 @@ int32_t qb_seed(qb_handle *h, uint64_t seed) {
 int32_t qb_inject_streams(qb_handle *h, const double *U_h, const double *U_v, const double *U_y, const double *Z_v, int64_t k,
                           int64_t B) {
     return guarded([&] {
-        QB_H(h);
+        QB_H_KEEP(h);
         QB_CHECK(U_h != nullptr && k >= 1 && B >= 1 && B <= h->Bmax, QB_E_ARG, "U_h required, k >= 1, 1 <= B <= max_batch");
         QB_CHECK(h->gaussian ? (Z_v != nullptr) : (U_v != nullptr), QB_E_ARG, "U_v (Bernoulli) or Z_v (Gaussian) required");
         QB_CHECK(h->L == 0 || U_y != nullptr, QB_E_ARG, "U_y required for classifier models");
@@ -869,7 +954,7 @@ int32_t qb_inject_streams(qb_handle *h, const double *U_h, const double *U_v, co
 
 int32_t qb_pcd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, double lr, double llr) {
     return guarded([&] {
-        QB_H(h);
+        QB_H_KEEP(h);
         check_step_args(h, B, k);
         Mat xb; const bf16 *xbT; int64_t ldT;
         batch_view(h, batch_index, B, xb, xbT, ldT);
@@ -898,7 +983,7 @@ static void epoch_impl(qb_handle *h, bool pcd, int64_t B, int64_t k, double lr, 
     for (int64_t m = 0; m < nb; m++) {
         Mat xb; const bf16 *xbT; int64_t ldT;
         batch_view(h, m, B, xb, xbT, ldT);
-        const bool timed = (times != nullptr);
+        const bool timed = (times != nullptr) && !(pcd && h->stale_chains);  // the overlapped step has no phase boundaries
         if (pcd) pcd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, timed ? h->ev : nullptr);
         else cd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, timed ? h->ev : nullptr);
         if (timed) {
@@ -920,7 +1005,7 @@ static void epoch_impl(qb_handle *h, bool pcd, int64_t B, int64_t k, double lr, 
 }
 
 int32_t qb_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]) {
-    return guarded([&] { QB_H(h); epoch_impl(h, true, B, k, lr, llr, times); });
+    return guarded([&] { QB_H_KEEP(h); epoch_impl(h, true, B, k, lr, llr, times); });
 }
 int32_t qb_cd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]) {
     return guarded([&] { QB_H(h); epoch_impl(h, false, B, k, lr, llr, times); });
@@ -1082,7 +1167,7 @@ int32_t qb_comm_init(qb_handle *h, const void *id128) {
 int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_launches, double *gemm_flops, int64_t *timed_gemms,
                         double *timed_gemm_ms, double *timed_gemm_flops) {
     return guarded([&] {
-        QB_H(h);
+        QB_H_KEEP(h);
         if (kernel_launches) *kernel_launches = h->launches;
         if (gemm_launches) *gemm_launches = h->gemm_launches;
         if (gemm_flops) *gemm_flops = h->gemm_flops;
@@ -1102,7 +1187,7 @@ int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_la
 }
 int32_t qb_reset_counters(qb_handle *h) {
     return guarded([&] {
-        QB_H(h);
+        QB_H_KEEP(h);
         h->launches = 0; h->gemm_launches = 0; h->gemm_flops = 0.0;
         h->gemm_ev_used = 0; h->gemm_timed = 0; h->gemm_timed_flops = 0.0;
         h->upd_ev_used = 0; h->upd_timed = 0;
@@ -1110,12 +1195,14 @@ int32_t qb_reset_counters(qb_handle *h) {
 }
 int32_t qb_set_option(qb_handle *h, const char *key, double value) {
     return guarded([&] {
-        QB_H(h);
+        QB_H_KEEP(h);
         QB_CHECK(key != nullptr, QB_E_ARG, "key is NULL");
         if (!strcmp(key, "force_bn")) {
             int bn = (int)value;
             QB_CHECK(bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 256, QB_E_ARG, "force_bn must be 0/32/64/128/256");
             h->force_bn = bn;
+        } else if (!strcmp(key, "stale_chains")) {
+            set_stale_mode(h, value != 0.0);
         } else if (!strcmp(key, "dbg")) {
             h->dbg = (int)value;
         } else if (!strcmp(key, "use_2cta")) {
@@ -1132,7 +1219,7 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
 }
 int32_t qb_get_update_timing(qb_handle *h, int64_t *timed_updates, double *timed_update_ms) {
     return guarded([&] {
-        QB_H(h);
+        QB_H_KEEP(h);
         double ms = 0.0;
         if (h->upd_ev_used) {
             QB_CUDA(cudaStreamSynchronize(h->stream));
@@ -1147,16 +1234,16 @@ int32_t qb_get_update_timing(qb_handle *h, int64_t *timed_updates, double *timed
     });
 }
 int32_t qb_sync(qb_handle *h) {
-    return guarded([&] { QB_H(h); QB_CUDA(cudaStreamSynchronize(h->stream)); });
+    return guarded([&] { QB_H_KEEP(h); wait_pending_update(h); QB_CUDA(cudaStreamSynchronize(h->stream)); });
 }
 int32_t qb_timer_start(qb_handle *h) {
-    return guarded([&] { QB_H(h); QB_CUDA(cudaEventRecord(h->timer_ev[0], h->stream)); });
+    return guarded([&] { QB_H_KEEP(h); QB_CUDA(cudaEventRecord(h->timer_ev[0], h->stream)); });
 }
 int32_t qb_timer_stop(qb_handle *h, double *elapsed_ms) {
     return guarded([&] {
-        QB_H(h);
+        QB_H_KEEP(h); wait_pending_update(h);
         QB_CHECK(elapsed_ms != nullptr, QB_E_ARG, "elapsed_ms is NULL");
-        QB_CUDA(cudaEventRecord(h->timer_ev[1], h->stream));
+        QB_CUDA(cudaEventRecord(h->timer_ev[1], h->stream));  // after QB_H: includes the last asynchronous update
         QB_CUDA(cudaEventSynchronize(h->timer_ev[1]));
         float t = 0.f;
         QB_CUDA(cudaEventElapsedTime(&t, h->timer_ev[0], h->timer_ev[1]));

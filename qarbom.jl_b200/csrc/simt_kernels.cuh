@@ -274,18 +274,21 @@ __global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16 *__restri
 
 // bias region: [acat (VL) | b (H)] stored contiguously after W with the same treatment (no weight decay)
 __global__ void update_bias_kernel(float *__restrict__ P, const float *__restrict__ G, float *__restrict__ Vel, int n_vis,
-                                   int V, int n_total, float lr, float llr, float momentum) {
+                                   int V, int n_total, float lr, float llr, float momentum, float *__restrict__ copy_out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_total) return;
     float lr_c = (i < n_vis && i >= V) ? llr : lr;  // label biases c use llr; a and b use lr
     float g = G[i];
+    float p = P[i];
     if (Vel) {
         float v = momentum * Vel[i] + lr_c * g;
         Vel[i] = v;
-        P[i] += v;
+        p += v;
     } else {
-        P[i] += lr_c * g;
+        p += lr_c * g;
     }
+    P[i] = p;
+    if (copy_out) copy_out[i] = p;  // versioned bias copy read by the GEMM epilogues (stale-chains mode)
 }
 
 // start of a step: G_a = cached data-side visible sums (or 0), G_b = 0 -- one launch instead of memcpy + memset

@@ -428,3 +428,55 @@ def test_2cta_variant_matches_oracle(q, bn, V, H, B):
         assert np.array_equal(a, b)
     for a, b in zip(outs[0][3:], outs[1][3:]):  # bias sums are float atomics: order-dependent last bits
         assert np.max(np.abs(a - b)) < 1e-6
+
+
+# ------------------------------------------------------------------------------ stale-chains (overlapped allreduce) mode
+def test_stale_chains_mode_matches_its_definition(q):
+    """Declared extension (SURVEY section 8(e) option 2): the chains of step t advance with the weights
+    of step t-1 while the allreduce + update of step t-1 are still in flight; the positive phase uses
+    the latest weights.  Emulated here in numpy (batched form, bf16-rounded weight versions)."""
+    rng = np.random.default_rng(77)
+    V, H, B, k, steps, lr = 96, 64, 32, 2, 4, 0.05
+    sig = lambda x: 1.0 / (1.0 + np.exp(-x))
+    m = make_oracle_model(rng, V, H, bf16=True)
+    X, _ = _data(rng, steps * B, V, 0, False, True)
+    cv, ch = bf16_round(u24(rng, B, V)), bf16_round(u24(rng, B, H))
+    Wm, a, b = m.W.copy(), m.a.copy(), m.b.copy()          # fp32 masters
+    versions = [(bf16_round(Wm), a.copy(), b.copy())]        # shadow versions as the tensor cores see them
+
+    def bern(u, p):  # guard-band near ties in place (same trick as GuardedStream)
+        near = np.abs(u - p) < 1e-4
+        out = u < p
+        u[near] = np.where(out[near], p[near] - 2e-4, p[near] + 2e-4).astype(np.float32)
+        return out.astype(np.float64)
+
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=B, precision="bf16") as dev:
+        dev.set_option("stale_chains", 1)
+        dev.set_data(X)
+        dev.init_chains(B, cv, ch)
+        for t in range(steps):
+            Wc, ac, bc = versions[max(t - 1, 0)]              # chains: one update old
+            Wp, ap, bp = versions[t]                          # positive phase: latest
+            U_h, U_v = u24(rng, k, B, H), u24(rng, k, B, V)
+            for s in range(k):
+                ch = bern(U_h[s], sig(bc + cv @ Wc))
+                cv = bern(U_v[s], sig(ac + ch @ Wc.T))
+            xb = X[t * B:(t + 1) * B]
+            hd = sig(bp + xb @ Wp)
+            Wm = Wm + (lr / B) * (xb.T @ hd - cv.T @ ch)
+            a = a + (lr / B) * (xb - cv).sum(0)
+            b = b + (lr / B) * (hd - ch).sum(0)
+            versions.append((bf16_round(Wm), f32_round(a), f32_round(b)))
+            dev.inject_streams(U_h, U_v)
+            dev.pcd_step(t, B, k, lr)
+            dv, dh, _ = dev.get_chains()
+            assert np.array_equal(dh, ch) and np.array_equal(dv, cv), f"chain states differ at step {t}"
+            dev.pull_params()
+            # keep the emulation on the device's masters so rounding differences cannot accumulate
+            assert rel_err(dev.rbm.W - versions[t][0], Wm - versions[t][0], atol=1e-6) < 5e-2 or t == 0
+            Wm, a, b = dev.rbm.W.copy(), dev.rbm.a.copy(), dev.rbm.b.copy()
+            versions[-1] = (bf16_round(Wm), a.copy(), b.copy())
+        # leaving the mode makes the last update current
+        dev.set_option("stale_chains", 0)
+        ph = dev.conditional_prob_h(X[:4])
+        assert np.max(np.abs(ph - sig(b + X[:4] @ bf16_round(Wm)))) < 2e-6
