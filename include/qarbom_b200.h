@@ -144,6 +144,11 @@ int32_t qb_reconstruct(qb_handle *h, const double *v, int64_t n_rows, const doub
 /* conditional_prob_h (src/rbm.jl:165,170-171) for n_rows rows; y may be NULL (2-arg form). */
 int32_t qb_conditional_prob_h(qb_handle *h, const double *v, const double *y, int64_t n_rows, double *out);
 
+/* conditional_prob_y_given_v (src/rbm.jl:191-194) for n_rows rows -> out[n_rows][L]; X == NULL uses the
+ * resident dataset.  `classify` (src/rbm.jl:226-229) and the Accuracy metric (src/evaluation.jl:9-14) are
+ * the caller's arg-max / comparison over these probabilities. */
+int32_t qb_conditional_prob_y_given_v(qb_handle *h, const void *X, int32_t x_dtype, int64_t n_rows, double *out);
+
 /* Data-parallel gradient allreduce over NCCL (new; the reference is single-process).
  * Rank 0 creates the id, the caller ships the 128 bytes to the other ranks. */
 int32_t qb_comm_unique_id(void *id128);

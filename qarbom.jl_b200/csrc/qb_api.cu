@@ -1144,6 +1144,46 @@ int32_t qb_conditional_prob_h(qb_handle *h, const double *v, const double *y, in
     });
 }
 
+// conditional_prob_y_given_v (src/rbm.jl:191-194): softmax(c + U * sigma(b + W'v)) for n_rows rows
+int32_t qb_conditional_prob_y_given_v(qb_handle *h, const void *X, int32_t x_dtype, int64_t n_rows, double *out) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(h->L > 0, QB_E_ARG, "model has no label units");
+        QB_CHECK(out != nullptr, QB_E_ARG, "out is NULL");
+        const bool resident = (X == nullptr);
+        if (resident) { QB_CHECK(h->N > 0, QB_E_STATE, "no resident dataset"); n_rows = h->N; }
+        QB_CHECK(n_rows > 0, QB_E_ARG, "n_rows <= 0");
+        for (int64_t r = 0; r < n_rows; r += h->Bmax) {
+            const int64_t nr = std::min(h->Bmax, n_rows - r);
+            Mat xs;
+            if (resident) xs = h->data.row_slice(r, nr);
+            else {
+                upload_rows(h, (const char *)X + (size_t)r * h->V * dt_size(x_dtype), x_dtype, nr, h->V, h->hb, 0, 0);
+                xs = h->hb.row_slice(0, nr);
+            }
+            HiddenOut ho; ho.prob = &h->phd; ho.prob_rm = true;
+            op_hidden(h, xs, nr, h->V, ho, Rng(), 0);  // 2-arg conditional_prob_h: labels are not inputs here
+            // label pre-activations c + U p_h: a GEMM over the L label rows of the visible-side weights only
+            if (h->bf) {
+                sm100::Operand A{h->WbT + h->V * h->ldh, h->L, h->H, h->ldh}, B{h->phd.b, nr, h->H, h->phd.ld};
+                sm100::EpiParams ep{};
+                ep.mode = sm100::EPI_SAMPLE; ep.M = (int)h->L; ep.N = (int)nr; ep.bias = bias_a(h) + h->V;
+                ep.act = sm100::ACT_SIGMOID; ep.sample = 0; ep.split = 0; ep.lab_pre = h->lab_pre; ep.ld_lab = h->L;
+                GemmScope gs(h, 2.0 * (double)h->L * (double)nr * (double)h->H);
+                sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn, 0);
+            } else {
+                simt_gemm(h, h->phd.f, h->phd.ld, 1, Wf(h) + h->V, h->ldv, 1, h->lab_pre, h->L, nr, h->L, h->H, 1.f, 0.f, acat(h) + h->V);
+            }
+            ensure_staging(h, (size_t)nr * h->L * sizeof(double));
+            label_softmax_kernel<<<grid1d(nr, 128), 128, 0, h->stream>>>(h->lab_pre, h->L, (int)nr, (int)h->L, (double *)h->staging);
+            QB_CUDA(cudaGetLastError());
+            h->launches++;
+            QB_CUDA(cudaMemcpyAsync(out + (size_t)r * h->L, h->staging, (size_t)nr * h->L * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            QB_CUDA(cudaStreamSynchronize(h->stream));
+        }
+    });
+}
+
 int32_t qb_comm_unique_id(void *id128) {
     return guarded([&] {
         QB_CHECK(id128 != nullptr, QB_E_ARG, "id buffer is NULL");

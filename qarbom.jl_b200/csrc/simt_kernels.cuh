@@ -437,6 +437,19 @@ __global__ void label_bf16_kernel(const float *__restrict__ lab_pre, int64_t ld_
     }
 }
 
+// conditional_prob_y_given_h (src/rbm.jl:196-205): row softmax of the L label pre-activations
+__global__ void label_softmax_kernel(const float *__restrict__ pre, int64_t ld, int rows, int L, double *__restrict__ out) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float *p = pre + (int64_t)r * ld;
+    float mx = -INFINITY;
+    for (int l = 0; l < L; l++) mx = fmaxf(mx, p[l]);
+    float s = 0.f;
+    for (int l = 0; l < L; l++) s += expf(p[l] - mx);
+    float lden = mx + logf(s);
+    for (int l = 0; l < L; l++) out[(int64_t)r * L + l] = (double)expf(p[l] - lden);
+}
+
 // _init_fantasy_data with the device stream: U[0,1) floats (src/fantasy_data.jl:66-86)
 __global__ void uniform_fill_kernel(float *__restrict__ f, bf16 *__restrict__ b, int64_t ld, int64_t rows, int64_t units,
                                     RngKey key, int64_t row0) {

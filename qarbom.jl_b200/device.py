@@ -162,6 +162,28 @@ class DeviceRBM:
         check(lib().qb_conditional_prob_h(self._h, ptr(v), ptr(y), v.shape[0], ptr(out)))
         return out
 
+    def conditional_prob_y_given_v(self, x=None) -> np.ndarray:
+        """softmax(c + U sigma(b + W'v)) per row (src/rbm.jl:191-194); x=None: the resident dataset."""
+        if x is None:
+            out = np.zeros((self.n_rows, self.L))
+            check(lib().qb_conditional_prob_y_given_v(self._h, None, 0, 0, ptr(out)))
+            return out
+        X, xdt = as_rows(x, self.V)
+        out = np.zeros((X.shape[0], self.L))
+        check(lib().qb_conditional_prob_y_given_v(self._h, ptr(X), xdt, X.shape[0], ptr(out)))
+        return out
+
+    def classify(self, x=None) -> np.ndarray:
+        """classify (src/rbm.jl:226-229): 1 where the label probability equals the row maximum."""
+        p = self.conditional_prob_y_given_v(x)
+        return (p == p.max(axis=1, keepdims=True)).astype(np.int64)
+
+    def eval_accuracy(self, x, y) -> float:
+        """_evaluate(Accuracy) through the classifier `evaluate` (src/evaluation.jl:9-14,28-50)."""
+        pred = self.classify(x)
+        y = np.rint(np.asarray(y, dtype=np.float64).reshape(pred.shape)).astype(np.int64)
+        return float(np.mean(np.all(pred == y, axis=1)))
+
     # ------------------------------------------------------------------ multi-GPU / counters
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -19,6 +19,7 @@ class CD(TrainingMethod): ...
 class PCD(TrainingMethod): ...
 class EvaluationMethod: ...
 class MeanSquaredError(EvaluationMethod): ...
+class Accuracy(EvaluationMethod): ...
 class FreeEnergy(EvaluationMethod): ...   # new metric (no reference counterpart)
 
 
@@ -27,6 +28,19 @@ def _diverged(history: Sequence[float]) -> bool:
     if len(history) == 1:
         return False
     return history[-1] > history[-2] or history[-1] > min(history)
+
+
+def _diverged_accuracy(history: Sequence[float]) -> bool:
+    """src/evaluation.jl:156-168 (Accuracy)."""
+    if len(history) == 1:
+        return False
+    if history[-1] < history[-2]:
+        print(f"Accuracy decreased from {history[-2]} to {history[-1]}")
+        return True
+    if history[-1] < max(history):
+        print(f"Accuracy {history[-1]} is not the maximum value {max(history)}")
+        return True
+    return False
 
 
 def _log_epoch(epoch, t_sample, t_gibbs, t_update, total_t):
@@ -50,9 +64,9 @@ def _log_finish(n_epochs, ts, tg, tu):
 
 def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int, learning_rate: Sequence[float],
           gibbs_steps: Optional[int] = None, batch_size: Optional[int] = None,
-          label_learning_rate: Optional[Sequence[float]] = None, metrics=(MeanSquaredError,),
+          label_learning_rate: Optional[Sequence[float]] = None, metrics=None,
           early_stopping: bool = False, store_best_rbm: bool = True, patience: int = 10,
-          stopping_metric=MeanSquaredError, x_test_dataset=None, file_path: Optional[str] = None,
+          stopping_metric=None, x_test_dataset=None, y_test_dataset=None, file_path: Optional[str] = None,
           # ---- extensions (defaults reproduce the reference)
           momentum: float = 0.0, weight_decay: float = 0.0, precision: str = "bf16", seed: int = 0, device: int = 0,
           verbose: bool = True, chains_init=None) -> dict:
@@ -60,6 +74,12 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
     clf = rbm.n_classifiers > 0
     if clf and label_train is None:
         raise ValueError("label_train is required for classifier models")
+    if clf and label_learning_rate is None:
+        raise TypeError("train!(::RBMClassifiers, ...) requires label_learning_rate")   # train_cd.jl:129
+    if metrics is None:          # defaults: [MeanSquaredError] (train_cd.jl:52) / [Accuracy] (train_cd.jl:130)
+        metrics = (Accuracy,) if clf else (MeanSquaredError,)
+    if stopping_metric is None:
+        stopping_metric = Accuracy if clf else MeanSquaredError
     if is_pcd and batch_size is None:
         raise TypeError("train!(..., PCD) requires batch_size")   # keyword without default, train_pcd.jl:139
     if gibbs_steps is None:
@@ -74,18 +94,25 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
     if len(learning_rate) < n_epochs:
         raise IndexError("learning_rate needs one entry per epoch")       # learning_rate[epoch], train_cd.jl:77
 
-    names = {MeanSquaredError: "mse", FreeEnergy: "free_energy"}
+    names = {MeanSquaredError: "mse", FreeEnergy: "free_energy", Accuracy: "accuracy"}
     keys = [names[m] for m in metrics]
     dev = DeviceRBM(rbm, max_batch=max(B, min(n, 4096)), precision=precision, device=device, seed=seed)
     try:
         dev.set_optimizer(momentum, weight_decay)
         dev.set_data(x_train, label_train)
 
+        use_test = x_test_dataset is not None and (not clf or y_test_dataset is not None)  # train_cd.jl:143-147
+
         def evaluate():
             out = {}
             for m in metrics:
-                xs = x_test_dataset
-                out[names[m]] = dev.eval_mse(xs) if m is MeanSquaredError else dev.eval_free_energy(xs)
+                xs = x_test_dataset if use_test else None
+                if m is MeanSquaredError:
+                    out[names[m]] = dev.eval_mse(xs)
+                elif m is Accuracy:
+                    out[names[m]] = dev.eval_accuracy(xs, y_test_dataset if use_test else label_train)
+                else:
+                    out[names[m]] = dev.eval_free_energy(xs)
             return out
 
         best = copy_rbm(rbm)
@@ -112,7 +139,8 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
                 tot[i] += t[i]
             for k, v in evaluate().items():
                 hist[k].append(v)
-            if _diverged([initial[stop_key]] + hist[stop_key]) if False else _diverged(hist[stop_key]):
+            diverged = _diverged_accuracy(hist[stop_key]) if stop_key == "accuracy" else _diverged(hist[stop_key])
+            if diverged:
                 if early_stopping:
                     if patience == 0:
                         print(f"Early stopping at epoch {epoch}")

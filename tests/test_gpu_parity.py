@@ -480,3 +480,37 @@ def test_stale_chains_mode_matches_its_definition(q):
         dev.set_option("stale_chains", 0)
         ph = dev.conditional_prob_h(X[:4])
         assert np.max(np.abs(ph - sig(b + X[:4] @ bf16_round(Wm)))) < 2e-6
+
+
+# ------------------------------------------------------------------------------ classifier evaluation
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_classify_and_accuracy(q, prec):
+    bf = prec == "bf16"
+    rng = np.random.default_rng(17)
+    V, H, L, n = 70, 33, 6, 90
+    m = make_oracle_model(rng, V, H, L, bf16=bf)
+    X, Y = _data(rng, n, V, L, False, bf)
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=32, precision=prec) as dev:
+        dev.set_data(X, Y)
+        p_res = dev.conditional_prob_y_given_v()
+        p_host = dev.conditional_prob_y_given_v(X)
+        acc = dev.eval_accuracy(None, Y)
+    if bf:
+        ref = np.stack([qo.conditional_prob_y_given_h(m, bf16_round(qo.conditional_prob_h(m, x))) for x in X])
+    else:
+        ref = np.stack([qo.conditional_prob_y_given_v(m, x) for x in X])
+    assert np.max(np.abs(p_res - ref)) < 5e-6 and np.max(np.abs(p_host - ref)) < 5e-6
+    assert abs(acc - qo.evaluate_accuracy(m, X, Y)) < 1e-12
+
+
+def test_train_classifier_reference_scenario(q, tmp_path):
+    """test/classification.jl:4-44: RBMClassifier(3,2,1) on x=[1,0,0], y=[1]; default metric Accuracy."""
+    x = [[1, 0, 0] for _ in range(200)]
+    y = [[1] for _ in range(200)]
+    rbm = q.RBMClassifier(3, 2, 1, rng=np.random.default_rng(2))
+    lr = [0.01 / (j ** 0.8) for j in range(1, 1001)]
+    hist = q.train(rbm, x, q.PCD, y, n_epochs=5, batch_size=2, learning_rate=lr, label_learning_rate=lr, early_stopping=True,
+                   file_path=str(tmp_path / "c.csv"), precision="fp32", verbose=False)
+    assert list(hist) == ["accuracy"] and len(hist["accuracy"]) >= 2
+    assert hist["accuracy"][-1] == 1.0   # a single label unit: softmax over one unit is always 1
+    assert (tmp_path / "c.csv").read_text().splitlines()[0] == "accuracy"
