@@ -97,6 +97,24 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic(kernel_prefix: str, fname: str):
+    """Average dram read+write bytes per launch of a kernel from the committed `ncu --set full` summary
+    (profiles/, produced by tools/ncu_summary.py); None if no capture is committed."""
+    path = os.path.join(ROOT, "profiles", fname)
+    if not os.path.exists(path):
+        return None
+    tot, n, cur = 0.0, 0, False
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for line in open(path):
+        if not line.startswith(" "):
+            cur = kernel_prefix in line
+            n += cur
+        elif cur and ("dram__bytes_read.sum " in line or "dram__bytes_write.sum " in line):
+            parts = line.split()
+            tot += float(parts[1]) * scale.get(parts[2], 1.0)
+    return tot / n if n else None
+
+
 def make_data(w, seed):
     rng = np.random.Generator(np.random.PCG64(seed))
     n = w["B"] * w["nb"]
@@ -334,8 +352,12 @@ def main():
     pk = peaks()
     F = flops_per_step(w) / world  # per GPU per step
     achieved = (timed_flops / 1e12) / (gemm_ms * 1e-3) if gemm_ms > 0 else None
+    cfg5_bf16 = args.workload == "cfg5" and args.precision == "bf16" and world == 1
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
-            "frac": (achieved / pk["tf"]) if achieved else None, "traffic": None,
+            "frac": (achieved / pk["tf"]) if achieved else None,
+            "traffic": ncu_traffic("gibbs_gemm_kernel", "r1_ncu_gemm_raw_summary.txt") if cfg5_bf16 else None,
+            "traffic_note": "dram read+write bytes per launch, mean over the GEMM launches of one `ncu --set full` capture "
+                            "of this command (profiles/r1_ncu_gemm_raw_summary.txt)",
             "kernel": "qb::sm100::gibbs_gemm_kernel (fused Gibbs half-step / gradient GEMMs)" if args.precision == "bf16"
             else "qb::simt_gemm_kernel (fp32 validation path)",
             "gemm_launches_timed": timed, "avg_launch_ms": gemm_ms / max(timed, 1),
@@ -348,7 +370,9 @@ def main():
     upd_bytes = (16.0 if args.precision == "bf16" else 12.0) * P_w
     upd_gbs = (upd_bytes * upd_n / 1e9) / (upd_ms * 1e-3) if upd_ms > 0 else None
     roof_upd = {"bound": "hbm", "achieved": upd_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                "frac": (upd_gbs / pk["hbm"]) if upd_gbs else None, "traffic": None, "kernel": "qb::update_w_kernel",
+                "frac": (upd_gbs / pk["hbm"]) if upd_gbs else None,
+                "traffic": ncu_traffic("update_w_kernel", "r1_ncu_update_raw_summary.txt") if cfg5_bf16 else None,
+                "kernel": "qb::update_w_kernel",
                 "bytes_per_launch": upd_bytes, "avg_launch_ms": upd_ms / max(upd_n, 1), "launches_timed": upd_n}
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
