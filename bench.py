@@ -200,6 +200,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: global batch fixed (BASELINE config); weak: per-GPU batch fixed (global batch x N)")
     ap.add_argument("--stale-chains", action="store_true", help="also time the stale-1 chains mode on one GPU")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
@@ -207,6 +209,8 @@ def main():
     w = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.scaling == "weak":
+        w["B"] *= world
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = {"workload": f"{args.workload}: {w['desc']}", "V": w["V"], "H": w["H"], "L": w["L"], "global_batch": w["B"],
            "gibbs_steps": w["k"], "algorithm": w["algo"], "rng": "philox4x32-10",
@@ -330,18 +334,24 @@ def main():
         xs = [torch.from_numpy(Xl[j * Bl:(j + 1) * Bl]).pin_memory() for j in range(nbuf)]
         ys = [torch.from_numpy(Yl[j * Bl:(j + 1) * Bl]).pin_memory() for j in range(nbuf)] if Yl is not None else None
         dev.set_option("async_steps", 0)
+        def host_step(i):  # the next mini-batch is uploaded (pinned -> HBM) while this one is being processed
+            j, jn = i % nbuf, (i + 1) % nbuf
+            return dev.step_host(w["algo"], xs[j], ys[j] if ys else None, k, lr, lr, next_x=xs[jn],
+                                 next_y=ys[jn] if ys else None)
+
         for i in range(args.warmup):
-            dev.step_host(w["algo"], xs[i % nbuf], ys[i % nbuf] if ys else None, k, lr, lr)
+            host_step(i)
         barrier()
         dev.timer_start()
         for i in range(args.steps):
-            dev.step_host(w["algo"], xs[i % nbuf], ys[i % nbuf] if ys else None, k, lr, lr)
+            host_step(args.warmup + i)
         ms2 = max_over_ranks(dev.timer_stop())
         barrier()
         h2d = int(xs[0].numel() * xs[0].element_size() + (ys[0].numel() * ys[0].element_size() if ys else 0))
         e2e = {"value": B * args.steps / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": 8 * world, "ms_per_step": ms2 / args.steps,
-               "api": f"qb_{'pcd' if pcd else 'cd'}_step_host (upload + step + reconstruction error readback)"}
+               "api": f"qb_{'pcd' if pcd else 'cd'}_step_host + qb_set_next_host_batch (pinned-host upload of every mini-batch, "
+                      "overlapped with the previous step; step; reconstruction error readback)"}
 
     if rank != 0:
         dev.close()
@@ -375,7 +385,7 @@ def main():
                 "kernel": "qb::update_w_kernel",
                 "bytes_per_launch": upd_bytes, "avg_launch_ms": upd_ms / max(upd_n, 1), "launches_timed": upd_n}
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": dict(cfg, l2="inputs cycle over %d resident mini-batches (%.2f GB incl. transposed copies) > 126 MB L2"
                                     % (nb, 2 * nb * Bl * w["V"] * 2 / 1e9)),

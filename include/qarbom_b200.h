@@ -131,6 +131,12 @@ int32_t qb_pcd_step_host(qb_handle *h, const void *X, int32_t x_dtype, const voi
 int32_t qb_cd_step_host(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype, int64_t B,
                         int64_t k, double lr, double llr, double *recon_sq_err);
 
+/* Pipelining hint for the two calls above: X/Y of the NEXT qb_*_step_host call.  Its upload starts on
+ * a copy stream inside the next step call and overlaps that step's kernels; the call after that, given
+ * the same X pointer and B, consumes it without a fresh copy.  The hinted host buffers (pinned memory
+ * for a truly asynchronous copy) must stay valid until the call that consumes them returns. */
+int32_t qb_set_next_host_batch(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype);
+
 /* evaluate + _evaluate(MeanSquaredError) + reconstruct (src/evaluation.jl:16-20,52-70;
  * src/rbm.jl:220-224): sum over samples of sum_units (x - reconstruct(x))^2 / n_rows.
  * X == NULL evaluates the resident dataset. Z (n_rows x V standard normals) optionally

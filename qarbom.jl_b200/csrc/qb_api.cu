@@ -107,6 +107,10 @@ struct qb_handle {
     // persistent chains and work buffers (Bmax rows)
     Mat cv, ch; int64_t n_chains = 0; bool chains_binary = false;
     Mat phd, hs, vm, phm, hb;  // pos-phase probs, sampled hidden, CD model visible, CD final probs, host-batch staging
+    // host-batch prefetch (qb_set_next_host_batch): second staging matrix filled on copy_stream while a step runs
+    Mat hb2; void *staging2 = nullptr; size_t staging2_bytes = 0;
+    const void *next_X = nullptr, *next_Y = nullptr; int next_xdt = 0, next_ydt = 0;   // hint for the next step_host call
+    const void *pf_X = nullptr; int64_t pf_B = 0; bool pf_valid = false; cudaEvent_t ev_pf = nullptr;
     float *pre_h = nullptr, *pre_v = nullptr, *lab_pre = nullptr, *softplus_rows = nullptr;
     float *out_f32 = nullptr;  // fp32 [Bmax][max(ldv, ldh)] API output staging
     float *znoise = nullptr;   // fp32 [Bmax][V] injected reconstruct noise (Gaussian visibles)
@@ -185,23 +189,35 @@ size_t dt_size(int dt) {
 }
 
 // host rows (n x cols of dtype) -> device matrix columns [col0, col0+cols) of dst rows [r0, r0+n)
+void upload_rows_on(qb_handle *h, cudaStream_t st, void *&staging, size_t &staging_bytes, const void *src, int dt, int64_t n,
+                    int64_t cols, Mat &dst, int64_t r0, int64_t col0);
+
 void upload_rows(qb_handle *h, const void *src, int dt, int64_t n, int64_t cols, Mat &dst, int64_t r0, int64_t col0) {
+    upload_rows_on(h, h->stream, h->staging, h->staging_bytes, src, dt, n, cols, dst, r0, col0);
+}
+
+void upload_rows_on(qb_handle *h, cudaStream_t st, void *&staging, size_t &staging_bytes, const void *src, int dt, int64_t n,
+                    int64_t cols, Mat &dst, int64_t r0, int64_t col0) {
     if (n == 0 || cols == 0) return;
     const size_t es = dt_size(dt);
     const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)((64u << 20) / (cols * es)));
     for (int64_t r = 0; r < n; r += chunk_rows) {
         const int64_t nr = std::min(chunk_rows, n - r);
-        ensure_staging(h, (size_t)nr * cols * es);
-        QB_CUDA(cudaMemcpyAsync(h->staging, (const char *)src + (size_t)r * cols * es, (size_t)nr * cols * es,
-                                cudaMemcpyHostToDevice, h->stream));
+        if (staging_bytes < (size_t)nr * cols * es) {
+            cudaFree(staging); staging = nullptr; staging_bytes = 0;
+            QB_CUDA(cudaMalloc(&staging, (size_t)nr * cols * es));
+            staging_bytes = (size_t)nr * cols * es;
+        }
+        QB_CUDA(cudaMemcpyAsync(staging, (const char *)src + (size_t)r * cols * es, (size_t)nr * cols * es,
+                                cudaMemcpyHostToDevice, st));
         float *df = dst.f ? dst.f + (r0 + r) * dst.ld : nullptr;
         bf16 *db = dst.b ? dst.b + (r0 + r) * dst.ld : nullptr;
         const int64_t tot = nr * cols;
         switch (dt) {
-            case QB_DT_F64: convert_rows_kernel<double><<<grid1d(tot), 256, 0, h->stream>>>((const double *)h->staging, cols, nr, df, db, dst.ld, col0); break;
-            case QB_DT_I64: convert_rows_kernel<long long><<<grid1d(tot), 256, 0, h->stream>>>((const long long *)h->staging, cols, nr, df, db, dst.ld, col0); break;
-            case QB_DT_F32: convert_rows_kernel<float><<<grid1d(tot), 256, 0, h->stream>>>((const float *)h->staging, cols, nr, df, db, dst.ld, col0); break;
-            default: convert_rows_kernel<unsigned char><<<grid1d(tot), 256, 0, h->stream>>>((const unsigned char *)h->staging, cols, nr, df, db, dst.ld, col0); break;
+            case QB_DT_F64: convert_rows_kernel<double><<<grid1d(tot), 256, 0, st>>>((const double *)staging, cols, nr, df, db, dst.ld, col0); break;
+            case QB_DT_I64: convert_rows_kernel<long long><<<grid1d(tot), 256, 0, st>>>((const long long *)staging, cols, nr, df, db, dst.ld, col0); break;
+            case QB_DT_F32: convert_rows_kernel<float><<<grid1d(tot), 256, 0, st>>>((const float *)staging, cols, nr, df, db, dst.ld, col0); break;
+            default: convert_rows_kernel<unsigned char><<<grid1d(tot), 256, 0, st>>>((const unsigned char *)staging, cols, nr, df, db, dst.ld, col0); break;
         }
         QB_CUDA(cudaGetLastError());
         h->launches++;
@@ -672,9 +688,33 @@ void batch_view(qb_handle *h, int64_t m, int64_t B, Mat &xb, const bf16 *&xbT, i
 void stage_host_batch(qb_handle *h, const void *X, int xdt, const void *Y, int ydt, int64_t B) {
     QB_CHECK(X != nullptr, QB_E_ARG, "X is NULL");
     QB_CHECK(h->L == 0 || Y != nullptr, QB_E_ARG, "labels required for classifier models");
-    upload_rows(h, X, xdt, B, h->V, h->hb, 0, 0);
-    if (h->L > 0) upload_rows(h, Y, ydt, B, h->L, h->hb, 0, h->V);
-    if (h->bf) transpose_into(h, h->hb.b, h->hb.ld, B, h->VL, h->hb.bT, h->hb.ldT);
+    if (h->pf_valid && h->pf_X == X && h->pf_B == B) {
+        // this batch was uploaded on copy_stream while the previous step was computing
+        QB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pf, 0));
+        std::swap(h->hb, h->hb2);
+    } else {
+        upload_rows(h, X, xdt, B, h->V, h->hb, 0, 0);
+        if (h->L > 0) upload_rows(h, Y, ydt, B, h->L, h->hb, 0, h->V);
+        if (h->bf) transpose_into(h, h->hb.b, h->hb.ld, B, h->VL, h->hb.bT, h->hb.ldT);
+    }
+    h->pf_valid = false;
+    if (h->next_X) {  // qb_set_next_host_batch: start the next upload now, it overlaps this step's kernels
+        if (!h->hb2.b && !h->hb2.f) {
+            h->hb2 = alloc_mat(h, h->Bmax, h->VL, true);
+            QB_CUDA(cudaEventCreateWithFlags(&h->ev_pf, cudaEventDisableTiming));
+        }
+        upload_rows_on(h, h->copy_stream, h->staging2, h->staging2_bytes, h->next_X, h->next_xdt, B, h->V, h->hb2, 0, 0);
+        if (h->L > 0) upload_rows_on(h, h->copy_stream, h->staging2, h->staging2_bytes, h->next_Y, h->next_ydt, B, h->L, h->hb2, 0, h->V);
+        if (h->bf) {
+            dim3 g((unsigned)ceil_div(h->VL, 32), (unsigned)ceil_div(B, 32));
+            transpose_bf16_kernel<<<g, 256, 0, h->copy_stream>>>(h->hb2.b, h->hb2.ld, (int)B, (int)h->VL, h->hb2.bT, h->hb2.ldT);
+            QB_CUDA(cudaGetLastError());
+            h->launches++;
+        }
+        QB_CUDA(cudaEventRecord(h->ev_pf, h->copy_stream));
+        h->pf_X = h->next_X; h->pf_B = B; h->pf_valid = true;
+        h->next_X = nullptr; h->next_Y = nullptr;
+    }
 }
 
 // sum over rows of sum_units (x - reconstruct(x))^2 for rows of `x` (chunked by Bmax), accumulated into dscal[0]
@@ -806,7 +846,8 @@ int32_t qb_destroy(qb_handle *h) {
         if (h->ev_grad) cudaEventDestroy(h->ev_grad);
         if (h->ev_upd) cudaEventDestroy(h->ev_upd);
         free_mat(h->data); cudaFree(h->dataT); cudaFree(h->datasum);
-        free_mat(h->cv); free_mat(h->ch); free_mat(h->phd); free_mat(h->hs); free_mat(h->vm); free_mat(h->phm); free_mat(h->hb);
+        free_mat(h->cv); free_mat(h->ch); free_mat(h->phd); free_mat(h->hs); free_mat(h->vm); free_mat(h->phm); free_mat(h->hb); free_mat(h->hb2);
+        cudaFree(h->staging2); if (h->ev_pf) cudaEventDestroy(h->ev_pf);
         cudaFree(h->pre_h); cudaFree(h->pre_v); cudaFree(h->lab_pre); cudaFree(h->softplus_rows); cudaFree(h->out_f32);
         cudaFree(h->dscal); cudaFree(h->znoise); cudaFree(h->staging); cudaFree(h->injUh); cudaFree(h->injUv); cudaFree(h->injZv);
         for (auto &e : h->ev) cudaEventDestroy(e);
@@ -1034,6 +1075,16 @@ int32_t qb_pcd_step_host(qb_handle *h, const void *X, int32_t x_dtype, const voi
 int32_t qb_cd_step_host(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype, int64_t B, int64_t k,
                         double lr, double llr, double *recon_sq_err) {
     return guarded([&] { QB_H(h); step_host_impl(h, false, X, x_dtype, Y, y_dtype, B, k, lr, llr, recon_sq_err); });
+}
+
+int32_t qb_set_next_host_batch(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype) {
+    return guarded([&] {
+        QB_H_KEEP(h);
+        QB_CHECK(X != nullptr, QB_E_ARG, "X is NULL");
+        QB_CHECK(h->L == 0 || Y != nullptr, QB_E_ARG, "labels required for classifier models");
+        dt_size(x_dtype);
+        h->next_X = X; h->next_Y = Y; h->next_xdt = x_dtype; h->next_ydt = y_dtype;
+    });
 }
 
 int32_t qb_eval_mse(qb_handle *h, const void *X, int32_t x_dtype, int64_t n_rows, const double *Z, double *out) {

@@ -119,9 +119,17 @@ class DeviceRBM:
         check(lib().qb_cd_epoch(self._h, B, k, lr, llr, t if timed else None))
         return tuple(t)
 
-    def step_host(self, method: str, x, y, k: int, lr: float, llr: float = 0.0, want_recon: bool = True) -> float:
+    def step_host(self, method: str, x, y, k: int, lr: float, llr: float = 0.0, want_recon: bool = True,
+                  next_x=None, next_y=None) -> float:
+        """One step on a host mini-batch.  `next_x`/`next_y` (the batch of the following call) are uploaded on a
+        copy stream while this step computes; pass the same arrays as x/y of the next call."""
         X, xdt = as_rows(x, self.V)
         Y, ydt = as_rows(y, self.L) if self.L else (None, 0)
+        if next_x is not None:
+            NX, nxdt = as_rows(next_x, self.V)
+            NY, nydt = as_rows(next_y, self.L) if self.L else (None, 0)
+            check(lib().qb_set_next_host_batch(self._h, ptr(NX), nxdt, ptr(NY), nydt))
+            self._keepalive = (NX, NY)  # borrowed by the library until the consuming call returns
         out = ctypes.c_double(0.0)
         fn = lib().qb_pcd_step_host if method.upper() == "PCD" else lib().qb_cd_step_host
         check(fn(self._h, ptr(X), xdt, ptr(Y), ydt, X.shape[0], k, lr, llr, ctypes.byref(out) if want_recon else None))

@@ -514,3 +514,37 @@ def test_train_classifier_reference_scenario(q, tmp_path):
     assert list(hist) == ["accuracy"] and len(hist["accuracy"]) >= 2
     assert hist["accuracy"][-1] == 1.0   # a single label unit: softmax over one unit is always 1
     assert (tmp_path / "c.csv").read_text().splitlines()[0] == "accuracy"
+
+
+# ------------------------------------------------------------------------------ host-batch (end-to-end) path
+@pytest.mark.parametrize("prec,L", [("fp32", 0), ("bf16", 0), ("bf16", 4)])
+def test_step_host_equals_resident_step_with_and_without_prefetch(q, prec, L):
+    rng = np.random.default_rng(31)
+    V, H, B, k, steps = 72, 40, 24, 2, 4
+    m = make_oracle_model(rng, V, H, L, bf16=(prec == "bf16"))
+    X, Y = _data(rng, steps * B, V, L, False, prec == "bf16")
+    Xu = X.astype(np.uint8)
+    Yu = None if Y is None else Y.astype(np.uint8)
+    results = []
+    for mode in ("resident", "host", "host+prefetch"):
+        rbm = to_host_rbm(q, m)
+        with q.DeviceRBM(rbm, max_batch=B, precision=prec, seed=11) as dev:
+            dev.init_chains(B)
+            if mode == "resident":
+                dev.set_data(Xu, Yu)
+            for t in range(steps):
+                sl = slice(t * B, (t + 1) * B)
+                if mode == "resident":
+                    dev.pcd_step(t, B, k, 0.05, 0.02)
+                else:
+                    nxt = slice((t + 1) * B, (t + 2) * B) if (mode == "host+prefetch" and t + 1 < steps) else None
+                    err = dev.step_host("PCD", Xu[sl], None if Yu is None else Yu[sl], k, 0.05, 0.02,
+                                        next_x=None if nxt is None else Xu[nxt],
+                                        next_y=None if (nxt is None or Yu is None) else Yu[nxt])
+                    assert np.isfinite(err) and err >= 0
+            dev.pull_params()
+            v, h, _ = dev.get_chains()
+            results.append((rbm.W.copy(), v, h))
+    for W, v, h in results[1:]:
+        assert np.array_equal(v, results[0][1]) and np.array_equal(h, results[0][2])
+        assert np.array_equal(W, results[0][0])
