@@ -36,8 +36,10 @@ WORKLOADS = {
     # name: V, H, L, gaussian, global batch, k, algo, n_batches, data density
     "cfg1": dict(V=784, H=500, L=0, gaussian=False, B=100, k=1, algo="CD", nb=600, density=0.1307,
                  desc="Binary RBM 784x500, CD-1, batch 100"),
-    "cfg2": dict(V=784, H=500, L=0, gaussian=False, B=256, k=1, algo="PCD", nb=234, density=0.1307,
-                 desc="Binary RBM 784x500, PCD k=1, batch 256 (chains = batch, reference semantics)"),
+    "cfg2": dict(V=784, H=500, L=0, gaussian=False, B=256, k=1, algo="PCD", nb=234, density=0.1307, chains=1000,
+                 desc="Binary RBM 784x500, PCD with 1000 persistent chains, k=1, batch 256"),
+    "cfg2r": dict(V=784, H=500, L=0, gaussian=False, B=256, k=1, algo="PCD", nb=234, density=0.1307,
+                  desc="Binary RBM 784x500, PCD k=1, batch 256, chains = batch (the reference's own semantics)"),
     "cfg3": dict(V=1024, H=2048, L=0, gaussian=True, B=1024, k=5, algo="CD", nb=64, density=None,
                  desc="Gaussian-Bernoulli RBM 1024x2048, CD-5, batch 1024"),
     "cfg4": dict(V=784, H=1000, L=10, gaussian=False, B=512, k=1, algo="CD", nb=117, density=0.1307,
@@ -141,8 +143,11 @@ def shard_rows(A, B, nb, rank, world):
 
 
 def flops_per_step(w):
-    """(2k+3) * 2 * B * (V+L) * H (de-duplicated forward + 2 gradient contractions)."""
-    return (2 * w["k"] + 3) * 2.0 * w["B"] * (w["V"] + w["L"]) * w["H"]
+    """SURVEY.md section 8(d): (2k+3) * 2 * B * (V+L) * H (de-duplicated forward + 2 gradient contractions);
+    with Nc != B persistent chains the 2k chain half-steps and one gradient product run over Nc rows."""
+    vh = 2.0 * (w["V"] + w["L"]) * w["H"]
+    nc = w.get("chains", w["B"])
+    return (2 * w["k"] + 1) * nc * vh + 2 * w["B"] * vh if w["algo"] == "PCD" else (2 * w["k"] + 3) * w["B"] * vh
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
@@ -160,13 +165,14 @@ def cpu_reference(w, seconds_target, steps, warmup, threads=None):
         m = c_oracle.CModel(W0, np.zeros(V), np.zeros(H), U0, np.zeros(L) if L else None, w["gaussian"])
         X = rng.standard_normal((rows, V)) if w["gaussian"] else (rng.random((rows, V)) < w["density"]).astype(np.float64)
         Y = np.eye(L)[np.arange(rows) % L] if L else None
-        chv, chh = rng.random((rows, V)), rng.random((rows, H))
-        chy = rng.random((rows, L)) if L else None
+        nch = max(1, int(round(rows * w.get("chains", w["B"]) / w["B"])))  # keep the chains : rows ratio of the workload
+        chv, chh = rng.random((nch, V)), rng.random((nch, H))
+        chy = rng.random((nch, L)) if L else None
         ts = []
         for _ in range(n_steps):
             t0 = time.perf_counter()
             if w["algo"] == "PCD":
-                c_oracle.pcd_epoch(m, X, Y, rows, k, 0.01, 0.01, chv, chh, chy, seed=1, threads=threads)
+                c_oracle.pcd_epoch(m, X, Y, rows, k, 0.01, 0.01, chv, chh, chy, seed=1, threads=threads, n_chains=nch)
             else:
                 c_oracle.cd_epoch(m, X, Y, rows, k, 0.01, 0.01, seed=1, threads=threads)
             ts.append(time.perf_counter() - t0)
@@ -213,7 +219,7 @@ def main():
         w["B"] *= world
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = {"workload": f"{args.workload}: {w['desc']}", "V": w["V"], "H": w["H"], "L": w["L"], "global_batch": w["B"],
-           "gibbs_steps": w["k"], "algorithm": w["algo"], "rng": "philox4x32-10",
+           "gibbs_steps": w["k"], "algorithm": w["algo"], "rng": "philox4x32-10", "persistent_chains": w.get("chains", w["B"]) if w["algo"] == "PCD" else None,
            "parallelism": f"dp{world} (rows/chains sharded, NCCL gradient allreduce)" if world > 1 else "single GPU"}
 
     if args.impl == "reference":
@@ -226,7 +232,7 @@ def main():
                 "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["threads"], "kind": "port",
                                  "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gibbs_steps_per_s": r["value"] * w["k"],
+                "gibbs_steps_per_s": r["value"] * w["k"] * (w.get("chains", w["B"]) / w["B"] if w["algo"] == "PCD" else 1.0),
                 "note": "CPU restatement of QARBoM.jl (C, Float64, per-sample GEMV + outer products; Julia not installable here)"}
         emit(line, out_fd)
         return 0
@@ -242,7 +248,7 @@ def main():
     B, k, nb = w["B"], w["k"], w["nb"]
     assert B % world == 0 and (B // world) % 4 == 0
     Bl = B // world
-    X, Y, W0, U0 = make_data(w, 1000 + int(args.workload[3:]))
+    X, Y, W0, U0 = make_data(w, 1000 + int(args.workload[3]))
     Xl, Yl = shard_rows(X, B, nb, rank, world), shard_rows(Y, B, nb, rank, world)
     if w["L"]:
         rbm = (q.GRBMClassifier if w["gaussian"] else q.RBMClassifier)(w["V"], w["H"], w["L"], W=W0, U=U0)
@@ -250,7 +256,8 @@ def main():
             rbm.a[:] = 0; rbm.b[:] = 0; rbm.c[:] = 0
     else:
         rbm = (q.GRBM if w["gaussian"] else q.RBM)(w["V"], w["H"], W=W0)
-    dev = q.DeviceRBM(rbm, max_batch=Bl, precision=args.precision, device=local_rank, rank=rank, world=world, seed=1234)
+    chains_l = w.get("chains", B) // world
+    dev = q.DeviceRBM(rbm, max_batch=max(Bl, chains_l), precision=args.precision, device=local_rank, rank=rank, world=world, seed=1234)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -260,7 +267,7 @@ def main():
     dev.set_data(Xl, Yl)
     pcd = w["algo"] == "PCD"
     if pcd:
-        dev.init_chains(Bl)
+        dev.init_chains(chains_l)
     lr = 0.01
     step = (lambda i: dev.pcd_step(i % nb, Bl, k, lr, lr)) if pcd else (lambda i: dev.cd_step(i % nb, Bl, k, lr, lr))
 
@@ -389,7 +396,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": dict(cfg, l2="inputs cycle over %d resident mini-batches (%.2f GB incl. transposed copies) > 126 MB L2"
                                     % (nb, 2 * nb * Bl * w["V"] * 2 / 1e9)),
-            "gibbs_steps_per_s": value * k, "gpu_launches": launches, "roofline": roof, "roofline_update": roof_upd, "clocks": clocks, "e2e": e2e}
+            "gibbs_steps_per_s": value * k * (w.get("chains", B) / B if pcd else 1.0), "gpu_launches": launches, "roofline": roof, "roofline_update": roof_upd, "clocks": clocks, "e2e": e2e}
     if overlap:
         line["overlap"] = overlap
     if not args.no_cpu_baseline:

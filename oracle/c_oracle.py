@@ -33,7 +33,7 @@ def lib():
         build()
         _lib = ctypes.CDLL(_SO)
         _lib.qo_pcd_epoch.restype = ctypes.c_int
-        _lib.qo_pcd_epoch.argtypes = [_i64, _i64, _i64, ctypes.c_int, _D, _D, _D, _D, _D, _D, _D, _i64, _i64, _i64,
+        _lib.qo_pcd_epoch.argtypes = [_i64, _i64, _i64, ctypes.c_int, _D, _D, _D, _D, _D, _D, _D, _i64, _i64, _i64, _i64,
                                       ctypes.c_double, ctypes.c_double, _D, _D, _D, _D, _i64, _D, _i64,
                                       ctypes.c_uint64, _i64, _i64, ctypes.c_int]
         _lib.qo_cd_epoch.restype = ctypes.c_int
@@ -79,13 +79,13 @@ class CModel:
 
 
 def pcd_epoch(m: CModel, X, Y, B, k, lr, llr, chv, chh, chy, u=None, z=None, seed=0, first_batch=0,
-              n_batches=-1, threads=1) -> int:
+              n_batches=-1, threads=1, n_chains=None) -> int:
     X = np.ascontiguousarray(X, dtype=np.float64)
     Y = None if Y is None else np.ascontiguousarray(Y, dtype=np.float64)
     u = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
     z = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
     return lib().qo_pcd_epoch(m.V, m.H, m.L, m.gaussian, _p(m.Wc), _p(m.a), _p(m.b), _p(m.Uc), _p(m.c), _p(X), _p(Y),
-                              X.shape[0], B, k, lr, llr, _p(chv), _p(chh), _p(chy),
+                              X.shape[0], B, B if n_chains is None else n_chains, k, lr, llr, _p(chv), _p(chh), _p(chy),
                               _p(u), 0 if u is None else u.size, _p(z), 0 if z is None else z.size,
                               seed, first_batch, n_batches, threads)
 

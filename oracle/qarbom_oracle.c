@@ -190,44 +190,75 @@ static void chain_step(const qo_model *m, double *cv, double *ch, double *cy, qo
  * [first_batch, first_batch + n_batches).  Returns 0, or 1 if an injected stream ran dry.
  */
 int qo_pcd_epoch(int64_t V, int64_t H, int64_t L, int gaussian, double *W, double *a, double *b, double *U, double *c,
-                 const double *X, const double *Y, int64_t N, int64_t B, int64_t k, double lr, double llr,
+                 const double *X, const double *Y, int64_t N, int64_t B, int64_t Nc, int64_t k, double lr, double llr,
                  double *chv, double *chh, double *chy, const double *u, int64_t un, const double *z, int64_t zn,
                  uint64_t seed, int64_t first_batch, int64_t n_batches, int threads) {
     qo_model m = {V, H, L, gaussian, W, a, b, U, c, threads < 1 ? 1 : threads};
     qo_stream st; stream_init(&st, u, un, z, zn, seed);
     int64_t nb_total = (N - N % B) / B; /* src/utils.jl:13-26 */
     if (n_batches < 0 || first_batch + n_batches > nb_total) n_batches = nb_total - first_batch;
+    if (Nc <= 0) Nc = B;
+    /* Nc == B: the reference.  Nc != B: declared extension (see qarbom_oracle.py::_pcd_minibatch_more_chains):
+     * dW = (Nc/B) sum_data - sum_chains, applied with lr / Nc. */
+    const double scale = (double)Nc / (double)B;
     double *tmpH = (double *)malloc(sizeof(double) * H), *hd = (double *)malloc(sizeof(double) * H);
+    double *zeroV = (double *)calloc(V > L ? V : L, sizeof(double)), *zeroH = (double *)calloc(H, sizeof(double));
+    double *sx = (double *)malloc(sizeof(double) * (V > L ? V : L));
     for (int64_t mb = first_batch; mb < first_batch + n_batches; mb++) {
         if (L == 0) /* chains first: train_pcd.jl:14-16 */
             for (int64_t s = 0; s < k; s++)
-                for (int64_t i = 0; i < B; i++) chain_step(&m, chv + i * V, chh + i * H, NULL, &st, tmpH);
+                for (int64_t i = 0; i < Nc; i++) chain_step(&m, chv + i * V, chh + i * H, NULL, &st, tmpH);
         double *dW = (double *)calloc(V * H, sizeof(double)), *da = (double *)calloc(V, sizeof(double));
         double *db = (double *)calloc(H, sizeof(double));
         double *dU = L ? (double *)calloc(L * H, sizeof(double)) : NULL, *dc = L ? (double *)calloc(L, sizeof(double)) : NULL;
-        for (int64_t idx = 0; idx < B; idx++) {
-            const double *vd = X + (mb * B + idx) * V;
-            const double *yd = L ? Y + (mb * B + idx) * L : NULL;
-            const double *cv = chv + idx * V, *ch = chh + idx * H, *cy = L ? chy + idx * L : NULL;
-            cond_prob_h(&m, vd, yd, hd);
-            dW = add_new(&m, dW, outer_diff(&m, V, vd, hd, cv, ch), V * H);
-            if (L) dU = add_new(&m, dU, outer_diff(&m, L, yd, hd, cy, ch), L * H);
-            for (int64_t i = 0; i < V; i++) da[i] += vd[i] - cv[i];
-            for (int64_t j = 0; j < H; j++) db[j] += hd[j] - ch[j];
-            for (int64_t l = 0; l < L; l++) dc[l] += yd[l] - cy[l];
+        if (Nc == B) {
+            for (int64_t idx = 0; idx < B; idx++) {
+                const double *vd = X + (mb * B + idx) * V;
+                const double *yd = L ? Y + (mb * B + idx) * L : NULL;
+                const double *cv = chv + idx * V, *ch = chh + idx * H, *cy = L ? chy + idx * L : NULL;
+                cond_prob_h(&m, vd, yd, hd);
+                dW = add_new(&m, dW, outer_diff(&m, V, vd, hd, cv, ch), V * H);
+                if (L) dU = add_new(&m, dU, outer_diff(&m, L, yd, hd, cy, ch), L * H);
+                for (int64_t i = 0; i < V; i++) da[i] += vd[i] - cv[i];
+                for (int64_t j = 0; j < H; j++) db[j] += hd[j] - ch[j];
+                for (int64_t l = 0; l < L; l++) dc[l] += yd[l] - cy[l];
+            }
+        } else {
+            for (int64_t idx = 0; idx < B; idx++) { /* positive statistics, scaled by Nc / B */
+                const double *vd = X + (mb * B + idx) * V;
+                const double *yd = L ? Y + (mb * B + idx) * L : NULL;
+                cond_prob_h(&m, vd, yd, hd);
+                for (int64_t i = 0; i < V; i++) sx[i] = scale * vd[i];
+                dW = add_new(&m, dW, outer_diff(&m, V, sx, hd, zeroV, zeroH), V * H);
+                for (int64_t i = 0; i < V; i++) da[i] += sx[i];
+                for (int64_t j = 0; j < H; j++) db[j] += scale * hd[j];
+                if (L) {
+                    for (int64_t l = 0; l < L; l++) sx[l] = scale * yd[l];
+                    dU = add_new(&m, dU, outer_diff(&m, L, sx, hd, zeroV, zeroH), L * H);
+                    for (int64_t l = 0; l < L; l++) dc[l] += sx[l];
+                }
+            }
+            for (int64_t i2 = 0; i2 < Nc; i2++) { /* negative statistics over all chains */
+                const double *cv = chv + i2 * V, *ch = chh + i2 * H, *cy = L ? chy + i2 * L : NULL;
+                dW = add_new(&m, dW, outer_diff(&m, V, zeroV, zeroH, cv, ch), V * H);
+                if (L) dU = add_new(&m, dU, outer_diff(&m, L, zeroV, zeroH, cy, ch), L * H);
+                for (int64_t i = 0; i < V; i++) da[i] -= cv[i];
+                for (int64_t j = 0; j < H; j++) db[j] -= ch[j];
+                for (int64_t l = 0; l < L; l++) dc[l] -= cy[l];
+            }
         }
         /* update_rbm!(rbm, dW, [dU,] da, db, [dc,] lr/B [, llr/B]): src/rbm.jl:120-136,152-163 */
-        axpy_inplace(&m, W, dW, lr / (double)B, V * H);
-        if (L) axpy_inplace(&m, U, dU, llr / (double)B, L * H);
-        for (int64_t i = 0; i < V; i++) a[i] += da[i] * (lr / (double)B);
-        for (int64_t j = 0; j < H; j++) b[j] += db[j] * (lr / (double)B);
-        for (int64_t l = 0; l < L; l++) c[l] += dc[l] * (llr / (double)B);
+        axpy_inplace(&m, W, dW, lr / (double)Nc, V * H);
+        if (L) axpy_inplace(&m, U, dU, llr / (double)Nc, L * H);
+        for (int64_t i = 0; i < V; i++) a[i] += da[i] * (lr / (double)Nc);
+        for (int64_t j = 0; j < H; j++) b[j] += db[j] * (lr / (double)Nc);
+        for (int64_t l = 0; l < L; l++) c[l] += dc[l] * (llr / (double)Nc);
         free(dW); free(da); free(db); free(dU); free(dc);
         if (L) /* classifier: chains AFTER the update, train_pcd.jl:89-92 */
             for (int64_t s = 0; s < k; s++)
-                for (int64_t i = 0; i < B; i++) chain_step(&m, chv + i * V, chh + i * H, chy + i * L, &st, tmpH);
+                for (int64_t i = 0; i < Nc; i++) chain_step(&m, chv + i * V, chh + i * H, chy + i * L, &st, tmpH);
     }
-    free(tmpH); free(hd);
+    free(tmpH); free(hd); free(zeroV); free(zeroH); free(sx);
     return st.err;
 }
 

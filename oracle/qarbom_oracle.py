@@ -434,6 +434,14 @@ def persistent_contrastive_divergence(m: Model, x: Sequence, mini_batches: List[
     """
     for mb in mini_batches:
         B = len(mb)
+        if len(chains) != B:
+            _pcd_minibatch_more_chains(m, x, mb, chains, steps, learning_rate, stream, y, label_learning_rate, momentum,
+                                       weight_decay, opt)
+            if trace is not None:
+                trace.append(dict(v=np.stack([c.v for c in chains]), h=np.stack([c.h for c in chains]),
+                                  y=None if not m.is_classifier else np.stack([c.y for c in chains]),
+                                  W=m.W.copy(), a=m.a.copy(), b=m.b.copy()))
+            continue
         if not m.is_classifier:
             _update_fantasy_data(m, chains, steps, stream)
         dW = np.zeros_like(m.W)
@@ -462,6 +470,45 @@ def persistent_contrastive_divergence(m: Model, x: Sequence, mini_batches: List[
             trace.append(dict(v=np.stack([c.v for c in chains]), h=np.stack([c.h for c in chains]),
                               y=None if not m.is_classifier else np.stack([c.y for c in chains]),
                               W=m.W.copy(), a=m.a.copy(), b=m.b.copy()))
+
+
+def _pcd_minibatch_more_chains(m, x, mb, chains, steps, learning_rate, stream, y, label_learning_rate, momentum,
+                               weight_decay, opt) -> None:
+    """Declared extension (BASELINE.json config 2: "1000 persistent chains, batch 256"; the reference
+    ties n_chains to batch_size, train_pcd.jl:162): with Nc != B chains, every chain advances k steps per
+    mini-batch and the negative statistics are averaged over ALL chains,
+        dW/lr = (1/B) sum_data x h_d' - (1/Nc) sum_chains v h',
+    implemented as  lr/Nc * ( (Nc/B) sum_data - sum_chains )  so that Nc == B is the reference update."""
+    B, Nc = len(mb), len(chains)
+    clf = m.is_classifier
+    if not clf:
+        _update_fantasy_data(m, chains, steps, stream)
+    scale = Nc / B
+    dW = np.zeros_like(m.W); da = np.zeros_like(m.a); db = np.zeros_like(m.b)
+    dU = np.zeros_like(m.U) if clf else None
+    dc = np.zeros_like(m.c) if clf else None
+    for i in mb:
+        v_data = np.asarray(x[i], dtype=np.float64)
+        if clf:
+            y_data = np.asarray(y[i], dtype=np.float64)
+            h_data = conditional_prob_h(m, v_data, y_data)
+            dU += scale * np.outer(y_data, h_data)
+            dc += scale * y_data
+        else:
+            h_data = conditional_prob_h(m, v_data)
+        dW += scale * np.outer(v_data, h_data)
+        da += scale * v_data
+        db += scale * h_data
+    for ch in chains:
+        dW -= np.outer(ch.v, ch.h)
+        da -= ch.v
+        db -= ch.h
+        if clf:
+            dU -= np.outer(ch.y, ch.h)
+            dc -= ch.y
+    apply_update(m, dW, da, db, learning_rate / Nc, dU, dc, label_learning_rate / Nc, momentum, weight_decay, opt)
+    if clf:
+        _update_fantasy_data(m, chains, steps, stream)
 
 
 # --------------------------------------------------------------------------- evaluation

@@ -290,6 +290,7 @@ struct HiddenOut {
     float *prob_f32 = nullptr; int64_t ld_pf = 0;  // bf16 path only: extra fp32 copy of the probabilities
     int bg_what = 0; float bg_sign = 0.f;          // bf16 path: fold the hidden bias gradient
     float *softplus_rows = nullptr;                // free-energy mode (no other outputs)
+    float pscale = 1.f;                            // positive phase with n_chains != batch: probabilities x (n_chains / batch)
 };
 
 // conditional_prob_h (+ gibbs_sample_hidden): in = visible-side rows [rows][kdim] (kdim = V or V+L)
@@ -323,6 +324,8 @@ void op_hidden(qb_handle *h, const Mat &in, int64_t rows, int64_t kdim, const Hi
     ep.bg_what = o.bg_what; ep.bg_sign = o.bg_sign; ep.bias_grad = G_b(h);
     ep.softplus_rows = o.softplus_rows;
     ep.dbg = h->dbg;
+    ep.pscale = o.pscale;
+    QB_CHECK(o.pscale == 1.f || sm100::pick_kind(ep) == sm100::K_FAST_PROB, QB_E_UNSUPPORTED, "pscale needs the fast probability epilogue");
     GemmScope gs(h, 2.0 * (double)h->H * (double)rows * (double)kdim);
     sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn, h->use_2cta);
 }
@@ -386,7 +389,7 @@ void op_visible(qb_handle *h, const Mat &in, int64_t rows, const VisibleOut &o, 
     ep.inj = rng.inj; ep.ld_inj = rng.ld_inj; ep.key = rng.key; ep.use_rng = rng.use_rng; ep.row0 = row0;
     if (o.bg_sign_neg) { ep.bg_what = 2; ep.bg_sign = -1.f; ep.bias_grad = G_a(h); }
     if (o.sqerr) { ep.sqerr = o.sqerr; ep.ref_rm = o.ref->b; ep.ld_ref = o.ref->ld; }
-    ep.dbg = h->dbg;
+    ep.dbg = h->dbg; ep.pscale = 1.f;
     {
         GemmScope gs(h, 2.0 * (double)h->VL * (double)rows * (double)h->H);
         sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn, h->use_2cta);
@@ -418,33 +421,35 @@ void colsum<bf16>(qb_handle *h, const bf16 *A, int64_t lda, int64_t rows, int64_
 }
 
 // G = posH' posV - negH' negV   (and the bias gradients that were not folded into epilogues)
+// `rows` data rows, `nrows` negative-phase rows (chains); pos_scale = nrows / rows multiplies the positive statistics
+// (on the bf16 path it was already applied to posH by the positive-phase epilogue)
 void op_grad(qb_handle *h, const Mat &posH, const Mat &posV, const bf16 *posV_T, int64_t posV_ldT, const Mat &negH,
-             const Mat &negV, int64_t rows) {
+             const Mat &negV, int64_t rows, int64_t nrows, float pos_scale) {
     if (!h->bf) {
-        simt_gemm(h, posH.f, 1, posH.ld, posV.f, posV.ld, 1, G_W(h), h->ldv, h->H, h->VL, rows, 1.f, 0.f, nullptr);
-        simt_gemm(h, negH.f, 1, negH.ld, negV.f, negV.ld, 1, G_W(h), h->ldv, h->H, h->VL, rows, -1.f, 1.f, nullptr);
-        colsum<float>(h, posV.f, posV.ld, rows, h->VL, 1.f, G_a(h));
-        colsum<float>(h, negV.f, negV.ld, rows, h->VL, -1.f, G_a(h));
-        colsum<float>(h, posH.f, posH.ld, rows, h->H, 1.f, G_b(h));
-        colsum<float>(h, negH.f, negH.ld, rows, h->H, -1.f, G_b(h));
+        simt_gemm(h, posH.f, 1, posH.ld, posV.f, posV.ld, 1, G_W(h), h->ldv, h->H, h->VL, rows, pos_scale, 0.f, nullptr);
+        simt_gemm(h, negH.f, 1, negH.ld, negV.f, negV.ld, 1, G_W(h), h->ldv, h->H, h->VL, nrows, -1.f, 1.f, nullptr);
+        colsum<float>(h, posV.f, posV.ld, rows, h->VL, pos_scale, G_a(h));
+        colsum<float>(h, negV.f, negV.ld, nrows, h->VL, -1.f, G_a(h));
+        colsum<float>(h, posH.f, posH.ld, rows, h->H, pos_scale, G_b(h));
+        colsum<float>(h, negH.f, negH.ld, nrows, h->H, -1.f, G_b(h));
         return;
     }
     sm100::Operand A{posH.bT, h->H, rows, posH.ldT}, B{posV_T, h->VL, rows, posV_ldT};
-    sm100::Operand A2{negH.bT, h->H, rows, negH.ldT}, B2{negV.bT, h->VL, rows, negV.ldT};
+    sm100::Operand A2{negH.bT, h->H, nrows, negH.ldT}, B2{negV.bT, h->VL, nrows, negV.ldT};
     sm100::EpiParams ep{};
     ep.mode = sm100::EPI_GRAD; ep.M = (int)h->H; ep.N = (int)h->VL;
     ep.out_f32 = G_W(h); ep.ld_out = h->ldv;
     {
-        GemmScope gs(h, 4.0 * (double)h->H * (double)h->VL * (double)rows);
+        GemmScope gs(h, 2.0 * (double)h->H * (double)h->VL * (double)(rows + nrows));
         sm100::launch(h->stream, A, B, &A2, &B2, ep, h->num_sms, h->force_bn, h->use_2cta);
     }
-    if (!h->cur_datasum) colsum<bf16>(h, posV.b, posV.ld, rows, h->VL, 1.f, G_a(h));  // data-side visible sums; the rest is folded
+    if (!h->cur_datasum) colsum<bf16>(h, posV.b, posV.ld, rows, h->VL, pos_scale, G_a(h));  // data-side visible sums; the rest is folded
 }
 
 // bias-gradient accumulators start at the data-side visible sums when those are cached
-void zero_bias_grads(qb_handle *h) {
+void zero_bias_grads(qb_handle *h, float pos_scale = 1.f) {
     const int n = (int)(h->ldv + h->ldh);
-    init_bias_grads_kernel<<<grid1d(n), 256, 0, h->stream>>>(G_a(h), h->bf ? h->cur_datasum : nullptr, (int)h->ldv, n);
+    init_bias_grads_kernel<<<grid1d(n), 256, 0, h->stream>>>(G_a(h), h->bf ? h->cur_datasum : nullptr, pos_scale, (int)h->ldv, n);
     QB_CUDA(cudaGetLastError());
     h->launches++;
 }
@@ -567,7 +572,7 @@ void check_step_args(qb_handle *h, int64_t B, int64_t k) {
     QB_CHECK(B >= 1 && B <= h->Bmax, QB_E_ARG, "batch rows must be in [1, max_batch]");
     QB_CHECK(k >= 1, QB_E_ARG, "gibbs steps must be >= 1");
     QB_CHECK(h->cfg.world == 1 || (B % 4) == 0, QB_E_ARG, "multi-GPU requires local batch rows % 4 == 0");
-    if (h->inj_active) QB_CHECK(h->inj_k >= k && h->inj_B == B, QB_E_ARG, "injected streams do not match (k, B) of the step");
+    if (h->inj_active) QB_CHECK(h->inj_k >= k, QB_E_ARG, "injected streams hold fewer Gibbs steps than the step needs");
 }
 
 // k Gibbs steps on the persistent chains (_update_fantasy_data!, src/fantasy_data.jl:12-29)
@@ -594,17 +599,20 @@ void fold_chain_bias_explicit(qb_handle *h, int64_t B) {
 
 // stale-chains variant of the PCD step (see qb_handle::stale_chains)
 void pcd_step_stale(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr) {
-    StepRng sr{h, B, h->inj_active};
+    const int64_t Nc = h->n_chains;
+    const float ps = (float)((double)Nc / (double)B);
+    QB_CHECK(!h->inj_active || h->inj_B == Nc, QB_E_ARG, "injected streams must have one row per chain");
+    StepRng sr{h, Nc, h->inj_active};
     const int64_t row0 = row0_of(h, B);
-    zero_bias_grads(h);
-    advance_chains(h, B, k, sr, true);  // previous weight version; overlaps the in-flight allreduce + update
-    adopt_pending_update(h);            // from here on: the latest weights
-    HiddenOut ho; ho.prob = &h->phd; ho.prob_T = true; ho.bg_what = 1; ho.bg_sign = 1.f;
+    zero_bias_grads(h, ps);
+    advance_chains(h, Nc, k, sr, true);  // previous weight version; overlaps the in-flight allreduce + update
+    adopt_pending_update(h);             // from here on: the latest weights
+    HiddenOut ho; ho.prob = &h->phd; ho.prob_T = true; ho.bg_what = 1; ho.bg_sign = 1.f; ho.pscale = ps;
     op_hidden(h, xb, B, h->VL, ho, Rng(), row0);
-    op_grad(h, h->phd, xb, xbT, xb_ldT, h->ch, h->cv, B);
+    op_grad(h, h->phd, xb, xbT, xb_ldT, h->ch, h->cv, B, Nc, ps);
     QB_CUDA(cudaEventRecord(h->ev_grad, h->stream));
     QB_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_grad, 0));
-    op_update_on(h, lr, llr, B, h->comm_stream, h->G, h->Wb_alt, h->WbT_alt, h->bias_buf[h->bias_cur ^ 1]);
+    op_update_on(h, lr, llr, Nc, h->comm_stream, h->G, h->Wb_alt, h->WbT_alt, h->bias_buf[h->bias_cur ^ 1]);
     QB_CUDA(cudaEventRecord(h->ev_upd, h->comm_stream));
     h->pending_update = true;
     std::swap(h->G, h->G_alt);  // the next step accumulates into the other gradient buffer
@@ -613,37 +621,44 @@ void pcd_step_stale(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT
 
 void pcd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr,
                    cudaEvent_t *ev) {
-    QB_CHECK(h->n_chains >= B, QB_E_STATE, "qb_init_chains must provide at least B chains");
+    QB_CHECK(h->n_chains >= 1, QB_E_STATE, "qb_init_chains has not been called");
     if (h->stale_chains) { pcd_step_stale(h, xb, xbT, xb_ldT, B, k, lr, llr); return; }
-    StepRng sr{h, B, h->inj_active};
+    // Nc chains; Nc == B is the reference (train_pcd.jl:162).  Nc != B (declared extension): all chains advance,
+    // negative statistics are averaged over all of them: G = (Nc/B) sum_data - sum_chains, applied with lr / Nc.
+    const int64_t Nc = h->n_chains;
+    const float ps = (float)((double)Nc / (double)B);
+    QB_CHECK(!h->inj_active || h->inj_B == Nc, QB_E_ARG, "injected streams must have one row per chain");
+    QB_CHECK(h->cfg.world == 1 || (Nc % 4) == 0, QB_E_ARG, "multi-GPU requires local chains % 4 == 0");
+    StepRng sr{h, Nc, h->inj_active};
     const int64_t row0 = row0_of(h, B);
-    zero_bias_grads(h);
+    zero_bias_grads(h, ps);
     const bool clf = h->L > 0;
     if (ev) QB_CUDA(cudaEventRecord(ev[0], h->stream));
-    if (!clf) advance_chains(h, B, k, sr, h->bf);  // chains FIRST: train_pcd.jl:14-16
+    if (!clf) advance_chains(h, Nc, k, sr, h->bf);  // chains FIRST: train_pcd.jl:14-16
     else if (h->bf) {
         // classifier: gradient uses the chains as they are (train_pcd.jl:57-86); their transposes and
         // column sums come from the previous step's epilogues, except before the very first update
         if (!h->chains_binary) {
-            transpose_into(h, h->cv.b, h->cv.ld, B, h->VL, h->cv.bT, h->cv.ldT);
-            transpose_into(h, h->ch.b, h->ch.ld, B, h->H, h->ch.bT, h->ch.ldT);
+            transpose_into(h, h->cv.b, h->cv.ld, Nc, h->VL, h->cv.bT, h->cv.ldT);
+            transpose_into(h, h->ch.b, h->ch.ld, Nc, h->H, h->ch.bT, h->ch.ldT);
         }
-        fold_chain_bias_explicit(h, B);
+        fold_chain_bias_explicit(h, Nc);
     }
     if (ev) QB_CUDA(cudaEventRecord(ev[1], h->stream));
-    HiddenOut ho; ho.prob = &h->phd; ho.prob_T = true; ho.bg_what = 1; ho.bg_sign = 1.f;  // conditional_prob_h(v_data[, y_data])
+    HiddenOut ho; ho.prob = &h->phd; ho.prob_T = true; ho.bg_what = 1; ho.bg_sign = 1.f; ho.pscale = ps;  // conditional_prob_h(v_data[, y_data])
     op_hidden(h, xb, B, h->VL, ho, Rng(), row0);
     if (ev) QB_CUDA(cudaEventRecord(ev[2], h->stream));
-    op_grad(h, h->phd, xb, xbT, xb_ldT, h->ch, h->cv, B);
-    op_update(h, lr, llr, B);
+    op_grad(h, h->phd, xb, xbT, xb_ldT, h->ch, h->cv, B, Nc, ps);
+    op_update(h, lr, llr, Nc);
     if (ev) QB_CUDA(cudaEventRecord(ev[3], h->stream));
-    if (clf) advance_chains(h, B, k, sr, false);  // classifier: chains AFTER the update, train_pcd.jl:89-92
+    if (clf) advance_chains(h, Nc, k, sr, false);  // classifier: chains AFTER the update, train_pcd.jl:89-92
     if (ev) QB_CUDA(cudaEventRecord(ev[4], h->stream));
     h->inj_active = false;
 }
 
 void cd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr,
                   cudaEvent_t *ev) {
+    QB_CHECK(!h->inj_active || h->inj_B == B, QB_E_ARG, "injected streams must have one row per mini-batch row");
     StepRng sr{h, B, h->inj_active};
     const int64_t row0 = row0_of(h, B);
     zero_bias_grads(h);
@@ -665,7 +680,7 @@ void cd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, 
     HiddenOut hm; hm.prob = &h->phm; hm.prob_T = true; hm.bg_what = 1; hm.bg_sign = -1.f;
     op_hidden(h, h->vm, B, h->V, hm, Rng(), row0);
     if (ev) QB_CUDA(cudaEventRecord(ev[2], h->stream));
-    op_grad(h, h->phd, xb, xbT, xb_ldT, h->phm, h->vm, B);
+    op_grad(h, h->phd, xb, xbT, xb_ldT, h->phm, h->vm, B, B, 1.f);
     op_update(h, lr, llr, B);
     if (ev) QB_CUDA(cudaEventRecord(ev[3], h->stream));
     h->inj_active = false;
@@ -1219,7 +1234,7 @@ int32_t qb_conditional_prob_y_given_v(qb_handle *h, const void *X, int32_t x_dty
                 sm100::Operand A{h->WbT + h->V * h->ldh, h->L, h->H, h->ldh}, B{h->phd.b, nr, h->H, h->phd.ld};
                 sm100::EpiParams ep{};
                 ep.mode = sm100::EPI_SAMPLE; ep.M = (int)h->L; ep.N = (int)nr; ep.bias = bias_a(h) + h->V;
-                ep.act = sm100::ACT_SIGMOID; ep.sample = 0; ep.split = 0; ep.lab_pre = h->lab_pre; ep.ld_lab = h->L;
+                ep.act = sm100::ACT_SIGMOID; ep.sample = 0; ep.split = 0; ep.lab_pre = h->lab_pre; ep.ld_lab = h->L; ep.pscale = 1.f;
                 GemmScope gs(h, 2.0 * (double)h->L * (double)nr * (double)h->H);
                 sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn, 0);
             } else {

@@ -292,9 +292,10 @@ __global__ void update_bias_kernel(float *__restrict__ P, const float *__restric
 }
 
 // start of a step: G_a = cached data-side visible sums (or 0), G_b = 0 -- one launch instead of memcpy + memset
-__global__ void init_bias_grads_kernel(float *__restrict__ Ga, const float *__restrict__ datasum, int n_vis, int n_total) {
+__global__ void init_bias_grads_kernel(float *__restrict__ Ga, const float *__restrict__ datasum, float scale, int n_vis,
+                                       int n_total) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_total) Ga[i] = (datasum && i < n_vis) ? datasum[i] : 0.f;
+    if (i < n_total) Ga[i] = (datasum && i < n_vis) ? scale * datasum[i] : 0.f;
 }
 
 // refresh both bf16 shadows from fp32 W (after qb_set_params)

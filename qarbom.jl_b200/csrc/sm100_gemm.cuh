@@ -68,6 +68,7 @@ struct EpiParams {
     float *softplus_rows;
     // ---- EPI_GRAD
     float *out_f32; long long ld_out;
+    float pscale;  // probabilities are multiplied by this before being stored / summed (n_chains / batch; 1 normally)
     int dbg;  // experiment switches (0 in production): 1 = skip row-major stores, 2 = skip Philox, 4 = skip sigmoid
 };
 
@@ -353,8 +354,9 @@ __device__ __forceinline__ void fast_chunk(const EpiParams &ep, const uint32_t (
             const int j = 4 * g + jj;
             const float p = sigmoid_mufu(__uint_as_float(r[j]) + bias);
             if (PROB) {
-                if (FULL || j < nv) bg_p += p;
-                pb[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(p));
+                const float ps = p * ep.pscale;
+                if (FULL || j < nv) bg_p += ps;
+                pb[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(ps));
             }
             if (SAMPLE) {
                 const bool on = u23(rnd[jj]) < p;

@@ -69,6 +69,7 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
           stopping_metric=None, x_test_dataset=None, y_test_dataset=None, file_path: Optional[str] = None,
           # ---- extensions (defaults reproduce the reference)
           momentum: float = 0.0, weight_decay: float = 0.0, precision: str = "bf16", seed: int = 0, device: int = 0,
+          n_chains: Optional[int] = None,
           verbose: bool = True, chains_init=None) -> dict:
     is_pcd = method is PCD or isinstance(method, PCD)
     clf = rbm.n_classifiers > 0
@@ -96,7 +97,8 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
 
     names = {MeanSquaredError: "mse", FreeEnergy: "free_energy", Accuracy: "accuracy"}
     keys = [names[m] for m in metrics]
-    dev = DeviceRBM(rbm, max_batch=max(B, min(n, 4096)), precision=precision, device=device, seed=seed)
+    nc = B if n_chains is None else int(n_chains)                  # reference: n_chains == batch_size (train_pcd.jl:162)
+    dev = DeviceRBM(rbm, max_batch=max(B, nc, min(n, 4096)), precision=precision, device=device, seed=seed)
     try:
         dev.set_optimizer(momentum, weight_decay)
         dev.set_data(x_train, label_train)
@@ -124,9 +126,9 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
             if verbose:
                 print("Setting mini-batches")
             if chains_init is not None:
-                dev.init_chains(B, *chains_init)
+                dev.init_chains(nc, *chains_init)
             else:
-                dev.init_chains(B)                                        # _init_fantasy_data(rbm, batch_size)
+                dev.init_chains(nc)                                        # _init_fantasy_data(rbm, batch_size)
             if verbose:
                 print("Starting training")
         stop_key = names.get(stopping_metric, keys[0])

@@ -295,3 +295,39 @@ def test_reference_scenario_learns_100(method):
     rec = qo.reconstruct(m, np.array([1, 0, 0]))
     assert rec[0] > 0.5 > max(rec[1], rec[2])
     assert hist["mse"][-1] <= hist["mse"][0]
+
+
+def test_more_chains_extension_reduces_to_reference_when_equal():
+    """The n_chains != batch formula, evaluated at n_chains == batch, is the reference update."""
+    rng = np.random.default_rng(41)
+    V, H, B, k = 10, 6, 4, 1
+    m1 = small_model(rng, V, H)
+    m2 = qo.copy_rbm(m1)
+    X = rng.integers(0, 2, (B, V)).astype(np.float64)
+    u = u24(rng, B * (V + H) + k * B * (V + H))
+    s1, s2 = qo.Stream(uniforms=u), qo.Stream(uniforms=u)
+    c1, c2 = qo._init_fantasy_data(m1, B, s1), qo._init_fantasy_data(m2, B, s2)
+    qo.persistent_contrastive_divergence(m1, X, [range(0, B)], c1, steps=k, learning_rate=0.1, stream=s1)
+    qo._pcd_minibatch_more_chains(m2, X, range(0, B), c2, k, 0.1, s2, None, 0.1, 0.0, 0.0, None)
+    assert np.allclose(m1.W, m2.W, rtol=0, atol=1e-14) and np.allclose(m1.a, m2.a, atol=1e-14)
+    assert np.allclose(m1.b, m2.b, atol=1e-14)
+
+
+@pytest.mark.parametrize("L", [0, 2])
+def test_more_chains_extension_numpy_and_c_agree(L):
+    rng = np.random.default_rng(43 + L)
+    V, H, B, Nc, k, nb = 9, 6, 4, 10, 2, 2
+    m = small_model(rng, V, H, L)
+    X = rng.integers(0, 2, (nb * B, V)).astype(np.float64)
+    Y = np.eye(L)[rng.integers(0, L, nb * B)] if L else None
+    u = u24(rng, Nc * (V + H + L) + nb * k * Nc * (V + H + L))
+    st = qo.Stream(uniforms=u)
+    chains = qo._init_fantasy_data(m, Nc, st)
+    chv = np.stack([c.v for c in chains]).copy(); chh = np.stack([c.h for c in chains]).copy()
+    chy = np.stack([c.y for c in chains]).copy() if L else None
+    cm = c_oracle.CModel(m.W, m.a, m.b, m.U, m.c)
+    qo.persistent_contrastive_divergence(m, X, qo._set_mini_batches(len(X), B), chains, steps=k, learning_rate=0.1,
+                                         stream=st, y=Y, label_learning_rate=0.05)
+    assert c_oracle.pcd_epoch(cm, X, Y, B, k, 0.1, 0.05, chv, chh, chy, u=u[Nc * (V + H + L):], n_chains=Nc) == 0
+    assert np.allclose(cm.W, m.W, rtol=0, atol=1e-13) and np.allclose(cm.b, m.b, atol=1e-13)
+    assert np.array_equal(chv, np.stack([c.v for c in chains]))
