@@ -111,7 +111,12 @@ int32_t qb_inject_streams(qb_handle *h, const double *U_h, const double *U_v, co
                           int64_t k, int64_t B);
 
 /* One mini-batch of persistent_contrastive_divergence! (src/training/train_pcd.jl:11-40;
- * classifier :57-92) on resident mini-batch `batch_index` with B local rows. */
+ * classifier :57-92) on resident mini-batch `batch_index` with B local rows.
+ * The number of chains is whatever qb_init_chains set: == B is the reference; != B is a declared
+ * extension (all chains advance, negative statistics are averaged over all of them).
+ * k == 0 leaves the chains untouched and uses them as externally supplied negative samples: with
+ * qb_init_chains(1, v_model, h_model, y_model) this is one mini-batch of persistent_qubo!
+ * (src/training/train_quantum_pcd.jl:10-37, :55-83) -- the sampler call itself stays in Julia. */
 int32_t qb_pcd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, double lr, double llr);
 /* One mini-batch of contrastive_divergence! (src/training/train_cd.jl:4-19, :25-41).
  * B == 1 is the reference (online); B > 1 is the declared mini-batch extension. */

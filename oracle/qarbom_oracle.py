@@ -511,6 +511,31 @@ def _pcd_minibatch_more_chains(m, x, mb, chains, steps, learning_rate, stream, y
         _update_fantasy_data(m, chains, steps, stream)
 
 
+def persistent_qubo_minibatch(m: Model, x: Sequence, mb: range, v_model, h_model, *, learning_rate: float,
+                              y: Optional[Sequence] = None, y_model=None, label_learning_rate: float = 0.1) -> None:
+    """One mini-batch of `persistent_qubo!` (src/training/train_quantum_pcd.jl:10-37, classifier :55-83)
+    with the sampler's output (v_model, h_model[, label_model]) injected: every sample of the batch is
+    paired with the SAME model sample; update with lr / B."""
+    B = len(mb)
+    v_model = np.asarray(v_model, dtype=np.float64); h_model = np.asarray(h_model, dtype=np.float64)
+    dW = np.zeros_like(m.W); da = np.zeros_like(m.a); db = np.zeros_like(m.b)
+    dU = np.zeros_like(m.U) if m.is_classifier else None
+    dc = np.zeros_like(m.c) if m.is_classifier else None
+    for i in mb:
+        v_data = np.asarray(x[i], dtype=np.float64)
+        if m.is_classifier:
+            y_data = np.asarray(y[i], dtype=np.float64)
+            h_data = conditional_prob_h(m, v_data, y_data)
+            dU += np.outer(y_data, h_data) - np.outer(y_model, h_model)
+            dc += y_data - np.asarray(y_model, dtype=np.float64)
+        else:
+            h_data = conditional_prob_h(m, v_data)
+        dW += np.outer(v_data, h_data) - np.outer(v_model, h_model)
+        da += v_data - v_model
+        db += h_data - h_model
+    apply_update(m, dW, da, db, learning_rate / B, dU, dc, label_learning_rate / B)
+
+
 # --------------------------------------------------------------------------- evaluation
 def evaluate_mse(m: Model, x_dataset: Sequence, stream: Optional[Stream] = None) -> float:
     """`_evaluate(MeanSquaredError)` through `evaluate` (src/evaluation.jl:16-20,52-70):

@@ -568,9 +568,9 @@ struct StepRng {  // per Gibbs step s: hidden uniforms, visible uniforms / norma
     }
 };
 
-void check_step_args(qb_handle *h, int64_t B, int64_t k) {
+void check_step_args(qb_handle *h, int64_t B, int64_t k, bool allow_k0 = false) {
     QB_CHECK(B >= 1 && B <= h->Bmax, QB_E_ARG, "batch rows must be in [1, max_batch]");
-    QB_CHECK(k >= 1, QB_E_ARG, "gibbs steps must be >= 1");
+    QB_CHECK(k >= (allow_k0 ? 0 : 1), QB_E_ARG, "gibbs steps must be >= 1 (>= 0 for qb_pcd_step: externally supplied negative samples)");
     QB_CHECK(h->cfg.world == 1 || (B % 4) == 0, QB_E_ARG, "multi-GPU requires local batch rows % 4 == 0");
     if (h->inj_active) QB_CHECK(h->inj_k >= k, QB_E_ARG, "injected streams hold fewer Gibbs steps than the step needs");
 }
@@ -634,11 +634,12 @@ void pcd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT,
     zero_bias_grads(h, ps);
     const bool clf = h->L > 0;
     if (ev) QB_CUDA(cudaEventRecord(ev[0], h->stream));
-    if (!clf) advance_chains(h, Nc, k, sr, h->bf);  // chains FIRST: train_pcd.jl:14-16
+    if (!clf && k > 0) advance_chains(h, Nc, k, sr, h->bf);  // chains FIRST: train_pcd.jl:14-16
     else if (h->bf) {
         // classifier: gradient uses the chains as they are (train_pcd.jl:57-86); their transposes and
-        // column sums come from the previous step's epilogues, except before the very first update
-        if (!h->chains_binary) {
+        // column sums come from the previous step's epilogues, except before the very first update.
+        // k == 0: the negative samples were supplied by the caller (persistent_qubo!, train_quantum_pcd.jl:10-37)
+        if (!h->chains_binary || k == 0) {
             transpose_into(h, h->cv.b, h->cv.ld, Nc, h->VL, h->cv.bT, h->cv.ldT);
             transpose_into(h, h->ch.b, h->ch.ld, Nc, h->H, h->ch.bT, h->ch.ldT);
         }
@@ -651,7 +652,7 @@ void pcd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT,
     op_grad(h, h->phd, xb, xbT, xb_ldT, h->ch, h->cv, B, Nc, ps);
     op_update(h, lr, llr, Nc);
     if (ev) QB_CUDA(cudaEventRecord(ev[3], h->stream));
-    if (clf) advance_chains(h, Nc, k, sr, false);  // classifier: chains AFTER the update, train_pcd.jl:89-92
+    if (clf && k > 0) advance_chains(h, Nc, k, sr, false);  // classifier: chains AFTER the update, train_pcd.jl:89-92
     if (ev) QB_CUDA(cudaEventRecord(ev[4], h->stream));
     h->inj_active = false;
 }
@@ -1011,7 +1012,7 @@ int32_t qb_inject_streams(qb_handle *h, const double *U_h, const double *U_v, co
 int32_t qb_pcd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, double lr, double llr) {
     return guarded([&] {
         QB_H_KEEP(h);
-        check_step_args(h, B, k);
+        check_step_args(h, B, k, /*allow_k0=*/!h->stale_chains);
         Mat xb; const bf16 *xbT; int64_t ldT;
         batch_view(h, batch_index, B, xb, xbT, ldT);
         pcd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, nullptr);

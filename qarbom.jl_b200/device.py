@@ -106,6 +106,14 @@ class DeviceRBM:
     def pcd_step(self, batch_index: int, B: int, k: int, lr: float, llr: float = 0.0):
         check(lib().qb_pcd_step(self._h, batch_index, B, k, lr, llr))
 
+    def qsampling_step(self, batch_index: int, B: int, v_model, h_model, lr: float, y_model=None, llr: float = 0.0):
+        """One mini-batch of persistent_qubo! (src/training/train_quantum_pcd.jl:10-37) with the sampler's
+        (v_model, h_model[, label_model]) supplied by the caller: positive phase, gradient and update on the GPU."""
+        self.init_chains(1, np.asarray(v_model, dtype=np.float64).reshape(1, -1),
+                         np.asarray(h_model, dtype=np.float64).reshape(1, -1),
+                         None if y_model is None else np.asarray(y_model, dtype=np.float64).reshape(1, -1))
+        check(lib().qb_pcd_step(self._h, batch_index, B, 0, lr, llr))
+
     def cd_step(self, batch_index: int, B: int, k: int, lr: float, llr: float = 0.0):
         check(lib().qb_cd_step(self._h, batch_index, B, k, lr, llr))
 

@@ -600,3 +600,37 @@ def test_pcd_with_n_chains_different_from_batch(q, prec, V, H, L, B, Nc):
             else:
                 assert rel_err(dev.rbm.W, m.W) < 1e-5 and np.max(np.abs(dev.rbm.a - m.a)) < 1e-6
                 assert np.max(np.abs(dev.rbm.b - m.b)) < 1e-6
+
+
+# ------------------------------------------------------------------------------ quantum-trainer positive phase
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("L", [0, 3])
+def test_persistent_qubo_minibatch_with_supplied_model_sample(q, prec, L):
+    """persistent_qubo! pairs every sample of the mini-batch with ONE (v~, h~) pair returned by the
+    annealer; here the pair is supplied by the caller and everything else runs on the GPU."""
+    bf = prec == "bf16"
+    rng = np.random.default_rng(61 + L)
+    V, H, B, steps = 48, 28, 12, 3
+    m = make_oracle_model(rng, V, H, L, bf16=bf)
+    X, Y = _data(rng, steps * B, V, L, False, bf)
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=B, precision=prec) as dev:
+        dev.set_data(X, Y)
+        Wprev = m.W.copy()
+        for t in range(steps):
+            v_m = rng.integers(0, 2, V).astype(np.float64)
+            h_m = rng.integers(0, 2, H).astype(np.float64)
+            y_m = rng.integers(0, 2, L).astype(np.float64) if L else None
+            W0 = m.W.copy()
+            qo.persistent_qubo_minibatch(m, X, range(t * B, (t + 1) * B), v_m, h_m, learning_rate=0.05, y=Y, y_model=y_m,
+                                         label_learning_rate=0.02)
+            dev.qsampling_step(t, B, v_m, h_m, 0.05, y_m, 0.02)
+            dev.pull_params()
+            if bf:
+                assert rel_err(dev.rbm.W - Wprev, m.W - W0) < 2e-2
+                Wprev = dev.rbm.W.copy()
+                _resync(m, dev, prec)
+            else:
+                assert rel_err(dev.rbm.W, m.W) < 1e-5 and np.max(np.abs(dev.rbm.a - m.a)) < 1e-6
+                assert np.max(np.abs(dev.rbm.b - m.b)) < 1e-6
+                if L:
+                    assert rel_err(dev.rbm.U, m.U) < 1e-5 and np.max(np.abs(dev.rbm.c - m.c)) < 1e-6
