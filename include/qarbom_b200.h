@@ -82,6 +82,12 @@ int32_t qb_destroy(qb_handle *h);
 int32_t qb_set_params(qb_handle *h, const double *W, const double *a, const double *b, const double *U, const double *c);
 int32_t qb_get_params(qb_handle *h, double *W, double *a, double *b, double *U, double *c);
 
+/* best_rbm = copy_rbm(rbm) / copy_rbm!(rbm, best_rbm) and the final copy_rbm!(best_rbm, rbm)
+ * (src/rbm.jl:231-255; src/training/train_cd.jl:60,99-102,109-111) kept in HBM: the epoch loop snapshots
+ * and restores without moving the parameters to the host. */
+int32_t qb_snapshot_params(qb_handle *h);
+int32_t qb_restore_params(qb_handle *h);
+
 /* Extension (absent from update_rbm!, src/rbm.jl:152-163): both default to 0, which
  * reproduces the reference update exactly. */
 int32_t qb_set_optimizer(qb_handle *h, double momentum, double weight_decay);

@@ -86,6 +86,7 @@ struct qb_handle {
     cudaEvent_t ev[8] = {};
     // flat parameter / gradient / velocity vectors: [W (H x ldv) | acat (ldv) | b (ldh)]
     float *P = nullptr, *G = nullptr, *Vel = nullptr;
+    float *P_best = nullptr;  // device-side best-model snapshot (copy_rbm / copy_rbm! without a host round trip)
     int64_t nW = 0, nP = 0;
     bf16 *Wb = nullptr, *WbT = nullptr;
     double momentum = 0.0, weight_decay = 0.0;
@@ -856,7 +857,7 @@ int32_t qb_destroy(qb_handle *h) {
         cudaSetDevice(h->cfg.device);
         cudaDeviceSynchronize();
         if (h->comm) nccl().CommDestroy(h->comm);
-        cudaFree(h->P); cudaFree(h->G); cudaFree(h->Vel); cudaFree(h->Wb); cudaFree(h->WbT);
+        cudaFree(h->P); cudaFree(h->G); cudaFree(h->Vel); cudaFree(h->P_best); cudaFree(h->Wb); cudaFree(h->WbT);
         cudaFree(h->Wb_alt); cudaFree(h->WbT_alt); cudaFree(h->G_alt); cudaFree(h->bias_buf[0]); cudaFree(h->bias_buf[1]);
         if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
         if (h->ev_grad) cudaEventDestroy(h->ev_grad);
@@ -910,6 +911,27 @@ int32_t qb_get_params(qb_handle *h, double *W, double *a, double *b, double *U, 
         if (a) for (int64_t i = 0; i < h->V; i++) a[i] = (double)p[h->nW + i];
         if (c) for (int64_t l = 0; l < h->L; l++) c[l] = (double)p[h->nW + h->V + l];
         if (b) for (int64_t j = 0; j < h->H; j++) b[j] = (double)p[h->nW + h->ldv + j];
+    });
+}
+
+// best_rbm = copy_rbm(rbm) / copy_rbm!(rbm, best_rbm) (src/training/train_cd.jl:60,99-102) kept in HBM
+int32_t qb_snapshot_params(qb_handle *h) {
+    return guarded([&] {
+        QB_H(h);
+        if (!h->P_best) h->P_best = dalloc<float>(h->nP);
+        QB_CUDA(cudaMemcpyAsync(h->P_best, h->P, h->nP * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        QB_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+// copy_rbm!(best_rbm, rbm) (src/training/train_cd.jl:109-111)
+int32_t qb_restore_params(qb_handle *h) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(h->P_best != nullptr, QB_E_STATE, "qb_snapshot_params has not been called");
+        QB_CUDA(cudaMemcpyAsync(h->P, h->P_best, h->nP * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        refresh_shadows(h);
+        if (h->bias_rd) QB_CUDA(cudaMemcpyAsync(h->bias_rd, acat(h), (h->ldv + h->ldh) * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        QB_CUDA(cudaStreamSynchronize(h->stream));
     });
 }
 

@@ -64,6 +64,14 @@ class DeviceRBM:
             r.U[...] = U
             r.c[...] = c
 
+    def snapshot_params(self):
+        """best_rbm = copy_rbm(rbm), on the device."""
+        check(lib().qb_snapshot_params(self._h))
+
+    def restore_params(self):
+        """copy_rbm!(best_rbm, rbm), on the device."""
+        check(lib().qb_restore_params(self._h))
+
     def set_optimizer(self, momentum: float = 0.0, weight_decay: float = 0.0):
         check(lib().qb_set_optimizer(self._h, momentum, weight_decay))
 

@@ -117,7 +117,7 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
                     out[names[m]] = dev.eval_free_energy(xs)
             return out
 
-        best = copy_rbm(rbm)
+        dev.snapshot_params()                                             # best_rbm = copy_rbm(rbm), kept in HBM
         initial = evaluate()                                              # initial_evaluation
         hist = {k: [] for k in keys}
         initial_patience = patience
@@ -152,16 +152,14 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
             else:
                 patience = initial_patience
                 if store_best_rbm:
-                    dev.pull_params()
-                    best = copy_rbm(rbm)
+                    dev.snapshot_params()                                 # copy_rbm!(rbm, best_rbm)
             if verbose:
                 _log_epoch(epoch, t[0], t[1], t[2], sum(tot))
                 for k in keys:
                     print(f"{k}: {hist[k][-1]}")
         if store_best_rbm:
-            copy_rbm_into(best, rbm)
-        else:
-            dev.pull_params()
+            dev.restore_params()                                          # copy_rbm!(best_rbm, rbm)
+        dev.pull_params()
         merged = {k: [initial[k]] + hist[k] for k in keys}                # merge_metrics
         if file_path:
             with open(file_path, "w", newline="") as f:

@@ -634,3 +634,22 @@ def test_persistent_qubo_minibatch_with_supplied_model_sample(q, prec, L):
                 assert np.max(np.abs(dev.rbm.b - m.b)) < 1e-6
                 if L:
                     assert rel_err(dev.rbm.U, m.U) < 1e-5 and np.max(np.abs(dev.rbm.c - m.c)) < 1e-6
+
+
+def test_device_side_snapshot_and_restore(q):
+    rng = np.random.default_rng(71)
+    V, H, B = 30, 20, 8
+    m = make_oracle_model(rng, V, H, bf16=True)
+    X, _ = _data(rng, 2 * B, V, 0, False, True)
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=B, precision="bf16", seed=3) as dev:
+        dev.set_data(X)
+        dev.init_chains(B)
+        p0 = dev.conditional_prob_h(X[:4])
+        dev.snapshot_params()
+        dev.pcd_step(0, B, 1, 0.5)
+        dev.pull_params()
+        assert np.max(np.abs(dev.rbm.W - m.W)) > 1e-4          # the step really moved the weights
+        dev.restore_params()
+        dev.pull_params()
+        assert np.array_equal(dev.rbm.W, m.W) and np.array_equal(dev.rbm.a, m.a) and np.array_equal(dev.rbm.b, m.b)
+        assert np.array_equal(dev.conditional_prob_h(X[:4]), p0)  # shadows were refreshed too
