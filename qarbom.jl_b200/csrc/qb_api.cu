@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "online_kernels.cuh"
 #include "simt_kernels.cuh"
 #include "sm100_gemm.cuh"
 
@@ -86,7 +87,10 @@ struct qb_handle {
     cudaEvent_t ev[8] = {};
     // flat parameter / gradient / velocity vectors: [W (H x ldv) | acat (ldv) | b (ldh)]
     float *P = nullptr, *G = nullptr, *Vel = nullptr;
-    float *P_best = nullptr;  // device-side best-model snapshot (copy_rbm / copy_rbm! without a host round trip)
+    float *P_best = nullptr;
+    // online (B = 1) CD kernel: fp32 transposed weights, exchange vectors, grid barrier, phase timers
+    float *W2 = nullptr, *online_vec = nullptr; unsigned int *online_bar = nullptr; unsigned long long *online_ns = nullptr;
+    bool online_kernel = true; int online_wpb = 0;  // device-side best-model snapshot (copy_rbm / copy_rbm! without a host round trip)
     int64_t nW = 0, nP = 0;
     bf16 *Wb = nullptr, *WbT = nullptr;
     double momentum = 0.0, weight_decay = 0.0;
@@ -857,7 +861,7 @@ int32_t qb_destroy(qb_handle *h) {
         cudaSetDevice(h->cfg.device);
         cudaDeviceSynchronize();
         if (h->comm) nccl().CommDestroy(h->comm);
-        cudaFree(h->P); cudaFree(h->G); cudaFree(h->Vel); cudaFree(h->P_best); cudaFree(h->Wb); cudaFree(h->WbT);
+        cudaFree(h->P); cudaFree(h->G); cudaFree(h->Vel); cudaFree(h->P_best); cudaFree(h->W2); cudaFree(h->online_vec); cudaFree(h->online_bar); cudaFree(h->online_ns); cudaFree(h->Wb); cudaFree(h->WbT);
         cudaFree(h->Wb_alt); cudaFree(h->WbT_alt); cudaFree(h->G_alt); cudaFree(h->bias_buf[0]); cudaFree(h->bias_buf[1]);
         if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
         if (h->ev_grad) cudaEventDestroy(h->ev_grad);
@@ -1000,7 +1004,7 @@ int32_t qb_inject_streams(qb_handle *h, const double *U_h, const double *U_v, co
                           int64_t B) {
     return guarded([&] {
         QB_H_KEEP(h);
-        QB_CHECK(U_h != nullptr && k >= 1 && B >= 1 && B <= h->Bmax, QB_E_ARG, "U_h required, k >= 1, 1 <= B <= max_batch");
+        QB_CHECK(U_h != nullptr && k >= 1 && B >= 1, QB_E_ARG, "U_h required, k >= 1, B >= 1");
         QB_CHECK(h->gaussian ? (Z_v != nullptr) : (U_v != nullptr), QB_E_ARG, "U_v (Bernoulli) or Z_v (Gaussian) required");
         QB_CHECK(h->L == 0 || U_y != nullptr, QB_E_ARG, "U_y required for classifier models");
         auto put = [&](float *&buf, size_t &cap, const std::vector<float> &src) {
@@ -1053,9 +1057,67 @@ int32_t qb_cd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, doub
     });
 }
 
+// contrastive_divergence! with the reference's own batch size 1 (src/training/train_cd.jl:2-21): one cooperative
+// persistent kernel for the whole epoch (online_kernels.cuh) instead of 2k+3 launches per sample
+static bool online_cd_epoch(qb_handle *h, int64_t k, double lr, double times[3]) {
+    if (!h->online_kernel || h->L > 0 || h->cfg.world > 1 || h->momentum != 0.0 || h->weight_decay != 0.0) return false;
+    const int64_t N = h->N;
+    if (h->inj_active) QB_CHECK(h->inj_B == N && h->inj_k >= k, QB_E_ARG, "injected streams must cover every sample of the epoch");
+    if (!h->W2) {
+        h->W2 = dalloc<float>(h->V * h->ldh);
+        h->online_vec = dalloc<float>(2 * (3 * h->H + h->V));
+        h->online_bar = dalloc<unsigned int>(1);
+        h->online_ns = dalloc<unsigned long long>(3);
+    }
+    {
+        dim3 g((unsigned)ceil_div(h->V, 32), (unsigned)ceil_div(h->H, 32));
+        transpose_f32_kernel<<<g, 256, 0, h->stream>>>(Wf(h), h->ldv, (int)h->H, (int)h->V, h->W2, h->ldh);
+        QB_CUDA(cudaGetLastError());
+    }
+    QB_CUDA(cudaMemsetAsync(h->online_bar, 0, sizeof(unsigned int), h->stream));
+    OnlineCdParams p{};
+    p.W1 = Wf(h); p.ldv = h->ldv; p.W2 = h->W2; p.ldh = h->ldh; p.a = acat(h); p.b = bh(h);
+    p.Xf = h->data.f; p.Xb = h->data.b; p.ldx = h->data.ld;
+    p.V = (int)h->V; p.H = (int)h->H; p.n_samples = (int)N; p.k = (int)k; p.gaussian = h->gaussian ? 1 : 0;
+    p.lr = (float)lr;
+    p.vec = h->online_vec; p.barrier = h->online_bar; p.phase_ns = h->online_ns;
+    if (h->inj_active) { p.injUh = h->injUh; p.injUv = h->gaussian ? h->injZv : h->injUv; }
+    p.key0.seed_lo = (uint32_t)h->seed; p.key0.seed_hi = (uint32_t)(h->seed >> 32);
+    p.key0.draw_lo = (uint32_t)h->draw; p.key0.draw_hi = (uint32_t)(h->draw >> 32) & 0x7FFFFFFFu;
+    // fewer, fatter CTAs make the grid barrier cheaper: one row per warp, up to 32 warps per CTA
+    const int64_t rows = std::max(h->H, h->V);
+    const int wpb = h->online_wpb > 0 ? h->online_wpb : (rows >= 148 * 16 ? 32 : (rows >= 148 * 4 ? 16 : 8));
+    int grid = (int)std::min<int64_t>(h->num_sms, std::max<int64_t>(1, ceil_div(rows, wpb)));
+    const size_t smem_vec = (size_t)(2 * h->V + 2 * h->H) * sizeof(float);
+    QB_CHECK(smem_vec <= 200 * 1024, QB_E_UNSUPPORTED, "model too large for the online kernel's shared-memory vectors");
+    // rows owned by a warp stay in shared memory for the whole epoch when they fit
+    const int64_t warps = (int64_t)grid * wpb;
+    const size_t smem_rows = (size_t)wpb * (size_t)(ceil_div(h->H, warps) * h->V + ceil_div(h->V, warps) * h->H) * sizeof(float);
+    const bool cache = smem_vec + smem_rows <= 200 * 1024;
+    const size_t smem = smem_vec + (cache ? smem_rows : 0);
+    void *args[] = {(void *)&p};
+    if (cache) {
+        if (smem > 48 * 1024) QB_CUDA(cudaFuncSetAttribute(online_cd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QB_CUDA(cudaLaunchCooperativeKernel((void *)online_cd_kernel<true>, dim3(grid), dim3(32 * wpb), args, smem, h->stream));
+    } else {
+        if (smem > 48 * 1024) QB_CUDA(cudaFuncSetAttribute(online_cd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        QB_CUDA(cudaLaunchCooperativeKernel((void *)online_cd_kernel<false>, dim3(grid), dim3(32 * wpb), args, smem, h->stream));
+    }
+    h->launches += 2;
+    h->draw += 2ull * (uint64_t)k * (uint64_t)N;
+    refresh_shadows(h);
+    unsigned long long ns[3] = {0, 0, 0};
+    QB_CUDA(cudaMemcpyAsync(ns, h->online_ns, sizeof(ns), cudaMemcpyDeviceToHost, h->stream));
+    QB_CUDA(cudaStreamSynchronize(h->stream));
+    if (times) for (int i = 0; i < 3; i++) times[i] = (double)ns[i] * 1e-9;
+    h->inj_active = false;
+    return true;
+}
+
 static void epoch_impl(qb_handle *h, bool pcd, int64_t B, int64_t k, double lr, double llr, double times[3]) {
     check_step_args(h, B, k);
-    QB_CHECK(!h->inj_active, QB_E_STATE, "injected streams are per step; use qb_pcd_step / qb_cd_step");
+    if (!pcd && B == 1 && h->N >= 1 && online_cd_epoch(h, k, lr, times)) return;
+    QB_CHECK(!h->inj_active, QB_E_STATE, "injected streams are per step (or per online CD epoch); use qb_pcd_step / qb_cd_step");
     QB_CHECK(h->N >= B, QB_E_ARG, "dataset smaller than one mini-batch");
     const int64_t nb = h->N / B;  // _set_mini_batches: trailing remainder dropped (src/utils.jl:13-26)
     double t[3] = {0, 0, 0};
@@ -1330,6 +1392,11 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
             int bn = (int)value;
             QB_CHECK(bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 256, QB_E_ARG, "force_bn must be 0/32/64/128/256");
             h->force_bn = bn;
+        } else if (!strcmp(key, "online_wpb")) {
+            QB_CHECK(value == 0 || value == 4 || value == 8 || value == 16 || value == 32, QB_E_ARG, "online_wpb must be 0/4/8/16/32");
+            h->online_wpb = (int)value;
+        } else if (!strcmp(key, "online_kernel")) {
+            h->online_kernel = value != 0.0;
         } else if (!strcmp(key, "stale_chains")) {
             set_stale_mode(h, value != 0.0);
         } else if (!strcmp(key, "dbg")) {

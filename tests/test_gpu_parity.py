@@ -653,3 +653,49 @@ def test_device_side_snapshot_and_restore(q):
         dev.pull_params()
         assert np.array_equal(dev.rbm.W, m.W) and np.array_equal(dev.rbm.a, m.a) and np.array_equal(dev.rbm.b, m.b)
         assert np.array_equal(dev.conditional_prob_h(X[:4]), p0)  # shadows were refreshed too
+
+
+# ------------------------------------------------------------------------------ online (B = 1) CD: cooperative persistent kernel
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("V,H,gaussian,k,n", [(3, 2, False, 3, 40), (50, 30, False, 1, 64), (784, 500, False, 2, 24), (24, 16, True, 2, 32)])
+def test_online_cd_epoch_matches_reference_algorithm(q, prec, V, H, gaussian, k, n):
+    """train!(rbm, x, CD) with the reference's own batch size 1 (src/training/train_cd.jl:2-21): the one-kernel
+    epoch must reproduce the oracle's per-sample online algorithm (injected streams, fp32 arithmetic in both
+    precision modes) ..."""
+    rng = np.random.default_rng(91 + V + k)
+    m = make_oracle_model(rng, V, H, 0, gaussian, scale=0.2)
+    X, _ = _data(rng, n, V, 0, gaussian, prec == "bf16")
+    ds = DenseStreams(rng, k, n, V, H, 0, gaussian)   # one "row" per sample: [k][n][units]
+    su, sz = ds.serial("cd")
+    st = qo.GuardedStream(su, sz)
+    m0 = qo.copy_rbm(m)
+    qo.contrastive_divergence(m, X, steps=k, learning_rate=0.02, stream=st, batch_size=1)
+    ds.absorb(st.u, "cd")
+    with q.DeviceRBM(to_host_rbm(q, m0), max_batch=4, precision=prec) as dev:
+        dev.set_data(X)
+        dev.inject_streams(ds.U_h, ds.U_v, None, ds.Z_v)
+        t = dev.cd_epoch(1, k, 0.02)
+        assert all(x >= 0 for x in t) and sum(t) > 0
+        dev.pull_params()
+        assert rel_err(dev.rbm.W, m.W) < 2e-5 and rel_err(dev.rbm.W - m0.W, m.W - m0.W) < 2e-4
+        assert np.max(np.abs(dev.rbm.a - m.a)) < 2e-6 and np.max(np.abs(dev.rbm.b - m.b)) < 2e-6
+
+
+def test_online_cd_kernel_equals_per_sample_steps(q):
+    """... and, with the production Philox stream, equal a sequence of qb_cd_step(B = 1) calls."""
+    rng = np.random.default_rng(93)
+    V, H, k, n = 64, 40, 2, 48
+    m = make_oracle_model(rng, V, H, scale=0.2)
+    X, _ = _data(rng, n, V, 0, False, False)
+    out = []
+    for online in (1, 0):
+        rbm = to_host_rbm(q, m)
+        with q.DeviceRBM(rbm, max_batch=4, precision="fp32", seed=21) as dev:
+            dev.set_option("online_kernel", online)
+            dev.set_data(X)
+            dev.cd_epoch(1, k, 0.02, timed=False)
+            dev.pull_params()
+            out.append((rbm.W.copy(), rbm.a.copy(), rbm.b.copy()))
+    for a, b in zip(*out):
+        assert np.max(np.abs(a - b)) < 2e-6
+    assert np.max(np.abs(out[0][0] - m.W)) > 1e-3
