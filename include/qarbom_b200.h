@@ -135,6 +135,12 @@ int32_t qb_cd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, doub
 int32_t qb_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]);
 int32_t qb_cd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]);
 
+/* One epoch of fast_persistent_contrastive_divergence! (src/training/train_fast_pcd.jl:1-57, RBM only): inside a
+ * mini-batch the slow weights are updated and the fast weights decayed (19/20) after every SAMPLE, then the
+ * chains advance with W + W_fast.  Fast weights restart at zero every call, as in the reference.  times[3] =
+ * (0, chain seconds, online sample+update seconds). */
+int32_t qb_fast_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double fast_lr, double times[3]);
+
 /* Same step, but the mini-batch comes from HOST memory on every call (end-to-end path:
  * upload, step, and a device->host read of the batch reconstruction error sum). */
 int32_t qb_pcd_step_host(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype, int64_t B,

@@ -511,6 +511,35 @@ def _pcd_minibatch_more_chains(m, x, mb, chains, steps, learning_rate, stream, y
         _update_fantasy_data(m, chains, steps, stream)
 
 
+def fast_persistent_contrastive_divergence(m: Model, x: Sequence, mini_batches: List[range], chains: List[FantasyData], *,
+                                           steps: int, learning_rate: float, fast_learning_rate: float, stream: Stream) -> None:
+    """One epoch of FastPCD for RBM (src/training/train_fast_pcd.jl:1-57; Tieleman & Hinton 2009).
+
+    The fast weights start at zero EVERY epoch (:12-14).  Inside a mini-batch the reference is online:
+    for each sample, h_data uses the current slow weights, the slow weights are updated right away with
+    lr/B (`update_rbm!` 5-arg form, src/rbm.jl:138-150) and the fast weights are decayed by 19/20 and
+    pushed by fast_lr/B times the same difference -- per SAMPLE (:34-43).  The chains then advance
+    with the effective parameters W + W_fast, a + a_fast, b + b_fast (src/fantasy_data.jl:31-47,
+    src/gibbs.jl:8-11,22-25, src/rbm.jl:167-168,184-185).  Bernoulli visibles only."""
+    assert not m.is_classifier and not m.gaussian
+    W_fast = np.zeros_like(m.W); a_fast = np.zeros_like(m.a); b_fast = np.zeros_like(m.b)
+    for mb in mini_batches:
+        B = len(mb)
+        for batch_index, i in enumerate(mb):
+            v_data = np.asarray(x[i], dtype=np.float64)
+            h_data = conditional_prob_h(m, v_data)
+            ch = chains[batch_index]
+            dW = np.outer(v_data, h_data) - np.outer(ch.v, ch.h)
+            m.W += (learning_rate / B) * dW
+            m.a += (learning_rate / B) * (v_data - ch.v)
+            m.b += (learning_rate / B) * (h_data - ch.h)
+            W_fast = W_fast * (19 / 20) + (fast_learning_rate / B) * dW
+            a_fast = a_fast * (19 / 20) + (fast_learning_rate / B) * (v_data - ch.v)
+            b_fast = b_fast * (19 / 20) + (fast_learning_rate / B) * (h_data - ch.h)
+        eff = Model(m.W + W_fast, m.a + a_fast, m.b + b_fast)
+        _update_fantasy_data(eff, chains, steps, stream)
+
+
 def persistent_qubo_minibatch(m: Model, x: Sequence, mb: range, v_model, h_model, *, learning_rate: float,
                               y: Optional[Sequence] = None, y_model=None, label_learning_rate: float = 0.1) -> None:
     """One mini-batch of `persistent_qubo!` (src/training/train_quantum_pcd.jl:10-37, classifier :55-83)

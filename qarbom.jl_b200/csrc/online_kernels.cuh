@@ -194,6 +194,99 @@ __global__ void __launch_bounds__(1024) online_cd_kernel(const OnlineCdParams p)
     if (timer) { p.phase_ns[0] = acc_ns[0]; p.phase_ns[1] = acc_ns[1]; p.phase_ns[2] = acc_ns[2]; }
 }
 
+// ----------------------------------------------------------------------------- FastPCD (online part of a mini-batch)
+// fast_persistent_contrastive_divergence! (src/training/train_fast_pcd.jl:16-49): for every sample of the
+// mini-batch, in order: h_data from the CURRENT slow weights, slow update with lr/B against chain i, fast
+// weights decayed by 19/20 and pushed with fast_lr/B -- one grid barrier per sample.  The chains advance
+// afterwards (batched GEMMs on the effective weights), outside this kernel.
+struct FastPcdParams {
+    float *W1, *F1; long long ldv;   // slow / fast weights [H][ldv]
+    float *W2, *F2; long long ldh;   // transposed copies [V][ldh]
+    float *a, *b, *fa, *fb;          // slow / fast biases
+    const float *Xf; const bf16 *Xb; long long ldx;      // the B data rows of this mini-batch
+    const float *CVf; const bf16 *CVb; long long ldcv;   // chain visibles [B][ldcv]
+    const float *CHf; const bf16 *CHb; long long ldch;   // chain hiddens  [B][ldch]
+    int V, H, B;
+    float lr, flr;                   // already divided by B
+    float *vec; unsigned int *barrier;
+};
+
+template <bool CACHE>
+__global__ void __launch_bounds__(1024) online_fastpcd_kernel(const FastPcdParams p) {
+    extern __shared__ float sm[];
+    const int V = p.V, H = p.H;
+    float *sx = sm, *scv = sx + V, *shd = scv + V, *sch = shd + H;   // x_i, chain v_i, h_data, chain h_i
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int rpw1 = (H + gridDim.x * wpb - 1) / (gridDim.x * wpb), rpw2 = (V + gridDim.x * wpb - 1) / (gridDim.x * wpb);
+    float *c1 = nullptr, *f1 = nullptr, *c2 = nullptr, *f2 = nullptr;
+    if (CACHE) {
+        float *base = sch + H + (long long)warp * 2 * (rpw1 * V + rpw2 * H);
+        c1 = base; f1 = c1 + rpw1 * V; c2 = f1 + rpw1 * V; f2 = c2 + rpw2 * H;
+        int m = 0;
+        for (int j = blockIdx.x * wpb + warp; j < H; j += gridDim.x * wpb, m++)
+            for (int c = lane; c < V; c += 32) { c1[m * V + c] = p.W1[(long long)j * p.ldv + c]; f1[m * V + c] = p.F1[(long long)j * p.ldv + c]; }
+        m = 0;
+        for (int i = blockIdx.x * wpb + warp; i < V; i += gridDim.x * wpb, m++)
+            for (int c = lane; c < H; c += 32) { c2[m * H + c] = p.W2[(long long)i * p.ldh + c]; f2[m * H + c] = p.F2[(long long)i * p.ldh + c]; }
+        __syncwarp();
+    }
+    unsigned int epoch = 0;
+    const float decay = 19.0f / 20.0f;
+    for (int n = 0; n < p.B; n++) {
+        float *g_hd = p.vec + (n & 1) * H;
+        for (int i = threadIdx.x; i < V; i += blockDim.x) {
+            sx[i] = p.Xf ? p.Xf[(long long)n * p.ldx + i] : __bfloat162float(p.Xb[(long long)n * p.ldx + i]);
+            scv[i] = p.CVf ? p.CVf[(long long)n * p.ldcv + i] : __bfloat162float(p.CVb[(long long)n * p.ldcv + i]);
+        }
+        for (int j = threadIdx.x; j < H; j += blockDim.x)
+            sch[j] = p.CHf ? p.CHf[(long long)n * p.ldch + j] : __bfloat162float(p.CHb[(long long)n * p.ldch + j]);
+        __syncthreads();
+        owned_rows(H, p.W1, p.ldv, V, sx, c1, [&](int j, float acc) { g_hd[j] = sigmoid_exact(acc + p.b[j]); });
+        grid_barrier(p.barrier, epoch, gridDim.x);
+        for (int j = threadIdx.x; j < H; j += blockDim.x) shd[j] = g_hd[j];
+        __syncthreads();
+        int m = 0;
+        for (int j = blockIdx.x * wpb + warp; j < H; j += gridDim.x * wpb, m++) {
+            float *w = CACHE ? c1 + (long long)m * V : p.W1 + (long long)j * p.ldv;
+            float *f = CACHE ? f1 + (long long)m * V : p.F1 + (long long)j * p.ldv;
+            const float hd = shd[j], hc = sch[j];
+            for (int c = lane; c < V; c += 32) {
+                const float d = sx[c] * hd - scv[c] * hc;
+                w[c] += p.lr * d;
+                f[c] = f[c] * decay + p.flr * d;
+            }
+            if (lane == 0) { p.b[j] += p.lr * (hd - hc); p.fb[j] = p.fb[j] * decay + p.flr * (hd - hc); }
+        }
+        m = 0;
+        for (int i = blockIdx.x * wpb + warp; i < V; i += gridDim.x * wpb, m++) {
+            float *w = CACHE ? c2 + (long long)m * H : p.W2 + (long long)i * p.ldh;
+            float *f = CACHE ? f2 + (long long)m * H : p.F2 + (long long)i * p.ldh;
+            const float xd = sx[i], xc = scv[i];
+            for (int c = lane; c < H; c += 32) {
+                const float d = xd * shd[c] - xc * sch[c];
+                w[c] += p.lr * d;
+                f[c] = f[c] * decay + p.flr * d;
+            }
+            if (lane == 0) { p.a[i] += p.lr * (xd - xc); p.fa[i] = p.fa[i] * decay + p.flr * (xd - xc); }
+        }
+        __syncthreads();
+    }
+    if (CACHE) {  // masters (and the transposed scratch copies, reused by the next mini-batch) go back to HBM
+        int m = 0;
+        for (int j = blockIdx.x * wpb + warp; j < H; j += gridDim.x * wpb, m++)
+            for (int c = lane; c < V; c += 32) { p.W1[(long long)j * p.ldv + c] = c1[m * V + c]; p.F1[(long long)j * p.ldv + c] = f1[m * V + c]; }
+        m = 0;
+        for (int i = blockIdx.x * wpb + warp; i < V; i += gridDim.x * wpb, m++)
+            for (int c = lane; c < H; c += 32) { p.W2[(long long)i * p.ldh + c] = c2[m * H + c]; p.F2[(long long)i * p.ldh + c] = f2[m * H + c]; }
+    }
+}
+
+// effective parameters of the FastPCD chains: Pe = P + F over the flat vector [W | a | b]
+__global__ void add_vectors_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
+
 // W2[v][h] = W1[h][v]  (fp32)
 __global__ void __launch_bounds__(256) transpose_f32_kernel(const float *__restrict__ src, long long lds, int rows, int cols,
                                                             float *__restrict__ dst, long long ldd) {

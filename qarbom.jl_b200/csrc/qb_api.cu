@@ -90,7 +90,8 @@ struct qb_handle {
     float *P_best = nullptr;
     // online (B = 1) CD kernel: fp32 transposed weights, exchange vectors, grid barrier, phase timers
     float *W2 = nullptr, *online_vec = nullptr; unsigned int *online_bar = nullptr; unsigned long long *online_ns = nullptr;
-    bool online_kernel = true; int online_wpb = 0;  // device-side best-model snapshot (copy_rbm / copy_rbm! without a host round trip)
+    bool online_kernel = true; int online_wpb = 0;
+    float *F = nullptr, *F2 = nullptr, *P_eff = nullptr;  // FastPCD: fast weights [W | a | b], their transpose, effective parameters  // device-side best-model snapshot (copy_rbm / copy_rbm! without a host round trip)
     int64_t nW = 0, nP = 0;
     bf16 *Wb = nullptr, *WbT = nullptr;
     double momentum = 0.0, weight_decay = 0.0;
@@ -861,7 +862,7 @@ int32_t qb_destroy(qb_handle *h) {
         cudaSetDevice(h->cfg.device);
         cudaDeviceSynchronize();
         if (h->comm) nccl().CommDestroy(h->comm);
-        cudaFree(h->P); cudaFree(h->G); cudaFree(h->Vel); cudaFree(h->P_best); cudaFree(h->W2); cudaFree(h->online_vec); cudaFree(h->online_bar); cudaFree(h->online_ns); cudaFree(h->Wb); cudaFree(h->WbT);
+        cudaFree(h->P); cudaFree(h->G); cudaFree(h->Vel); cudaFree(h->P_best); cudaFree(h->F); cudaFree(h->F2); cudaFree(h->P_eff); cudaFree(h->W2); cudaFree(h->online_vec); cudaFree(h->online_bar); cudaFree(h->online_ns); cudaFree(h->Wb); cudaFree(h->WbT);
         cudaFree(h->Wb_alt); cudaFree(h->WbT_alt); cudaFree(h->G_alt); cudaFree(h->bias_buf[0]); cudaFree(h->bias_buf[1]);
         if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
         if (h->ev_grad) cudaEventDestroy(h->ev_grad);
@@ -1114,6 +1115,86 @@ static bool online_cd_epoch(qb_handle *h, int64_t k, double lr, double times[3])
     return true;
 }
 
+// fast_persistent_contrastive_divergence! (src/training/train_fast_pcd.jl:1-57): one epoch
+static void fast_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double flr, double times[3]) {
+    check_step_args(h, B, k);
+    QB_CHECK(h->L == 0 && !h->gaussian, QB_E_UNSUPPORTED, "FastPCD is implemented for RBM (Bernoulli visibles, no label units)");
+    QB_CHECK(h->cfg.world == 1, QB_E_UNSUPPORTED, "FastPCD updates the weights after every sample and does not shard");
+    QB_CHECK(h->momentum == 0.0 && h->weight_decay == 0.0, QB_E_UNSUPPORTED, "FastPCD has no momentum / weight decay");
+    QB_CHECK(h->n_chains == B, QB_E_STATE, "FastPCD pairs sample i with chain i: qb_init_chains(B) first");
+    QB_CHECK(h->N >= B, QB_E_ARG, "dataset smaller than one mini-batch");
+    if (!h->W2) {
+        h->W2 = dalloc<float>(h->V * h->ldh);
+        h->online_vec = dalloc<float>(2 * (3 * h->H + h->V));
+        h->online_bar = dalloc<unsigned int>(1);
+        h->online_ns = dalloc<unsigned long long>(3);
+    }
+    if (!h->F) { h->F = dalloc<float>(h->nP); h->F2 = dalloc<float>(h->V * h->ldh); h->P_eff = dalloc<float>(h->nP); }
+    QB_CUDA(cudaMemsetAsync(h->F, 0, h->nP * sizeof(float), h->stream));          // W_fast = a_fast = b_fast = 0 every epoch (:12-14)
+    QB_CUDA(cudaMemsetAsync(h->F2, 0, h->V * h->ldh * sizeof(float), h->stream));
+    {
+        dim3 g((unsigned)ceil_div(h->V, 32), (unsigned)ceil_div(h->H, 32));
+        transpose_f32_kernel<<<g, 256, 0, h->stream>>>(Wf(h), h->ldv, (int)h->H, (int)h->V, h->W2, h->ldh);
+        QB_CUDA(cudaGetLastError());
+    }
+    const int64_t rows = std::max(h->H, h->V);
+    const int wpb = h->online_wpb > 0 ? h->online_wpb : (rows >= 148 * 16 ? 32 : (rows >= 148 * 4 ? 16 : 8));
+    const int grid = (int)std::min<int64_t>(h->num_sms, std::max<int64_t>(1, ceil_div(rows, wpb)));
+    const int64_t warps = (int64_t)grid * wpb;
+    const size_t smem_vec = (size_t)(2 * h->V + 2 * h->H) * sizeof(float);
+    const size_t smem_rows = 2 * (size_t)wpb * (size_t)(ceil_div(h->H, warps) * h->V + ceil_div(h->V, warps) * h->H) * sizeof(float);
+    QB_CHECK(smem_vec <= 200 * 1024, QB_E_UNSUPPORTED, "model too large for the online kernel's shared-memory vectors");
+    const bool cache = smem_vec + smem_rows <= 200 * 1024;
+    const size_t smem = smem_vec + (cache ? smem_rows : 0);
+    if (smem > 48 * 1024) {
+        if (cache) QB_CUDA(cudaFuncSetAttribute(online_fastpcd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else QB_CUDA(cudaFuncSetAttribute(online_fastpcd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    const int64_t nb = h->N / B;
+    float t_online = 0.f, t_chain = 0.f;
+    float *P_true = h->P;
+    for (int64_t mb = 0; mb < nb; mb++) {
+        Mat xb = h->data.row_slice(mb * B, B);
+        FastPcdParams p{};
+        p.W1 = P_true; p.F1 = h->F; p.ldv = h->ldv; p.W2 = h->W2; p.F2 = h->F2; p.ldh = h->ldh;
+        p.a = P_true + h->nW; p.b = P_true + h->nW + h->ldv; p.fa = h->F + h->nW; p.fb = h->F + h->nW + h->ldv;
+        p.Xf = xb.f; p.Xb = xb.b; p.ldx = xb.ld;
+        p.CVf = h->cv.f; p.CVb = h->cv.b; p.ldcv = h->cv.ld; p.CHf = h->ch.f; p.CHb = h->ch.b; p.ldch = h->ch.ld;
+        p.V = (int)h->V; p.H = (int)h->H; p.B = (int)B;
+        p.lr = (float)(lr / (double)B); p.flr = (float)(flr / (double)B);
+        p.vec = h->online_vec; p.barrier = h->online_bar;
+        QB_CUDA(cudaMemsetAsync(h->online_bar, 0, sizeof(unsigned int), h->stream));
+        if (times) QB_CUDA(cudaEventRecord(h->ev[0], h->stream));
+        void *args[] = {(void *)&p};
+        if (cache) QB_CUDA(cudaLaunchCooperativeKernel((void *)online_fastpcd_kernel<true>, dim3(grid), dim3(32 * wpb), args, smem, h->stream));
+        else QB_CUDA(cudaLaunchCooperativeKernel((void *)online_fastpcd_kernel<false>, dim3(grid), dim3(32 * wpb), args, smem, h->stream));
+        if (times) QB_CUDA(cudaEventRecord(h->ev[1], h->stream));
+        // chains advance with the effective parameters W + W_fast, a + a_fast, b + b_fast (src/fantasy_data.jl:31-47)
+        add_vectors_kernel<<<grid1d(h->nP), 256, 0, h->stream>>>(P_true, h->F, h->P_eff, h->nP);
+        QB_CUDA(cudaGetLastError());
+        h->launches += 2;
+        h->P = h->P_eff;
+        float *saved_bias_rd = h->bias_rd; h->bias_rd = nullptr;
+        try {
+            refresh_shadows(h);
+            StepRng sr{h, B, false};
+            advance_chains(h, B, k, sr, false);
+        } catch (...) { h->P = P_true; h->bias_rd = saved_bias_rd; throw; }
+        h->P = P_true; h->bias_rd = saved_bias_rd;
+        if (times) {
+            QB_CUDA(cudaEventRecord(h->ev[2], h->stream));
+            QB_CUDA(cudaStreamSynchronize(h->stream));
+            float a = 0, b = 0;
+            QB_CUDA(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+            QB_CUDA(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+            t_online += a; t_chain += b;
+        }
+    }
+    refresh_shadows(h);
+    QB_CUDA(cudaStreamSynchronize(h->stream));
+    if (times) { times[0] = 0.0; times[1] = t_chain * 1e-3; times[2] = t_online * 1e-3; }  // sample+update are fused in the online kernel
+}
+
 static void epoch_impl(qb_handle *h, bool pcd, int64_t B, int64_t k, double lr, double llr, double times[3]) {
     check_step_args(h, B, k);
     if (!pcd && B == 1 && h->N >= 1 && online_cd_epoch(h, k, lr, times)) return;
@@ -1147,6 +1228,9 @@ static void epoch_impl(qb_handle *h, bool pcd, int64_t B, int64_t k, double lr, 
 
 int32_t qb_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]) {
     return guarded([&] { QB_H_KEEP(h); epoch_impl(h, true, B, k, lr, llr, times); });
+}
+int32_t qb_fast_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double fast_lr, double times[3]) {
+    return guarded([&] { QB_H(h); fast_pcd_epoch(h, B, k, lr, fast_lr, times); });
 }
 int32_t qb_cd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]) {
     return guarded([&] { QB_H(h); epoch_impl(h, false, B, k, lr, llr, times); });

@@ -130,6 +130,11 @@ class DeviceRBM:
         check(lib().qb_pcd_epoch(self._h, B, k, lr, llr, t if timed else None))
         return tuple(t)
 
+    def fast_pcd_epoch(self, B: int, k: int, lr: float, fast_lr: float, timed: bool = True):
+        t = (ctypes.c_double * 3)()
+        check(lib().qb_fast_pcd_epoch(self._h, B, k, lr, fast_lr, t if timed else None))
+        return tuple(t)
+
     def cd_epoch(self, B: int, k: int, lr: float, llr: float = 0.0, timed: bool = True):
         t = (ctypes.c_double * 3)()
         check(lib().qb_cd_epoch(self._h, B, k, lr, llr, t if timed else None))

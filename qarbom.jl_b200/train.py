@@ -17,6 +17,7 @@ from .rbm import AbstractRBM, copy_rbm, copy_rbm_into
 class TrainingMethod: ...
 class CD(TrainingMethod): ...
 class PCD(TrainingMethod): ...
+class FastPCD(TrainingMethod): ...
 class EvaluationMethod: ...
 class MeanSquaredError(EvaluationMethod): ...
 class Accuracy(EvaluationMethod): ...
@@ -64,14 +65,17 @@ def _log_finish(n_epochs, ts, tg, tu):
 
 def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int, learning_rate: Sequence[float],
           gibbs_steps: Optional[int] = None, batch_size: Optional[int] = None,
-          label_learning_rate: Optional[Sequence[float]] = None, metrics=None,
+          label_learning_rate: Optional[Sequence[float]] = None, fast_learning_rate: Optional[float] = None, metrics=None,
           early_stopping: bool = False, store_best_rbm: bool = True, patience: int = 10,
           stopping_metric=None, x_test_dataset=None, y_test_dataset=None, file_path: Optional[str] = None,
           # ---- extensions (defaults reproduce the reference)
           momentum: float = 0.0, weight_decay: float = 0.0, precision: str = "bf16", seed: int = 0, device: int = 0,
           n_chains: Optional[int] = None,
           verbose: bool = True, chains_init=None) -> dict:
-    is_pcd = method is PCD or isinstance(method, PCD)
+    is_fast = method is FastPCD or isinstance(method, FastPCD)
+    is_pcd = is_fast or method is PCD or isinstance(method, PCD)
+    if is_fast and fast_learning_rate is None:
+        raise TypeError("train!(..., FastPCD) requires fast_learning_rate")   # keyword without default, train_fast_pcd.jl:177
     clf = rbm.n_classifiers > 0
     if clf and label_train is None:
         raise ValueError("label_train is required for classifier models")
@@ -87,7 +91,7 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
         gibbs_steps = 1 if is_pcd else 3                         # train_pcd.jl:138 / train_cd.jl:50
     B = int(batch_size) if batch_size is not None else 1        # CD default = the reference's online update
     if file_path is None:
-        file_path = ("pcd" if is_pcd else "cd") + ("_classifier" if clf else "") + "_metrics.csv"
+        file_path = ("fast_pcd" if is_fast else "pcd" if is_pcd else "cd") + ("_classifier" if clf else "") + "_metrics.csv"
     n = len(x_train)
     if n % B:
         # `_set_mini_batches`, src/utils.jl:13-26
@@ -136,7 +140,10 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
         for epoch in range(1, n_epochs + 1):
             lr = float(learning_rate[epoch - 1])
             llr = float(label_learning_rate[epoch - 1]) if clf else 0.0
-            t = dev.pcd_epoch(B, gibbs_steps, lr, llr) if is_pcd else dev.cd_epoch(B, gibbs_steps, lr, llr)
+            if is_fast:
+                t = dev.fast_pcd_epoch(B, gibbs_steps, lr, float(fast_learning_rate))
+            else:
+                t = dev.pcd_epoch(B, gibbs_steps, lr, llr) if is_pcd else dev.cd_epoch(B, gibbs_steps, lr, llr)
             for i in range(3):
                 tot[i] += t[i]
             for k, v in evaluate().items():

@@ -699,3 +699,60 @@ def test_online_cd_kernel_equals_per_sample_steps(q):
     for a, b in zip(*out):
         assert np.max(np.abs(a - b)) < 2e-6
     assert np.max(np.abs(out[0][0] - m.W)) > 1e-3
+
+
+# ------------------------------------------------------------------------------ FastPCD
+def _fastpcd_oracle(m, X, B, k, lr, flr, seed, cv0, ch0, nb):
+    """Oracle FastPCD epoch fed with the uniforms the device's Philox contract defines."""
+    V, H = m.n_visible, m.n_hidden
+    parts = []
+    for mb in range(nb):
+        for s in range(k):
+            uh = philox_ref.uniforms(seed, 2 + 2 * (mb * k + s), B, H)
+            uv = philox_ref.uniforms(seed, 3 + 2 * (mb * k + s), B, V)
+            for i in range(B):
+                parts += [uh[i], uv[i]]
+    chains = chains_from_arrays(cv0, ch0)
+    qo.fast_persistent_contrastive_divergence(m, X, qo._set_mini_batches(len(X), B), chains, steps=k, learning_rate=lr,
+                                              fast_learning_rate=flr, stream=qo.Stream(np.concatenate(parts)))
+    return chains_to_arrays(chains)
+
+
+@pytest.mark.parametrize("V,H,B,k,nb", [(3, 2, 2, 1, 6), (40, 24, 8, 2, 3), (784, 500, 16, 1, 2)])
+def test_fast_pcd_epoch_matches_reference_algorithm(q, V, H, B, k, nb):
+    """fast_persistent_contrastive_divergence! (train_fast_pcd.jl:1-57): per-sample slow update + fast-weight
+    decay inside a mini-batch, chains on W + W_fast.  fp32 mode, Philox stream replayed into the oracle."""
+    rng = np.random.default_rng(5 + V)
+    seed, lr, flr = 1234, 0.05, 0.1
+    m = make_oracle_model(rng, V, H, scale=0.2)
+    X, _ = _data(rng, nb * B + 1, V, 0, False, False)     # + 1: the trailing remainder is dropped
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=B, precision="fp32", seed=seed) as dev:
+        dev.set_data(X)
+        dev.init_chains(B)                                 # draws 0, 1
+        cv0, ch0, _ = dev.get_chains()
+        t = dev.fast_pcd_epoch(B, k, lr, flr)
+        assert t[1] > 0 and t[2] > 0
+        dv, dh, _ = dev.get_chains()
+        dev.pull_params()
+        ov, oh, _ = _fastpcd_oracle(m, X, B, k, lr, flr, seed, cv0, ch0, nb)
+        assert np.mean(dv != ov) < 2e-3 and np.mean(dh != oh) < 2e-3     # near-ties of the fixed Philox stream only
+        assert rel_err(dev.rbm.W, m.W) < 1e-4 and np.max(np.abs(dev.rbm.b - m.b)) < 1e-4
+
+
+def test_fast_pcd_bf16_chains_stay_close_to_fp32(q):
+    rng = np.random.default_rng(6)
+    V, H, B, k, nb = 96, 64, 16, 1, 4
+    m = make_oracle_model(rng, V, H, scale=0.2, bf16=True)
+    X, _ = _data(rng, nb * B, V, 0, False, True)
+    Ws = {}
+    for prec in ("fp32", "bf16"):
+        rbm = to_host_rbm(q, m)
+        with q.DeviceRBM(rbm, max_batch=B, precision=prec, seed=9) as dev:
+            dev.set_data(X)
+            dev.init_chains(B)
+            dev.fast_pcd_epoch(B, k, 0.05, 0.1, timed=False)
+            dev.pull_params()
+            Ws[prec] = rbm.W.copy()
+            # the tensor-core shadows hold the slow weights again after the epoch
+            assert np.max(np.abs(dev.conditional_prob_h(X[:2]) - 1 / (1 + np.exp(-(rbm.b + X[:2] @ (bf16_round(rbm.W) if prec == "bf16" else rbm.W)))))) < 5e-6
+    assert rel_err(Ws["bf16"] - m.W, Ws["fp32"] - m.W) < 0.25   # different chain trajectories (bf16-rounded W + W_fast), same learning signal
