@@ -16,13 +16,14 @@ module QARBoMB200
 
 using Printf
 
-export RBM, GRBM, RBMClassifier, GRBMClassifier, CD, PCD, MeanSquaredError, FreeEnergy
+export RBM, GRBM, RBMClassifier, GRBMClassifier, CD, PCD, FastPCD, MeanSquaredError, FreeEnergy
 
 const LIB = get(ENV, "QARBOM_B200_LIB", joinpath(@__DIR__, "..", "lib", "libqarbom_b200.so"))
 
 abstract type TrainingMethod end
 abstract type PCD <: TrainingMethod end
 abstract type CD <: TrainingMethod end
+abstract type FastPCD <: TrainingMethod end
 abstract type EvaluationMethod end
 abstract type MeanSquaredError <: EvaluationMethod end
 abstract type FreeEnergy <: EvaluationMethod end   # new metric
@@ -143,6 +144,23 @@ function epoch!(d::Device, ::Type{CD}, B, k, lr, llr)
     check(ccall((:qb_cd_epoch, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Float64, Float64, Ptr{Float64}), d.h, B, k, lr, llr, t))
     return t[1], t[2], t[3]
 end
+
+"fast_persistent_contrastive_divergence! for one epoch (src/training/train_fast_pcd.jl:1-57); RBM only"
+function fast_pcd_epoch!(d::Device, B, k, lr, fast_lr)
+    t = zeros(3)
+    check(ccall((:qb_fast_pcd_epoch, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Float64, Float64, Ptr{Float64}), d.h, B, k, lr, fast_lr, t))
+    return t[1], t[2], t[3]
+end
+
+"One mini-batch of persistent_qubo! (src/training/train_quantum_pcd.jl:10-37): the annealer's (v~, h~) come from Julia"
+function qsampling_step!(d::Device, batch_index::Int, B::Int, v_model::Vector{Float64}, h_model::Vector{Float64}, lr::Float64)
+    GC.@preserve v_model h_model check(ccall((:qb_init_chains, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                                               d.h, 1, pointer(v_model), pointer(h_model), C_NULL))
+    check(ccall((:qb_pcd_step, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int64, Float64, Float64), d.h, batch_index, B, 0, lr, 0.0))
+end
+
+snapshot!(d::Device) = check(ccall((:qb_snapshot_params, LIB), Int32, (Ptr{Cvoid},), d.h))   # best_rbm = copy_rbm(rbm), in HBM
+restore!(d::Device) = check(ccall((:qb_restore_params, LIB), Int32, (Ptr{Cvoid},), d.h))     # copy_rbm!(best_rbm, rbm)
 
 # ------------------------------------------------------------------------------ reference plumbing kept in Julia
 function _diverged(h::Vector{Float64})           # src/evaluation.jl:132-142
