@@ -401,8 +401,9 @@ def main():
         line["overlap"] = overlap
     if not args.no_cpu_baseline:
         r = cpu_reference(w, args.cpu_seconds, 3, 1)
+        r1 = cpu_reference(w, args.cpu_seconds / 2, 2, 1, threads=1)   # the Julia code itself is single-threaded
         line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["threads"], "kind": "port",
-                                "sample": r["sample"]}
+                                "sample": r["sample"], "value_1_thread": r1["value"], "sample_1_thread": r1["sample"]}
     emit(line, out_fd)
     dev.close()
     if world > 1:
