@@ -129,7 +129,7 @@ struct qb_handle {
     ncclComm_t comm = nullptr;
     int64_t launches = 0, gemm_launches = 0;
     double gemm_flops = 0.0;
-    int force_bn = 0, use_2cta = 1, dbg = 0;
+    int force_bn = 0, use_2cta = 1;
     bool async_steps = false;   // step calls return without a stream sync (qb_sync to wait)
     bool time_gemms = false;    // bracket every GEMM launch with CUDA events on the launching stream
     std::vector<cudaEvent_t> gemm_ev; size_t gemm_ev_used = 0; int64_t gemm_timed = 0; double gemm_timed_flops = 0.0;
@@ -329,7 +329,6 @@ void op_hidden(qb_handle *h, const Mat &in, int64_t rows, int64_t kdim, const Hi
     ep.inj = rng.inj; ep.ld_inj = rng.ld_inj; ep.key = rng.key; ep.use_rng = rng.use_rng; ep.row0 = row0;
     ep.bg_what = o.bg_what; ep.bg_sign = o.bg_sign; ep.bias_grad = G_b(h);
     ep.softplus_rows = o.softplus_rows;
-    ep.dbg = h->dbg;
     ep.pscale = o.pscale;
     QB_CHECK(o.pscale == 1.f || sm100::pick_kind(ep) == sm100::K_FAST_PROB, QB_E_UNSUPPORTED, "pscale needs the fast probability epilogue");
     GemmScope gs(h, 2.0 * (double)h->H * (double)rows * (double)kdim);
@@ -395,7 +394,7 @@ void op_visible(qb_handle *h, const Mat &in, int64_t rows, const VisibleOut &o, 
     ep.inj = rng.inj; ep.ld_inj = rng.ld_inj; ep.key = rng.key; ep.use_rng = rng.use_rng; ep.row0 = row0;
     if (o.bg_sign_neg) { ep.bg_what = 2; ep.bg_sign = -1.f; ep.bias_grad = G_a(h); }
     if (o.sqerr) { ep.sqerr = o.sqerr; ep.ref_rm = o.ref->b; ep.ld_ref = o.ref->ld; }
-    ep.dbg = h->dbg; ep.pscale = 1.f;
+    ep.pscale = 1.f;
     {
         GemmScope gs(h, 2.0 * (double)h->VL * (double)rows * (double)h->H);
         sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn, h->use_2cta);
@@ -1483,8 +1482,6 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
             h->online_kernel = value != 0.0;
         } else if (!strcmp(key, "stale_chains")) {
             set_stale_mode(h, value != 0.0);
-        } else if (!strcmp(key, "dbg")) {
-            h->dbg = (int)value;
         } else if (!strcmp(key, "use_2cta")) {
             QB_CHECK(value == 0.0 || value == 1.0 || value == 2.0, QB_E_ARG, "use_2cta must be 0, 1 or 2");
             h->use_2cta = (int)value;

@@ -69,7 +69,6 @@ struct EpiParams {
     // ---- EPI_GRAD
     float *out_f32; long long ld_out;
     float pscale;  // probabilities are multiplied by this before being stored / summed (n_chains / batch; 1 normally)
-    int dbg;  // experiment switches (0 in production): 1 = skip row-major stores, 2 = skip Philox, 4 = skip sigmoid
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
