@@ -95,8 +95,20 @@ class ClockSampler:
                         reasons.add(n)
             except Exception:
                 pass
+        after = False
+        if not sm:  # timed region shorter than nvidia-smi's start-up: one query right after it
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+                r = [x.strip() for x in out.split(",")]
+                sm.append(float(r[0])); mx = float(r[1]); after = True
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sampled_after_region": after}
 
 
 def ncu_traffic(kernel_prefix: str, fname: str):
