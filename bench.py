@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: use ncclAllReduce + update kernel instead of the fused peer-memory kernel")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: global batch fixed (BASELINE config); weak: per-GPU batch fixed (global batch x N)")
     ap.add_argument("--stale-chains", action="store_true", help="also time the stale-1 chains mode on one GPU")
@@ -232,7 +233,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = {"workload": f"{args.workload}: {w['desc']}", "V": w["V"], "H": w["H"], "L": w["L"], "global_batch": w["B"],
            "gibbs_steps": w["k"], "algorithm": w["algo"], "rng": "philox4x32-10", "persistent_chains": w.get("chains", w["B"]) if w["algo"] == "PCD" else None,
-           "parallelism": f"dp{world} (rows/chains sharded, NCCL gradient allreduce)" if world > 1 else "single GPU"}
+           "parallelism": (f"dp{world} (rows/chains sharded; gradient exchange: " +
+                           ("ncclAllReduce + update" if (args.no_p2p or args.precision != "bf16") else
+                            "fused NVLink peer-memory reduce-scatter + update + bf16 all-gather kernel") + ")") if world > 1 else "single GPU"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -276,6 +279,12 @@ def main():
             uid.copy_(torch.frombuffer(bytearray(q.DeviceRBM.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         dev.comm_init(bytes(uid.cpu().numpy().tobytes()))
+        if args.precision == "bf16" and not args.no_p2p:
+            # NVLink peer-memory path: reduce-scatter + update + all-gather of the bf16 shadows in one kernel per rank
+            mine = torch.frombuffer(bytearray(dev.p2p_export()), dtype=torch.uint8).cuda()
+            allh = torch.empty(320 * world, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(allh, mine)
+            dev.p2p_import(allh.cpu().numpy().tobytes())
     dev.set_data(Xl, Yl)
     pcd = w["algo"] == "PCD"
     if pcd:
@@ -331,7 +340,7 @@ def main():
     # ---------------- optional leg: declared stale-1 chains mode (allreduce + update overlapped with the next
     # step's chain advance; statistical parity only)
     overlap = None
-    if pcd and args.precision == "bf16" and w["L"] == 0 and (world > 1 or args.stale_chains):
+    if pcd and args.precision == "bf16" and w["L"] == 0 and ((world > 1 and args.no_p2p) or args.stale_chains):
         dev.set_option("stale_chains", 1)
         for i in range(args.warmup):
             step(i)

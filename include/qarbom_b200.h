@@ -177,6 +177,15 @@ int32_t qb_conditional_prob_y_given_v(qb_handle *h, const void *X, int32_t x_dty
 int32_t qb_comm_unique_id(void *id128);
 int32_t qb_comm_init(qb_handle *h, const void *id128);
 
+/* Optional NVLink peer-memory path (bf16 mode, 2..8 ranks on one node): after qb_comm_init (still used for nothing
+ * but kept as the fallback) every rank exports 5 CUDA IPC handles (320 bytes), the caller all-gathers them
+ * (world x 320 bytes, rank-major) and every rank imports the lot.  From then on the gradient exchange is ONE
+ * kernel per rank: reduce-scatter by P2P loads, update of the owned shard of the fp32 master, all-gather of the new
+ * bf16 shadows by P2P stores.  The master is sharded by hidden rows; qb_get_params / qb_snapshot_params gather it and
+ * must therefore be called by all ranks at the same point of the training loop. */
+int32_t qb_p2p_export(qb_handle *h, void *handles320);
+int32_t qb_p2p_import(qb_handle *h, const void *all_handles);
+
 /* Introspection for benchmarks.  Counters since the last reset: kernels launched by this
  * library on this handle, GEMM launches and their algorithmic flops; with option
  * "time_gemms" = 1 every GEMM launch is bracketed by CUDA events on the launching stream and

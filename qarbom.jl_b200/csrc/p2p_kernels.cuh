@@ -1,0 +1,157 @@
+// Data-parallel exchange over NVLink peer memory, fused with the parameter update (bf16 mode, world > 1).
+//
+// After the gradient GEMM every rank holds its partial G.  Instead of ncclAllReduce(G) followed by an update
+// kernel that every rank repeats on the full matrix, ONE kernel per rank does
+//     reduce-scatter : for the hidden rows it OWNS, g = sum over ranks of G_r[h][c]   (P2P 128-bit loads)
+//     update         : w += lr/B * g (+ momentum / weight decay) on its shard of the fp32 master
+//     all-gather     : the new bf16 shadows Wb[h][c] and WbT[c][h] are stored straight into EVERY rank's
+//                      shadow buffers (P2P stores)
+// so the bytes that cross NVLink are 4 B/param in and 4 B/param out per shard (the all-gather moves bf16, not
+// fp32), the update work is 1/world per rank, and no reduced fp32 gradient is ever written back.  Two
+// system-scope flag barriers bracket the kernel: "every G is complete" and "every push has landed".
+// The kernel is launched cooperatively (grid barrier between the flag barriers and the tile loop); each GPU
+// runs its own kernel, ranks never share a GPU.
+#pragma once
+#include "common.cuh"
+#include "online_kernels.cuh"  // grid_barrier
+
+namespace qb {
+
+constexpr int QB_MAX_PEERS = 8;
+
+struct P2pParams {
+    int rank, world;
+    const float *G[QB_MAX_PEERS];       // every rank's gradient buffer [W | a | b]
+    bf16 *Wb[QB_MAX_PEERS], *WbT[QB_MAX_PEERS];
+    unsigned int *flags[QB_MAX_PEERS];  // flags[p][r]: written by rank r, polled by rank p
+    float *W, *Vel;                     // local fp32 master / velocity ([H][ldv] + biases)
+    float *bias_rd;                     // optional versioned bias copy (stale-chains mode), else nullptr
+    int H, VL, V, h_begin, h_end;
+    long long ldv, ldh, nW;
+    float lr, llr, momentum, wd;
+    unsigned int epoch;                 // flag value of the first barrier of this launch (second = epoch + 1)
+    unsigned int *grid_bar;
+};
+
+__device__ __forceinline__ void xgpu_barrier(const P2pParams &p, unsigned int value) {
+    if (threadIdx.x < (unsigned)p.world) {
+        __threadfence_system();
+        unsigned int *remote = p.flags[threadIdx.x] + p.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(value) : "memory");
+        const unsigned int *mine = p.flags[p.rank] + threadIdx.x;
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+        } while ((int)(seen - value) < 0);
+    }
+    __syncthreads();
+}
+
+template <bool VEL>
+__global__ void __launch_bounds__(256) p2p_reduce_update_kernel(const P2pParams p) {
+    constexpr int TH = 64, TC = 128, PITCH = TC + 8, ROWS = 4;
+    __shared__ __align__(16) unsigned short tile[TH][PITCH];
+    unsigned int gepoch = 0;
+    if (blockIdx.x == 0) xgpu_barrier(p, p.epoch);  // every rank's G is complete
+    grid_barrier(p.grid_bar, gepoch, gridDim.x);
+
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tiles_c = (p.VL + TC - 1) / TC;
+    const int tiles_h = (p.h_end - p.h_begin + TH - 1) / TH;
+    for (int t = blockIdx.x; t < tiles_c * tiles_h; t += gridDim.x) {
+        const int c = (t % tiles_c) * TC + 4 * tx;
+        const int h0 = p.h_begin + (t / tiles_c) * TH;
+        const bool vec = (c + 3 < p.VL);
+        float lrc[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) lrc[i] = (c + i < p.V) ? p.lr : p.llr;
+#pragma unroll 1
+        for (int pass = 0; pass < TH / (8 * ROWS); pass++) {
+            float4 w[ROWS], g[ROWS], v[ROWS];
+#pragma unroll
+            for (int it = 0; it < ROWS; it++) {
+                const int h = h0 + ty + 8 * (pass * ROWS + it);
+                w[it] = make_float4(0.f, 0.f, 0.f, 0.f); g[it] = w[it];
+                if (VEL) v[it] = w[it];
+                if (h < p.h_end && c < p.VL) {
+                    const long long o = (long long)h * p.ldv + c;  // ldv % 8 == 0, padding columns are zero: 128-bit loads stay in bounds
+                    w[it] = *reinterpret_cast<const float4 *>(p.W + o);
+                    if (VEL) v[it] = *reinterpret_cast<const float4 *>(p.Vel + o);
+                    for (int r = 0; r < p.world; r++) {
+                        const float4 q = __ldcg(reinterpret_cast<const float4 *>(p.G[r] + o));
+                        g[it].x += q.x; g[it].y += q.y; g[it].z += q.z; g[it].w += q.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < ROWS; it++) {
+                const int hl = ty + 8 * (pass * ROWS + it), h = h0 + hl;
+                float *wp = reinterpret_cast<float *>(&w[it]), *gp = reinterpret_cast<float *>(&g[it]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (VEL) {
+                        float *vp = reinterpret_cast<float *>(&v[it]);
+                        vp[i] = p.momentum * vp[i] + lrc[i] * gp[i] - lrc[i] * p.wd * wp[i];
+                        wp[i] += vp[i];
+                    } else {
+                        wp[i] += lrc[i] * gp[i];
+                    }
+                    if (!vec && c + i >= p.VL) wp[i] = 0.f;
+                }
+                __nv_bfloat162 b01 = __floats2bfloat162_rn(wp[0], wp[1]), b23 = __floats2bfloat162_rn(wp[2], wp[3]);
+                const uint2 packed = make_uint2(*reinterpret_cast<uint32_t *>(&b01), *reinterpret_cast<uint32_t *>(&b23));
+                *reinterpret_cast<uint2 *>(&tile[hl][4 * tx]) = packed;
+                if (h < p.h_end && c < p.VL) {
+                    const long long o = (long long)h * p.ldv + c;
+                    *reinterpret_cast<float4 *>(p.W + o) = w[it];
+                    if (VEL) *reinterpret_cast<float4 *>(p.Vel + o) = v[it];
+                    for (int r = 0; r < p.world; r++) *reinterpret_cast<uint2 *>(p.Wb[r] + o) = packed;  // all-gather, row-major shadow
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 2; q++) {  // all-gather, transposed shadow: 32 B per (column, 16-row chunk)
+            const int task = threadIdx.x + 256 * q;
+            const int cl = task & (TC - 1), hc = task >> 7;
+            const int cc = (t % tiles_c) * TC + cl, hb = h0 + 16 * hc;
+            if (cc >= p.VL || hb >= p.h_end) continue;
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) pk[i] = (uint32_t)tile[16 * hc + 2 * i][cl] | ((uint32_t)tile[16 * hc + 2 * i + 1][cl] << 16);
+            for (int r = 0; r < p.world; r++) {
+                unsigned short *dst = reinterpret_cast<unsigned short *>(p.WbT[r]) + (long long)cc * p.ldh + hb;
+                if (hb + 16 <= p.h_end) {
+                    reinterpret_cast<uint4 *>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    reinterpret_cast<uint4 *>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                } else {
+                    for (int i = 0; i < 16; i++)
+                        if (hb + i < p.h_end) dst[i] = tile[16 * hc + i][cl];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // biases [acat | b]: tiny, every rank reduces and updates its own full copy (same order => identical everywhere)
+    const int nbias = (int)(p.ldv + p.ldh);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nbias; i += gridDim.x * blockDim.x) {
+        float g = 0.f;
+        for (int r = 0; r < p.world; r++) g += __ldcg(p.G[r] + p.nW + i);
+        const float lr_c = (i < p.ldv && i >= p.V) ? p.llr : p.lr;
+        float b = p.W[p.nW + i];
+        if (VEL) {
+            float vv = p.momentum * p.Vel[p.nW + i] + lr_c * g;
+            p.Vel[p.nW + i] = vv;
+            b += vv;
+        } else {
+            b += lr_c * g;
+        }
+        p.W[p.nW + i] = b;
+        if (p.bias_rd) p.bias_rd[i] = b;
+    }
+    __threadfence_system();
+    grid_barrier(p.grid_bar, gepoch, gridDim.x);
+    if (blockIdx.x == 0) xgpu_barrier(p, p.epoch + 1);  // every push has landed; nobody still reads my G
+}
+
+}  // namespace qb

@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "online_kernels.cuh"
+#include "p2p_kernels.cuh"
 #include "simt_kernels.cuh"
 #include "sm100_gemm.cuh"
 
@@ -127,6 +128,13 @@ struct qb_handle {
     size_t injUh_cap = 0, injUv_cap = 0, injZv_cap = 0;
     uint64_t seed = 0, draw = 0;
     ncclComm_t comm = nullptr;
+    // NVLink peer-memory exchange fused with the update (p2p_kernels.cuh): peers' G / shadows / flags / masters
+    bool p2p = false;
+    float *peerG[QB_MAX_PEERS] = {}, *peerP[QB_MAX_PEERS] = {};
+    bf16 *peerWb[QB_MAX_PEERS] = {}, *peerWbT[QB_MAX_PEERS] = {};
+    unsigned int *peerFlags[QB_MAX_PEERS] = {}, *p2p_flags = nullptr, *p2p_grid_bar = nullptr;
+    unsigned int p2p_epoch = 1;
+    int64_t shard_rows = 0;
     int64_t launches = 0, gemm_launches = 0;
     double gemm_flops = 0.0;
     int force_bn = 0, use_2cta = 1;
@@ -461,8 +469,11 @@ void zero_bias_grads(qb_handle *h, float pos_scale = 1.f) {
 
 // update_rbm!(rbm, dW, [dU,] da, db, [dc,] lr/B [, llr/B]) after the data-parallel sum of G.
 // `st` is the stream it runs on; (Wb_out, WbT_out, bias_out) the shadow set it refreshes.
+void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local);
+
 void op_update_on(qb_handle *h, double lr, double llr, int64_t B_local, cudaStream_t st, float *G, bf16 *Wb_out, bf16 *WbT_out,
                   float *bias_out) {
+    if (h->p2p && st == h->stream && G == h->G && Wb_out == h->Wb) { p2p_update(h, lr, llr, B_local); return; }
     if (h->comm) {
         QB_NCCL(nccl().AllReduce(G, G, (size_t)h->nP, /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->comm, st));
     }
@@ -495,6 +506,52 @@ void op_update(qb_handle *h, double lr, double llr, int64_t B_local) {
     op_update_on(h, lr, llr, B_local, h->stream, h->G, h->Wb, h->WbT, h->bias_rd);
 }
 
+// reduce-scatter + update + all-gather of the bf16 shadows in one kernel over NVLink peer memory
+void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local) {
+    const double Bg = (double)B_local * (double)h->cfg.world;
+    const bool use_vel = (h->momentum != 0.0 || h->weight_decay != 0.0);
+    if (use_vel && !h->Vel) h->Vel = dalloc<float>(h->nP);
+    P2pParams p{};
+    p.rank = h->cfg.rank; p.world = h->cfg.world;
+    for (int r = 0; r < p.world; r++) {
+        p.G[r] = h->peerG[r]; p.Wb[r] = h->peerWb[r]; p.WbT[r] = h->peerWbT[r]; p.flags[r] = h->peerFlags[r];
+    }
+    p.W = h->P; p.Vel = use_vel ? h->Vel : nullptr; p.bias_rd = h->bias_rd;
+    p.H = (int)h->H; p.VL = (int)h->VL; p.V = (int)h->V; p.ldv = h->ldv; p.ldh = h->ldh; p.nW = h->nW;
+    p.h_begin = (int)std::min<int64_t>(h->H, (int64_t)p.rank * h->shard_rows);
+    p.h_end = (int)std::min<int64_t>(h->H, (int64_t)(p.rank + 1) * h->shard_rows);
+    p.lr = (float)(lr / Bg); p.llr = (float)(llr / Bg); p.momentum = (float)h->momentum; p.wd = (float)h->weight_decay;
+    p.epoch = h->p2p_epoch; h->p2p_epoch += 2;
+    p.grid_bar = h->p2p_grid_bar;
+    QB_CUDA(cudaMemsetAsync(h->p2p_grid_bar, 0, sizeof(unsigned int), h->stream));
+    size_t ei = 0; bool timed = false;
+    if (h->time_gemms && h->upd_ev_used + 2 <= 4096) {
+        while (h->upd_ev.size() < h->upd_ev_used + 2) { cudaEvent_t e; QB_CUDA(cudaEventCreate(&e)); h->upd_ev.push_back(e); }
+        ei = h->upd_ev_used; h->upd_ev_used += 2; h->upd_timed++; timed = true;
+        QB_CUDA(cudaEventRecord(h->upd_ev[ei], h->stream));
+    }
+    void *args[] = {(void *)&p};
+    if (use_vel) QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<true>, dim3(h->num_sms), dim3(256), args, 0, h->stream));
+    else QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<false>, dim3(h->num_sms), dim3(256), args, 0, h->stream));
+    if (timed) QB_CUDA(cudaEventRecord(h->upd_ev[ei + 1], h->stream));
+    h->launches += 1;
+}
+
+// p2p mode: the fp32 master is sharded by hidden rows; pull the other ranks' shards (collective by convention:
+// every rank is between steps when any rank calls this)
+void p2p_gather_master(qb_handle *h) {
+    if (!h->p2p) return;
+    QB_CUDA(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < h->cfg.world; r++) {
+        if (r == h->cfg.rank) continue;
+        const int64_t b = std::min<int64_t>(h->H, (int64_t)r * h->shard_rows), e = std::min<int64_t>(h->H, (int64_t)(r + 1) * h->shard_rows);
+        if (e > b)
+            QB_CUDA(cudaMemcpyAsync(h->P + b * h->ldv, h->peerP[r] + b * h->ldv, (size_t)(e - b) * h->ldv * sizeof(float),
+                                    cudaMemcpyDefault, h->stream));
+    }
+    QB_CUDA(cudaStreamSynchronize(h->stream));
+}
+
 // stale-chains mode: make the asynchronously updated weight version the current one
 void adopt_pending_update(qb_handle *h) {
     if (!h->pending_update) return;
@@ -514,6 +571,7 @@ void wait_pending_update(qb_handle *h) {
 
 void set_stale_mode(qb_handle *h, bool on) {
     QB_CHECK(!on || (h->bf && h->L == 0), QB_E_UNSUPPORTED, "stale_chains needs bf16 precision and a model without label units");
+    QB_CHECK(!on || !h->p2p, QB_E_UNSUPPORTED, "stale_chains uses the NCCL path: do not import peer memory (qb_p2p_import) on this handle");
     adopt_pending_update(h);
     QB_CUDA(cudaStreamSynchronize(h->stream));
     if (on && !h->Wb_alt) {
@@ -861,6 +919,13 @@ int32_t qb_destroy(qb_handle *h) {
         cudaSetDevice(h->cfg.device);
         cudaDeviceSynchronize();
         if (h->comm) nccl().CommDestroy(h->comm);
+        if (h->p2p)
+            for (int r = 0; r < h->cfg.world; r++)
+                if (r != h->cfg.rank) {
+                    cudaIpcCloseMemHandle(h->peerG[r]); cudaIpcCloseMemHandle(h->peerWb[r]); cudaIpcCloseMemHandle(h->peerWbT[r]);
+                    cudaIpcCloseMemHandle(h->peerFlags[r]); cudaIpcCloseMemHandle(h->peerP[r]);
+                }
+        cudaFree(h->p2p_flags); cudaFree(h->p2p_grid_bar);
         cudaFree(h->P); cudaFree(h->G); cudaFree(h->Vel); cudaFree(h->P_best); cudaFree(h->F); cudaFree(h->F2); cudaFree(h->P_eff); cudaFree(h->W2); cudaFree(h->online_vec); cudaFree(h->online_bar); cudaFree(h->online_ns); cudaFree(h->Wb); cudaFree(h->WbT);
         cudaFree(h->Wb_alt); cudaFree(h->WbT_alt); cudaFree(h->G_alt); cudaFree(h->bias_buf[0]); cudaFree(h->bias_buf[1]);
         if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
@@ -905,6 +970,7 @@ int32_t qb_set_params(qb_handle *h, const double *W, const double *a, const doub
 int32_t qb_get_params(qb_handle *h, double *W, double *a, double *b, double *U, double *c) {
     return guarded([&] {
         QB_H_KEEP(h); wait_pending_update(h);
+        p2p_gather_master(h);
         std::vector<float> p((size_t)h->nP);
         QB_CUDA(cudaMemcpyAsync(p.data(), h->P, p.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         QB_CUDA(cudaStreamSynchronize(h->stream));
@@ -923,6 +989,7 @@ int32_t qb_snapshot_params(qb_handle *h) {
     return guarded([&] {
         QB_H(h);
         if (!h->P_best) h->P_best = dalloc<float>(h->nP);
+        p2p_gather_master(h);
         QB_CUDA(cudaMemcpyAsync(h->P_best, h->P, h->nP * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
         QB_CUDA(cudaStreamSynchronize(h->stream));
     });
@@ -1435,6 +1502,44 @@ int32_t qb_comm_init(qb_handle *h, const void *id128) {
         ncclUniqueId id;
         memcpy(&id, id128, sizeof(id));
         QB_NCCL(nccl().CommInitRank(&h->comm, h->cfg.world, id, h->cfg.rank));
+    });
+}
+
+// ---- NVLink peer-memory path: 5 IPC handles per rank (G, Wb, WbT, flags, P), 64 bytes each
+int32_t qb_p2p_export(qb_handle *h, void *handles320) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(handles320 != nullptr, QB_E_ARG, "handle buffer is NULL");
+        QB_CHECK(h->bf && h->cfg.world > 1 && h->cfg.world <= QB_MAX_PEERS, QB_E_UNSUPPORTED, "peer-memory exchange needs bf16 precision and 2..8 ranks");
+        QB_CHECK(!h->stale_chains, QB_E_UNSUPPORTED, "peer-memory exchange and stale_chains are mutually exclusive");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        if (!h->p2p_flags) { h->p2p_flags = dalloc<unsigned int>(QB_MAX_PEERS); h->p2p_grid_bar = dalloc<unsigned int>(1); }
+        cudaIpcMemHandle_t hd[5];
+        QB_CUDA(cudaIpcGetMemHandle(&hd[0], h->G));
+        QB_CUDA(cudaIpcGetMemHandle(&hd[1], h->Wb));
+        QB_CUDA(cudaIpcGetMemHandle(&hd[2], h->WbT));
+        QB_CUDA(cudaIpcGetMemHandle(&hd[3], h->p2p_flags));
+        QB_CUDA(cudaIpcGetMemHandle(&hd[4], h->P));
+        memcpy(handles320, hd, sizeof(hd));
+    });
+}
+int32_t qb_p2p_import(qb_handle *h, const void *all_handles) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(all_handles != nullptr && h->p2p_flags != nullptr, QB_E_STATE, "call qb_p2p_export on every rank first");
+        const cudaIpcMemHandle_t *hd = (const cudaIpcMemHandle_t *)all_handles;
+        for (int r = 0; r < h->cfg.world; r++) {
+            if (r == h->cfg.rank) {
+                h->peerG[r] = h->G; h->peerWb[r] = h->Wb; h->peerWbT[r] = h->WbT; h->peerFlags[r] = h->p2p_flags; h->peerP[r] = h->P;
+                continue;
+            }
+            void *ptr[5];
+            for (int i = 0; i < 5; i++) QB_CUDA(cudaIpcOpenMemHandle(&ptr[i], hd[r * 5 + i], cudaIpcMemLazyEnablePeerAccess));
+            h->peerG[r] = (float *)ptr[0]; h->peerWb[r] = (bf16 *)ptr[1]; h->peerWbT[r] = (bf16 *)ptr[2];
+            h->peerFlags[r] = (unsigned int *)ptr[3]; h->peerP[r] = (float *)ptr[4];
+        }
+        h->shard_rows = round_up(ceil_div(h->H, h->cfg.world), 64);
+        h->p2p = true;
     });
 }
 

@@ -224,6 +224,15 @@ class DeviceRBM:
         buf = ctypes.create_string_buffer(uid, 128)
         check(lib().qb_comm_init(self._h, buf))
 
+    def p2p_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(320)
+        check(lib().qb_p2p_export(self._h, buf))
+        return buf.raw
+
+    def p2p_import(self, all_handles: bytes):
+        buf = ctypes.create_string_buffer(all_handles, len(all_handles))
+        check(lib().qb_p2p_import(self._h, buf))
+
     def counters(self):
         """(kernel launches, GEMM launches) since the last reset."""
         return self.counters_full()[:2]

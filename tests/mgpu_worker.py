@@ -15,6 +15,7 @@ from bench import shard_rows  # noqa: E402
 
 def main():
     prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+    exchange = sys.argv[2] if len(sys.argv) > 2 else "nccl"   # "p2p": NVLink peer-memory reduce+update kernel
     rank, world, lr_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr_)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr_))
@@ -33,11 +34,20 @@ def main():
                 uid.copy_(torch.frombuffer(bytearray(q.DeviceRBM.comm_unique_id()), dtype=torch.uint8))
             dist.broadcast(uid, 0)
             dev.comm_init(uid.cpu().numpy().tobytes())
+            if exchange == "p2p":
+                mine = torch.frombuffer(bytearray(dev.p2p_export()), dtype=torch.uint8).cuda()
+                allh = torch.empty(320 * world, dtype=torch.uint8, device="cuda")
+                dist.all_gather_into_tensor(allh, mine)
+                dev.p2p_import(allh.cpu().numpy().tobytes())
         dev.set_data(Xs)
         dev.init_chains(Brows)
         for t in range(steps):
             dev.pcd_step(t % nb, Brows, k, 0.05)
+        if comm:
+            dist.barrier()   # pull_params gathers the sharded master in p2p mode: every rank must be between steps
         dev.pull_params()
+        if comm:
+            dist.barrier()
         v, h, _ = dev.get_chains()
         dev.close()
         return rbm.W.copy(), rbm.a.copy(), rbm.b.copy(), v, h
@@ -54,7 +64,7 @@ def main():
         drel = np.linalg.norm((Wm - W0) - (Ws - W0)) / np.linalg.norm(Ws - W0)
         vcat = np.concatenate([g[1] for g in gathered]); hcat = np.concatenate([g[2] for g in gathered])
         mis = float(np.mean(vcat != vs)), float(np.mean(hcat != hs))
-        print(f"MGPU world={world} prec={prec} relW={rel:.3e} rel_dW={drel:.3e} state_mismatch={mis}")
+        print(f"MGPU world={world} prec={prec} exchange={exchange} relW={rel:.3e} rel_dW={drel:.3e} state_mismatch={mis}")
         ok = rel < 1e-5 and drel < (2e-2 if prec == "bf16" else 1e-4) and max(mis) < 1e-3
     dist.barrier()
     dist.destroy_process_group()

@@ -10,15 +10,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
-def test_two_rank_pcd_matches_single_gpu(prec):
+@pytest.mark.parametrize("prec,exchange", [("fp32", "nccl"), ("bf16", "nccl"), ("bf16", "p2p")])
+def test_two_rank_pcd_matches_single_gpu(prec, exchange):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
-           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_worker.py"), prec]
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_worker.py"), prec, exchange]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "MGPU" in out.stdout
