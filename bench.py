@@ -218,7 +218,10 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: use ncclAllReduce + update kernel instead of the fused peer-memory kernel")
+    ap.add_argument("--p2p-blocks", type=int, default=0, help="experiment: CTAs per SM of the peer-memory exchange kernel")
+    ap.add_argument("--p2p", action="store_true",
+                    help="multi-GPU: fused NVLink peer-memory reduce-scatter + update + all-gather kernel instead of ncclAllReduce + "
+                         "update (measured slower at 8 GPUs this round, see profiles/README.md)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: global batch fixed (BASELINE config); weak: per-GPU batch fixed (global batch x N)")
     ap.add_argument("--stale-chains", action="store_true", help="also time the stale-1 chains mode on one GPU")
@@ -234,7 +237,7 @@ def main():
     cfg = {"workload": f"{args.workload}: {w['desc']}", "V": w["V"], "H": w["H"], "L": w["L"], "global_batch": w["B"],
            "gibbs_steps": w["k"], "algorithm": w["algo"], "rng": "philox4x32-10", "persistent_chains": w.get("chains", w["B"]) if w["algo"] == "PCD" else None,
            "parallelism": (f"dp{world} (rows/chains sharded; gradient exchange: " +
-                           ("ncclAllReduce + update" if (args.no_p2p or args.precision != "bf16") else
+                           ("ncclAllReduce + update" if ((not args.p2p) or args.precision != "bf16") else
                             "fused NVLink peer-memory reduce-scatter + update + bf16 all-gather kernel") + ")") if world > 1 else "single GPU"}
 
     if args.impl == "reference":
@@ -279,12 +282,14 @@ def main():
             uid.copy_(torch.frombuffer(bytearray(q.DeviceRBM.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         dev.comm_init(bytes(uid.cpu().numpy().tobytes()))
-        if args.precision == "bf16" and not args.no_p2p:
+        if args.precision == "bf16" and not (not args.p2p):
             # NVLink peer-memory path: reduce-scatter + update + all-gather of the bf16 shadows in one kernel per rank
             mine = torch.frombuffer(bytearray(dev.p2p_export()), dtype=torch.uint8).cuda()
             allh = torch.empty(320 * world, dtype=torch.uint8, device="cuda")
             dist.all_gather_into_tensor(allh, mine)
             dev.p2p_import(allh.cpu().numpy().tobytes())
+            if args.p2p_blocks:
+                dev.set_option("p2p_blocks_per_sm", args.p2p_blocks)
     dev.set_data(Xl, Yl)
     pcd = w["algo"] == "PCD"
     if pcd:
@@ -316,6 +321,8 @@ def main():
         sampler.start()
     barrier()
     dev.reset_counters()
+    if world > 1 and args.precision == "bf16" and not (not args.p2p):
+        dev.p2p_timing()  # reset the in-kernel phase timers
     dev.timer_start()
     for i in range(args.steps):
         step(args.warmup + i)
@@ -325,6 +332,7 @@ def main():
     ms = max_over_ranks(ms)
     launches = dev.counters_full()[0]
     value = B * args.steps / (ms * 1e-3)
+    p2p_t = dev.p2p_timing() if (world > 1 and args.precision == "bf16" and not (not args.p2p)) else None
     dev.reset_counters()
     dev.set_option("time_gemms", 1)
     barrier()
@@ -340,7 +348,7 @@ def main():
     # ---------------- optional leg: declared stale-1 chains mode (allreduce + update overlapped with the next
     # step's chain advance; statistical parity only)
     overlap = None
-    if pcd and args.precision == "bf16" and w["L"] == 0 and ((world > 1 and args.no_p2p) or args.stale_chains):
+    if pcd and args.precision == "bf16" and w["L"] == 0 and ((world > 1 and (not args.p2p)) or args.stale_chains):
         dev.set_option("stale_chains", 1)
         for i in range(args.warmup):
             step(i)
@@ -420,6 +428,10 @@ def main():
             "gibbs_steps_per_s": value * k * (w.get("chains", B) / B if pcd else 1.0), "gpu_launches": launches, "roofline": roof, "roofline_update": roof_upd, "clocks": clocks, "e2e": e2e}
     if overlap:
         line["overlap"] = overlap
+    if p2p_t:
+        line["exchange"] = {"kernel": "qb::p2p_reduce_update_kernel", "wait_for_peers_ms_per_step": p2p_t[0] / args.steps,
+                            "reduce_update_push_ms_per_step": p2p_t[1] / args.steps,
+                            "nvlink_bytes_per_step_per_gpu": 2 * 4.0 * (w["V"] + w["L"]) * w["H"] * (world - 1) / world}
     if not args.no_cpu_baseline:
         r = cpu_reference(w, args.cpu_seconds, 3, 1)
         r1 = cpu_reference(w, args.cpu_seconds / 2, 2, 1, threads=1)   # the Julia code itself is single-threaded

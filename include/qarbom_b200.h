@@ -185,6 +185,9 @@ int32_t qb_comm_init(qb_handle *h, const void *id128);
  * must therefore be called by all ranks at the same point of the training loop. */
 int32_t qb_p2p_export(qb_handle *h, void *handles320);
 int32_t qb_p2p_import(qb_handle *h, const void *all_handles);
+/* milliseconds accumulated inside the fused exchange kernels since the last call: waiting for the peers' gradients,
+ * and reduce + update + push */
+int32_t qb_get_p2p_timing(qb_handle *h, double *wait_ms, double *work_ms);
 
 /* Introspection for benchmarks.  Counters since the last reset: kernels launched by this
  * library on this handle, GEMM launches and their algorithmic flops; with option

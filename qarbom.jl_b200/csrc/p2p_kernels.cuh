@@ -31,6 +31,7 @@ struct P2pParams {
     float lr, llr, momentum, wd;
     unsigned int epoch;                 // flag value of the first barrier of this launch (second = epoch + 1)
     unsigned int *grid_bar;
+    unsigned long long *phase_ns;       // [2] accumulated ns: waiting for the peers' gradients, reduce + update + push
 };
 
 __device__ __forceinline__ void xgpu_barrier(const P2pParams &p, unsigned int value) {
@@ -49,11 +50,14 @@ __device__ __forceinline__ void xgpu_barrier(const P2pParams &p, unsigned int va
 
 template <bool VEL>
 __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(const P2pParams p) {
-    constexpr int TH = 64, TC = 128, PITCH = TC + 8, ROWS = 4;
+    constexpr int TH = 64, TC = 128, PITCH = TC + 8, ROWS = 2;
     __shared__ __align__(16) unsigned short tile[TH][PITCH];
     unsigned int gepoch = 0;
+    const bool timer = blockIdx.x == 0 && threadIdx.x == 0 && p.phase_ns != nullptr;
+    unsigned long long t0 = timer ? gtimer() : 0ull;
     if (blockIdx.x == 0) xgpu_barrier(p, p.epoch);  // every rank's G is complete
     grid_barrier(p.grid_bar, gepoch, gridDim.x);
+    unsigned long long t1 = timer ? gtimer() : 0ull;
 
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int tiles_c = (p.VL + TC - 1) / TC;
@@ -67,21 +71,31 @@ __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(const P2pParams 
         for (int i = 0; i < 4; i++) lrc[i] = (c + i < p.V) ? p.lr : p.llr;
 #pragma unroll 1
         for (int pass = 0; pass < TH / (8 * ROWS); pass++) {
-            float4 w[ROWS], g[ROWS], v[ROWS];
+            float4 w[ROWS], g[ROWS], v[ROWS], q[ROWS][QB_MAX_PEERS];
+            // issue every load first (fully unrolled, predicated on the rank count): a remote 128-bit load takes
+            // ~2-3 us over NVLink, so ROWS x world of them must be in flight per thread, not one after the other
 #pragma unroll
             for (int it = 0; it < ROWS; it++) {
                 const int h = h0 + ty + 8 * (pass * ROWS + it);
-                w[it] = make_float4(0.f, 0.f, 0.f, 0.f); g[it] = w[it];
+                const bool ok = h < p.h_end && c < p.VL;
+                const long long o = (long long)h * p.ldv + c;  // ldv % 8 == 0, padding columns are zero: 128-bit loads stay in bounds
+                w[it] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (VEL) v[it] = w[it];
-                if (h < p.h_end && c < p.VL) {
-                    const long long o = (long long)h * p.ldv + c;  // ldv % 8 == 0, padding columns are zero: 128-bit loads stay in bounds
+#pragma unroll
+                for (int r = 0; r < QB_MAX_PEERS; r++) {
+                    q[it][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok && r < p.world) q[it][r] = __ldcg(reinterpret_cast<const float4 *>(p.G[r] + o));
+                }
+                if (ok) {
                     w[it] = *reinterpret_cast<const float4 *>(p.W + o);
                     if (VEL) v[it] = *reinterpret_cast<const float4 *>(p.Vel + o);
-                    for (int r = 0; r < p.world; r++) {
-                        const float4 q = __ldcg(reinterpret_cast<const float4 *>(p.G[r] + o));
-                        g[it].x += q.x; g[it].y += q.y; g[it].z += q.z; g[it].w += q.w;
-                    }
                 }
+            }
+#pragma unroll
+            for (int it = 0; it < ROWS; it++) {
+                g[it] = q[it][0];
+#pragma unroll
+                for (int r = 1; r < QB_MAX_PEERS; r++) { g[it].x += q[it][r].x; g[it].y += q[it][r].y; g[it].z += q[it][r].z; g[it].w += q[it][r].w; }
             }
 #pragma unroll
             for (int it = 0; it < ROWS; it++) {
@@ -151,6 +165,7 @@ __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(const P2pParams 
     }
     __threadfence_system();
     grid_barrier(p.grid_bar, gepoch, gridDim.x);
+    if (timer) { const unsigned long long t2 = gtimer(); p.phase_ns[0] += t1 - t0; p.phase_ns[1] += t2 - t1; }
     if (blockIdx.x == 0) xgpu_barrier(p, p.epoch + 1);  // every push has landed; nobody still reads my G
 }
 

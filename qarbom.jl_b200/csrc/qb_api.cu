@@ -133,7 +133,7 @@ struct qb_handle {
     float *peerG[QB_MAX_PEERS] = {}, *peerP[QB_MAX_PEERS] = {};
     bf16 *peerWb[QB_MAX_PEERS] = {}, *peerWbT[QB_MAX_PEERS] = {};
     unsigned int *peerFlags[QB_MAX_PEERS] = {}, *p2p_flags = nullptr, *p2p_grid_bar = nullptr;
-    unsigned int p2p_epoch = 1;
+    unsigned int p2p_epoch = 1; unsigned long long *p2p_ns = nullptr; int p2p_blocks_per_sm = 3;
     int64_t shard_rows = 0;
     int64_t launches = 0, gemm_launches = 0;
     double gemm_flops = 0.0;
@@ -522,7 +522,8 @@ void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local) {
     p.h_end = (int)std::min<int64_t>(h->H, (int64_t)(p.rank + 1) * h->shard_rows);
     p.lr = (float)(lr / Bg); p.llr = (float)(llr / Bg); p.momentum = (float)h->momentum; p.wd = (float)h->weight_decay;
     p.epoch = h->p2p_epoch; h->p2p_epoch += 2;
-    p.grid_bar = h->p2p_grid_bar;
+    p.grid_bar = h->p2p_grid_bar; p.phase_ns = h->p2p_ns;
+    const int p2p_grid = h->num_sms * h->p2p_blocks_per_sm;
     QB_CUDA(cudaMemsetAsync(h->p2p_grid_bar, 0, sizeof(unsigned int), h->stream));
     size_t ei = 0; bool timed = false;
     if (h->time_gemms && h->upd_ev_used + 2 <= 4096) {
@@ -531,8 +532,8 @@ void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local) {
         QB_CUDA(cudaEventRecord(h->upd_ev[ei], h->stream));
     }
     void *args[] = {(void *)&p};
-    if (use_vel) QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<true>, dim3(h->num_sms), dim3(256), args, 0, h->stream));
-    else QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<false>, dim3(h->num_sms), dim3(256), args, 0, h->stream));
+    if (use_vel) QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<true>, dim3(p2p_grid), dim3(256), args, 0, h->stream));
+    else QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<false>, dim3(p2p_grid), dim3(256), args, 0, h->stream));
     if (timed) QB_CUDA(cudaEventRecord(h->upd_ev[ei + 1], h->stream));
     h->launches += 1;
 }
@@ -925,7 +926,7 @@ int32_t qb_destroy(qb_handle *h) {
                     cudaIpcCloseMemHandle(h->peerG[r]); cudaIpcCloseMemHandle(h->peerWb[r]); cudaIpcCloseMemHandle(h->peerWbT[r]);
                     cudaIpcCloseMemHandle(h->peerFlags[r]); cudaIpcCloseMemHandle(h->peerP[r]);
                 }
-        cudaFree(h->p2p_flags); cudaFree(h->p2p_grid_bar);
+        cudaFree(h->p2p_flags); cudaFree(h->p2p_grid_bar); cudaFree(h->p2p_ns);
         cudaFree(h->P); cudaFree(h->G); cudaFree(h->Vel); cudaFree(h->P_best); cudaFree(h->F); cudaFree(h->F2); cudaFree(h->P_eff); cudaFree(h->W2); cudaFree(h->online_vec); cudaFree(h->online_bar); cudaFree(h->online_ns); cudaFree(h->Wb); cudaFree(h->WbT);
         cudaFree(h->Wb_alt); cudaFree(h->WbT_alt); cudaFree(h->G_alt); cudaFree(h->bias_buf[0]); cudaFree(h->bias_buf[1]);
         if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
@@ -1513,7 +1514,7 @@ int32_t qb_p2p_export(qb_handle *h, void *handles320) {
         QB_CHECK(h->bf && h->cfg.world > 1 && h->cfg.world <= QB_MAX_PEERS, QB_E_UNSUPPORTED, "peer-memory exchange needs bf16 precision and 2..8 ranks");
         QB_CHECK(!h->stale_chains, QB_E_UNSUPPORTED, "peer-memory exchange and stale_chains are mutually exclusive");
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-        if (!h->p2p_flags) { h->p2p_flags = dalloc<unsigned int>(QB_MAX_PEERS); h->p2p_grid_bar = dalloc<unsigned int>(1); }
+        if (!h->p2p_flags) { h->p2p_flags = dalloc<unsigned int>(QB_MAX_PEERS); h->p2p_grid_bar = dalloc<unsigned int>(1); h->p2p_ns = dalloc<unsigned long long>(2); }
         cudaIpcMemHandle_t hd[5];
         QB_CUDA(cudaIpcGetMemHandle(&hd[0], h->G));
         QB_CUDA(cudaIpcGetMemHandle(&hd[1], h->Wb));
@@ -1580,6 +1581,9 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
             int bn = (int)value;
             QB_CHECK(bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 256, QB_E_ARG, "force_bn must be 0/32/64/128/256");
             h->force_bn = bn;
+        } else if (!strcmp(key, "p2p_blocks_per_sm")) {
+            QB_CHECK(value >= 1 && value <= 4, QB_E_ARG, "p2p_blocks_per_sm must be 1..4");
+            h->p2p_blocks_per_sm = (int)value;
         } else if (!strcmp(key, "online_wpb")) {
             QB_CHECK(value == 0 || value == 4 || value == 8 || value == 16 || value == 32, QB_E_ARG, "online_wpb must be 0/4/8/16/32");
             h->online_wpb = (int)value;
@@ -1597,6 +1601,20 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
         } else {
             throw Error(QB_E_ARG, std::string("unknown option ") + key);
         }
+    });
+}
+// p2p mode: accumulated ns inside the fused exchange kernel: [waiting for the peers' gradients, reduce + update + push]
+int32_t qb_get_p2p_timing(qb_handle *h, double *wait_ms, double *work_ms) {
+    return guarded([&] {
+        QB_H_KEEP(h);
+        unsigned long long ns[2] = {0, 0};
+        if (h->p2p_ns) {
+            QB_CUDA(cudaStreamSynchronize(h->stream));
+            QB_CUDA(cudaMemcpy(ns, h->p2p_ns, sizeof(ns), cudaMemcpyDeviceToHost));
+            QB_CUDA(cudaMemset(h->p2p_ns, 0, sizeof(ns)));
+        }
+        if (wait_ms) *wait_ms = ns[0] * 1e-6;
+        if (work_ms) *work_ms = ns[1] * 1e-6;
     });
 }
 int32_t qb_get_update_timing(qb_handle *h, int64_t *timed_updates, double *timed_update_ms) {

@@ -233,6 +233,11 @@ class DeviceRBM:
         buf = ctypes.create_string_buffer(all_handles, len(all_handles))
         check(lib().qb_p2p_import(self._h, buf))
 
+    def p2p_timing(self):
+        a, b = ctypes.c_double(0), ctypes.c_double(0)
+        check(lib().qb_get_p2p_timing(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     def counters(self):
         """(kernel launches, GEMM launches) since the last reset."""
         return self.counters_full()[:2]
