@@ -111,6 +111,9 @@ struct qb_handle {
     bf16 *dataT = nullptr; int64_t dataT_B = 0, dataT_nb = 0, dataT_ld = 0;
     float *datasum = nullptr;          // [nb][ldv] column sums of every resident mini-batch (data side of delta_a)
     const float *cur_datasum = nullptr;  // sums of the mini-batch being processed (nullptr: compute them)
+    bool bias_grads_clean = false;       // the bias region of G is zero (left so by the previous update)
+    bool datasum_in_update = false;      // the cached data sums are added by the update kernel, not by the init kernel
+    float datasum_scale = 1.f;
     // persistent chains and work buffers (Bmax rows)
     Mat cv, ch; int64_t n_chains = 0; bool chains_binary = false;
     Mat phd, hs, vm, phm, hb;  // pos-phase probs, sampled hidden, CD model visible, CD final probs, host-batch staging
@@ -462,7 +465,16 @@ void op_grad(qb_handle *h, const Mat &posH, const Mat &posV, const bf16 *posV_T,
 // bias-gradient accumulators start at the data-side visible sums when those are cached
 void zero_bias_grads(qb_handle *h, float pos_scale = 1.f) {
     const int n = (int)(h->ldv + h->ldh);
-    init_bias_grads_kernel<<<grid1d(n), 256, 0, h->stream>>>(G_a(h), h->bf ? h->cur_datasum : nullptr, pos_scale, (int)h->ldv, n);
+    // single GPU, synchronous update: the update kernel adds the cached data sums itself and leaves the
+    // accumulators at zero, so a step needs no init launch at all
+    h->datasum_in_update = h->bf && h->cur_datasum != nullptr && h->cfg.world == 1 && !h->stale_chains;
+    h->datasum_scale = pos_scale;
+    // multi-GPU / stale mode: the data sums must be inside G before the exchange
+    const float *init_sum = (h->bf && !h->datasum_in_update) ? h->cur_datasum : nullptr;
+    const bool clean = h->bias_grads_clean;
+    h->bias_grads_clean = false;  // this step dirties the accumulators; the update kernel re-establishes the invariant
+    if (clean && !init_sum) return;
+    init_bias_grads_kernel<<<grid1d(n), 256, 0, h->stream>>>(G_a(h), init_sum, pos_scale, (int)h->ldv, n);
     QB_CUDA(cudaGetLastError());
     h->launches++;
 }
@@ -481,7 +493,15 @@ void op_update_on(qb_handle *h, double lr, double llr, int64_t B_local, cudaStre
     const float lr_e = (float)(lr / Bg), llr_e = (float)(llr / Bg);
     const bool use_vel = (h->momentum != 0.0 || h->weight_decay != 0.0);
     if (use_vel && !h->Vel) h->Vel = dalloc<float>(h->nP);
-    dim3 g((unsigned)ceil_div(h->VL, 128), (unsigned)ceil_div(h->H, 64));
+    // one launch: W tiles plus one extra row of blocks for the bias region [acat | b]
+    dim3 g((unsigned)ceil_div(h->VL, 128), (unsigned)ceil_div(h->H, 64) + 1);
+    const int nb = (int)(h->ldv + h->ldh);
+    const bool own_step = (st == h->stream && G == h->G);
+    BiasTail bt{};
+    bt.P = acat(h); bt.G = G + h->nW; bt.Vel = use_vel ? h->Vel + h->nW : nullptr;
+    bt.datasum = (own_step && h->datasum_in_update) ? h->cur_datasum : nullptr; bt.dscale = h->datasum_scale;
+    bt.copy_out = bias_out; bt.n_vis = (int)h->ldv; bt.n_total = nb;
+    bt.zero_after = (own_step && h->cfg.world == 1 && !h->stale_chains) ? 1 : 0;
     size_t ei = 0; bool timed = false;
     if (h->time_gemms && h->upd_ev_used + 2 <= 4096) {
         while (h->upd_ev.size() < h->upd_ev_used + 2) { cudaEvent_t e; QB_CUDA(cudaEventCreate(&e)); h->upd_ev.push_back(e); }
@@ -490,17 +510,14 @@ void op_update_on(qb_handle *h, double lr, double llr, int64_t B_local, cudaStre
     }
     if (use_vel)
         update_w_kernel<true><<<g, 256, 0, st>>>(Wf(h), G, h->Vel, (int)h->H, (int)h->VL, (int)h->V, h->ldv, lr_e, llr_e,
-                                                 (float)h->momentum, (float)h->weight_decay, Wb_out, WbT_out, h->ldh);
+                                                 (float)h->momentum, (float)h->weight_decay, Wb_out, WbT_out, h->ldh, bt);
     else
         update_w_kernel<false><<<g, 256, 0, st>>>(Wf(h), G, nullptr, (int)h->H, (int)h->VL, (int)h->V, h->ldv, lr_e, llr_e, 0.f, 0.f,
-                                                  Wb_out, WbT_out, h->ldh);
+                                                  Wb_out, WbT_out, h->ldh, bt);
     if (timed) QB_CUDA(cudaEventRecord(h->upd_ev[ei + 1], st));
     QB_CUDA(cudaGetLastError());
-    const int nb = (int)(h->ldv + h->ldh);
-    update_bias_kernel<<<grid1d(nb), 256, 0, st>>>(acat(h), G + h->nW, use_vel ? h->Vel + h->nW : nullptr, (int)h->ldv, (int)h->V, nb,
-                                                   lr_e, llr_e, (float)h->momentum, bias_out);
-    QB_CUDA(cudaGetLastError());
-    h->launches += 2;
+    h->launches += 1;
+    if (own_step) h->bias_grads_clean = bt.zero_after != 0;
 }
 void op_update(qb_handle *h, double lr, double llr, int64_t B_local) {
     op_update_on(h, lr, llr, B_local, h->stream, h->G, h->Wb, h->WbT, h->bias_rd);

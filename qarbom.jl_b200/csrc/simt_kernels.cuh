@@ -148,12 +148,39 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T *__restrict__ A, in
 //   vel = momentum*vel + lr_c*g - lr_c*wd*w ;  w += vel     (momentum = wd = 0: w += lr_c*g,
 //   i.e. update_rbm!, src/rbm.jl:152-163 / :120-136 with lr_c = lr/B for c < V, llr/B for labels)
 // Algorithmic bytes per parameter: 12 (read w, read g, write w) + 4 (two bf16 shadows); +8 with velocity.
+// The bias region [acat | b] that follows W in the flat vectors is updated by one extra row of blocks
+// (blockIdx.y == tiles over H) of the same launch: g = G + dscale * datasum (cached data-side visible sums,
+// single-GPU path), optional versioned copy, and optionally G <- 0 so the next step needs no init kernel.
+struct BiasTail {
+    float *P, *G, *Vel; const float *datasum; float dscale; float *copy_out; int n_vis, n_total, zero_after;
+};
+
 template <bool VEL>
 __global__ void __launch_bounds__(256, 3) update_w_kernel(float *__restrict__ W, const float *__restrict__ G,
                                                           float *__restrict__ Vel, int H, int VL, int V, int64_t ldv,
                                                           float lr, float llr, float momentum, float wd,
-                                                          bf16 *__restrict__ Wb, bf16 *__restrict__ WbT, int64_t ldh) {
+                                                          bf16 *__restrict__ Wb, bf16 *__restrict__ WbT, int64_t ldh,
+                                                          const BiasTail bt) {
     constexpr int TH = 64, TC = 128, PITCH = TC + 8, ROWS = 4;  // ROWS rows in flight per thread
+    if ((int)blockIdx.y * TH >= H) {  // the bias blocks
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < bt.n_total; i += gridDim.x * blockDim.x) {
+            const float lr_c = (i < bt.n_vis && i >= V) ? llr : lr;  // label biases c use llr; a and b use lr
+            float g = bt.G[i];
+            if (bt.datasum && i < bt.n_vis) g += bt.dscale * bt.datasum[i];
+            float pv = bt.P[i];
+            if (VEL) {
+                const float v = momentum * bt.Vel[i] + lr_c * g;
+                bt.Vel[i] = v;
+                pv += v;
+            } else {
+                pv += lr_c * g;
+            }
+            bt.P[i] = pv;
+            if (bt.copy_out) bt.copy_out[i] = pv;
+            if (bt.zero_after) bt.G[i] = 0.f;
+        }
+        return;
+    }
     __shared__ __align__(16) unsigned short tile[TH][PITCH];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * TC + 4 * tx;
@@ -270,25 +297,6 @@ __global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const bf16 *__restri
             if (c + i < cols) atomicAdd(out + c + i, sign * s2);
         }
     }
-}
-
-// bias region: [acat (VL) | b (H)] stored contiguously after W with the same treatment (no weight decay)
-__global__ void update_bias_kernel(float *__restrict__ P, const float *__restrict__ G, float *__restrict__ Vel, int n_vis,
-                                   int V, int n_total, float lr, float llr, float momentum, float *__restrict__ copy_out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_total) return;
-    float lr_c = (i < n_vis && i >= V) ? llr : lr;  // label biases c use llr; a and b use lr
-    float g = G[i];
-    float p = P[i];
-    if (Vel) {
-        float v = momentum * Vel[i] + lr_c * g;
-        Vel[i] = v;
-        p += v;
-    } else {
-        p += lr_c * g;
-    }
-    P[i] = p;
-    if (copy_out) copy_out[i] = p;  // versioned bias copy read by the GEMM epilogues (stale-chains mode)
 }
 
 // start of a step: G_a = cached data-side visible sums (or 0), G_b = 0 -- one launch instead of memcpy + memset
