@@ -508,12 +508,21 @@ void op_update_on(qb_handle *h, double lr, double llr, int64_t B_local, cudaStre
         ei = h->upd_ev_used; h->upd_ev_used += 2; h->upd_timed++; timed = true;
         QB_CUDA(cudaEventRecord(h->upd_ev[ei], st));
     }
-    if (use_vel)
-        update_w_kernel<true><<<g, 256, 0, st>>>(Wf(h), G, h->Vel, (int)h->H, (int)h->VL, (int)h->V, h->ldv, lr_e, llr_e,
-                                                 (float)h->momentum, (float)h->weight_decay, Wb_out, WbT_out, h->ldh, bt);
-    else
-        update_w_kernel<false><<<g, 256, 0, st>>>(Wf(h), G, nullptr, (int)h->H, (int)h->VL, (int)h->V, h->ldv, lr_e, llr_e, 0.f, 0.f,
-                                                  Wb_out, WbT_out, h->ldh, bt);
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = g; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        float *Wp = Wf(h), *Velp = use_vel ? h->Vel : nullptr;
+        const float *Gp = G;
+        int Hh = (int)h->H, VLl = (int)h->VL, Vv = (int)h->V;
+        int64_t ldv = h->ldv, ldh = h->ldh;
+        float mom = use_vel ? (float)h->momentum : 0.f, wd = use_vel ? (float)h->weight_decay : 0.f;
+        if (use_vel) QB_CUDA(cudaLaunchKernelEx(&cfg, update_w_kernel<true>, Wp, Gp, Velp, Hh, VLl, Vv, ldv, lr_e, llr_e, mom, wd, Wb_out, WbT_out, ldh, bt));
+        else QB_CUDA(cudaLaunchKernelEx(&cfg, update_w_kernel<false>, Wp, Gp, Velp, Hh, VLl, Vv, ldv, lr_e, llr_e, mom, wd, Wb_out, WbT_out, ldh, bt));
+    }
     if (timed) QB_CUDA(cudaEventRecord(h->upd_ev[ei + 1], st));
     QB_CUDA(cudaGetLastError());
     h->launches += 1;

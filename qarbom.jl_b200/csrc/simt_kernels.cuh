@@ -162,6 +162,9 @@ __global__ void __launch_bounds__(256, 3) update_w_kernel(float *__restrict__ W,
                                                           bf16 *__restrict__ Wb, bf16 *__restrict__ WbT, int64_t ldh,
                                                           const BiasTail bt) {
     constexpr int TH = 64, TC = 128, PITCH = TC + 8, ROWS = 4;  // ROWS rows in flight per thread
+    // programmatic dependent launch: wait for the gradient GEMM, then let the next GEMM start its prologue
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if ((int)blockIdx.y * TH >= H) {  // the bias blocks
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < bt.n_total; i += gridDim.x * blockDim.x) {
             const float lr_c = (i < bt.n_vis && i >= V) ? llr : lr;  // label biases c use llr; a and b use lr
