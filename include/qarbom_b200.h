@@ -135,11 +135,17 @@ int32_t qb_cd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, doub
 int32_t qb_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]);
 int32_t qb_cd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]);
 
-/* One epoch of fast_persistent_contrastive_divergence! (src/training/train_fast_pcd.jl:1-57, RBM only): inside a
- * mini-batch the slow weights are updated and the fast weights decayed (19/20) after every SAMPLE, then the
- * chains advance with W + W_fast.  Fast weights restart at zero every call, as in the reference.  times[3] =
- * (0, chain seconds, online sample+update seconds). */
-int32_t qb_fast_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double fast_lr, double times[3]);
+/* One epoch of fast_persistent_contrastive_divergence! (src/training/train_fast_pcd.jl:1-57; classifiers :59-127):
+ * inside a mini-batch the slow weights are updated and the fast weights decayed (19/20) after every SAMPLE, then
+ * the chains advance with W + W_fast (U + U_fast, ...; src/fantasy_data.jl:31-64).  Fast weights restart at zero
+ * every call, as in the reference.  llr / fast_llr (label_learning_rate, fast_label_learning_rate) are used by
+ * classifiers only.  Reference quirks kept: (1) classifiers pair EVERY sample of a mini-batch with chain 1
+ * (`batch_index` is never advanced, :77-119) -- option "fast_pcd_pair_chains" = 1 pairs sample i with chain i;
+ * (2) on Gaussian visibles the fast chain step thresholds the noisy value, v = 1[u < mean + z]
+ * (src/gibbs.jl:22-25 + src/rbm.jl:188-189), so the chains turn binary.  Philox stream only.
+ * times[3] = (0, chain seconds, online sample+update seconds). */
+int32_t qb_fast_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double fast_lr, double llr, double fast_llr,
+                          double times[3]);
 
 /* Same step, but the mini-batch comes from HOST memory on every call (end-to-end path:
  * upload, step, and a device->host read of the batch reconstruction error sum). */

@@ -511,33 +511,70 @@ def _pcd_minibatch_more_chains(m, x, mb, chains, steps, learning_rate, stream, y
         _update_fantasy_data(m, chains, steps, stream)
 
 
+def _update_fantasy_data_fast(m: Model, eff: Model, chains: List[FantasyData], steps: int, stream: Stream) -> None:
+    """`_update_fantasy_data!` with fast weights (src/fantasy_data.jl:31-64).  `eff` holds the effective
+    parameters W + W_fast, ... (src/rbm.jl:167-168,173-189,207-218).  The fast `gibbs_sample_visible` has a
+    single method for every model (src/gibbs.jl:22-25): it thresholds ``rand() < conditional_prob_v(...)``,
+    and for Gaussian visibles that "probability" is the noisy sample mu + randn() (src/rbm.jl:188-189) --
+    so a GRBM's chain visibles become BINARY here; draw order per chain: H uniforms, V normals, V uniforms
+    [, L uniforms]."""
+    for _ in range(steps):
+        for ch in chains:
+            if m.is_classifier:
+                ch.h = gibbs_sample_hidden(eff, ch.v, stream, ch.y).astype(np.float64)
+            else:
+                ch.h = gibbs_sample_hidden(eff, ch.v, stream).astype(np.float64)
+            ch.v = stream.bernoulli(conditional_prob_v(eff, ch.h, stream)).astype(np.float64)
+            if m.is_classifier:
+                ch.y = gibbs_sample_label(eff, ch.h, stream).astype(np.float64)
+
+
 def fast_persistent_contrastive_divergence(m: Model, x: Sequence, mini_batches: List[range], chains: List[FantasyData], *,
-                                           steps: int, learning_rate: float, fast_learning_rate: float, stream: Stream) -> None:
-    """One epoch of FastPCD for RBM (src/training/train_fast_pcd.jl:1-57; Tieleman & Hinton 2009).
+                                           steps: int, learning_rate: float, fast_learning_rate: float, stream: Stream,
+                                           y: Optional[Sequence] = None, label_learning_rate: float = 0.1,
+                                           fast_label_learning_rate: float = 0.1, pair_chains: Optional[bool] = None) -> None:
+    """One epoch of FastPCD (src/training/train_fast_pcd.jl:1-57, classifier :59-127; Tieleman & Hinton 2009).
 
     The fast weights start at zero EVERY epoch (:12-14).  Inside a mini-batch the reference is online:
     for each sample, h_data uses the current slow weights, the slow weights are updated right away with
-    lr/B (`update_rbm!` 5-arg form, src/rbm.jl:138-150) and the fast weights are decayed by 19/20 and
-    pushed by fast_lr/B times the same difference -- per SAMPLE (:34-43).  The chains then advance
-    with the effective parameters W + W_fast, a + a_fast, b + b_fast (src/fantasy_data.jl:31-47,
-    src/gibbs.jl:8-11,22-25, src/rbm.jl:167-168,184-185).  Bernoulli visibles only."""
-    assert not m.is_classifier and not m.gaussian
+    lr/B (`update_rbm!` per-sample form, src/rbm.jl:101-118,138-150) and the fast weights are decayed by
+    19/20 and pushed by fast_lr/B times the same difference -- per SAMPLE (:34-43).  The chains then advance
+    with the effective parameters (see `_update_fantasy_data_fast`).
+
+    Classifier quirk: `batch_index` is initialised to 1 per mini-batch and never incremented (:77-119), so
+    EVERY sample of a mini-batch is paired with chain 1.  `pair_chains=None` follows the reference (False for
+    classifiers, True otherwise); `pair_chains=True` is the corrected pairing (extension)."""
+    clf = m.is_classifier
+    if pair_chains is None:
+        pair_chains = not clf
     W_fast = np.zeros_like(m.W); a_fast = np.zeros_like(m.a); b_fast = np.zeros_like(m.b)
+    if clf:
+        U_fast = np.zeros_like(m.U); c_fast = np.zeros_like(m.c)
     for mb in mini_batches:
         B = len(mb)
+        lr, flr = learning_rate / B, fast_learning_rate / B
+        llr, fllr = label_learning_rate / B, fast_label_learning_rate / B
         for batch_index, i in enumerate(mb):
             v_data = np.asarray(x[i], dtype=np.float64)
-            h_data = conditional_prob_h(m, v_data)
-            ch = chains[batch_index]
+            y_data = np.asarray(y[i], dtype=np.float64) if clf else None
+            h_data = conditional_prob_h(m, v_data, y_data)
+            ch = chains[batch_index if pair_chains else 0]
             dW = np.outer(v_data, h_data) - np.outer(ch.v, ch.h)
-            m.W += (learning_rate / B) * dW
-            m.a += (learning_rate / B) * (v_data - ch.v)
-            m.b += (learning_rate / B) * (h_data - ch.h)
-            W_fast = W_fast * (19 / 20) + (fast_learning_rate / B) * dW
-            a_fast = a_fast * (19 / 20) + (fast_learning_rate / B) * (v_data - ch.v)
-            b_fast = b_fast * (19 / 20) + (fast_learning_rate / B) * (h_data - ch.h)
-        eff = Model(m.W + W_fast, m.a + a_fast, m.b + b_fast)
-        _update_fantasy_data(eff, chains, steps, stream)
+            m.W += lr * dW
+            m.a += lr * (v_data - ch.v)
+            m.b += lr * (h_data - ch.h)
+            W_fast = W_fast * (19 / 20) + flr * dW
+            a_fast = a_fast * (19 / 20) + flr * (v_data - ch.v)
+            b_fast = b_fast * (19 / 20) + flr * (h_data - ch.h)
+            if clf:
+                dU = np.outer(y_data, h_data) - np.outer(ch.y, ch.h)
+                m.U += llr * dU
+                m.c += llr * (y_data - ch.y)
+                U_fast = U_fast * (19 / 20) + fllr * dU
+                c_fast = c_fast * (19 / 20) + fllr * (y_data - ch.y)
+        eff = Model(m.W + W_fast, m.a + a_fast, m.b + b_fast, (m.U + U_fast) if clf else None,
+                    (m.c + c_fast) if clf else None, m.gaussian)
+        _update_fantasy_data_fast(m, eff, chains, steps, stream)
 
 
 def persistent_qubo_minibatch(m: Model, x: Sequence, mb: range, v_model, h_model, *, learning_rate: float,

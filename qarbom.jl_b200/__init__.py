@@ -7,6 +7,6 @@ from . import _ffi, build as _build  # noqa: F401
 from ._ffi import QbError, lib  # noqa: F401
 from .device import DeviceRBM  # noqa: F401
 from .rbm import GRBM, RBM, AbstractRBM, GRBMClassifier, RBMClassifier, copy_rbm  # noqa: F401
-from .train import CD, PCD, FastPCD, Accuracy, FreeEnergy, MeanSquaredError, reconstruct, train  # noqa: F401
+from .train import CD, PCD, FastPCD, Accuracy, CrossEntropy, FreeEnergy, MeanSquaredError, reconstruct, train  # noqa: F401
 
 build = _build.build

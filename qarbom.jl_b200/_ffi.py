@@ -73,7 +73,7 @@ def lib():
         "qb_cd_step": [_P, _i64, _i64, _i64, _f64, _f64],
         "qb_pcd_epoch": [_P, _i64, _i64, _f64, _f64, _P],
         "qb_cd_epoch": [_P, _i64, _i64, _f64, _f64, _P],
-        "qb_fast_pcd_epoch": [_P, _i64, _i64, _f64, _f64, _P],
+        "qb_fast_pcd_epoch": [_P, _i64, _i64, _f64, _f64, _f64, _f64, _P],
         "qb_pcd_step_host": [_P, _P, _i32, _P, _i32, _i64, _i64, _f64, _f64, _P],
         "qb_cd_step_host": [_P, _P, _i32, _P, _i32, _i64, _i64, _f64, _f64, _P],
         "qb_set_next_host_batch": [_P, _P, _i32, _P, _i32],

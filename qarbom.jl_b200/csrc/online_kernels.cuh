@@ -206,8 +206,10 @@ struct FastPcdParams {
     const float *Xf; const bf16 *Xb; long long ldx;      // the B data rows of this mini-batch
     const float *CVf; const bf16 *CVb; long long ldcv;   // chain visibles [B][ldcv]
     const float *CHf; const bf16 *CHb; long long ldch;   // chain hiddens  [B][ldch]
-    int V, H, B;
-    float lr, flr;                   // already divided by B
+    int V, H, B;                     // V counts the label units too ([v | y] rows)
+    int Vx;                          // visible units proper: columns >= Vx are label units (llr / fllr)
+    int chain_stride;                // 1: sample n pairs with chain n; 0: every sample pairs with chain 0 (reference classifier)
+    float lr, flr, llr, fllr;        // already divided by B
     float *vec; unsigned int *barrier;
 };
 
@@ -234,12 +236,13 @@ __global__ void __launch_bounds__(1024) online_fastpcd_kernel(const FastPcdParam
     const float decay = 19.0f / 20.0f;
     for (int n = 0; n < p.B; n++) {
         float *g_hd = p.vec + (n & 1) * H;
+        const long long nc = (long long)n * p.chain_stride;
         for (int i = threadIdx.x; i < V; i += blockDim.x) {
             sx[i] = p.Xf ? p.Xf[(long long)n * p.ldx + i] : __bfloat162float(p.Xb[(long long)n * p.ldx + i]);
-            scv[i] = p.CVf ? p.CVf[(long long)n * p.ldcv + i] : __bfloat162float(p.CVb[(long long)n * p.ldcv + i]);
+            scv[i] = p.CVf ? p.CVf[nc * p.ldcv + i] : __bfloat162float(p.CVb[nc * p.ldcv + i]);
         }
         for (int j = threadIdx.x; j < H; j += blockDim.x)
-            sch[j] = p.CHf ? p.CHf[(long long)n * p.ldch + j] : __bfloat162float(p.CHb[(long long)n * p.ldch + j]);
+            sch[j] = p.CHf ? p.CHf[nc * p.ldch + j] : __bfloat162float(p.CHb[nc * p.ldch + j]);
         __syncthreads();
         owned_rows(H, p.W1, p.ldv, V, sx, c1, [&](int j, float acc) { g_hd[j] = sigmoid_exact(acc + p.b[j]); });
         grid_barrier(p.barrier, epoch, gridDim.x);
@@ -252,8 +255,8 @@ __global__ void __launch_bounds__(1024) online_fastpcd_kernel(const FastPcdParam
             const float hd = shd[j], hc = sch[j];
             for (int c = lane; c < V; c += 32) {
                 const float d = sx[c] * hd - scv[c] * hc;
-                w[c] += p.lr * d;
-                f[c] = f[c] * decay + p.flr * d;
+                w[c] += (c < p.Vx ? p.lr : p.llr) * d;
+                f[c] = f[c] * decay + (c < p.Vx ? p.flr : p.fllr) * d;
             }
             if (lane == 0) { p.b[j] += p.lr * (hd - hc); p.fb[j] = p.fb[j] * decay + p.flr * (hd - hc); }
         }
@@ -262,12 +265,13 @@ __global__ void __launch_bounds__(1024) online_fastpcd_kernel(const FastPcdParam
             float *w = CACHE ? c2 + (long long)m * H : p.W2 + (long long)i * p.ldh;
             float *f = CACHE ? f2 + (long long)m * H : p.F2 + (long long)i * p.ldh;
             const float xd = sx[i], xc = scv[i];
+            const float lr_i = i < p.Vx ? p.lr : p.llr, flr_i = i < p.Vx ? p.flr : p.fllr;
             for (int c = lane; c < H; c += 32) {
                 const float d = xd * shd[c] - xc * sch[c];
-                w[c] += p.lr * d;
-                f[c] = f[c] * decay + p.flr * d;
+                w[c] += lr_i * d;
+                f[c] = f[c] * decay + flr_i * d;
             }
-            if (lane == 0) { p.a[i] += p.lr * (xd - xc); p.fa[i] = p.fa[i] * decay + p.flr * (xd - xc); }
+            if (lane == 0) { p.a[i] += lr_i * (xd - xc); p.fa[i] = p.fa[i] * decay + flr_i * (xd - xc); }
         }
         __syncthreads();
     }

@@ -83,6 +83,8 @@ struct qb_handle {
     qb_config cfg{};
     int64_t V = 0, H = 0, L = 0, VL = 0, ldv = 0, ldh = 0, Bmax = 0, ldb = 0;
     bool bf = false, gaussian = false;
+    bool gauss_threshold = false;  // FastPCD chain advance on Gaussian visibles: v = 1[u < mean + z] (src/gibbs.jl:22-25)
+    bool fast_pcd_pair_chains = false;  // classifier FastPCD: pair sample i with chain i instead of the reference's chain 1
     int num_sms = 148;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[8] = {};
@@ -358,7 +360,8 @@ struct VisibleOut {
 
 // conditional_prob_v / gibbs_sample_visible (+ gibbs_sample_label): in = hidden rows [rows][H]
 void op_visible(qb_handle *h, const Mat &in, int64_t rows, const VisibleOut &o, const Rng &rng, int64_t row0) {
-    const int act = h->gaussian ? 1 : 0;
+    const int act = h->gaussian ? (h->gauss_threshold ? 2 : 1) : 0;
+    QB_CHECK(act != 2 || (!rng.inj && rng.use_rng), QB_E_UNSUPPORTED, "thresholded Gaussian visibles draw from the Philox stream only");
     if (!h->bf) {
         simt_gemm(h, in.f, in.ld, 1, Wf(h), h->ldv, 1, h->pre_v, h->ldv, rows, h->VL, h->H, 1.f, 0.f, acat(h));
         // value written for each visible unit: sampled state (sample), probability (Bernoulli
@@ -395,7 +398,7 @@ void op_visible(qb_handle *h, const Mat &in, int64_t rows, const VisibleOut &o, 
     sm100::EpiParams ep{};
     ep.mode = sm100::EPI_SAMPLE; ep.M = (int)h->VL; ep.N = (int)rows;
     ep.bias = bias_a(h); ep.split = (int)h->V; ep.lab_pre = h->lab_pre; ep.ld_lab = h->L > 0 ? h->L : 1;
-    ep.act = act ? sm100::ACT_GAUSSIAN : sm100::ACT_SIGMOID;
+    ep.act = act == 2 ? sm100::ACT_GAUSS_THRESH : (act ? sm100::ACT_GAUSSIAN : sm100::ACT_SIGMOID);
     ep.sample = o.sample || (act == 1 && (rng.inj || rng.use_rng));
     if (o.state) {
         if (o.state_rm) { ep.state_rm = o.state->b; ep.ld_srm = o.state->ld; }
@@ -1209,33 +1212,33 @@ static bool online_cd_epoch(qb_handle *h, int64_t k, double lr, double times[3])
 }
 
 // fast_persistent_contrastive_divergence! (src/training/train_fast_pcd.jl:1-57): one epoch
-static void fast_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double flr, double times[3]) {
+static void fast_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double flr, double llr, double fllr, double times[3]) {
     check_step_args(h, B, k);
-    QB_CHECK(h->L == 0 && !h->gaussian, QB_E_UNSUPPORTED, "FastPCD is implemented for RBM (Bernoulli visibles, no label units)");
+    QB_CHECK(!h->inj_active, QB_E_STATE, "FastPCD epochs draw from the Philox stream (injected streams are per step)");
     QB_CHECK(h->cfg.world == 1, QB_E_UNSUPPORTED, "FastPCD updates the weights after every sample and does not shard");
     QB_CHECK(h->momentum == 0.0 && h->weight_decay == 0.0, QB_E_UNSUPPORTED, "FastPCD has no momentum / weight decay");
     QB_CHECK(h->n_chains == B, QB_E_STATE, "FastPCD pairs sample i with chain i: qb_init_chains(B) first");
     QB_CHECK(h->N >= B, QB_E_ARG, "dataset smaller than one mini-batch");
     if (!h->W2) {
-        h->W2 = dalloc<float>(h->V * h->ldh);
-        h->online_vec = dalloc<float>(2 * (3 * h->H + h->V));
+        h->W2 = dalloc<float>(h->VL * h->ldh);
+        h->online_vec = dalloc<float>(2 * (3 * h->H + h->VL));
         h->online_bar = dalloc<unsigned int>(1);
         h->online_ns = dalloc<unsigned long long>(3);
     }
-    if (!h->F) { h->F = dalloc<float>(h->nP); h->F2 = dalloc<float>(h->V * h->ldh); h->P_eff = dalloc<float>(h->nP); }
-    QB_CUDA(cudaMemsetAsync(h->F, 0, h->nP * sizeof(float), h->stream));          // W_fast = a_fast = b_fast = 0 every epoch (:12-14)
-    QB_CUDA(cudaMemsetAsync(h->F2, 0, h->V * h->ldh * sizeof(float), h->stream));
+    if (!h->F) { h->F = dalloc<float>(h->nP); h->F2 = dalloc<float>(h->VL * h->ldh); h->P_eff = dalloc<float>(h->nP); }
+    QB_CUDA(cudaMemsetAsync(h->F, 0, h->nP * sizeof(float), h->stream));          // W_fast = U_fast = a_fast = b_fast = c_fast = 0 every epoch (:12-14,:73-77)
+    QB_CUDA(cudaMemsetAsync(h->F2, 0, h->VL * h->ldh * sizeof(float), h->stream));
     {
-        dim3 g((unsigned)ceil_div(h->V, 32), (unsigned)ceil_div(h->H, 32));
-        transpose_f32_kernel<<<g, 256, 0, h->stream>>>(Wf(h), h->ldv, (int)h->H, (int)h->V, h->W2, h->ldh);
+        dim3 g((unsigned)ceil_div(h->VL, 32), (unsigned)ceil_div(h->H, 32));
+        transpose_f32_kernel<<<g, 256, 0, h->stream>>>(Wf(h), h->ldv, (int)h->H, (int)h->VL, h->W2, h->ldh);
         QB_CUDA(cudaGetLastError());
     }
-    const int64_t rows = std::max(h->H, h->V);
+    const int64_t rows = std::max(h->H, h->VL);
     const int wpb = h->online_wpb > 0 ? h->online_wpb : (rows >= 148 * 16 ? 32 : (rows >= 148 * 4 ? 16 : 8));
     const int grid = (int)std::min<int64_t>(h->num_sms, std::max<int64_t>(1, ceil_div(rows, wpb)));
     const int64_t warps = (int64_t)grid * wpb;
-    const size_t smem_vec = (size_t)(2 * h->V + 2 * h->H) * sizeof(float);
-    const size_t smem_rows = 2 * (size_t)wpb * (size_t)(ceil_div(h->H, warps) * h->V + ceil_div(h->V, warps) * h->H) * sizeof(float);
+    const size_t smem_vec = (size_t)(2 * h->VL + 2 * h->H) * sizeof(float);
+    const size_t smem_rows = 2 * (size_t)wpb * (size_t)(ceil_div(h->H, warps) * h->VL + ceil_div(h->VL, warps) * h->H) * sizeof(float);
     QB_CHECK(smem_vec <= 200 * 1024, QB_E_UNSUPPORTED, "model too large for the online kernel's shared-memory vectors");
     const bool cache = smem_vec + smem_rows <= 200 * 1024;
     const size_t smem = smem_vec + (cache ? smem_rows : 0);
@@ -1253,8 +1256,11 @@ static void fast_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double
         p.a = P_true + h->nW; p.b = P_true + h->nW + h->ldv; p.fa = h->F + h->nW; p.fb = h->F + h->nW + h->ldv;
         p.Xf = xb.f; p.Xb = xb.b; p.ldx = xb.ld;
         p.CVf = h->cv.f; p.CVb = h->cv.b; p.ldcv = h->cv.ld; p.CHf = h->ch.f; p.CHb = h->ch.b; p.ldch = h->ch.ld;
-        p.V = (int)h->V; p.H = (int)h->H; p.B = (int)B;
+        p.V = (int)h->VL; p.Vx = (int)h->V; p.H = (int)h->H; p.B = (int)B;
+        // classifier: the reference never advances batch_index, every sample pairs with chain 1 (train_fast_pcd.jl:77-119)
+        p.chain_stride = (h->L == 0 || h->fast_pcd_pair_chains) ? 1 : 0;
         p.lr = (float)(lr / (double)B); p.flr = (float)(flr / (double)B);
+        p.llr = (float)(llr / (double)B); p.fllr = (float)(fllr / (double)B);
         p.vec = h->online_vec; p.barrier = h->online_bar;
         QB_CUDA(cudaMemsetAsync(h->online_bar, 0, sizeof(unsigned int), h->stream));
         if (times) QB_CUDA(cudaEventRecord(h->ev[0], h->stream));
@@ -1268,12 +1274,13 @@ static void fast_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double
         h->launches += 2;
         h->P = h->P_eff;
         float *saved_bias_rd = h->bias_rd; h->bias_rd = nullptr;
+        h->gauss_threshold = h->gaussian;  // the fast gibbs_sample_visible thresholds even Gaussian "probabilities" (src/gibbs.jl:22-25)
         try {
             refresh_shadows(h);
             StepRng sr{h, B, false};
             advance_chains(h, B, k, sr, false);
-        } catch (...) { h->P = P_true; h->bias_rd = saved_bias_rd; throw; }
-        h->P = P_true; h->bias_rd = saved_bias_rd;
+        } catch (...) { h->P = P_true; h->bias_rd = saved_bias_rd; h->gauss_threshold = false; throw; }
+        h->P = P_true; h->bias_rd = saved_bias_rd; h->gauss_threshold = false;
         if (times) {
             QB_CUDA(cudaEventRecord(h->ev[2], h->stream));
             QB_CUDA(cudaStreamSynchronize(h->stream));
@@ -1322,8 +1329,8 @@ static void epoch_impl(qb_handle *h, bool pcd, int64_t B, int64_t k, double lr, 
 int32_t qb_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]) {
     return guarded([&] { QB_H_KEEP(h); epoch_impl(h, true, B, k, lr, llr, times); });
 }
-int32_t qb_fast_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double fast_lr, double times[3]) {
-    return guarded([&] { QB_H(h); fast_pcd_epoch(h, B, k, lr, fast_lr, times); });
+int32_t qb_fast_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double fast_lr, double llr, double fast_llr, double times[3]) {
+    return guarded([&] { QB_H(h); fast_pcd_epoch(h, B, k, lr, fast_lr, llr, fast_llr, times); });
 }
 int32_t qb_cd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]) {
     return guarded([&] { QB_H(h); epoch_impl(h, false, B, k, lr, llr, times); });
@@ -1615,6 +1622,8 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
             h->online_wpb = (int)value;
         } else if (!strcmp(key, "online_kernel")) {
             h->online_kernel = value != 0.0;
+        } else if (!strcmp(key, "fast_pcd_pair_chains")) {
+            h->fast_pcd_pair_chains = value != 0.0;
         } else if (!strcmp(key, "stale_chains")) {
             set_stale_mode(h, value != 0.0);
         } else if (!strcmp(key, "use_2cta")) {

@@ -92,7 +92,10 @@ __global__ void act_sample_kernel(const float *__restrict__ pre, int64_t ld, int
             float z = 0.f;
             if (inj) z = inj[(int64_t)r * ldi + u];
             else if (use_rng) z = rng_normal(key, (uint32_t)u, (uint64_t)(row0 + r));
-            state[(int64_t)r * lds + u] = x + z;
+            float s = x + z;
+            // act 2 (FastPCD chains of a GRBM, src/gibbs.jl:22-25): the noisy value is thresholded like a probability
+            if (act == 2) s = (rng_uniform(key, (uint32_t)u, (uint64_t)(row0 + r)) < s) ? 1.f : 0.f;
+            state[(int64_t)r * lds + u] = s;
         }
     }
 }

@@ -44,7 +44,7 @@ struct Shape {
     static constexpr int WGS = (KIND != K_GENERIC && BN >= 64) ? 4 : 2;
     static constexpr int THREADS = 128 + 128 * WGS;
 };
-enum { ACT_SIGMOID = 0, ACT_GAUSSIAN = 1 };
+enum { ACT_SIGMOID = 0, ACT_GAUSSIAN = 1, ACT_GAUSS_THRESH = 2 };  // THRESH: 1[u < x + z] (FastPCD chains of a GRBM, src/gibbs.jl:22-25)
 
 struct EpiParams {
     int mode;
@@ -206,6 +206,10 @@ __device__ __forceinline__ void epilogue_sample(const EpiParams &ep, uint32_t tm
                 } else {
                     rng_normal2(ep.key, (uint32_t)unit, (uint32_t)(grow >> 1), zn[0], zn[1]);
                     rng_normal2(ep.key, (uint32_t)unit, (uint32_t)(grow >> 1) + 1u, zn[2], zn[3]);
+                    if (ep.act == ACT_GAUSS_THRESH) {
+                        Philox4 ph = rng_uniform4(ep.key, (uint32_t)unit, (uint32_t)(grow >> 2));
+                        rnd[0] = ph.x; rnd[1] = ph.y; rnd[2] = ph.z; rnd[3] = ph.w;
+                    }
                 }
             }
 #pragma unroll
@@ -230,6 +234,7 @@ __device__ __forceinline__ void epilogue_sample(const EpiParams &ep, uint32_t tm
                         float z = zn[jj];
                         if (ep.inj) z = (uvalid && row < ep.N) ? ep.inj[(long long)row * ep.ld_inj + unit] : 0.f;
                         s = x + z;
+                        if (ep.act == ACT_GAUSS_THRESH) s = (u23(rnd[jj]) < s) ? 1.f : 0.f;
                     }
                 }
                 pv[j] = p;

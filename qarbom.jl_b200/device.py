@@ -130,9 +130,11 @@ class DeviceRBM:
         check(lib().qb_pcd_epoch(self._h, B, k, lr, llr, t if timed else None))
         return tuple(t)
 
-    def fast_pcd_epoch(self, B: int, k: int, lr: float, fast_lr: float, timed: bool = True):
+    def fast_pcd_epoch(self, B: int, k: int, lr: float, fast_lr: float, llr: float = 0.0, fast_llr: float = 0.0,
+                       timed: bool = True):
+        """fast_persistent_contrastive_divergence! for one epoch (src/training/train_fast_pcd.jl:1-127)."""
         t = (ctypes.c_double * 3)()
-        check(lib().qb_fast_pcd_epoch(self._h, B, k, lr, fast_lr, t if timed else None))
+        check(lib().qb_fast_pcd_epoch(self._h, B, k, lr, fast_lr, llr, fast_llr, t if timed else None))
         return tuple(t)
 
     def cd_epoch(self, B: int, k: int, lr: float, llr: float = 0.0, timed: bool = True):
@@ -206,6 +208,17 @@ class DeviceRBM:
         """classify (src/rbm.jl:226-229): 1 where the label probability equals the row maximum."""
         p = self.conditional_prob_y_given_v(x)
         return (p == p.max(axis=1, keepdims=True)).astype(np.int64)
+
+    def eval_cross_entropy(self, x, y) -> float:
+        """_evaluate(CrossEntropy) through the classifier `evaluate` (src/evaluation.jl:22-26,28-50), literally:
+        the reference feeds the ROUNDED prediction (1 at the row maximum, else 0) into
+        sum(y log p + (1 - y) log(1 - p)) / N, so every term is 0 * -Inf or -Inf and the metric is NaN (or -Inf)
+        for any data -- reproduced, not repaired."""
+        pred = self.classify(x).astype(np.float64)
+        y = np.asarray(y, dtype=np.float64).reshape(pred.shape)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            per_sample = np.sum(y * np.log(pred) + (1.0 - y) * np.log(1.0 - pred), axis=1)
+            return float(np.sum(per_sample / pred.shape[0]))
 
     def eval_accuracy(self, x, y) -> float:
         """_evaluate(Accuracy) through the classifier `evaluate` (src/evaluation.jl:9-14,28-50)."""

@@ -145,10 +145,11 @@ function epoch!(d::Device, ::Type{CD}, B, k, lr, llr)
     return t[1], t[2], t[3]
 end
 
-"fast_persistent_contrastive_divergence! for one epoch (src/training/train_fast_pcd.jl:1-57); RBM only"
-function fast_pcd_epoch!(d::Device, B, k, lr, fast_lr)
+"fast_persistent_contrastive_divergence! for one epoch (src/training/train_fast_pcd.jl:1-57, classifiers :59-127)"
+function fast_pcd_epoch!(d::Device, B, k, lr, fast_lr, llr = 0.0, fast_llr = 0.0)
     t = zeros(3)
-    check(ccall((:qb_fast_pcd_epoch, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Float64, Float64, Ptr{Float64}), d.h, B, k, lr, fast_lr, t))
+    check(ccall((:qb_fast_pcd_epoch, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Float64, Float64, Float64, Float64, Ptr{Float64}),
+                d.h, B, k, lr, fast_lr, llr, fast_llr, t))
     return t[1], t[2], t[3]
 end
 

@@ -21,11 +21,12 @@ class FastPCD(TrainingMethod): ...
 class EvaluationMethod: ...
 class MeanSquaredError(EvaluationMethod): ...
 class Accuracy(EvaluationMethod): ...
+class CrossEntropy(EvaluationMethod): ...
 class FreeEnergy(EvaluationMethod): ...   # new metric (no reference counterpart)
 
 
 def _diverged(history: Sequence[float]) -> bool:
-    """src/evaluation.jl:132-142 (MeanSquaredError)."""
+    """src/evaluation.jl:132-154 (MeanSquaredError, CrossEntropy: same rule; NaN compares false, as in Julia)."""
     if len(history) == 1:
         return False
     return history[-1] > history[-2] or history[-1] > min(history)
@@ -65,7 +66,8 @@ def _log_finish(n_epochs, ts, tg, tu):
 
 def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int, learning_rate: Sequence[float],
           gibbs_steps: Optional[int] = None, batch_size: Optional[int] = None,
-          label_learning_rate: Optional[Sequence[float]] = None, fast_learning_rate: Optional[float] = None, metrics=None,
+          label_learning_rate: Optional[Sequence[float]] = None, fast_learning_rate: Optional[float] = None,
+          fast_label_learning_rate: float = 0.1, metrics=None,
           early_stopping: bool = False, store_best_rbm: bool = True, patience: int = 10,
           stopping_metric=None, x_test_dataset=None, y_test_dataset=None, file_path: Optional[str] = None,
           # ---- extensions (defaults reproduce the reference)
@@ -74,9 +76,11 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
           verbose: bool = True, chains_init=None) -> dict:
     is_fast = method is FastPCD or isinstance(method, FastPCD)
     is_pcd = is_fast or method is PCD or isinstance(method, PCD)
-    if is_fast and fast_learning_rate is None:
-        raise TypeError("train!(..., FastPCD) requires fast_learning_rate")   # keyword without default, train_fast_pcd.jl:177
     clf = rbm.n_classifiers > 0
+    if is_fast and fast_learning_rate is None:
+        if not clf:
+            raise TypeError("train!(..., FastPCD) requires fast_learning_rate")   # keyword without default, train_fast_pcd.jl:177
+        fast_learning_rate = 0.1                                                  # classifier default, train_fast_pcd.jl:290
     if clf and label_train is None:
         raise ValueError("label_train is required for classifier models")
     if clf and label_learning_rate is None:
@@ -99,7 +103,7 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
     if len(learning_rate) < n_epochs:
         raise IndexError("learning_rate needs one entry per epoch")       # learning_rate[epoch], train_cd.jl:77
 
-    names = {MeanSquaredError: "mse", FreeEnergy: "free_energy", Accuracy: "accuracy"}
+    names = {MeanSquaredError: "mse", FreeEnergy: "free_energy", Accuracy: "accuracy", CrossEntropy: "cross_entropy"}
     keys = [names[m] for m in metrics]
     nc = B if n_chains is None else int(n_chains)                  # reference: n_chains == batch_size (train_pcd.jl:162)
     dev = DeviceRBM(rbm, max_batch=max(B, nc, min(n, 4096)), precision=precision, device=device, seed=seed)
@@ -117,6 +121,8 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
                     out[names[m]] = dev.eval_mse(xs)
                 elif m is Accuracy:
                     out[names[m]] = dev.eval_accuracy(xs, y_test_dataset if use_test else label_train)
+                elif m is CrossEntropy:
+                    out[names[m]] = dev.eval_cross_entropy(xs, y_test_dataset if use_test else label_train)
                 else:
                     out[names[m]] = dev.eval_free_energy(xs)
             return out
@@ -141,7 +147,7 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
             lr = float(learning_rate[epoch - 1])
             llr = float(label_learning_rate[epoch - 1]) if clf else 0.0
             if is_fast:
-                t = dev.fast_pcd_epoch(B, gibbs_steps, lr, float(fast_learning_rate))
+                t = dev.fast_pcd_epoch(B, gibbs_steps, lr, float(fast_learning_rate), llr, float(fast_label_learning_rate))
             else:
                 t = dev.pcd_epoch(B, gibbs_steps, lr, llr) if is_pcd else dev.cd_epoch(B, gibbs_steps, lr, llr)
             for i in range(3):

@@ -702,57 +702,125 @@ def test_online_cd_kernel_equals_per_sample_steps(q):
 
 
 # ------------------------------------------------------------------------------ FastPCD
-def _fastpcd_oracle(m, X, B, k, lr, flr, seed, cv0, ch0, nb):
-    """Oracle FastPCD epoch fed with the uniforms the device's Philox contract defines."""
-    V, H = m.n_visible, m.n_hidden
-    parts = []
+def _fastpcd_oracle(m, X, B, k, lr, flr, seed, cv0, ch0, nb, Y=None, cy0=None, llr=0.0, fllr=0.0, pair=None):
+    """Oracle FastPCD epoch fed with the uniforms / normals the device's Philox contract defines."""
+    V, H, L = m.n_visible, m.n_hidden, m.n_classifiers
+    us, zs = [], []
     for mb in range(nb):
         for s in range(k):
             uh = philox_ref.uniforms(seed, 2 + 2 * (mb * k + s), B, H)
-            uv = philox_ref.uniforms(seed, 3 + 2 * (mb * k + s), B, V)
+            uv = philox_ref.uniforms(seed, 3 + 2 * (mb * k + s), B, V + L)   # label units ride on the visible draw
+            zv = philox_ref.normals(seed, 3 + 2 * (mb * k + s), B, V) if m.gaussian else None
             for i in range(B):
-                parts += [uh[i], uv[i]]
-    chains = chains_from_arrays(cv0, ch0)
+                us += [uh[i], uv[i]]            # serial order per chain: H uniforms, (V normals,) V uniforms, L uniforms
+                if m.gaussian:
+                    zs.append(zv[i])
+    chains = chains_from_arrays(cv0, ch0, cy0)
+    stream = qo.Stream(np.concatenate(us), np.concatenate(zs) if zs else None)
     qo.fast_persistent_contrastive_divergence(m, X, qo._set_mini_batches(len(X), B), chains, steps=k, learning_rate=lr,
-                                              fast_learning_rate=flr, stream=qo.Stream(np.concatenate(parts)))
+                                              fast_learning_rate=flr, stream=stream, y=Y, label_learning_rate=llr,
+                                              fast_label_learning_rate=fllr, pair_chains=pair)
     return chains_to_arrays(chains)
 
 
-@pytest.mark.parametrize("V,H,B,k,nb", [(3, 2, 2, 1, 6), (40, 24, 8, 2, 3), (784, 500, 16, 1, 2)])
-def test_fast_pcd_epoch_matches_reference_algorithm(q, V, H, B, k, nb):
-    """fast_persistent_contrastive_divergence! (train_fast_pcd.jl:1-57): per-sample slow update + fast-weight
-    decay inside a mini-batch, chains on W + W_fast.  fp32 mode, Philox stream replayed into the oracle."""
-    rng = np.random.default_rng(5 + V)
-    seed, lr, flr = 1234, 0.05, 0.1
-    m = make_oracle_model(rng, V, H, scale=0.2)
-    X, _ = _data(rng, nb * B + 1, V, 0, False, False)     # + 1: the trailing remainder is dropped
+@pytest.mark.parametrize("V,H,L,gaussian,B,k,nb,pair", [
+    (3, 2, 0, False, 2, 1, 6, None), (40, 24, 0, False, 8, 2, 3, None), (784, 500, 0, False, 16, 1, 2, None),
+    (40, 24, 5, False, 8, 2, 3, None),      # classifier, reference pairing: every sample with chain 1 (train_fast_pcd.jl:77-119)
+    (40, 24, 5, False, 8, 1, 3, True),      # classifier, corrected pairing (option fast_pcd_pair_chains)
+    (784, 500, 10, False, 16, 1, 2, None),
+    (40, 24, 0, True, 8, 2, 3, None),       # GRBM: the fast chain step thresholds mean + z (gibbs.jl:22-25, rbm.jl:188-189)
+    (33, 20, 4, True, 8, 1, 2, None),       # GRBMClassifier
+])
+def test_fast_pcd_epoch_matches_reference_algorithm(q, V, H, L, gaussian, B, k, nb, pair):
+    """fast_persistent_contrastive_divergence! (train_fast_pcd.jl:1-57, classifiers :59-127): per-sample slow update +
+    fast-weight decay inside a mini-batch, chains on W + W_fast.  fp32 mode, Philox stream replayed into the oracle."""
+    rng = np.random.default_rng(5 + V + L)
+    seed, lr, flr, llr, fllr = 1234, 0.05, 0.1, 0.04, 0.08
+    m = make_oracle_model(rng, V, H, L, gaussian=gaussian, scale=0.2)
+    X, Y = _data(rng, nb * B + 1, V, L, gaussian, False)     # + 1: the trailing remainder is dropped
     with q.DeviceRBM(to_host_rbm(q, m), max_batch=B, precision="fp32", seed=seed) as dev:
-        dev.set_data(X)
+        dev.set_data(X, Y)
+        if pair:
+            dev.set_option("fast_pcd_pair_chains", 1)
         dev.init_chains(B)                                 # draws 0, 1
-        cv0, ch0, _ = dev.get_chains()
-        t = dev.fast_pcd_epoch(B, k, lr, flr)
+        cv0, ch0, cy0 = dev.get_chains()
+        t = dev.fast_pcd_epoch(B, k, lr, flr, llr, fllr)
         assert t[1] > 0 and t[2] > 0
-        dv, dh, _ = dev.get_chains()
+        dv, dh, dy = dev.get_chains()
         dev.pull_params()
-        ov, oh, _ = _fastpcd_oracle(m, X, B, k, lr, flr, seed, cv0, ch0, nb)
+        ov, oh, oy = _fastpcd_oracle(m, X, B, k, lr, flr, seed, cv0, ch0, nb, Y, cy0, llr, fllr, pair)
         assert np.mean(dv != ov) < 2e-3 and np.mean(dh != oh) < 2e-3     # near-ties of the fixed Philox stream only
+        if gaussian:
+            assert set(np.unique(dv)) <= {0.0, 1.0}        # the reference's fast chains turn a GRBM's visibles binary
         assert rel_err(dev.rbm.W, m.W) < 1e-4 and np.max(np.abs(dev.rbm.b - m.b)) < 1e-4
+        assert np.max(np.abs(dev.rbm.a - m.a)) < 1e-4
+        if L:
+            assert np.mean(dy != oy) < 5e-3
+            assert rel_err(dev.rbm.U, m.U) < 1e-4 and np.max(np.abs(dev.rbm.c - m.c)) < 1e-4
 
 
-def test_fast_pcd_bf16_chains_stay_close_to_fp32(q):
-    rng = np.random.default_rng(6)
-    V, H, B, k, nb = 96, 64, 16, 1, 4
-    m = make_oracle_model(rng, V, H, scale=0.2, bf16=True)
-    X, _ = _data(rng, nb * B, V, 0, False, True)
+def test_cross_entropy_metric_is_reference_literal(q):
+    """_evaluate(CrossEntropy) (src/evaluation.jl:22-26) is fed the rounded prediction by `evaluate` (:28-50): every
+    term is 0 * -Inf or -Inf, so the reference's metric is NaN for any data; the host mirror reproduces that."""
+    rng = np.random.default_rng(3)
+    m = make_oracle_model(rng, 12, 6, 3, scale=0.3)
+    X, Y = _data(rng, 10, 12, 3, False, False)
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=16, precision="fp32") as dev:
+        ce = dev.eval_cross_entropy(X, Y)
+        pred = np.stack([qo.classify(m, x) for x in X]).astype(np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ref = np.sum(Y * np.log(pred) + (1 - Y) * np.log(1 - pred)) / len(X)
+        assert np.isnan(ce) and np.isnan(ref)
+
+
+@pytest.mark.parametrize("L,gaussian", [(0, False), (6, False), (0, True), (6, True)])
+def test_fast_pcd_bf16_chains_stay_close_to_fp32(q, L, gaussian):
+    rng = np.random.default_rng(6 + L)
+    V, H, B, k, nb = 96, 64, 16, 2, 4
+    m = make_oracle_model(rng, V, H, L, gaussian=gaussian, scale=0.2, bf16=True)
+    X, Y = _data(rng, nb * B, V, L, gaussian, True)
     Ws = {}
     for prec in ("fp32", "bf16"):
         rbm = to_host_rbm(q, m)
         with q.DeviceRBM(rbm, max_batch=B, precision=prec, seed=9) as dev:
-            dev.set_data(X)
+            dev.set_data(X, Y)
+            dev.set_option("fast_pcd_pair_chains", 1)
             dev.init_chains(B)
-            dev.fast_pcd_epoch(B, k, 0.05, 0.1, timed=False)
+            dev.fast_pcd_epoch(B, k, 0.05, 0.1, 0.05, 0.1, timed=False)
             dev.pull_params()
             Ws[prec] = rbm.W.copy()
+            cv, ch, cy = dev.get_chains()
+            assert set(np.unique(cv)) <= {0.0, 1.0} and set(np.unique(ch)) <= {0.0, 1.0}   # binary even for Gaussian visibles
             # the tensor-core shadows hold the slow weights again after the epoch
-            assert np.max(np.abs(dev.conditional_prob_h(X[:2]) - 1 / (1 + np.exp(-(rbm.b + X[:2] @ (bf16_round(rbm.W) if prec == "bf16" else rbm.W)))))) < 5e-6
-    assert rel_err(Ws["bf16"] - m.W, Ws["fp32"] - m.W) < 0.25   # different chain trajectories (bf16-rounded W + W_fast), same learning signal
+            Wr = bf16_round(rbm.W) if prec == "bf16" else rbm.W
+            assert np.max(np.abs(dev.conditional_prob_h(X[:2]) - 1 / (1 + np.exp(-(rbm.b + X[:2] @ Wr))))) < 5e-6
+    assert rel_err(Ws["bf16"] - m.W, Ws["fp32"] - m.W) < 0.3   # different chain trajectories (bf16-rounded W + W_fast), same learning signal
+
+
+def test_train_fast_pcd_classifier_runs_like_reference_smoke_test(q, tmp_path):
+    """test/classification.jl:40-57 scenario shape: train!(rbm, x, y, FastPCD; ...) on a tiny classifier."""
+    rng = np.random.default_rng(2)
+    x = [[1, 0, 0, 1]] * 40 + [[0, 1, 1, 0]] * 40
+    y = [[1, 0]] * 40 + [[0, 1]] * 40
+    rbm = q.RBMClassifier(4, 3, 2, W=rng.standard_normal((4, 3)) * 0.1, U=rng.standard_normal((2, 3)) * 0.1)
+    out = q.train(rbm, x, q.FastPCD, y, n_epochs=5, batch_size=4, learning_rate=[0.05] * 5, label_learning_rate=[0.05] * 5,
+                  fast_learning_rate=0.05, fast_label_learning_rate=0.05, metrics=[q.Accuracy, q.CrossEntropy], precision="fp32",
+                  file_path=str(tmp_path / "m.csv"), verbose=False)
+    assert len(out["accuracy"]) == 6 and len(out["cross_entropy"]) == 6
+    assert all(np.isnan(v) for v in out["cross_entropy"])        # the reference's metric, literally (see eval_cross_entropy)
+    assert (tmp_path / "m.csv").read_text().splitlines()[0] == "accuracy,cross_entropy"
+    assert np.all(np.isfinite(rbm.W)) and np.all(np.isfinite(rbm.U))
+
+
+def test_train_fast_pcd_classifier_reference_scenario(q, tmp_path):
+    """test/classification.jl:46-67 `fast_pcd()`: RBMClassifier(3,2,1), x=[1,0,0], y=[1], batch 2, fast rates 0.1, early
+    stopping; the reference only checks that it runs and classifies."""
+    x = [[1, 0, 0] for _ in range(200)]
+    y = [[1] for _ in range(200)]
+    rbm = q.RBMClassifier(3, 2, 1, rng=np.random.default_rng(2))
+    lr = [0.01 / (j ** 0.8) for j in range(1, 1001)]
+    hist = q.train(rbm, x, q.FastPCD, y, n_epochs=5, batch_size=2, learning_rate=lr, label_learning_rate=lr, fast_learning_rate=0.1,
+                   fast_label_learning_rate=0.1, early_stopping=True, file_path=str(tmp_path / "f.csv"), precision="fp32", verbose=False)
+    assert list(hist) == ["accuracy"] and hist["accuracy"][-1] == 1.0
+    with q.DeviceRBM(rbm, max_batch=1, precision="fp32") as dev:
+        assert dev.classify([[1, 0, 0]]).tolist() == [[1]]
