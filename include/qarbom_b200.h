@@ -204,8 +204,12 @@ int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_la
 /* with "time_gemms": number and summed CUDA-event duration of the update_w kernel launches */
 int32_t qb_get_update_timing(qb_handle *h, int64_t *timed_updates, double *timed_update_ms);
 int32_t qb_reset_counters(qb_handle *h);
-/* Options: "async_steps" (qb_pcd_step / qb_cd_step return without waiting; use qb_sync),
- * "time_gemms", "force_bn" (tile width override for experiments). */
+/* Options: "async_steps" (qb_pcd_step / qb_cd_step return without waiting; use qb_sync), "time_gemms",
+ * "stale_chains" (declared extension: allreduce + update of step t overlap the chain advance of step t + 1),
+ * "online_kernel" (0: batch-size-1 CD through per-sample launches instead of the cooperative epoch kernel),
+ * "online_wpb" (warps per block of the cooperative kernels), "fast_pcd_pair_chains" (classifier FastPCD pairs
+ * sample i with chain i instead of the reference's chain 1), "p2p_blocks_per_sm", and for experiments / tests
+ * "force_bn" (GEMM tile width) and "use_2cta" (0 never, 1 automatic, 2 always). */
 int32_t qb_set_option(qb_handle *h, const char *key, double value);
 int32_t qb_sync(qb_handle *h);
 /* CUDA-event stopwatch on the handle's stream (the stream every kernel is launched on). */
