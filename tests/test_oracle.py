@@ -331,3 +331,42 @@ def test_more_chains_extension_numpy_and_c_agree(L):
     assert c_oracle.pcd_epoch(cm, X, Y, B, k, 0.1, 0.05, chv, chh, chy, u=u[Nc * (V + H + L):], n_chains=Nc) == 0
     assert np.allclose(cm.W, m.W, rtol=0, atol=1e-13) and np.allclose(cm.b, m.b, atol=1e-13)
     assert np.array_equal(chv, np.stack([c.v for c in chains]))
+
+
+def test_fast_pcd_classifier_pairs_every_sample_with_chain_one():
+    """train_fast_pcd.jl:77-119: `batch_index` is never advanced in the classifier method, so only chain 1 enters the
+    update; chains 2..B matter only through the chain advance."""
+    rng = np.random.default_rng(0)
+    V, H, L, B = 6, 4, 3, 4
+    X = rng.integers(0, 2, (B, V)).astype(float)
+    Y = np.eye(L)[rng.integers(0, L, B)]
+
+    def run(perturb, pair=None):
+        m = qo.make_model(V, H, L, W=np.full((V, H), 0.1), U=np.full((L, H), 0.1))
+        r = np.random.default_rng(1)
+        chains = [qo.FantasyData(r.random(V), r.random(H), r.random(L)) for _ in range(B)]
+        if perturb:
+            for c in chains[1:]:
+                c.v[:] = 1 - c.v
+                c.h[:] = 1 - c.h
+                c.y[:] = 1 - c.y
+        qo.fast_persistent_contrastive_divergence(m, X, [range(B)], chains, steps=1, learning_rate=0.1, fast_learning_rate=0.1,
+                                                  stream=qo.NumpyStream(3), y=Y, label_learning_rate=0.1,
+                                                  fast_label_learning_rate=0.1, pair_chains=pair)
+        return m
+    a, b = run(False), run(True)
+    assert np.array_equal(a.W, b.W) and np.array_equal(a.U, b.U) and np.array_equal(a.c, b.c)
+    c, d = run(False, True), run(True, True)
+    assert not np.array_equal(c.W, d.W)       # the corrected pairing does depend on chains 2..B
+
+
+def test_fast_pcd_gaussian_chains_turn_binary():
+    """src/gibbs.jl:22-25 has one fast `gibbs_sample_visible` for every model: it thresholds rand() < mu + randn()."""
+    rng = np.random.default_rng(0)
+    V, H, B = 5, 3, 4
+    m = qo.make_model(V, H, 0, True, W=rng.standard_normal((V, H)) * 0.1)
+    X = rng.standard_normal((B, V))
+    chains = [qo.FantasyData(rng.random(V), rng.random(H)) for _ in range(B)]
+    qo.fast_persistent_contrastive_divergence(m, X, [range(B)], chains, steps=1, learning_rate=0.1, fast_learning_rate=0.1,
+                                              stream=qo.NumpyStream(3))
+    assert all(set(np.unique(c.v)) <= {0.0, 1.0} for c in chains)
