@@ -768,3 +768,67 @@ def serial_normals(Z_v: np.ndarray, order: str) -> np.ndarray:
     if order == "pcd":
         return np.asarray(Z_v, dtype=np.float64).reshape(-1)
     return np.asarray(Z_v, dtype=np.float64).transpose(1, 0, 2).reshape(-1)
+
+
+# --------------------------------------------------------------------------- batched (BLAS-3) formulation
+def batched_step(m: Model, X: np.ndarray, Y: Optional[np.ndarray], algo: str, k: int, lr: float, llr: float = 0.0, *,
+                 cv: Optional[np.ndarray] = None, ch: Optional[np.ndarray] = None, cy: Optional[np.ndarray] = None,
+                 U_h=None, U_v=None, U_y=None, Z_v=None, rng: Optional[np.random.Generator] = None):
+    """One mini-batch step of PCD (a20/a22) or mini-batch CD (a16/a17 with the batch extension) written with
+    matrix-matrix products over the whole batch -- the formulation the device implements, and the BEST CASE for a
+    CPU (threaded dgemm instead of the reference's per-sample gemv + outer products).  Used (1) by tests to show it
+    equals the per-sample restatement on the same streams and (2) by bench.py as the `value_batched_blas` CPU figure.
+    Random numbers: dense arrays U_h[k][B][H], U_v[k][B][V] (or Z_v), U_y[k][B][L], or a numpy Generator."""
+    clf, B = m.is_classifier, X.shape[0]
+
+    def uni(arr, s, shape):
+        return arr[s] if arr is not None else rng.random(shape)
+
+    def hidden_pre(v, y):
+        pre = m.b + v @ m.W
+        return pre + y @ m.U if (clf and y is not None) else pre
+
+    def gibbs(v, y, s):
+        h = (uni(U_h, s, (v.shape[0], m.n_hidden)) < logistic(hidden_pre(v, y))).astype(np.float64)
+        mu = m.a + h @ m.W.T
+        if m.gaussian:
+            v2 = mu + (Z_v[s] if Z_v is not None else rng.standard_normal(mu.shape))
+        else:
+            v2 = (uni(U_v, s, mu.shape) < logistic(mu)).astype(np.float64)
+        y2 = None
+        if clf:
+            lp = m.c + h @ m.U.T
+            lp = lp - lp.max(axis=1, keepdims=True)
+            py = np.exp(lp - np.log(np.exp(lp).sum(axis=1, keepdims=True)))
+            y2 = (uni(U_y, s, py.shape) < py).astype(np.float64)
+        return v2, h, y2
+
+    if algo.upper() == "PCD":
+        if not clf:                                        # chains first (train_pcd.jl:15-17)
+            for s in range(k):
+                cv, ch, _ = gibbs(cv, None, s)
+        hd = logistic(hidden_pre(X, Y))
+        dW = X.T @ hd - cv.T @ ch
+        da, db = (X - cv).sum(0), (hd - ch).sum(0)
+        if clf:
+            dU, dc = Y.T @ hd - cy.T @ ch, (Y - cy).sum(0)
+    else:
+        hd = logistic(hidden_pre(X, Y))
+        v, y, h = X, Y, None
+        for s in range(k):
+            v, h, y = gibbs(v, y, s)
+        hm = logistic(hidden_pre(v, None))                 # 2-arg form: ignores y~ (train_cd.jl:34)
+        dW = X.T @ hd - v.T @ hm
+        da, db = (X - v).sum(0), (hd - hm).sum(0)
+        if clf:
+            dU, dc = Y.T @ hd - y.T @ hm, (Y - y).sum(0)
+    m.W += dW * (lr / B)
+    m.a += da * (lr / B)
+    m.b += db * (lr / B)
+    if clf:
+        m.U += dU * (llr / B)
+        m.c += dc * (llr / B)
+        if algo.upper() == "PCD":                          # classifier PCD: chains advance AFTER the update (train_pcd.jl:89-92)
+            for s in range(k):
+                cv, ch, cy = gibbs(cv, cy, s)
+    return cv, ch, cy

@@ -182,17 +182,7 @@ def test_diverged_predicates():
 # ----------------------------------------------------------------- batched == per-sample
 def batched_pcd_step(m, X, cv, ch, k, lr, U_h, U_v):
     """The batched-GEMM formulation the device implements."""
-    for s in range(k):
-        ph = qo.logistic(m.b + cv @ m.W)
-        ch = (U_h[s] < ph).astype(np.float64)
-        pv = qo.logistic(m.a + ch @ m.W.T)
-        cv = (U_v[s] < pv).astype(np.float64)
-    hd = qo.logistic(m.b + X @ m.W)
-    B = X.shape[0]
-    dW = X.T @ hd - cv.T @ ch
-    m.W += dW * (lr / B)
-    m.a += (X - cv).sum(0) * (lr / B)
-    m.b += (hd - ch).sum(0) * (lr / B)
+    cv, ch, _ = qo.batched_step(m, X, None, "PCD", k, lr, cv=cv, ch=ch, U_h=U_h, U_v=U_v)
     return cv, ch
 
 
@@ -370,3 +360,35 @@ def test_fast_pcd_gaussian_chains_turn_binary():
     qo.fast_persistent_contrastive_divergence(m, X, [range(B)], chains, steps=1, learning_rate=0.1, fast_learning_rate=0.1,
                                               stream=qo.NumpyStream(3))
     assert all(set(np.unique(c.v)) <= {0.0, 1.0} for c in chains)
+
+
+@pytest.mark.parametrize("algo", ["PCD", "CD"])
+@pytest.mark.parametrize("L,gaussian", [(0, False), (3, False), (0, True), (2, True)])
+def test_batched_step_equals_per_sample_restatement(algo, L, gaussian):
+    """`batched_step` (BLAS-3; also bench.py's best-case CPU figure) against the per-sample restatement on the same streams."""
+    rng = np.random.default_rng(5 + L + 3 * gaussian)
+    V, H, B, k = 10, 7, 6, 2
+    m = small_model(rng, V, H, L, gaussian, scale=0.4)
+    mb = qo.copy_rbm(m)
+    X = rng.standard_normal((B, V)) if gaussian else rng.integers(0, 2, (B, V)).astype(np.float64)
+    Y = np.eye(L)[rng.integers(0, L, B)] if L else None
+    U_h = u24(rng, k, B, H)
+    U_v = None if gaussian else u24(rng, k, B, V)
+    Z_v = rng.standard_normal((k, B, V)) if gaussian else None
+    U_y = u24(rng, k, B, L) if L else None
+    cv, ch = rng.random((B, V)), rng.random((B, H))
+    cy = rng.random((B, L)) if L else None
+    if algo == "PCD":
+        chains = [qo.FantasyData(cv[i].copy(), ch[i].copy(), None if cy is None else cy[i].copy()) for i in range(B)]
+        st = qo.Stream(qo.serial_uniforms_pcd(U_h, U_v, U_y), None if Z_v is None else qo.serial_normals(Z_v, "pcd"))
+        qo.persistent_contrastive_divergence(m, X, [range(B)], chains, steps=k, learning_rate=0.05, stream=st, y=Y,
+                                             label_learning_rate=0.03)
+        cv2, ch2, cy2 = qo.batched_step(mb, X, Y, "PCD", k, 0.05, 0.03, cv=cv, ch=ch, cy=cy, U_h=U_h, U_v=U_v, U_y=U_y, Z_v=Z_v)
+        assert np.allclose(cv2, np.stack([c.v for c in chains]), atol=1e-12) and np.array_equal(ch2, np.stack([c.h for c in chains]))
+    else:
+        st = qo.Stream(qo.serial_uniforms_cd(U_h, U_v, U_y), None if Z_v is None else qo.serial_normals(Z_v, "cd"))
+        qo.contrastive_divergence(m, X, steps=k, learning_rate=0.05, stream=st, y=Y, label_learning_rate=0.03, batch_size=B)
+        qo.batched_step(mb, X, Y, "CD", k, 0.05, 0.03, U_h=U_h, U_v=U_v, U_y=U_y, Z_v=Z_v)
+    assert np.allclose(m.W, mb.W, atol=1e-12) and np.allclose(m.a, mb.a, atol=1e-12) and np.allclose(m.b, mb.b, atol=1e-12)
+    if L:
+        assert np.allclose(m.U, mb.U, atol=1e-12) and np.allclose(m.c, mb.c, atol=1e-12)
