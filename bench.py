@@ -270,6 +270,8 @@ def main():
     ap.add_argument("--p2p", action="store_true",
                     help="multi-GPU: fused NVLink peer-memory reduce-scatter + update + all-gather kernel instead of ncclAllReduce + "
                          "update (measured slower at 8 GPUs this round, see profiles/README.md)")
+    ap.add_argument("--sharded-update", type=int, default=-1,
+                    help="multi-GPU exchange: 1 = NCCL reduce-scatter + shard update + bf16 all-gather, 0 = allreduce + full update, -1 = library default")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: global batch fixed (BASELINE config); weak: per-GPU batch fixed (global batch x N)")
     ap.add_argument("--stale-chains", action="store_true", help="also time the stale-1 chains mode on one GPU")
@@ -285,8 +287,9 @@ def main():
     cfg = {"workload": f"{args.workload}: {w['desc']}", "V": w["V"], "H": w["H"], "L": w["L"], "global_batch": w["B"],
            "gibbs_steps": w["k"], "algorithm": w["algo"], "rng": "philox4x32-10", "persistent_chains": w.get("chains", w["B"]) if w["algo"] == "PCD" else None,
            "parallelism": (f"dp{world} (rows/chains sharded; gradient exchange: " +
-                           ("ncclAllReduce + update" if ((not args.p2p) or args.precision != "bf16") else
-                            "fused NVLink peer-memory reduce-scatter + update + bf16 all-gather kernel") + ")") if world > 1 else "single GPU"}
+                           ("fused NVLink peer-memory reduce-scatter + update + bf16 all-gather kernel" if (args.p2p and args.precision == "bf16") else
+                            "ncclReduceScatter + shard update + bf16 ncclAllGather + local transpose" if (args.sharded_update != 0 and args.precision == "bf16" and w["H"] % world == 0) else
+                            "ncclAllReduce + update") + ")") if world > 1 else "single GPU"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -338,6 +341,8 @@ def main():
             dev.p2p_import(allh.cpu().numpy().tobytes())
             if args.p2p_blocks:
                 dev.set_option("p2p_blocks_per_sm", args.p2p_blocks)
+        elif args.precision == "bf16" and args.sharded_update >= 0 and w["H"] % world == 0:
+            dev.set_option("sharded_update", args.sharded_update)
     dev.set_data(Xl, Yl)
     pcd = w["algo"] == "PCD"
     if pcd:

@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <climits>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -29,6 +30,11 @@ struct Nccl {
     int (*GetUniqueId)(ncclUniqueId *) = nullptr;
     int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*ReduceScatter)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, void *) = nullptr;  // optional (NCCL >= 2.18)
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
@@ -44,12 +50,23 @@ Nccl &nccl() {
         n.GetUniqueId = (decltype(n.GetUniqueId))dlsym(n.lib, "ncclGetUniqueId");
         n.CommInitRank = (decltype(n.CommInitRank))dlsym(n.lib, "ncclCommInitRank");
         n.AllReduce = (decltype(n.AllReduce))dlsym(n.lib, "ncclAllReduce");
+        n.ReduceScatter = (decltype(n.ReduceScatter))dlsym(n.lib, "ncclReduceScatter");
+        n.AllGather = (decltype(n.AllGather))dlsym(n.lib, "ncclAllGather");
+        n.CommSplit = (decltype(n.CommSplit))dlsym(n.lib, "ncclCommSplit");
+        n.GroupStart = (decltype(n.GroupStart))dlsym(n.lib, "ncclGroupStart");
+        n.GroupEnd = (decltype(n.GroupEnd))dlsym(n.lib, "ncclGroupEnd");
         n.CommDestroy = (decltype(n.CommDestroy))dlsym(n.lib, "ncclCommDestroy");
         n.GetErrorString = (decltype(n.GetErrorString))dlsym(n.lib, "ncclGetErrorString");
-        QB_CHECK(n.GetUniqueId && n.CommInitRank && n.AllReduce && n.CommDestroy, QB_E_NCCL, "NCCL symbols missing");
+        QB_CHECK(n.GetUniqueId && n.CommInitRank && n.AllReduce && n.CommDestroy && n.ReduceScatter && n.AllGather && n.GroupStart &&
+                     n.GroupEnd, QB_E_NCCL, "NCCL symbols missing");
     }
     return n;
 }
+// ncclConfig_t as of NCCL 2.18 (size / magic / version let newer libraries accept the shorter struct)
+struct NcclConfig218 {
+    size_t size; unsigned int magic; unsigned int version;
+    int blocking, cgaClusterSize, minCTAs, maxCTAs; const char *netName; int splitShare;
+};
 #define QB_NCCL(expr)                                                                          \
     do {                                                                                       \
         int _r = (expr);                                                                       \
@@ -59,6 +76,8 @@ Nccl &nccl() {
 }  // namespace
 
 // ----------------------------------------------------------------------------- device matrices
+constexpr int QB_OVERLAP_CTAS = 16;
+
 struct Mat {
     float *f = nullptr;  // fp32 [rows][ld]        (QB_PREC_FP32)
     bf16 *b = nullptr;   // bf16 [rows][ld]        (QB_PREC_BF16)
@@ -107,6 +126,10 @@ struct qb_handle {
     float *bias_rd = nullptr;  // [acat | b] as read by the GEMM epilogues (P's own bias region unless stale mode)
     int bias_cur = 0;
     cudaStream_t comm_stream = nullptr;
+    // overlap needs SMs: the exchange of the stale mode runs on a communicator limited to QB_OVERLAP_CTAS CTAs while the
+    // GEMMs leave that many SMs free (their persistent CTAs own a whole SM each, NCCL could not start beside them)
+    ncclComm_t comm_overlap = nullptr;
+    int gemm_sms = 148;
     cudaEvent_t ev_grad = nullptr, ev_upd = nullptr;
     // resident dataset
     Mat data; int64_t N = 0;
@@ -140,6 +163,10 @@ struct qb_handle {
     unsigned int *peerFlags[QB_MAX_PEERS] = {}, *p2p_flags = nullptr, *p2p_grid_bar = nullptr;
     unsigned int p2p_epoch = 1; unsigned long long *p2p_ns = nullptr; int p2p_blocks_per_sm = 3;
     int64_t shard_rows = 0;
+    // NCCL variant of the sharded update (option "sharded_update", bf16, H % world == 0): reduce-scatter of the fp32
+    // gradient, update of the owned hidden rows only, all-gather of the bf16 shadow, local transpose.  Moves 3/4 of the
+    // allreduce bytes and does 1/world of the update work; the fp32 master is then sharded like in the p2p path.
+    bool sharded_update = false, master_sharded = false;
     int64_t launches = 0, gemm_launches = 0;
     double gemm_flops = 0.0;
     int force_bn = 0, use_2cta = 1;
@@ -345,7 +372,7 @@ void op_hidden(qb_handle *h, const Mat &in, int64_t rows, int64_t kdim, const Hi
     ep.pscale = o.pscale;
     QB_CHECK(o.pscale == 1.f || sm100::pick_kind(ep) == sm100::K_FAST_PROB, QB_E_UNSUPPORTED, "pscale needs the fast probability epilogue");
     GemmScope gs(h, 2.0 * (double)h->H * (double)rows * (double)kdim);
-    sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn, h->use_2cta);
+    sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->gemm_sms, h->force_bn, h->use_2cta);
 }
 
 struct VisibleOut {
@@ -411,7 +438,7 @@ void op_visible(qb_handle *h, const Mat &in, int64_t rows, const VisibleOut &o, 
     ep.pscale = 1.f;
     {
         GemmScope gs(h, 2.0 * (double)h->VL * (double)rows * (double)h->H);
-        sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->num_sms, h->force_bn, h->use_2cta);
+        sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->gemm_sms, h->force_bn, h->use_2cta);
     }
     if (h->L > 0 && o.sample && o.state) {
         label_bf16_kernel<<<grid1d(rows, 128), 128, 0, h->stream>>>(
@@ -460,7 +487,7 @@ void op_grad(qb_handle *h, const Mat &posH, const Mat &posV, const bf16 *posV_T,
     ep.out_f32 = G_W(h); ep.ld_out = h->ldv;
     {
         GemmScope gs(h, 2.0 * (double)h->H * (double)h->VL * (double)(rows + nrows));
-        sm100::launch(h->stream, A, B, &A2, &B2, ep, h->num_sms, h->force_bn, h->use_2cta);
+        sm100::launch(h->stream, A, B, &A2, &B2, ep, h->gemm_sms, h->force_bn, h->use_2cta);
     }
     if (!h->cur_datasum) colsum<bf16>(h, posV.b, posV.ld, rows, h->VL, pos_scale, G_a(h));  // data-side visible sums; the rest is folded
 }
@@ -489,15 +516,25 @@ void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local);
 void op_update_on(qb_handle *h, double lr, double llr, int64_t B_local, cudaStream_t st, float *G, bf16 *Wb_out, bf16 *WbT_out,
                   float *bias_out) {
     if (h->p2p && st == h->stream && G == h->G && Wb_out == h->Wb) { p2p_update(h, lr, llr, B_local); return; }
-    if (h->comm) {
-        QB_NCCL(nccl().AllReduce(G, G, (size_t)h->nP, /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->comm, st));
+    ncclComm_t comm = (st == h->comm_stream && h->comm_overlap) ? h->comm_overlap : h->comm;
+    const bool sharded = comm && h->sharded_update && h->bf && (h->H % h->cfg.world) == 0;
+    const int64_t sr = sharded ? h->H / h->cfg.world : h->H, hr0 = sharded ? sr * h->cfg.rank : 0;
+    if (sharded) {
+        // in-place reduce-scatter: this rank ends up with the summed gradient of the hidden rows it owns; the biases are tiny
+        QB_NCCL(nccl().GroupStart());
+        QB_NCCL(nccl().ReduceScatter(G, G + hr0 * h->ldv, (size_t)(sr * h->ldv), /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, st));
+        QB_NCCL(nccl().AllReduce(G + h->nW, G + h->nW, (size_t)(h->ldv + h->ldh), 7, 0, comm, st));
+        QB_NCCL(nccl().GroupEnd());
+        h->master_sharded = true;
+    } else if (comm) {
+        QB_NCCL(nccl().AllReduce(G, G, (size_t)h->nP, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, st));
     }
     const double Bg = (double)B_local * (double)h->cfg.world;
     const float lr_e = (float)(lr / Bg), llr_e = (float)(llr / Bg);
     const bool use_vel = (h->momentum != 0.0 || h->weight_decay != 0.0);
     if (use_vel && !h->Vel) h->Vel = dalloc<float>(h->nP);
     // one launch: W tiles plus one extra row of blocks for the bias region [acat | b]
-    dim3 g((unsigned)ceil_div(h->VL, 128), (unsigned)ceil_div(h->H, 64) + 1);
+    dim3 g((unsigned)ceil_div(h->VL, 128), (unsigned)ceil_div(sr, 64) + 1);
     const int nb = (int)(h->ldv + h->ldh);
     const bool own_step = (st == h->stream && G == h->G);
     BiasTail bt{};
@@ -518,17 +555,26 @@ void op_update_on(qb_handle *h, double lr, double llr, int64_t B_local, cudaStre
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        float *Wp = Wf(h), *Velp = use_vel ? h->Vel : nullptr;
-        const float *Gp = G;
-        int Hh = (int)h->H, VLl = (int)h->VL, Vv = (int)h->V;
+        float *Wp = Wf(h) + hr0 * h->ldv, *Velp = use_vel ? h->Vel + hr0 * h->ldv : nullptr;
+        const float *Gp = G + hr0 * h->ldv;
+        bf16 *Wb_rows = Wb_out + hr0 * h->ldv;
+        bf16 *WbT_cols = sharded ? nullptr : WbT_out;   // sharded: the transposed shadow is rebuilt after the all-gather
+        int Hh = (int)sr, VLl = (int)h->VL, Vv = (int)h->V;
         int64_t ldv = h->ldv, ldh = h->ldh;
         float mom = use_vel ? (float)h->momentum : 0.f, wd = use_vel ? (float)h->weight_decay : 0.f;
-        if (use_vel) QB_CUDA(cudaLaunchKernelEx(&cfg, update_w_kernel<true>, Wp, Gp, Velp, Hh, VLl, Vv, ldv, lr_e, llr_e, mom, wd, Wb_out, WbT_out, ldh, bt));
-        else QB_CUDA(cudaLaunchKernelEx(&cfg, update_w_kernel<false>, Wp, Gp, Velp, Hh, VLl, Vv, ldv, lr_e, llr_e, mom, wd, Wb_out, WbT_out, ldh, bt));
+        if (use_vel) QB_CUDA(cudaLaunchKernelEx(&cfg, update_w_kernel<true>, Wp, Gp, Velp, Hh, VLl, Vv, ldv, lr_e, llr_e, mom, wd, Wb_rows, WbT_cols, ldh, bt));
+        else QB_CUDA(cudaLaunchKernelEx(&cfg, update_w_kernel<false>, Wp, Gp, Velp, Hh, VLl, Vv, ldv, lr_e, llr_e, mom, wd, Wb_rows, WbT_cols, ldh, bt));
     }
     if (timed) QB_CUDA(cudaEventRecord(h->upd_ev[ei + 1], st));
     QB_CUDA(cudaGetLastError());
     h->launches += 1;
+    if (sharded) {
+        QB_NCCL(nccl().AllGather(Wb_out + hr0 * h->ldv, Wb_out, (size_t)(sr * h->ldv), /*ncclBfloat16*/ 9, comm, st));
+        dim3 gt((unsigned)ceil_div(h->VL, 128), (unsigned)ceil_div(h->H, 64));
+        transpose_bf16_wide_kernel<<<gt, 256, 0, st>>>(Wb_out, h->ldv, (int)h->H, (int)h->VL, WbT_out, h->ldh);
+        QB_CUDA(cudaGetLastError());
+        h->launches += 1;
+    }
     if (own_step) h->bias_grads_clean = bt.zero_after != 0;
 }
 void op_update(qb_handle *h, double lr, double llr, int64_t B_local) {
@@ -570,6 +616,13 @@ void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local) {
 // p2p mode: the fp32 master is sharded by hidden rows; pull the other ranks' shards (collective by convention:
 // every rank is between steps when any rank calls this)
 void p2p_gather_master(qb_handle *h) {
+    if (h->master_sharded && h->comm && !h->p2p) {  // NCCL sharded update: in-place all-gather of the owned hidden rows
+        const int64_t sr = h->H / h->cfg.world;
+        QB_NCCL(nccl().AllGather(h->P + sr * h->cfg.rank * h->ldv, h->P, (size_t)(sr * h->ldv), /*ncclFloat32*/ 7, h->comm, h->stream));
+        QB_CUDA(cudaStreamSynchronize(h->stream));
+        h->master_sharded = false;
+        return;
+    }
     if (!h->p2p) return;
     QB_CUDA(cudaStreamSynchronize(h->stream));
     for (int r = 0; r < h->cfg.world; r++) {
@@ -614,6 +667,14 @@ void set_stale_mode(qb_handle *h, bool on) {
         QB_CUDA(cudaEventCreateWithFlags(&h->ev_grad, cudaEventDisableTiming));
         QB_CUDA(cudaEventCreateWithFlags(&h->ev_upd, cudaEventDisableTiming));
     }
+    if (on && h->comm && !h->comm_overlap && nccl().CommSplit) {  // collective: every rank switches the mode at the same point
+        NcclConfig218 c{};
+        c.size = sizeof(c); c.magic = 0xcafebeef; c.version = 21800;
+        c.blocking = INT_MIN; c.cgaClusterSize = INT_MIN; c.minCTAs = INT_MIN; c.maxCTAs = QB_OVERLAP_CTAS; c.netName = nullptr;
+        c.splitShare = INT_MIN;
+        QB_NCCL(nccl().CommSplit(h->comm, 0, h->cfg.rank, &h->comm_overlap, &c));
+    }
+    h->gemm_sms = (on && h->comm_overlap) ? std::max(2, (h->num_sms - QB_OVERLAP_CTAS) & ~1) : h->num_sms;
     if (on) {
         h->bias_cur = 0;
         QB_CUDA(cudaMemcpyAsync(h->bias_buf[0], acat(h), (h->ldv + h->ldh) * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
@@ -913,6 +974,7 @@ int32_t qb_create(qb_handle **out, const qb_config *cfg) {
         h->bf = cfg->precision == QB_PREC_BF16;
         h->gaussian = cfg->visible_kind == QB_VISIBLE_GAUSSIAN;
         h->num_sms = prop.multiProcessorCount;
+        h->gemm_sms = h->num_sms;
         QB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         QB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         for (auto &e : h->ev) QB_CUDA(cudaEventCreate(&e));
@@ -948,6 +1010,7 @@ int32_t qb_destroy(qb_handle *h) {
         if (!h) return;
         cudaSetDevice(h->cfg.device);
         cudaDeviceSynchronize();
+        if (h->comm_overlap) nccl().CommDestroy(h->comm_overlap);
         if (h->comm) nccl().CommDestroy(h->comm);
         if (h->p2p)
             for (int r = 0; r < h->cfg.world; r++)
@@ -1536,6 +1599,9 @@ int32_t qb_comm_init(qb_handle *h, const void *id128) {
         ncclUniqueId id;
         memcpy(&id, id128, sizeof(id));
         QB_NCCL(nccl().CommInitRank(&h->comm, h->cfg.world, id, h->cfg.rank));
+        // default exchange in bf16 mode: reduce-scatter + shard update + bf16 all-gather (measured 6 % faster than allreduce +
+        // full update at 8 GPUs, equal at 2); option "sharded_update" = 0 goes back to the allreduce
+        h->sharded_update = h->bf && (h->H % h->cfg.world) == 0;
     });
 }
 
@@ -1622,6 +1688,11 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
             h->online_wpb = (int)value;
         } else if (!strcmp(key, "online_kernel")) {
             h->online_kernel = value != 0.0;
+        } else if (!strcmp(key, "sharded_update")) {
+            QB_CHECK(value == 0.0 || (h->bf && h->cfg.world > 1 && (h->H % h->cfg.world) == 0), QB_E_UNSUPPORTED,
+                     "sharded_update needs bf16 precision, world > 1 and n_hidden % world == 0");
+            QB_CHECK(!h->master_sharded || value != 0.0, QB_E_STATE, "gather the master (qb_get_params) before switching sharded_update off");
+            h->sharded_update = value != 0.0;
         } else if (!strcmp(key, "fast_pcd_pair_chains")) {
             h->fast_pcd_pair_chains = value != 0.0;
         } else if (!strcmp(key, "stale_chains")) {

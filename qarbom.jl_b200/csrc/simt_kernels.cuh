@@ -370,6 +370,41 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16 *__restr
     }
 }
 
+// dst[c][r] = src[r][c] with 128-bit loads and 2 x 128-bit stores per task (64 x 128 tiles): the whole-matrix transpose of
+// the sharded update path (32 MB in, 32 MB out at cfg5).  lds, ldd multiples of 8 elements, 16-byte aligned bases.
+__global__ void __launch_bounds__(256) transpose_bf16_wide_kernel(const bf16 *__restrict__ src, int64_t lds, int rows, int cols,
+                                                                  bf16 *__restrict__ dst, int64_t ldd) {
+    constexpr int TR = 64, TC = 128, PITCH = TC + 8;
+    __shared__ __align__(16) unsigned short tile[TR][PITCH];
+    const int c0 = blockIdx.x * TC, r0 = blockIdx.y * TR;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int idx = threadIdx.x + 256 * q, r = idx >> 4, cv = (idx & 15) * 8;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r0 + r < rows && c0 + cv < cols) v = *reinterpret_cast<const uint4 *>(src + (int64_t)(r0 + r) * lds + c0 + cv);  // row padding (ld % 8 == 0) is readable
+        *reinterpret_cast<uint4 *>(&tile[r][cv]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int task = threadIdx.x + 256 * q;
+        const int cl = task & (TC - 1), hc = task >> 7;
+        const int cc = c0 + cl, hb = r0 + 16 * hc;
+        if (cc >= cols || hb >= rows) continue;
+        unsigned short *d = reinterpret_cast<unsigned short *>(dst) + (int64_t)cc * ldd + hb;
+        if (hb + 16 <= rows) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) pk[i] = (uint32_t)tile[16 * hc + 2 * i][cl] | ((uint32_t)tile[16 * hc + 2 * i + 1][cl] << 16);
+            reinterpret_cast<uint4 *>(d)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            reinterpret_cast<uint4 *>(d)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+            for (int i = 0; i < 16; i++)
+                if (hb + i < rows) d[i] = tile[16 * hc + i][cl];
+        }
+    }
+}
+
 __global__ void f32_to_bf16_kernel(const float *__restrict__ src, bf16 *__restrict__ dst, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = __float2bfloat16(src[i]);

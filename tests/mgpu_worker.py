@@ -15,7 +15,7 @@ from bench import shard_rows  # noqa: E402
 
 def main():
     prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
-    exchange = sys.argv[2] if len(sys.argv) > 2 else "nccl"   # "p2p": NVLink peer-memory reduce+update kernel
+    exchange = sys.argv[2] if len(sys.argv) > 2 else "nccl"   # "p2p": NVLink peer-memory reduce+update kernel; "sharded": NCCL RS + AG
     rank, world, lr_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr_)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr_))
@@ -34,6 +34,8 @@ def main():
                 uid.copy_(torch.frombuffer(bytearray(q.DeviceRBM.comm_unique_id()), dtype=torch.uint8))
             dist.broadcast(uid, 0)
             dev.comm_init(uid.cpu().numpy().tobytes())
+            if prec == "bf16":   # "sharded" (the bf16 default): NCCL reduce-scatter + shard update + bf16 all-gather + local transpose
+                dev.set_option("sharded_update", 0 if exchange == "nccl" else 1)
             if exchange == "p2p":
                 mine = torch.frombuffer(bytearray(dev.p2p_export()), dtype=torch.uint8).cuda()
                 allh = torch.empty(320 * world, dtype=torch.uint8, device="cuda")
@@ -41,6 +43,8 @@ def main():
                 dev.p2p_import(allh.cpu().numpy().tobytes())
         dev.set_data(Xs)
         dev.init_chains(Brows)
+        if exchange == "stale":      # stale-1 chains on both sides: the overlapped exchange (CTA-limited communicator) must not change results
+            dev.set_option("stale_chains", 1)
         for t in range(steps):
             dev.pcd_step(t % nb, Brows, k, 0.05)
         if comm:
