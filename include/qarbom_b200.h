@@ -178,8 +178,11 @@ int32_t qb_conditional_prob_h(qb_handle *h, const double *v, const double *y, in
  * the caller's arg-max / comparison over these probabilities. */
 int32_t qb_conditional_prob_y_given_v(qb_handle *h, const void *X, int32_t x_dtype, int64_t n_rows, double *out);
 
-/* Data-parallel gradient allreduce over NCCL (new; the reference is single-process).
- * Rank 0 creates the id, the caller ships the 128 bytes to the other ranks. */
+/* Data-parallel gradient exchange over NCCL (new; the reference is single-process).
+ * Rank 0 creates the id, the caller ships the 128 bytes to the other ranks.  fp32 mode: one allreduce of the flat
+ * gradient per step, replicated masters.  bf16 mode with n_hidden % world == 0 (option "sharded_update", default 1):
+ * reduce-scatter, update of the owned hidden rows, all-gather of the bf16 shadow; the fp32 master is then sharded and
+ * qb_get_params / qb_snapshot_params gather it -- they are collective, call them on every rank at the same point. */
 int32_t qb_comm_unique_id(void *id128);
 int32_t qb_comm_init(qb_handle *h, const void *id128);
 
@@ -205,7 +208,9 @@ int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_la
 int32_t qb_get_update_timing(qb_handle *h, int64_t *timed_updates, double *timed_update_ms);
 int32_t qb_reset_counters(qb_handle *h);
 /* Options: "async_steps" (qb_pcd_step / qb_cd_step return without waiting; use qb_sync), "time_gemms",
- * "stale_chains" (declared extension: allreduce + update of step t overlap the chain advance of step t + 1),
+ * "stale_chains" (declared extension: exchange + update of step t overlap the chain advance of step t + 1; collective
+ * when a communicator exists: it splits off a CTA-limited communicator), "sharded_update" (multi-GPU bf16 exchange:
+ * 1 = reduce-scatter + shard update + bf16 all-gather, the default when n_hidden % world == 0; 0 = allreduce),
  * "online_kernel" (0: batch-size-1 CD through per-sample launches instead of the cooperative epoch kernel),
  * "online_wpb" (warps per block of the cooperative kernels), "fast_pcd_pair_chains" (classifier FastPCD pairs
  * sample i with chain i instead of the reference's chain 1), "p2p_blocks_per_sm", and for experiments / tests
