@@ -1053,6 +1053,7 @@ int32_t qb_set_params(qb_handle *h, const double *W, const double *a, const doub
         for (int64_t l = 0; l < h->L; l++) p[h->nW + h->V + l] = (float)c[l];
         for (int64_t j = 0; j < h->H; j++) p[h->nW + h->ldv + j] = (float)b[j];
         QB_CUDA(cudaMemcpyAsync(h->P, p.data(), p.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        h->master_sharded = false;
         if (h->Vel) QB_CUDA(cudaMemsetAsync(h->Vel, 0, h->nP * sizeof(float), h->stream));
         refresh_shadows(h);
         if (h->bias_rd) QB_CUDA(cudaMemcpyAsync(h->bias_rd, acat(h), (h->ldv + h->ldh) * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
@@ -1093,6 +1094,7 @@ int32_t qb_restore_params(qb_handle *h) {
         QB_H(h);
         QB_CHECK(h->P_best != nullptr, QB_E_STATE, "qb_snapshot_params has not been called");
         QB_CUDA(cudaMemcpyAsync(h->P, h->P_best, h->nP * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        h->master_sharded = false;  // the snapshot holds every row
         refresh_shadows(h);
         if (h->bias_rd) QB_CUDA(cudaMemcpyAsync(h->bias_rd, acat(h), (h->ldv + h->ldh) * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
         QB_CUDA(cudaStreamSynchronize(h->stream));
