@@ -148,7 +148,10 @@ int32_t qb_fast_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double 
                           double times[3]);
 
 /* Same step, but the mini-batch comes from HOST memory on every call (end-to-end path:
- * upload, step, and a device->host read of the batch reconstruction error sum). */
+ * upload, step, and a device->host read of the batch reconstruction error sum: sum over the batch rows and the
+ * visible units of (x - reconstruct(x))^2, src/rbm.jl:220-224.  PCD on binary models without label units and with
+ * chains == batch rows takes it inside the step from the positive-phase p(h | x) it computes anyway, i.e. with the
+ * weights BEFORE the update; every other case reconstructs after the step, with the updated weights). */
 int32_t qb_pcd_step_host(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype, int64_t B,
                          int64_t k, double lr, double llr, double *recon_sq_err);
 int32_t qb_cd_step_host(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype, int64_t B,

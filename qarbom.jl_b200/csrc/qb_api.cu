@@ -136,6 +136,9 @@ struct qb_handle {
     bf16 *dataT = nullptr; int64_t dataT_B = 0, dataT_nb = 0, dataT_ld = 0;
     float *datasum = nullptr;          // [nb][ldv] column sums of every resident mini-batch (data side of delta_a)
     const float *cur_datasum = nullptr;  // sums of the mini-batch being processed (nullptr: compute them)
+    // qb_pcd_step_host: the batch reconstruction error is taken inside the step, from the positive-phase p(h | x) that the
+    // step computes anyway (one GEMM instead of two; weights before the update).  Binary models without label units.
+    bool step_recon_wanted = false, step_recon_done = false;
     bool bias_grads_clean = false;       // the bias region of G is zero (left so by the previous update)
     bool datasum_in_update = false;      // the cached data sums are added by the update kernel, not by the init kernel
     float datasum_scale = 1.f;
@@ -801,7 +804,15 @@ void pcd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT,
     }
     if (ev) QB_CUDA(cudaEventRecord(ev[1], h->stream));
     HiddenOut ho; ho.prob = &h->phd; ho.prob_T = true; ho.bg_what = 1; ho.bg_sign = 1.f; ho.pscale = ps;  // conditional_prob_h(v_data[, y_data])
+    const bool fused_recon = h->step_recon_wanted && !clf && !h->gaussian && Nc == B;
+    if (fused_recon) ho.prob_rm = true;  // the reconstruction below reads p(h | x) row-major
     op_hidden(h, xb, B, h->VL, ho, Rng(), row0);
+    if (fused_recon) {  // reconstruct(x) = sigma(a + W p(h | x)) against x, squared error summed into dscal[0] (src/rbm.jl:220-224)
+        QB_CUDA(cudaMemsetAsync(h->dscal, 0, sizeof(double), h->stream));
+        VisibleOut vo; vo.state = &h->vm; vo.sample = false; vo.state_rm = !h->bf; vo.ref = &xb; vo.sqerr = h->dscal;
+        op_visible(h, h->phd, B, vo, Rng(), row0);
+        h->step_recon_done = true;
+    }
     if (ev) QB_CUDA(cudaEventRecord(ev[2], h->stream));
     op_grad(h, h->phd, xb, xbT, xb_ldT, h->ch, h->cv, B, Nc, ps);
     op_update(h, lr, llr, Nc);
@@ -1406,11 +1417,17 @@ static void step_host_impl(qb_handle *h, bool pcd, const void *X, int xdt, const
     check_step_args(h, B, k);
     h->cur_datasum = nullptr;
     stage_host_batch(h, X, xdt, Y, ydt, B);
-    if (pcd) pcd_step_impl(h, h->hb, h->hb.bT, h->hb.ldT, B, k, lr, llr, nullptr);
-    else cd_step_impl(h, h->hb, h->hb.bT, h->hb.ldT, B, k, lr, llr, nullptr);
+    h->step_recon_wanted = recon != nullptr; h->step_recon_done = false;
+    try {
+        if (pcd) pcd_step_impl(h, h->hb, h->hb.bT, h->hb.ldT, B, k, lr, llr, nullptr);
+        else cd_step_impl(h, h->hb, h->hb.bT, h->hb.ldT, B, k, lr, llr, nullptr);
+    } catch (...) { h->step_recon_wanted = false; throw; }
+    h->step_recon_wanted = false;
     if (recon) {
-        QB_CUDA(cudaMemsetAsync(h->dscal, 0, sizeof(double), h->stream));
-        recon_sqerr(h, h->hb, B, nullptr, row0_of(h, B));
+        if (!h->step_recon_done) {  // other models / modes: reconstruction of the batch after the step (two GEMMs)
+            QB_CUDA(cudaMemsetAsync(h->dscal, 0, sizeof(double), h->stream));
+            recon_sqerr(h, h->hb, B, nullptr, row0_of(h, B));
+        }
         *recon = read_scalar(h, 0);
     } else {
         QB_CUDA(cudaStreamSynchronize(h->stream));

@@ -348,6 +348,21 @@ def test_argument_errors(q):
         with pytest.raises(q.QbError):
             dev.pcd_step(0, 8, 1, 0.1)          # B > max_batch
         dev.pcd_step(1, 4, 1, 0.1)
+        with pytest.raises(q.QbError):
+            dev.cd_step(0, 4, 0, 0.1)           # CD needs k >= 1 (k = 0 is the qb_pcd_step-only "external negative samples" form)
+        with pytest.raises(q.QbError):
+            dev.set_data(np.zeros((0, 4)))      # empty dataset
+        with pytest.raises(q.QbError):
+            dev.eval_mse(np.zeros((0, 4)))      # empty evaluation set
+        with pytest.raises(q.QbError):
+            dev.set_option("no_such_option", 1)
+        with pytest.raises(q.QbError):
+            dev.set_option("sharded_update", 1)  # needs bf16 and a communicator world > 1
+        with pytest.raises(q.QbError):
+            dev.fast_pcd_epoch(2, 1, 0.1, 0.1)   # FastPCD pairs sample i with chain i: chains != batch rows
+        assert dev.eval_mse() >= 0.0             # the failed calls left the handle usable
+    with pytest.raises(q.QbError):
+        q.DeviceRBM(q.RBM(4, 3), max_batch=0)    # invalid configuration
 
 
 # ------------------------------------------------------------------------------ optimizer extension
@@ -824,3 +839,30 @@ def test_train_fast_pcd_classifier_reference_scenario(q, tmp_path):
     assert list(hist) == ["accuracy"] and hist["accuracy"][-1] == 1.0
     with q.DeviceRBM(rbm, max_batch=1, precision="fp32") as dev:
         assert dev.classify([[1, 0, 0]]).tolist() == [[1]]
+
+
+@pytest.mark.parametrize("prec,L", [("fp32", 0), ("bf16", 0), ("fp32", 3)])
+def test_step_host_reconstruction_error_value(q, prec, L):
+    """qb_pcd_step_host returns sum over rows and visible units of (x - reconstruct(x))^2 (src/rbm.jl:220-224): for binary
+    models without labels taken inside the step with the weights BEFORE the update (from the positive-phase p(h|x)),
+    otherwise after the step with the updated weights."""
+    bf = prec == "bf16"
+    rng = np.random.default_rng(77 + L)
+    V, H, B, k = 48, 28, 16, 1
+    m = make_oracle_model(rng, V, H, L, bf16=bf)
+    X, Y = _data(rng, 2 * B, V, L, False, bf)
+    rbm = to_host_rbm(q, m)
+    with q.DeviceRBM(rbm, max_batch=B, precision=prec, seed=5) as dev:
+        dev.init_chains(B)
+        for t in range(2):
+            sl = slice(t * B, (t + 1) * B)
+            dev.pull_params()
+            before = qo.Model(rbm.W.copy(), rbm.a.copy(), rbm.b.copy(), None if not L else rbm.U.copy(), None if not L else rbm.c.copy())
+            err = dev.step_host("PCD", X[sl], None if Y is None else Y[sl], k, 0.05, 0.02)
+            dev.pull_params()
+            after = qo.Model(rbm.W.copy(), rbm.a.copy(), rbm.b.copy(), None if not L else rbm.U.copy(), None if not L else rbm.c.copy())
+            ref_model = before if L == 0 else after
+            if bf:
+                ref_model = qo.Model(bf16_round(ref_model.W), ref_model.a, ref_model.b)
+            ref = sum(float(np.sum((x - qo.reconstruct(ref_model, x)) ** 2)) for x in X[sl])
+            assert abs(err - ref) / ref < (2e-3 if bf else 1e-5), (err, ref)
