@@ -176,6 +176,17 @@ int32_t qb_reconstruct(qb_handle *h, const double *v, int64_t n_rows, const doub
 /* conditional_prob_h (src/rbm.jl:165,170-171) for n_rows rows; y may be NULL (2-arg form). */
 int32_t qb_conditional_prob_h(qb_handle *h, const double *v, const double *y, int64_t n_rows, double *out);
 
+/* Single sampling half-steps, for unit tests and callers that drive their own chains.
+ * qb_sample_hidden = gibbs_sample_hidden (src/gibbs.jl:3-6; with y: :29-32): out[n_rows][H] = 1[u < p(h | v[, y])].
+ * qb_sample_visible = gibbs_sample_visible (src/gibbs.jl:13-16; Gaussian visibles :18-20: mean + z, a real value) and,
+ * for classifiers, gibbs_sample_label (src/gibbs.jl:46-49) into out_y (may be NULL).
+ * U / R / Ry are the caller's random numbers, one per unit in unit order (R: uniforms, or standard normals for
+ * Gaussian visibles; Ry: label uniforms, required with R on a classifier); NULL draws from the Philox stream
+ * (one draw id per call, row index = global row).  In bf16 mode a Gaussian sample comes back rounded to bf16. */
+int32_t qb_sample_hidden(qb_handle *h, const double *v, const double *y, int64_t n_rows, const double *U, double *out);
+int32_t qb_sample_visible(qb_handle *h, const double *hid, int64_t n_rows, const double *R, const double *Ry,
+                          double *out_v, double *out_y);
+
 /* conditional_prob_y_given_v (src/rbm.jl:191-194) for n_rows rows -> out[n_rows][L]; X == NULL uses the
  * resident dataset.  `classify` (src/rbm.jl:226-229) and the Accuracy metric (src/evaluation.jl:9-14) are
  * the caller's arg-max / comparison over these probabilities. */

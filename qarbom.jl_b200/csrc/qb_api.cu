@@ -152,6 +152,7 @@ struct qb_handle {
     float *pre_h = nullptr, *pre_v = nullptr, *lab_pre = nullptr, *softplus_rows = nullptr;
     float *out_f32 = nullptr;  // fp32 [Bmax][max(ldv, ldh)] API output staging
     float *znoise = nullptr;   // fp32 [Bmax][V] injected reconstruct noise (Gaussian visibles)
+    float *rand_rows = nullptr;  // fp32 [Bmax][max(VL, H)] caller-supplied random numbers of qb_sample_hidden / qb_sample_visible
     double *dscal = nullptr;   // device scalar accumulators [4]
     void *staging = nullptr; size_t staging_bytes = 0;
     // injected streams for the next step
@@ -1039,7 +1040,7 @@ int32_t qb_destroy(qb_handle *h) {
         free_mat(h->cv); free_mat(h->ch); free_mat(h->phd); free_mat(h->hs); free_mat(h->vm); free_mat(h->phm); free_mat(h->hb); free_mat(h->hb2);
         cudaFree(h->staging2); if (h->ev_pf) cudaEventDestroy(h->ev_pf);
         cudaFree(h->pre_h); cudaFree(h->pre_v); cudaFree(h->lab_pre); cudaFree(h->softplus_rows); cudaFree(h->out_f32);
-        cudaFree(h->dscal); cudaFree(h->znoise); cudaFree(h->staging); cudaFree(h->injUh); cudaFree(h->injUv); cudaFree(h->injZv);
+        cudaFree(h->dscal); cudaFree(h->znoise); cudaFree(h->rand_rows); cudaFree(h->staging); cudaFree(h->injUh); cudaFree(h->injUv); cudaFree(h->injZv);
         for (auto &e : h->ev) cudaEventDestroy(e);
         for (auto &e : h->timer_ev) cudaEventDestroy(e);
         for (auto &e : h->gemm_ev) cudaEventDestroy(e);
@@ -1538,6 +1539,59 @@ int32_t qb_reconstruct(qb_handle *h, const double *v, int64_t n_rows, const doub
             else vo.state = &of;
             op_visible(h, h->phd, nr, vo, rng, r);
             download_rows(h, of, 0, 0, nr, h->V, out + (size_t)r * h->V);
+        }
+    });
+}
+
+// gibbs_sample_hidden (src/gibbs.jl:3-6, 29-32) for n_rows rows
+int32_t qb_sample_hidden(qb_handle *h, const double *v, const double *y, int64_t n_rows, const double *U, double *out) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(v && out && n_rows > 0, QB_E_ARG, "NULL argument or n_rows <= 0");
+        QB_CHECK(y == nullptr || h->L > 0, QB_E_ARG, "y given for a model without label units");
+        if (U && !h->rand_rows) h->rand_rows = dalloc<float>(h->Bmax * std::max(h->VL, h->H));
+        const Rng philox = U ? Rng() : philox_rng(h);  // one draw id for the whole call, rows keyed by their index
+        for (int64_t r = 0; r < n_rows; r += h->Bmax) {
+            const int64_t nr = std::min(h->Bmax, n_rows - r);
+            upload_rows(h, v + (size_t)r * h->V, QB_DT_F64, nr, h->V, h->hb, 0, 0);
+            if (y) upload_rows(h, y + (size_t)r * h->L, QB_DT_F64, nr, h->L, h->hb, 0, h->V);
+            Rng rng = philox;
+            if (U) {
+                Mat uf; uf.f = h->rand_rows; uf.ld = h->H; uf.rows = nr; uf.units = h->H;
+                upload_rows(h, U + (size_t)r * h->H, QB_DT_F64, nr, h->H, uf, 0, 0);
+                rng = injected_rng(h->rand_rows, h->H);
+            }
+            HiddenOut ho; ho.state = &h->hs; ho.state_rm = true;
+            op_hidden(h, h->hb, nr, y ? h->VL : h->V, ho, rng, r);
+            download_rows(h, h->hs, 0, 0, nr, h->H, out + (size_t)r * h->H);
+        }
+    });
+}
+
+// gibbs_sample_visible (src/gibbs.jl:13-20) and gibbs_sample_label (src/gibbs.jl:46-49) for n_rows rows
+int32_t qb_sample_visible(qb_handle *h, const double *hid, int64_t n_rows, const double *R, const double *Ry, double *out_v,
+                          double *out_y) {
+    return guarded([&] {
+        QB_H(h);
+        QB_CHECK(hid && out_v && n_rows > 0, QB_E_ARG, "NULL argument or n_rows <= 0");
+        QB_CHECK(h->L == 0 || R == nullptr || Ry != nullptr, QB_E_ARG, "label uniforms Ry are required with R on a classifier");
+        QB_CHECK(out_y == nullptr || h->L > 0, QB_E_ARG, "out_y given for a model without label units");
+        if (R && !h->rand_rows) h->rand_rows = dalloc<float>(h->Bmax * std::max(h->VL, h->H));
+        const Rng philox = R ? Rng() : philox_rng(h);
+        for (int64_t r = 0; r < n_rows; r += h->Bmax) {
+            const int64_t nr = std::min(h->Bmax, n_rows - r);
+            upload_rows(h, hid + (size_t)r * h->H, QB_DT_F64, nr, h->H, h->hs, 0, 0);
+            Rng rng = philox;
+            if (R) {  // one [rows][V + L] array: visible uniforms (normals for Gaussian visibles), then label uniforms
+                Mat uf; uf.f = h->rand_rows; uf.ld = h->VL; uf.rows = nr; uf.units = h->VL;
+                upload_rows(h, R + (size_t)r * h->V, QB_DT_F64, nr, h->V, uf, 0, 0);
+                if (h->L > 0) upload_rows(h, Ry + (size_t)r * h->L, QB_DT_F64, nr, h->L, uf, 0, h->V);
+                rng = injected_rng(h->rand_rows, h->VL);
+            }
+            VisibleOut vo; vo.state = &h->vm; vo.sample = true; vo.state_rm = true;
+            op_visible(h, h->hs, nr, vo, rng, r);
+            download_rows(h, h->vm, 0, 0, nr, h->V, out_v + (size_t)r * h->V);
+            if (out_y) download_rows(h, h->vm, 0, h->V, nr, h->L, out_y + (size_t)r * h->L);
         }
     });
 }

@@ -193,6 +193,27 @@ class DeviceRBM:
         check(lib().qb_conditional_prob_h(self._h, ptr(v), ptr(y), v.shape[0], ptr(out)))
         return out
 
+    def sample_hidden(self, v, y=None, U=None) -> np.ndarray:
+        """gibbs_sample_hidden (src/gibbs.jl:3-6,29-32) per row; U = the caller's uniforms [rows][H], None = Philox."""
+        v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1, self.V))
+        y = None if y is None else np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1, self.L))
+        U = None if U is None else np.ascontiguousarray(np.asarray(U, dtype=np.float64).reshape(-1, self.H))
+        out = np.zeros((v.shape[0], self.H))
+        check(lib().qb_sample_hidden(self._h, ptr(v), ptr(y), v.shape[0], ptr(U), ptr(out)))
+        return out
+
+    def sample_visible(self, h, R=None, Ry=None):
+        """gibbs_sample_visible (+ gibbs_sample_label for classifiers) per row (src/gibbs.jl:13-20,46-49).  R: uniforms
+        (standard normals for Gaussian visibles) [rows][V], Ry: label uniforms [rows][L]; None = Philox.
+        Returns v, or (v, y) for classifiers."""
+        h = np.ascontiguousarray(np.asarray(h, dtype=np.float64).reshape(-1, self.H))
+        R = None if R is None else np.ascontiguousarray(np.asarray(R, dtype=np.float64).reshape(-1, self.V))
+        Ry = None if Ry is None else np.ascontiguousarray(np.asarray(Ry, dtype=np.float64).reshape(-1, self.L))
+        out_v = np.zeros((h.shape[0], self.V))
+        out_y = np.zeros((h.shape[0], self.L)) if self.L else None
+        check(lib().qb_sample_visible(self._h, ptr(h), h.shape[0], ptr(R), ptr(Ry), ptr(out_v), ptr(out_y)))
+        return (out_v, out_y) if self.L else out_v
+
     def conditional_prob_y_given_v(self, x=None) -> np.ndarray:
         """softmax(c + U sigma(b + W'v)) per row (src/rbm.jl:191-194); x=None: the resident dataset."""
         if x is None:

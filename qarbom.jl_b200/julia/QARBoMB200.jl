@@ -145,6 +145,21 @@ function epoch!(d::Device, ::Type{CD}, B, k, lr, llr)
     return t[1], t[2], t[3]
 end
 
+"gibbs_sample_hidden / gibbs_sample_visible for a batch of rows (columns of the V x n / H x n matrices); Philox stream"
+function sample_hidden(d::Device, rbm::AbstractRBM, v::Matrix{Float64})
+    out = zeros(rbm.n_hidden, size(v, 2))
+    GC.@preserve v out check(ccall((:qb_sample_hidden, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}),
+                                   d.h, pointer(v), C_NULL, size(v, 2), C_NULL, pointer(out)))
+    return out
+end
+function sample_visible(d::Device, rbm::AbstractRBM, h::Matrix{Float64})
+    out = zeros(rbm.n_visible, size(h, 2))
+    GC.@preserve h out check(ccall((:qb_sample_visible, LIB), Int32,
+                                   (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                                   d.h, pointer(h), size(h, 2), C_NULL, C_NULL, pointer(out), C_NULL))
+    return out
+end
+
 "fast_persistent_contrastive_divergence! for one epoch (src/training/train_fast_pcd.jl:1-57, classifiers :59-127)"
 function fast_pcd_epoch!(d::Device, B, k, lr, fast_lr, llr = 0.0, fast_llr = 0.0)
     t = zeros(3)

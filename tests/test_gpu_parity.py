@@ -866,3 +866,60 @@ def test_step_host_reconstruction_error_value(q, prec, L):
                 ref_model = qo.Model(bf16_round(ref_model.W), ref_model.a, ref_model.b)
             ref = sum(float(np.sum((x - qo.reconstruct(ref_model, x)) ** 2)) for x in X[sl])
             assert abs(err - ref) / ref < (2e-3 if bf else 1e-5), (err, ref)
+
+
+# ------------------------------------------------------------------------------ single sampling half-steps
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("V,H,L,gaussian", [(3, 2, 0, False), (70, 33, 0, False), (40, 24, 5, False), (40, 24, 0, True), (30, 18, 3, True)])
+def test_sample_hidden_and_visible_half_steps(q, prec, V, H, L, gaussian):
+    """qb_sample_hidden / qb_sample_visible against gibbs_sample_hidden / gibbs_sample_visible / gibbs_sample_label
+    (src/gibbs.jl:3-20,29-32,46-49) with the caller's random numbers, then with the Philox stream."""
+    bf = prec == "bf16"
+    rng = np.random.default_rng(V + H + L)
+    n = 13
+    m = make_oracle_model(rng, V, H, L, gaussian=gaussian, bf16=bf, scale=0.3)
+    X, Y = _data(rng, n, V, L, gaussian, bf)
+    Hs = rng.integers(0, 2, (n, H)).astype(np.float64)
+    seed = 321
+    with q.DeviceRBM(to_host_rbm(q, m), max_batch=8, precision=prec, seed=seed) as dev:     # max_batch < n: chunked
+        for use_y in ([False, True] if L else [False]):
+            st = qo.GuardedStream(u24(rng, n * H))
+            ref = np.stack([qo.gibbs_sample_hidden(m, X[i], st, Y[i] if use_y else None) for i in range(n)])
+            out = dev.sample_hidden(X, Y if use_y else None, U=st.u.reshape(n, H))
+            assert np.array_equal(out, ref)
+        if gaussian:
+            Z = f32_round(rng.standard_normal((n, V)))
+            st = qo.GuardedStream(u24(rng, n * L) if L else None, Z.reshape(-1))
+        else:
+            st = qo.GuardedStream(u24(rng, n * (V + L)))
+        ref_v, ref_y = [], []
+        for i in range(n):
+            ref_v.append(np.asarray(qo.gibbs_sample_visible(m, Hs[i], st), dtype=np.float64))
+            if L:
+                ref_y.append(qo.gibbs_sample_label(m, Hs[i], st))
+        if gaussian:
+            R, Ry = Z, (st.u.reshape(n, L) if L else None)
+        else:
+            u = st.u.reshape(n, V + L)
+            R, Ry = u[:, :V], (u[:, V:] if L else None)
+        res = dev.sample_visible(Hs, R, Ry)
+        out_v, out_y = res if L else (res, None)
+        if gaussian:
+            assert np.max(np.abs(out_v - np.stack(ref_v))) < (5e-2 if bf else 1e-5)     # bf16: the sample is stored in bf16
+        else:
+            assert np.array_equal(out_v, np.stack(ref_v))
+        if L:
+            assert np.array_equal(out_y, np.stack(ref_y))
+        # Philox: draws 0 (hidden) and 1 (visible + labels) of this handle
+        out = dev.sample_hidden(X)
+        ph = np.stack([qo.conditional_prob_h(m, x) for x in X])
+        uh = philox_ref.uniforms(seed, 0, n, H)
+        safe = np.abs(uh - ph) > 1e-4
+        assert np.array_equal(out[safe], (uh < ph).astype(np.float64)[safe])
+        res = dev.sample_visible(Hs)
+        out_v = res[0] if L else res
+        if not gaussian:
+            pv = np.stack([qo.conditional_prob_v(m, h) for h in Hs])
+            uv = philox_ref.uniforms(seed, 1, n, V + L)[:, :V]
+            safe = np.abs(uv - pv) > 1e-4
+            assert np.array_equal(out_v[safe], (uv < pv).astype(np.float64)[safe])
