@@ -295,11 +295,12 @@ def main():
         if rank != 0:
             return 0
         r = cpu_reference(w, 60.0, args.steps, args.warmup)
+        rb = cpu_batched_blas(w, 5.0)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["threads"], "kind": "port",
-                                 "sample": r["sample"]},
+                                 "sample": r["sample"], "value_batched_blas": rb["value"], "sample_batched_blas": rb["sample"]},
                 "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gibbs_steps_per_s": r["value"] * w["k"] * (w.get("chains", w["B"]) / w["B"] if w["algo"] == "PCD" else 1.0),
                 "note": "CPU restatement of QARBoM.jl (C, Float64, per-sample GEMV + outer products; Julia not installable here)"}
