@@ -272,6 +272,8 @@ def main():
                          "update (measured slower at 8 GPUs this round, see profiles/README.md)")
     ap.add_argument("--sharded-update", type=int, default=-1,
                     help="multi-GPU exchange: 1 = NCCL reduce-scatter + shard update + bf16 all-gather, 0 = allreduce + full update, -1 = library default")
+    ap.add_argument("--state-exchange", type=int, default=-1,
+                    help="multi-GPU PCD: 1 = reduce-scatter of the positive product behind the chains + bit-packed chain-state all-gather")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: global batch fixed (BASELINE config); weak: per-GPU batch fixed (global batch x N)")
     ap.add_argument("--stale-chains", action="store_true", help="also time the stale-1 chains mode on one GPU")
@@ -344,6 +346,8 @@ def main():
                 dev.set_option("p2p_blocks_per_sm", args.p2p_blocks)
         elif args.precision == "bf16" and args.sharded_update >= 0 and w["H"] % world == 0:
             dev.set_option("sharded_update", args.sharded_update)
+        if args.precision == "bf16" and args.state_exchange >= 0 and not args.p2p and args.sharded_update != 0 and w["H"] % world == 0:
+            dev.set_option("state_exchange", args.state_exchange)
     dev.set_data(Xl, Yl)
     pcd = w["algo"] == "PCD"
     if pcd:

@@ -130,6 +130,11 @@ struct qb_handle {
     // GEMMs leave that many SMs free (their persistent CTAs own a whole SM each, NCCL could not start beside them)
     ncclComm_t comm_overlap = nullptr;
     int gemm_sms = 148;
+    // "state_exchange" (multi-GPU PCD, bf16, binary model without labels; exact semantics): the positive product is
+    // reduce-scattered BEHIND the chain advance, and instead of reducing the negative product the ranks all-gather their
+    // chain states as BITS (1/16 of bf16) and each computes its own shard of the full negative product.
+    bool state_exchange = false;
+    uint8_t *bits_loc = nullptr, *bits_all = nullptr; bf16 *cvT_all = nullptr, *chT_all = nullptr; int64_t sx_rows = 0;
     cudaEvent_t ev_grad = nullptr, ev_upd = nullptr;
     // resident dataset
     Mat data; int64_t N = 0;
@@ -171,6 +176,7 @@ struct qb_handle {
     // gradient, update of the owned hidden rows only, all-gather of the bf16 shadow, local transpose.  Moves 3/4 of the
     // allreduce bytes and does 1/world of the update work; the fp32 master is then sharded like in the p2p path.
     bool sharded_update = false, master_sharded = false;
+    bool exchange_done = false;  // the step already reduced its gradient shard and the bias gradients (state_exchange)
     int64_t launches = 0, gemm_launches = 0;
     double gemm_flops = 0.0;
     int force_bn = 0, use_2cta = 1;
@@ -523,7 +529,9 @@ void op_update_on(qb_handle *h, double lr, double llr, int64_t B_local, cudaStre
     ncclComm_t comm = (st == h->comm_stream && h->comm_overlap) ? h->comm_overlap : h->comm;
     const bool sharded = comm && h->sharded_update && h->bf && (h->H % h->cfg.world) == 0;
     const int64_t sr = sharded ? h->H / h->cfg.world : h->H, hr0 = sharded ? sr * h->cfg.rank : 0;
-    if (sharded) {
+    if (sharded && h->exchange_done) {
+        h->master_sharded = true;
+    } else if (sharded) {
         // in-place reduce-scatter: this rank ends up with the summed gradient of the hidden rows it owns; the biases are tiny
         QB_NCCL(nccl().GroupStart());
         QB_NCCL(nccl().ReduceScatter(G, G + hr0 * h->ldv, (size_t)(sr * h->ldv), /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, st));
@@ -656,6 +664,23 @@ void wait_pending_update(qb_handle *h) {
     if (h->pending_update) QB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_upd, 0));
 }
 
+// second stream + events + (when a communicator exists) a communicator limited to QB_OVERLAP_CTAS CTAs, for exchanges that
+// run under GEMMs.  Collective when it has to split the communicator.
+void ensure_overlap_resources(qb_handle *h) {
+    if (!h->comm_stream) {
+        QB_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        QB_CUDA(cudaEventCreateWithFlags(&h->ev_grad, cudaEventDisableTiming));
+        QB_CUDA(cudaEventCreateWithFlags(&h->ev_upd, cudaEventDisableTiming));
+    }
+    if (h->comm && !h->comm_overlap && nccl().CommSplit) {
+        NcclConfig218 c{};
+        c.size = sizeof(c); c.magic = 0xcafebeef; c.version = 21800;
+        c.blocking = INT_MIN; c.cgaClusterSize = INT_MIN; c.minCTAs = INT_MIN; c.maxCTAs = QB_OVERLAP_CTAS; c.netName = nullptr;
+        c.splitShare = INT_MIN;
+        QB_NCCL(nccl().CommSplit(h->comm, 0, h->cfg.rank, &h->comm_overlap, &c));
+    }
+}
+
 void set_stale_mode(qb_handle *h, bool on) {
     QB_CHECK(!on || (h->bf && h->L == 0), QB_E_UNSUPPORTED, "stale_chains needs bf16 precision and a model without label units");
     QB_CHECK(!on || !h->p2p, QB_E_UNSUPPORTED, "stale_chains uses the NCCL path: do not import peer memory (qb_p2p_import) on this handle");
@@ -667,18 +692,9 @@ void set_stale_mode(qb_handle *h, bool on) {
         h->G_alt = dalloc<float>(h->nP);
         h->bias_buf[0] = dalloc<float>(h->ldv + h->ldh);
         h->bias_buf[1] = dalloc<float>(h->ldv + h->ldh);
-        QB_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
-        QB_CUDA(cudaEventCreateWithFlags(&h->ev_grad, cudaEventDisableTiming));
-        QB_CUDA(cudaEventCreateWithFlags(&h->ev_upd, cudaEventDisableTiming));
     }
-    if (on && h->comm && !h->comm_overlap && nccl().CommSplit) {  // collective: every rank switches the mode at the same point
-        NcclConfig218 c{};
-        c.size = sizeof(c); c.magic = 0xcafebeef; c.version = 21800;
-        c.blocking = INT_MIN; c.cgaClusterSize = INT_MIN; c.minCTAs = INT_MIN; c.maxCTAs = QB_OVERLAP_CTAS; c.netName = nullptr;
-        c.splitShare = INT_MIN;
-        QB_NCCL(nccl().CommSplit(h->comm, 0, h->cfg.rank, &h->comm_overlap, &c));
-    }
-    h->gemm_sms = (on && h->comm_overlap) ? std::max(2, (h->num_sms - QB_OVERLAP_CTAS) & ~1) : h->num_sms;
+    if (on) ensure_overlap_resources(h);  // collective: every rank switches the mode at the same point
+    h->gemm_sms = ((on || h->state_exchange) && h->comm_overlap) ? std::max(2, (h->num_sms - QB_OVERLAP_CTAS) & ~1) : h->num_sms;
     if (on) {
         h->bias_cur = 0;
         QB_CUDA(cudaMemcpyAsync(h->bias_buf[0], acat(h), (h->ldv + h->ldh) * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
@@ -777,10 +793,75 @@ void pcd_step_stale(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT
     h->inj_active = false;
 }
 
+// "state_exchange" variant of the multi-GPU PCD step (see qb_handle::state_exchange).  Same arithmetic as pcd_step_impl: all
+// GEMMs of the step use W_t, so the positive phase may run before the chain advance; G = sum_ranks(X' Hd) - Cv_all' Ch_all.
+void pcd_step_state_exchange(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr) {
+    const int world = h->cfg.world, rank = h->cfg.rank;
+    const int64_t sr = h->H / world, hr0 = sr * rank, Kall = (int64_t)world * B, units = h->VL + h->H, bpr = B / 8;
+    if (h->sx_rows != B) {
+        cudaFree(h->bits_loc); cudaFree(h->bits_all); cudaFree(h->cvT_all); cudaFree(h->chT_all);
+        h->bits_loc = dalloc<uint8_t>(units * bpr); h->bits_all = dalloc<uint8_t>((size_t)world * units * bpr);
+        h->cvT_all = dalloc<bf16>(h->VL * Kall); h->chT_all = dalloc<bf16>(sr * Kall);
+        h->sx_rows = B;
+    }
+    QB_CHECK(!h->inj_active || h->inj_B == B, QB_E_ARG, "injected streams must have one row per chain");
+    StepRng sr_rng{h, B, h->inj_active};
+    const int64_t row0 = row0_of(h, B);
+    zero_bias_grads(h, 1.f);
+    // positive phase and positive product first; its reduce-scatter then runs behind the chain advance
+    HiddenOut ho; ho.prob = &h->phd; ho.prob_T = true; ho.bg_what = 1; ho.bg_sign = 1.f;
+    op_hidden(h, xb, B, h->VL, ho, Rng(), row0);
+    {
+        sm100::Operand A{h->phd.bT, h->H, B, h->phd.ldT}, Bo{xbT, h->VL, B, xb_ldT};
+        sm100::EpiParams ep{};
+        ep.mode = sm100::EPI_GRAD; ep.M = (int)h->H; ep.N = (int)h->VL; ep.out_f32 = G_W(h); ep.ld_out = h->ldv;
+        GemmScope gs(h, 2.0 * (double)h->H * (double)h->VL * (double)B);
+        sm100::launch(h->stream, A, Bo, nullptr, nullptr, ep, h->gemm_sms, h->force_bn, h->use_2cta);
+    }
+    if (!h->cur_datasum) colsum<bf16>(h, xb.b, xb.ld, B, h->VL, 1.f, G_a(h));
+    QB_CUDA(cudaEventRecord(h->ev_grad, h->stream));
+    QB_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_grad, 0));
+    QB_NCCL(nccl().ReduceScatter(h->G, h->G + hr0 * h->ldv, (size_t)(sr * h->ldv), /*ncclFloat32*/ 7, /*ncclSum*/ 0,
+                                 h->comm_overlap ? h->comm_overlap : h->comm, h->comm_stream));
+    QB_CUDA(cudaEventRecord(h->ev_upd, h->comm_stream));
+    advance_chains(h, B, k, sr_rng, true);
+    // chain states of every rank, as bits: [visible units | hidden units] x B / 8 bytes per rank
+    pack_state_bits_kernel<<<grid1d(h->VL * bpr), 256, 0, h->stream>>>(h->cv.bT, h->cv.ldT, (int)h->VL, (int)B, h->bits_loc);
+    pack_state_bits_kernel<<<grid1d(h->H * bpr), 256, 0, h->stream>>>(h->ch.bT, h->ch.ldT, (int)h->H, (int)B, h->bits_loc + h->VL * bpr);
+    QB_CUDA(cudaGetLastError());
+    QB_NCCL(nccl().GroupStart());
+    QB_NCCL(nccl().AllGather(h->bits_loc, h->bits_all, (size_t)(units * bpr), /*ncclUint8*/ 1, h->comm, h->stream));
+    QB_NCCL(nccl().AllReduce(h->G + h->nW, h->G + h->nW, (size_t)(h->ldv + h->ldh), 7, 0, h->comm, h->stream));
+    QB_NCCL(nccl().GroupEnd());
+    unpack_state_bits_kernel<<<grid1d(h->VL * world * bpr), 256, 0, h->stream>>>(h->bits_all, world, (int)units, 0, (int)h->VL, (int)B,
+                                                                                 h->cvT_all, Kall);
+    unpack_state_bits_kernel<<<grid1d(sr * world * bpr), 256, 0, h->stream>>>(h->bits_all, world, (int)units, (int)(h->VL + hr0), (int)sr,
+                                                                              (int)B, h->chT_all, Kall);
+    QB_CUDA(cudaGetLastError());
+    h->launches += 4;
+    QB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_upd, 0));  // the reduced positive part of the owned hidden rows has arrived
+    {   // owned shard of the negative product over the chains of ALL ranks, subtracted in place
+        sm100::Operand A{h->chT_all, sr, Kall, Kall}, Bo{h->cvT_all, h->VL, Kall, Kall};
+        sm100::EpiParams ep{};
+        ep.mode = sm100::EPI_GRAD; ep.M = (int)sr; ep.N = (int)h->VL; ep.out_f32 = G_W(h) + hr0 * h->ldv; ep.ld_out = h->ldv; ep.grad_sub = 1;
+        GemmScope gs(h, 2.0 * (double)sr * (double)h->VL * (double)Kall);
+        sm100::launch(h->stream, A, Bo, nullptr, nullptr, ep, h->gemm_sms, h->force_bn, h->use_2cta);
+    }
+    h->exchange_done = true;  // op_update_on: gradient shard and bias gradients are already reduced
+    op_update(h, lr, llr, B);
+    h->exchange_done = false;
+    h->inj_active = false;
+}
+
 void pcd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr,
                    cudaEvent_t *ev) {
     QB_CHECK(h->n_chains >= 1, QB_E_STATE, "qb_init_chains has not been called");
     if (h->stale_chains) { pcd_step_stale(h, xb, xbT, xb_ldT, B, k, lr, llr); return; }
+    if (h->state_exchange && h->comm && h->sharded_update && !h->p2p && h->L == 0 && !h->gaussian && k > 0 && h->n_chains == B &&
+        (B % 8) == 0 && xbT != nullptr && ev == nullptr) {
+        pcd_step_state_exchange(h, xb, xbT, xb_ldT, B, k, lr, llr);
+        return;
+    }
     // Nc chains; Nc == B is the reference (train_pcd.jl:162).  Nc != B (declared extension): all chains advance,
     // negative statistics are averaged over all of them: G = (Nc/B) sum_data - sum_chains, applied with lr / Nc.
     const int64_t Nc = h->n_chains;
@@ -1032,6 +1113,7 @@ int32_t qb_destroy(qb_handle *h) {
                 }
         cudaFree(h->p2p_flags); cudaFree(h->p2p_grid_bar); cudaFree(h->p2p_ns);
         cudaFree(h->P); cudaFree(h->G); cudaFree(h->Vel); cudaFree(h->P_best); cudaFree(h->F); cudaFree(h->F2); cudaFree(h->P_eff); cudaFree(h->W2); cudaFree(h->online_vec); cudaFree(h->online_bar); cudaFree(h->online_ns); cudaFree(h->Wb); cudaFree(h->WbT);
+        cudaFree(h->bits_loc); cudaFree(h->bits_all); cudaFree(h->cvT_all); cudaFree(h->chT_all);
         cudaFree(h->Wb_alt); cudaFree(h->WbT_alt); cudaFree(h->G_alt); cudaFree(h->bias_buf[0]); cudaFree(h->bias_buf[1]);
         if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
         if (h->ev_grad) cudaEventDestroy(h->ev_grad);
@@ -1766,6 +1848,13 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
                      "sharded_update needs bf16 precision, world > 1 and n_hidden % world == 0");
             QB_CHECK(!h->master_sharded || value != 0.0, QB_E_STATE, "gather the master (qb_get_params) before switching sharded_update off");
             h->sharded_update = value != 0.0;
+        } else if (!strcmp(key, "state_exchange")) {
+            QB_CHECK(value == 0.0 || (h->bf && h->comm && h->sharded_update), QB_E_UNSUPPORTED,
+                     "state_exchange needs bf16 precision, a communicator and the sharded update");
+            QB_CUDA(cudaStreamSynchronize(h->stream));
+            h->state_exchange = value != 0.0;
+            if (h->state_exchange) ensure_overlap_resources(h);  // collective (communicator split)
+            h->gemm_sms = ((h->stale_chains || h->state_exchange) && h->comm_overlap) ? std::max(2, (h->num_sms - QB_OVERLAP_CTAS) & ~1) : h->num_sms;
         } else if (!strcmp(key, "fast_pcd_pair_chains")) {
             h->fast_pcd_pair_chains = value != 0.0;
         } else if (!strcmp(key, "stale_chains")) {

@@ -405,6 +405,44 @@ __global__ void __launch_bounds__(256) transpose_bf16_wide_kernel(const bf16 *__
     }
 }
 
+// Binary states as bits for the multi-GPU state exchange.  src: transposed bf16 states [units][ld] (0 / 1), `rows` a multiple
+// of 8; bits[u][j] bit i = (src[u][8 j + i] != 0).
+__global__ void pack_state_bits_kernel(const bf16 *__restrict__ src, int64_t ld, int units, int rows, uint8_t *__restrict__ bits) {
+    const int bpr = rows >> 3;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)units * bpr) return;
+    const int u = (int)(i / bpr), j = (int)(i % bpr);
+    const uint4 v = *reinterpret_cast<const uint4 *>(src + (int64_t)u * ld + 8 * j);  // ld % 8 == 0: 16-byte aligned
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t b = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        b |= ((w[q] & 0xFFFFu) != 0u ? 1u : 0u) << (2 * q);
+        b |= ((w[q] >> 16) != 0u ? 1u : 0u) << (2 * q + 1);
+    }
+    bits[i] = (uint8_t)b;
+}
+
+// bits_all: [world][units_total][rows_l / 8] (the all-gathered packs); dst[u][r * rows_l + 8 j + i] = bit ? 1 : 0 for the unit
+// range [u0, u0 + units) -- the K-major gradient operand over the rows of ALL ranks
+__global__ void unpack_state_bits_kernel(const uint8_t *__restrict__ bits_all, int world, int units_total, int u0, int units, int rows_l,
+                                         bf16 *__restrict__ dst, int64_t ldd) {
+    const int bpr = rows_l >> 3;
+    const int64_t per_unit = (int64_t)world * bpr;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)units * per_unit) return;
+    const int u = (int)(i / per_unit);
+    const int rj = (int)(i % per_unit), r = rj / bpr, j = rj % bpr;
+    const uint32_t b = bits_all[((int64_t)r * units_total + u0 + u) * bpr + j];
+    const uint32_t one = 0x3F80u;  // bf16 1.0
+    uint4 v;
+    v.x = ((b & 1u) ? one : 0u) | ((b & 2u) ? one << 16 : 0u);
+    v.y = ((b & 4u) ? one : 0u) | ((b & 8u) ? one << 16 : 0u);
+    v.z = ((b & 16u) ? one : 0u) | ((b & 32u) ? one << 16 : 0u);
+    v.w = ((b & 64u) ? one : 0u) | ((b & 128u) ? one << 16 : 0u);
+    *reinterpret_cast<uint4 *>(dst + (int64_t)u * ldd + (int64_t)r * rows_l + 8 * j) = v;
+}
+
 __global__ void f32_to_bf16_kernel(const float *__restrict__ src, bf16 *__restrict__ dst, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = __float2bfloat16(src[i]);

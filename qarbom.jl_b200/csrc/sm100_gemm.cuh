@@ -68,6 +68,7 @@ struct EpiParams {
     float *softplus_rows;
     // ---- EPI_GRAD
     float *out_f32; long long ld_out;
+    int grad_sub;  // out = out - acc instead of out = acc (negative statistics subtracted from an already reduced positive part)
     float pscale;  // probabilities are multiplied by this before being stored / summed (n_chains / batch; 1 normally)
 };
 
@@ -455,6 +456,11 @@ __device__ __forceinline__ void epilogue_grad(const EpiParams &ep, uint32_t tmem
         const int n0 = n_blk * BN + c0;
         if (n0 >= ep.N || m >= ep.M) continue;
         float *dst = ep.out_f32 + (long long)m * ep.ld_out + n0;
+        if (ep.grad_sub) {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (n0 + j < ep.N) r[j] = __float_as_uint(dst[j] - __uint_as_float(r[j]));
+        }
         if (n0 + 16 <= ep.N) {
 #pragma unroll
             for (int q = 0; q < 4; q++)

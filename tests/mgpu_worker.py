@@ -36,6 +36,8 @@ def main():
             dev.comm_init(uid.cpu().numpy().tobytes())
             if prec == "bf16":   # "sharded" (the bf16 default): NCCL reduce-scatter + shard update + bf16 all-gather + local transpose
                 dev.set_option("sharded_update", 0 if exchange == "nccl" else 1)
+            if exchange == "state":     # positive product reduce-scattered behind the chains + bit-packed chain-state all-gather
+                dev.set_option("state_exchange", 1)
             if exchange == "p2p":
                 mine = torch.frombuffer(bytearray(dev.p2p_export()), dtype=torch.uint8).cuda()
                 allh = torch.empty(320 * world, dtype=torch.uint8, device="cuda")
