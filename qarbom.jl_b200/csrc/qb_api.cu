@@ -33,6 +33,10 @@ struct Nccl {
     int (*ReduceScatter)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, void *) = nullptr;  // optional (NCCL >= 2.18)
+    int (*MemAlloc)(void **, size_t) = nullptr;                              // optional (NCCL >= 2.19): registered user buffers
+    int (*MemFree)(void *) = nullptr;
+    int (*CommRegister)(ncclComm_t, void *, size_t, void **) = nullptr;
+    int (*CommDeregister)(ncclComm_t, void *) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
@@ -53,6 +57,10 @@ Nccl &nccl() {
         n.ReduceScatter = (decltype(n.ReduceScatter))dlsym(n.lib, "ncclReduceScatter");
         n.AllGather = (decltype(n.AllGather))dlsym(n.lib, "ncclAllGather");
         n.CommSplit = (decltype(n.CommSplit))dlsym(n.lib, "ncclCommSplit");
+        n.MemAlloc = (decltype(n.MemAlloc))dlsym(n.lib, "ncclMemAlloc");
+        n.MemFree = (decltype(n.MemFree))dlsym(n.lib, "ncclMemFree");
+        n.CommRegister = (decltype(n.CommRegister))dlsym(n.lib, "ncclCommRegister");
+        n.CommDeregister = (decltype(n.CommDeregister))dlsym(n.lib, "ncclCommDeregister");
         n.GroupStart = (decltype(n.GroupStart))dlsym(n.lib, "ncclGroupStart");
         n.GroupEnd = (decltype(n.GroupEnd))dlsym(n.lib, "ncclGroupEnd");
         n.CommDestroy = (decltype(n.CommDestroy))dlsym(n.lib, "ncclCommDestroy");
@@ -130,6 +138,8 @@ struct qb_handle {
     // GEMMs leave that many SMs free (their persistent CTAs own a whole SM each, NCCL could not start beside them)
     ncclComm_t comm_overlap = nullptr;
     int gemm_sms = 148;
+    // exchange buffers re-homed into ncclMemAlloc memory and registered with the communicator (zero-copy / NVLS paths)
+    std::vector<void *> nccl_mem, nccl_reg; bool reg_tried = false;
     // "state_exchange" (multi-GPU PCD, bf16, binary model without labels; exact semantics): the positive product is
     // reduce-scattered BEHIND the chain advance, and instead of reducing the negative product the ranks all-gather their
     // chain states as BITS (1/16 of bf16) and each computes its own shard of the full negative product.
@@ -793,6 +803,36 @@ void pcd_step_stale(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT
     h->inj_active = false;
 }
 
+// Move the gradient and the row-major bf16 shadow into ncclMemAlloc memory and register them with the communicator, so
+// that the in-place reduce-scatter / all-gather of the sharded update can take NCCL's registered-buffer (zero-copy, NVLS)
+// paths.  Best effort: any failure leaves the plain cudaMalloc buffers in place.
+void register_exchange_buffers(qb_handle *h) {
+    Nccl &n = nccl();
+    if (!n.MemAlloc || !n.MemFree || !n.CommRegister || !n.CommDeregister) return;
+    auto rehome = [&](void **slot, size_t bytes) {
+        void *fresh = nullptr;
+        if (n.MemAlloc(&fresh, bytes) != 0 || !fresh) return;
+        if (cudaMemcpy(fresh, *slot, bytes, cudaMemcpyDeviceToDevice) != cudaSuccess) { n.MemFree(fresh); cudaGetLastError(); return; }
+        void *reg = nullptr;
+        if (n.CommRegister(h->comm, fresh, bytes, &reg) != 0) { n.MemFree(fresh); return; }
+        cudaFree(*slot);
+        *slot = fresh;
+        h->nccl_mem.push_back(fresh);
+        if (reg) h->nccl_reg.push_back(reg);
+    };
+    QB_CUDA(cudaStreamSynchronize(h->stream));
+    rehome((void **)&h->G, (size_t)h->nP * sizeof(float));
+    rehome((void **)&h->Wb, (size_t)h->H * h->ldv * sizeof(bf16));
+}
+
+// first data-parallel step with the sharded update (after a possible qb_p2p_import, whose CUDA IPC export needs plain
+// cudaMalloc memory): move the exchange buffers into registered NCCL memory
+void maybe_register_exchange_buffers(qb_handle *h) {
+    if (h->reg_tried || !h->comm || !h->sharded_update || h->p2p) return;
+    h->reg_tried = true;
+    if (!getenv("QB_NO_NCCL_REGISTER")) register_exchange_buffers(h);
+}
+
 // "state_exchange" variant of the multi-GPU PCD step (see qb_handle::state_exchange).  Same arithmetic as pcd_step_impl: all
 // GEMMs of the step use W_t, so the positive phase may run before the chain advance; G = sum_ranks(X' Hd) - Cv_all' Ch_all.
 void pcd_step_state_exchange(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr) {
@@ -856,6 +896,7 @@ void pcd_step_state_exchange(qb_handle *h, const Mat &xb, const bf16 *xbT, int64
 void pcd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr,
                    cudaEvent_t *ev) {
     QB_CHECK(h->n_chains >= 1, QB_E_STATE, "qb_init_chains has not been called");
+    maybe_register_exchange_buffers(h);
     if (h->stale_chains) { pcd_step_stale(h, xb, xbT, xb_ldT, B, k, lr, llr); return; }
     if (h->state_exchange && h->comm && h->sharded_update && !h->p2p && h->L == 0 && !h->gaussian && k > 0 && h->n_chains == B &&
         (B % 8) == 0 && xbT != nullptr && ev == nullptr) {
@@ -907,6 +948,7 @@ void pcd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT,
 void cd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr,
                   cudaEvent_t *ev) {
     QB_CHECK(!h->inj_active || h->inj_B == B, QB_E_ARG, "injected streams must have one row per mini-batch row");
+    maybe_register_exchange_buffers(h);
     StepRng sr{h, B, h->inj_active};
     const int64_t row0 = row0_of(h, B);
     zero_bias_grads(h);
@@ -1103,6 +1145,11 @@ int32_t qb_destroy(qb_handle *h) {
         if (!h) return;
         cudaSetDevice(h->cfg.device);
         cudaDeviceSynchronize();
+        auto dfree = [&](void *p) {  // buffers re-homed by register_exchange_buffers belong to NCCL's allocator
+            if (p && std::find(h->nccl_mem.begin(), h->nccl_mem.end(), p) != h->nccl_mem.end()) nccl().MemFree(p);
+            else cudaFree(p);
+        };
+        if (h->comm) for (void *r : h->nccl_reg) nccl().CommDeregister(h->comm, r);
         if (h->comm_overlap) nccl().CommDestroy(h->comm_overlap);
         if (h->comm) nccl().CommDestroy(h->comm);
         if (h->p2p)
@@ -1112,9 +1159,9 @@ int32_t qb_destroy(qb_handle *h) {
                     cudaIpcCloseMemHandle(h->peerFlags[r]); cudaIpcCloseMemHandle(h->peerP[r]);
                 }
         cudaFree(h->p2p_flags); cudaFree(h->p2p_grid_bar); cudaFree(h->p2p_ns);
-        cudaFree(h->P); cudaFree(h->G); cudaFree(h->Vel); cudaFree(h->P_best); cudaFree(h->F); cudaFree(h->F2); cudaFree(h->P_eff); cudaFree(h->W2); cudaFree(h->online_vec); cudaFree(h->online_bar); cudaFree(h->online_ns); cudaFree(h->Wb); cudaFree(h->WbT);
+        cudaFree(h->P); dfree(h->G); cudaFree(h->Vel); cudaFree(h->P_best); cudaFree(h->F); cudaFree(h->F2); cudaFree(h->P_eff); cudaFree(h->W2); cudaFree(h->online_vec); cudaFree(h->online_bar); cudaFree(h->online_ns); dfree(h->Wb); cudaFree(h->WbT);
         cudaFree(h->bits_loc); cudaFree(h->bits_all); cudaFree(h->cvT_all); cudaFree(h->chT_all);
-        cudaFree(h->Wb_alt); cudaFree(h->WbT_alt); cudaFree(h->G_alt); cudaFree(h->bias_buf[0]); cudaFree(h->bias_buf[1]);
+        dfree(h->Wb_alt); cudaFree(h->WbT_alt); dfree(h->G_alt); cudaFree(h->bias_buf[0]); cudaFree(h->bias_buf[1]);
         if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
         if (h->ev_grad) cudaEventDestroy(h->ev_grad);
         if (h->ev_upd) cudaEventDestroy(h->ev_upd);
@@ -1757,6 +1804,7 @@ int32_t qb_comm_init(qb_handle *h, const void *id128) {
         // default exchange in bf16 mode: reduce-scatter + shard update + bf16 all-gather (measured 6 % faster than allreduce +
         // full update at 8 GPUs, equal at 2); option "sharded_update" = 0 goes back to the allreduce
         h->sharded_update = h->bf && (h->H % h->cfg.world) == 0;
+
     });
 }
 
