@@ -225,6 +225,8 @@ int32_t qb_reset_counters(qb_handle *h);
  * "stale_chains" (declared extension: exchange + update of step t overlap the chain advance of step t + 1; collective
  * when a communicator exists: it splits off a CTA-limited communicator), "sharded_update" (multi-GPU bf16 exchange:
  * 1 = reduce-scatter + shard update + bf16 all-gather, the default when n_hidden % world == 0; 0 = allreduce),
+ * "state_exchange" (multi-GPU PCD on binary models without labels, exact: positive product reduce-scattered behind the
+ * chain advance + bit-packed chain-state all-gather; collective, measured neutral, off by default),
  * "online_kernel" (0: batch-size-1 CD through per-sample launches instead of the cooperative epoch kernel),
  * "online_wpb" (warps per block of the cooperative kernels), "fast_pcd_pair_chains" (classifier FastPCD pairs
  * sample i with chain i instead of the reference's chain 1), "p2p_blocks_per_sm", and for experiments / tests
