@@ -1425,7 +1425,8 @@ static void fast_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double
     QB_CHECK(h->cfg.world == 1, QB_E_UNSUPPORTED, "FastPCD updates the weights after every sample and does not shard");
     QB_CHECK(h->momentum == 0.0 && h->weight_decay == 0.0, QB_E_UNSUPPORTED, "FastPCD has no momentum / weight decay");
     QB_CHECK(h->n_chains == B, QB_E_STATE, "FastPCD pairs sample i with chain i: qb_init_chains(B) first");
-    QB_CHECK(h->N >= B, QB_E_ARG, "dataset smaller than one mini-batch");
+    QB_CHECK(h->N > 0, QB_E_STATE, "qb_set_data has not been called");
+    // N < B: _set_mini_batches drops the whole (short) batch, the epoch trains nothing (src/utils.jl:13-26)
     if (!h->W2) {
         h->W2 = dalloc<float>(h->VL * h->ldh);
         h->online_vec = dalloc<float>(2 * (3 * h->H + h->VL));
@@ -1506,8 +1507,8 @@ static void epoch_impl(qb_handle *h, bool pcd, int64_t B, int64_t k, double lr, 
     check_step_args(h, B, k);
     if (!pcd && B == 1 && h->N >= 1 && online_cd_epoch(h, k, lr, times)) return;
     QB_CHECK(!h->inj_active, QB_E_STATE, "injected streams are per step (or per online CD epoch); use qb_pcd_step / qb_cd_step");
-    QB_CHECK(h->N >= B, QB_E_ARG, "dataset smaller than one mini-batch");
-    const int64_t nb = h->N / B;  // _set_mini_batches: trailing remainder dropped (src/utils.jl:13-26)
+    QB_CHECK(h->N > 0, QB_E_STATE, "qb_set_data has not been called");
+    const int64_t nb = h->N / B;  // _set_mini_batches: trailing remainder dropped -- all of it when N < B (src/utils.jl:13-26)
     double t[3] = {0, 0, 0};
     for (int64_t m = 0; m < nb; m++) {
         Mat xb; const bf16 *xbT; int64_t ldT;

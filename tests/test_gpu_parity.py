@@ -361,6 +361,11 @@ def test_argument_errors(q):
         with pytest.raises(q.QbError):
             dev.fast_pcd_epoch(2, 1, 0.1, 0.1)   # FastPCD pairs sample i with chain i: chains != batch rows
         assert dev.eval_mse() >= 0.0             # the failed calls left the handle usable
+        dev.set_data(np.zeros((2, 4)))           # fewer samples than one mini-batch: `_set_mini_batches` drops them all,
+        dev.pull_params(); W0 = rbm.W.copy()     # the epoch trains nothing (src/utils.jl:13-26)
+        assert dev.pcd_epoch(4, 1, 0.1) == (0.0, 0.0, 0.0) and dev.cd_epoch(4, 1, 0.1) == (0.0, 0.0, 0.0)
+        dev.pull_params()
+        assert np.array_equal(rbm.W, W0)
     with pytest.raises(q.QbError):
         q.DeviceRBM(q.RBM(4, 3), max_batch=0)    # invalid configuration
 
