@@ -202,19 +202,20 @@ function restore_params!(r::AbstractRBM, p)
 end
 
 """
-    train!(rbm, x_train, CD | PCD; n_epochs, learning_rate, [batch_size], [gibbs_steps], ...)
-    train!(rbm::RBMClassifiers, x_train, label_train, CD | PCD; ..., label_learning_rate, ...)
+    train!(rbm, x_train, CD | PCD | FastPCD; n_epochs, learning_rate, [batch_size], [gibbs_steps], ...)
+    train!(rbm::RBMClassifiers, x_train, label_train, CD | PCD | FastPCD; ..., label_learning_rate, ...)
 
-Same keyword arguments as QARBoM.train! for CD / PCD; the per-epoch Gibbs chains, gradient,
+Same keyword arguments as QARBoM.train! for CD / PCD / FastPCD (`fast_learning_rate`, `fast_label_learning_rate`); the per-epoch Gibbs chains, gradient,
 update and MSE evaluation run on the B200.  New keywords (`batch_size` for CD, `momentum`,
 `weight_decay`, `precision`, `seed`) default to the reference's behaviour.
 """
 function train!(rbm::AbstractRBM, x_train, method::Type{<:TrainingMethod}; label_train = nothing,
                 n_epochs::Int, learning_rate::Vector{Float64}, label_learning_rate::Vector{Float64} = learning_rate,
-                gibbs_steps::Int = method === PCD ? 1 : 3, batch_size::Int = method === PCD ? error("batch_size required") : 1,
+                fast_learning_rate::Float64 = 0.1, fast_label_learning_rate::Float64 = 0.1,
+                gibbs_steps::Int = method === CD ? 3 : 1, batch_size::Int = method === CD ? 1 : error("batch_size required"),
                 metrics = [MeanSquaredError], early_stopping::Bool = false, store_best_rbm::Bool = true,
                 patience::Int = 10, stopping_metric = MeanSquaredError, x_test_dataset = nothing,
-                file_path = method === PCD ? "pcd_metrics.csv" : "cd_metrics.csv",
+                file_path = method === FastPCD ? "fast_pcd_metrics.csv" : (method === PCD ? "pcd_metrics.csv" : "cd_metrics.csv"),
                 momentum::Float64 = 0.0, weight_decay::Float64 = 0.0, precision::Symbol = :bf16, seed::UInt64 = UInt64(0))
     N = length(x_train)
     if N % batch_size > 0   # _set_mini_batches, src/utils.jl:13-26
@@ -226,7 +227,7 @@ function train!(rbm::AbstractRBM, x_train, method::Type{<:TrainingMethod}; label
     best = copy_params(rbm)
     initial_patience = patience
     mse = Float64[eval_mse(d, x_test_dataset)]          # initial_evaluation
-    if method === PCD
+    if method !== CD
         println("Setting mini-batches")
         check(ccall((:qb_init_chains, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                     d.h, batch_size, C_NULL, C_NULL, C_NULL))   # _init_fantasy_data(rbm, batch_size)
@@ -235,7 +236,10 @@ function train!(rbm::AbstractRBM, x_train, method::Type{<:TrainingMethod}; label
     tot = (0.0, 0.0, 0.0)
     hist = Float64[]
     for epoch in 1:n_epochs
-        t = epoch!(d, method, batch_size, gibbs_steps, learning_rate[epoch], label_learning_rate[epoch])
+        t = method === FastPCD ?
+            fast_pcd_epoch!(d, batch_size, gibbs_steps, learning_rate[epoch], fast_learning_rate, label_learning_rate[epoch],
+                            fast_label_learning_rate) :
+            epoch!(d, method, batch_size, gibbs_steps, learning_rate[epoch], label_learning_rate[epoch])
         tot = tot .+ t
         push!(hist, eval_mse(d, x_test_dataset))
         if _diverged(hist)
