@@ -40,6 +40,10 @@ def lib():
         _lib.qo_cd_epoch.argtypes = [_i64, _i64, _i64, ctypes.c_int, _D, _D, _D, _D, _D, _D, _D, _i64, _i64, _i64,
                                      ctypes.c_double, ctypes.c_double, _D, _i64, _D, _i64, ctypes.c_uint64,
                                      _i64, _i64, ctypes.c_int]
+        _lib.qo_fast_pcd_epoch.restype = ctypes.c_int
+        _lib.qo_fast_pcd_epoch.argtypes = [_i64, _i64, _i64, ctypes.c_int, _D, _D, _D, _D, _D, _D, _D, _i64, _i64, _i64,
+                                           ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, _D, _D, _D,
+                                           _D, _i64, _D, _i64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int]
         _lib.qo_eval_mse.restype = ctypes.c_double
         _lib.qo_eval_mse.argtypes = [_i64, _i64, ctypes.c_int, _D, _D, _D, _D, _i64, _D, _i64, ctypes.c_uint64,
                                      ctypes.c_int]
@@ -88,6 +92,19 @@ def pcd_epoch(m: CModel, X, Y, B, k, lr, llr, chv, chh, chy, u=None, z=None, see
                               X.shape[0], B, B if n_chains is None else n_chains, k, lr, llr, _p(chv), _p(chh), _p(chy),
                               _p(u), 0 if u is None else u.size, _p(z), 0 if z is None else z.size,
                               seed, first_batch, n_batches, threads)
+
+
+def fast_pcd_epoch(m: CModel, X, Y, B, k, lr, flr, llr, fllr, chv, chh, chy, u=None, z=None, seed=0, pair_chains=None,
+                   threads=1) -> int:
+    """One epoch of fast_persistent_contrastive_divergence! (src/training/train_fast_pcd.jl:1-127)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Y = None if Y is None else np.ascontiguousarray(Y, dtype=np.float64)
+    u = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
+    z = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
+    return lib().qo_fast_pcd_epoch(m.V, m.H, m.L, m.gaussian, _p(m.Wc), _p(m.a), _p(m.b), _p(m.Uc), _p(m.c), _p(X), _p(Y),
+                                   X.shape[0], B, k, lr, flr, llr, fllr, _p(chv), _p(chh), _p(chy),
+                                   _p(u), 0 if u is None else u.size, _p(z), 0 if z is None else z.size, seed,
+                                   -1 if pair_chains is None else int(bool(pair_chains)), threads)
 
 
 def cd_epoch(m: CModel, X, Y, B, k, lr, llr, u=None, z=None, seed=0, first_batch=0, n_batches=-1, threads=1) -> int:

@@ -263,6 +263,71 @@ int qo_pcd_epoch(int64_t V, int64_t H, int64_t L, int gaussian, double *W, doubl
 }
 
 /*
+ * fast_persistent_contrastive_divergence!  (src/training/train_fast_pcd.jl:1-57, classifier :59-127): one epoch.
+ * Inside a mini-batch the slow parameters are updated per SAMPLE with lr/B (update_rbm! per-sample form, src/rbm.jl:101-118,
+ * 138-150) and the fast parameters are decayed by 19/20 and pushed by fast_lr/B times the same difference; they start at
+ * zero every call.  The chains then advance with W + W_fast, ... (src/fantasy_data.jl:31-64); the fast gibbs_sample_visible
+ * thresholds rand() < conditional_prob_v(...) for EVERY model (src/gibbs.jl:22-25), i.e. a Gaussian model's noisy value
+ * mu + randn() too (src/rbm.jl:188-189).  pair_chains < 0: the reference (classifier: batch_index is never advanced, every
+ * sample pairs with chain 1, :77-119; otherwise sample i with chain i); 0 / 1 force it.
+ */
+int qo_fast_pcd_epoch(int64_t V, int64_t H, int64_t L, int gaussian, double *W, double *a, double *b, double *U, double *c,
+                      const double *X, const double *Y, int64_t N, int64_t B, int64_t k, double lr, double flr, double llr,
+                      double fllr, double *chv, double *chh, double *chy, const double *u, int64_t un, const double *z,
+                      int64_t zn, uint64_t seed, int pair_chains, int threads) {
+    qo_model m = {V, H, L, gaussian, W, a, b, U, c, threads < 1 ? 1 : threads};
+    qo_stream st; stream_init(&st, u, un, z, zn, seed);
+    const int64_t nb = (N - N % B) / B;
+    const int pair = pair_chains < 0 ? (L == 0) : (pair_chains != 0);
+    const double decay = 19.0 / 20.0, s = lr / (double)B, fs = flr / (double)B, ls = llr / (double)B, fls = fllr / (double)B;
+    double *Wf = (double *)calloc(V * H, sizeof(double)), *af = (double *)calloc(V, sizeof(double));
+    double *bf = (double *)calloc(H, sizeof(double));
+    double *Uf = L ? (double *)calloc(L * H, sizeof(double)) : NULL, *cf = L ? (double *)calloc(L, sizeof(double)) : NULL;
+    double *We = (double *)malloc(sizeof(double) * V * H), *ae = (double *)malloc(sizeof(double) * V);
+    double *be = (double *)malloc(sizeof(double) * H);
+    double *Ue = L ? (double *)malloc(sizeof(double) * L * H) : NULL, *ce = L ? (double *)malloc(sizeof(double) * L) : NULL;
+    double *hd = (double *)malloc(sizeof(double) * H), *tmpH = (double *)malloc(sizeof(double) * H);
+    for (int64_t mb = 0; mb < nb; mb++) {
+        for (int64_t idx = 0; idx < B; idx++) {
+            const double *vd = X + (mb * B + idx) * V;
+            const double *yd = L ? Y + (mb * B + idx) * L : NULL;
+            const int64_t ci = pair ? idx : 0;
+            const double *cv = chv + ci * V, *ch = chh + ci * H, *cy = L ? chy + ci * L : NULL;
+            cond_prob_h(&m, vd, yd, hd);
+            double *t = outer_diff(&m, V, vd, hd, cv, ch);
+            for (int64_t e = 0; e < V * H; e++) { W[e] += s * t[e]; Wf[e] = Wf[e] * decay + fs * t[e]; }
+            free(t);
+            for (int64_t i = 0; i < V; i++) { a[i] += s * (vd[i] - cv[i]); af[i] = af[i] * decay + fs * (vd[i] - cv[i]); }
+            if (L) {
+                t = outer_diff(&m, L, yd, hd, cy, ch);
+                for (int64_t e = 0; e < L * H; e++) { U[e] += ls * t[e]; Uf[e] = Uf[e] * decay + fls * t[e]; }
+                free(t);
+                for (int64_t l = 0; l < L; l++) { c[l] += ls * (yd[l] - cy[l]); cf[l] = cf[l] * decay + fls * (yd[l] - cy[l]); }
+            }
+            /* b last: hd was computed with the b of before this sample's update, like the reference */
+            for (int64_t j = 0; j < H; j++) { b[j] += s * (hd[j] - ch[j]); bf[j] = bf[j] * decay + fs * (hd[j] - ch[j]); }
+        }
+        for (int64_t e = 0; e < V * H; e++) We[e] = W[e] + Wf[e];
+        for (int64_t i = 0; i < V; i++) ae[i] = a[i] + af[i];
+        for (int64_t j = 0; j < H; j++) be[j] = b[j] + bf[j];
+        for (int64_t e = 0; e < L * H; e++) Ue[e] = U[e] + Uf[e];
+        for (int64_t l = 0; l < L; l++) ce[l] = c[l] + cf[l];
+        qo_model eff = {V, H, L, gaussian, We, ae, be, Ue, ce, m.threads};
+        for (int64_t sN = 0; sN < k; sN++)
+            for (int64_t i = 0; i < B; i++) {
+                double *cv = chv + i * V, *ch = chh + i * H, *cy = L ? chy + i * L : NULL;
+                sample_hidden(&eff, cv, cy, &st, ch, tmpH);
+                visible_mean(&eff, ch, cv);
+                for (int64_t q = 0; q < V; q++) cv[q] = gaussian ? cv[q] + 1.0 * s_randn(&st) : logistic(cv[q]);
+                for (int64_t q = 0; q < V; q++) cv[q] = (s_rand(&st) < cv[q]) ? 1.0 : 0.0;
+                if (L) sample_label(&eff, ch, &st, cy);
+            }
+    }
+    free(Wf); free(af); free(bf); free(Uf); free(cf); free(We); free(ae); free(be); free(Ue); free(ce); free(hd); free(tmpH);
+    return st.err;
+}
+
+/*
  * contrastive_divergence!  (src/training/train_cd.jl:2-21, classifier :23-43).
  * batch_size == 1 is the reference (online, in-place rank-2 update src/rbm.jl:101-118,
  * 138-150); batch_size > 1 is the declared mini-batch extension (see qarbom_oracle.py).

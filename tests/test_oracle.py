@@ -392,3 +392,28 @@ def test_batched_step_equals_per_sample_restatement(algo, L, gaussian):
     assert np.allclose(m.W, mb.W, atol=1e-12) and np.allclose(m.a, mb.a, atol=1e-12) and np.allclose(m.b, mb.b, atol=1e-12)
     if L:
         assert np.allclose(m.U, mb.U, atol=1e-12) and np.allclose(m.c, mb.c, atol=1e-12)
+
+
+@pytest.mark.parametrize("L,gaussian,pair", [(0, False, None), (3, False, None), (3, False, True), (0, True, None), (2, True, None)])
+def test_numpy_and_c_restatements_agree_fast_pcd(L, gaussian, pair):
+    """Two independent restatements of fast_persistent_contrastive_divergence! (train_fast_pcd.jl:1-127) on the same streams."""
+    rng = np.random.default_rng(41 + L + 5 * gaussian)
+    V, H, B, k, nb = 11, 7, 4, 2, 3
+    m = small_model(rng, V, H, L, gaussian, scale=0.4)
+    X = rng.standard_normal((nb * B + 1, V)) if gaussian else rng.integers(0, 2, (nb * B + 1, V)).astype(np.float64)
+    Y = np.eye(L)[rng.integers(0, L, nb * B + 1)] if L else None
+    u = u24(rng, nb * k * B * (H + V + L))
+    z = rng.standard_normal(nb * k * B * V) if gaussian else None
+    chains = [qo.FantasyData(rng.random(V), rng.random(H), rng.random(L) if L else None) for _ in range(B)]
+    chv = np.stack([c.v for c in chains]).copy(); chh = np.stack([c.h for c in chains]).copy()
+    chy = np.stack([c.y for c in chains]).copy() if L else None
+    cm = c_oracle.CModel(m.W, m.a, m.b, m.U, m.c, gaussian)
+    qo.fast_persistent_contrastive_divergence(m, X, qo._set_mini_batches(len(X), B), chains, steps=k, learning_rate=0.1,
+                                              fast_learning_rate=0.2, stream=qo.Stream(u, z), y=Y, label_learning_rate=0.05,
+                                              fast_label_learning_rate=0.15, pair_chains=pair)
+    assert c_oracle.fast_pcd_epoch(cm, X, Y, B, k, 0.1, 0.2, 0.05, 0.15, chv, chh, chy, u=u, z=z, pair_chains=pair) == 0
+    assert np.allclose(cm.W, m.W, rtol=0, atol=1e-13) and np.allclose(cm.a, m.a, atol=1e-13) and np.allclose(cm.b, m.b, atol=1e-13)
+    if L:
+        assert np.allclose(cm.U, m.U, atol=1e-13) and np.allclose(cm.c, m.c, atol=1e-13)
+        assert np.array_equal(chy, np.stack([c.y for c in chains]))
+    assert np.array_equal(chv, np.stack([c.v for c in chains])) and np.array_equal(chh, np.stack([c.h for c in chains]))
