@@ -1,6 +1,8 @@
-"""World-size-2 CPU (gloo) test of the data-parallel decomposition the multi-GPU path relies on:
-each rank owns B/G rows and chains of every mini-batch (bench.shard_rows), statistics are
-summed with one all-reduce, every rank applies the same update.  Computed here with the
+"""World-size-2 CPU (gloo) tests of the data-parallel decompositions the multi-GPU path relies on:
+each rank owns B/G rows and chains of every mini-batch (bench.shard_rows); the statistics are either
+summed with one all-reduce and every rank applies the same update, or reduce-scattered over the hidden
+units with a shard update and an all-gather of the weights ("sharded_update"), or exchanged as bit-packed
+chain states ("state_exchange").  Computed here with the
 oracle's arithmetic on the CPU: the sharded + all-reduced run must equal the single-process
 run, including the chain states (random numbers are keyed by the GLOBAL row)."""
 import os
@@ -46,7 +48,47 @@ def _problem():
     return X, W, cv, ch, U_h, U_v
 
 
-def _worker(rank, world, port, ret):
+def _allreduce(x):
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).copy())
+    dist.all_reduce(t)
+    return t.numpy()
+
+
+def _allgather(x, world):
+    t = torch.from_numpy(np.ascontiguousarray(x).copy())
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [o.numpy() for o in out]
+
+
+def _pcd_sharded_update(W, a, b, X, cv, ch, U_h, U_v, lr, B_global, rank, world, state_exchange):
+    """The two exchanges of the bf16 multi-GPU path, with the oracle's arithmetic: every rank owns H / world hidden
+    units.  state_exchange = False: reduce-scatter of the gradient, update of the owned columns, all-gather of the
+    weights ("sharded_update").  True: only the POSITIVE product is reduce-scattered (the device does that behind the
+    chain advance); the binary chain states are all-gathered as bits and every rank computes its own shard of the full
+    negative product ("state_exchange")."""
+    sig = lambda x: 1.0 / (1.0 + np.exp(-x))
+    hs = slice(rank * (H // world), (rank + 1) * (H // world))
+    hd = sig(b + X @ W)                                   # positive phase first: every GEMM of the step uses W_t
+    for s in range(K):
+        ch = (U_h[s] < sig(b + cv @ W)).astype(np.float64)
+        cv = (U_v[s] < sig(a + ch @ W.T)).astype(np.float64)
+    if state_exchange:
+        pos = _allreduce(X.T @ hd)[:, hs]                 # reduce-scatter: keep the owned hidden columns
+        bits = _allgather(np.packbits(np.concatenate([cv, ch], axis=1).astype(np.uint8), axis=0), world)   # bits along the rows
+        both = np.concatenate([np.unpackbits(x, axis=0)[:cv.shape[0]] for x in bits]).astype(np.float64)
+        cv_all, ch_all = both[:, :V], both[:, V:]
+        g = pos - cv_all.T @ ch_all[:, hs]
+    else:
+        g = _allreduce(X.T @ hd - cv.T @ ch)[:, hs]
+    bias = _allreduce(np.concatenate([(X - cv).sum(0), (hd - ch).sum(0)]))
+    W = np.concatenate(_allgather(W[:, hs] + g * (lr / B_global), world), axis=1)   # shard update, then all-gather of the weights
+    a = a + bias[:V] * (lr / B_global)
+    b = b + bias[V:] * (lr / B_global)
+    return W, a, b, cv, ch
+
+
+def _worker(rank, world, port, ret, mode="allreduce"):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from bench import shard_rows
@@ -63,7 +105,12 @@ def _worker(rank, world, port, ret):
         return t.numpy()
 
     for t in range(NB):
-        W, a, b, cv, ch = _pcd_batched(W, a, b, Xl[t * Bl:(t + 1) * Bl], cv, ch, U_h[t][:, sl], U_v[t][:, sl], 0.1, B, reduce)
+        if mode == "allreduce":
+            W, a, b, cv, ch = _pcd_batched(W, a, b, Xl[t * Bl:(t + 1) * Bl], cv, ch, U_h[t][:, sl], U_v[t][:, sl], 0.1, B, reduce)
+        else:
+            # (the uniform-float chains of _init_fantasy_data become binary in the first advance, before they are packed)
+            W, a, b, cv, ch = _pcd_sharded_update(W, a, b, Xl[t * Bl:(t + 1) * Bl], cv, ch, U_h[t][:, sl], U_v[t][:, sl], 0.1, B,
+                                                  rank, world, mode == "state_exchange")
     out = [None] * world
     dist.all_gather_object(out, (W, a, b, cv, ch))
     if rank == 0:
@@ -71,11 +118,12 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_sharded_allreduce_equals_single_process():
+@pytest.mark.parametrize("mode,port", [("allreduce", 29611), ("sharded_update", 29612), ("state_exchange", 29613)])
+def test_sharded_allreduce_equals_single_process(mode, port):
     world = 2
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, 29611, ret)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret, mode)) for r in range(world)]
     for p in procs:
         p.start()
     out = ret.get(timeout=120)
