@@ -496,7 +496,7 @@ def main():
         line["exchange"] = {"kernel": "qb::p2p_reduce_update_kernel", "wait_for_peers_ms_per_step": p2p_t[0] / args.steps,
                             "reduce_update_push_ms_per_step": p2p_t[1] / args.steps,
                             "nvlink_bytes_per_step_per_gpu": 2 * 4.0 * (w["V"] + w["L"]) * w["H"] * (world - 1) / world}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the CPU baseline is a single-GPU-run item (rank 0 at N = 1 only)
         r = cpu_reference(w, args.cpu_seconds, 3, 1)
         r1 = cpu_reference(w, args.cpu_seconds / 2, 2, 1, threads=1)   # the Julia code itself is single-threaded
         rb = cpu_batched_blas(w, args.cpu_seconds / 3)                 # best case for a CPU: batched BLAS-3 form (not the reference's shape)
