@@ -474,7 +474,10 @@ def main():
             "gemm_share_of_step": gemm_ms / ms_instr if ms_instr > 0 else None,
             "instrumented_ms_per_step": ms_instr / args.steps,
             "algorithmic_flops_per_step_per_gpu": F, "issued_flops_per_step_per_gpu": gflops / args.steps,
-            "peak_source": pk["src"], "whole_step_tflops": F * args.steps / (ms * 1e-3) / 1e12}
+            "peak_source": pk["src"],
+            "peak_note": "the denominator is a MEASURED cuBLAS bf16 8192^3 throughput (MEASURED_PEAKS.json), not the nominal 2250 TFLOP/s; "
+                         "a fraction slightly above 1 means these GEMMs ran faster than cuBLAS did in the same power regime",
+            "whole_step_tflops": F * args.steps / (ms * 1e-3) / 1e12}
     # update kernel (HBM-bound): 12 B/param fp32 read-modify-write + 4 B/param for the two bf16 shadows
     P_w = (w["V"] + w["L"]) * w["H"]
     upd_bytes = (16.0 if args.precision == "bf16" else 12.0) * P_w
