@@ -48,6 +48,17 @@ WORKLOADS = {
                  desc="Binary RBM 4096x4096, PCD k=10, batch 8192"),
 }
 METRIC = "PCD/CD-k training samples/sec"
+# `ncu --set full` summaries of this round (tools/ncu_summary.py raw <rep>), committed under profiles/
+NCU_GEMM_SUMMARY = "r2_ncu_gemm_raw_summary.txt"
+NCU_UPDATE_SUMMARY = "r2_ncu_update_raw_summary.txt"
+
+
+def gemm_mix(w):
+    """Launches per step by kernel specialisation (template argument text of the ncu kernel name)."""
+    k = w["k"]
+    if w["algo"] == "PCD":
+        return {", 2>": 2 * k, ", 3>": 1, ", 1>": 1}      # K_FAST_SAMPLE, K_FAST_PROB, K_GRAD
+    return {", 2>": 2 * k - 1, ", 4>": 1, ", 3>": 1, ", 1>": 1}
 
 
 def peaks():
@@ -111,22 +122,44 @@ class ClockSampler:
                 "samples": len(sm), "sampled_after_region": after}
 
 
-def ncu_traffic(kernel_prefix: str, fname: str):
-    """Average dram read+write bytes per launch of a kernel from the committed `ncu --set full` summary
-    (profiles/, produced by tools/ncu_summary.py); None if no capture is committed."""
+def ncu_traffic(fname: str, kernel_prefix: str, mix=None):
+    """dram read+write bytes per launch from a committed `ncu --set full` summary (profiles/, tools/ncu_summary.py).
+    `mix` = {template-argument substring: launches per step} weights the per-specialisation means by the launch mix of the
+    step (e.g. 20 sampling : 1 probability : 1 gradient GEMM); without it, the plain mean over the captured launches.
+    None if no capture is committed."""
     path = os.path.join(ROOT, "profiles", fname)
     if not os.path.exists(path):
         return None
-    tot, n, cur = 0.0, 0, False
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = {}   # kernel name -> [bytes, launches]
+    cur = None
     for line in open(path):
         if not line.startswith(" "):
-            cur = kernel_prefix in line
-            n += cur
+            cur = line.strip() if kernel_prefix in line else None
+            if cur:
+                per.setdefault(cur, [0.0, 0])[1] += 1
         elif cur and ("dram__bytes_read.sum " in line or "dram__bytes_write.sum " in line):
             parts = line.split()
-            tot += float(parts[1]) * scale.get(parts[2], 1.0)
-    return tot / n if n else None
+            per[cur][0] += float(parts[1]) * scale.get(parts[2], 1.0)
+    if not per:
+        return None
+    if not mix:
+        return sum(b for b, _ in per.values()) / sum(n for _, n in per.values())
+    tot, wsum = 0.0, 0.0
+    for key, weight in mix.items():
+        hit = [(b, n) for name, (b, n) in per.items() if key in name and n]
+        if hit:
+            tot += weight * sum(b for b, _ in hit) / sum(n for _, n in hit)
+            wsum += weight
+    return tot / wsum if wsum else None
+
+
+def host_cores() -> int:
+    """Cores this process may run on (NOT omp_get_max_threads: torch.distributed.run exports OMP_NUM_THREADS=1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def make_data(w, seed):
@@ -167,7 +200,7 @@ def cpu_reference(w, seconds_target, steps, warmup, threads=None):
     """Times the C restatement of the reference on a bounded sample: `rows` rows of one
     mini-batch per step (per-sample cost of the reference does not depend on the batch size)."""
     from oracle import c_oracle
-    threads = threads or c_oracle.max_threads()
+    threads = threads or host_cores()   # explicit num_threads() in the C code: independent of torchrun's OMP_NUM_THREADS=1
     V, H, L, k = w["V"], w["H"], w["L"], w["k"]
     rng = np.random.Generator(np.random.PCG64(7))
     W0 = 0.01 * rng.standard_normal((V, H))
@@ -205,11 +238,13 @@ def cpu_batched_blas(w, seconds_target):
     threaded dgemm), on a bounded sample of rows.  Not the reference's algorithm shape (it is per-sample gemv), reported
     next to it so that the GPU/CPU ratio can be read against a CPU that is used well."""
     from oracle import qarbom_oracle as qo
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([d.get("num_threads", 1) for d in threadpool_info()] or [1])
+    threads = host_cores()
+    try:   # numpy's BLAS pool may have been sized by OMP_NUM_THREADS=1 (torchrun): resize it to the host's cores
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=threads)
+        threads = max([d.get("num_threads", 1) for d in threadpool_info()] or [threads])
     except Exception:  # noqa: BLE001
-        threads = os.cpu_count() or 1
+        pass
     V, H, L, k = w["V"], w["H"], w["L"], w["k"]
     rng = np.random.default_rng(7)
     rows = int(min(w["B"], 1024))
@@ -278,6 +313,10 @@ def main():
                     help="strong: global batch fixed (BASELINE config); weak: per-GPU batch fixed (global batch x N)")
     ap.add_argument("--stale-chains", action="store_true", help="also time the stale-1 chains mode on one GPU")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--sustained-seconds", type=float, default=3.0,
+                    help="extra leg: run steps back to back for this long (own clock record) so that one of the two measured "
+                         "bf16 peaks (burst / sustained) is in-regime; 0 disables it")
+    ap.add_argument("--no-e2e-i64", action="store_true", help="skip the end-to-end leg on Int64 host rows (Vector{Vector{Int}})")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = dict(WORKLOADS[args.workload])
@@ -286,7 +325,12 @@ def main():
     if args.scaling == "weak":
         w["B"] *= world
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    Bl_cfg = w["B"] // max(world, 1)
     cfg = {"workload": f"{args.workload}: {w['desc']}", "V": w["V"], "H": w["H"], "L": w["L"], "global_batch": w["B"],
+           "l2": "inputs cycle over %d resident mini-batches (%.2f GB incl. transposed copies) > 126 MB L2"
+                 % (w["nb"], 2 * w["nb"] * Bl_cfg * w["V"] * 2 / 1e9) if 2 * w["nb"] * Bl_cfg * w["V"] * 2 > 126e6 else
+                 "inputs cycle over %d resident mini-batches (%.3f GB): smaller than the 126 MB L2, which is the steady state of "
+                 "training on this dataset (every epoch re-reads it); no flush between steps" % (w["nb"], 2 * w["nb"] * Bl_cfg * w["V"] * 2 / 1e9),
            "gibbs_steps": w["k"], "algorithm": w["algo"], "rng": "philox4x32-10", "persistent_chains": w.get("chains", w["B"]) if w["algo"] == "PCD" else None,
            "parallelism": (f"dp{world} (rows/chains sharded; gradient exchange: " +
                            ("fused NVLink peer-memory reduce-scatter + update + bf16 all-gather kernel" if (args.p2p and args.precision == "bf16") else
@@ -403,6 +447,33 @@ def main():
     upd_n, upd_ms = dev.update_timing()
     dev.set_option("time_gemms", 0)
 
+    # ---------------- sustained leg: >= `--sustained-seconds` of back-to-back steps with every GEMM bracketed by events and its
+    # own clock record: the regime the sustained bf16 peak of MEASURED_PEAKS.json was measured in (the K-step region above is
+    # a burst of a few hundred ms at most).  Event bracketing is only meaningful for long kernels; tiny configs report the
+    # whole-step figure alone.
+    sustained = None
+    if args.sustained_seconds > 0 and args.precision == "bf16":
+        n_sus = int(min(20000, max(args.steps, np.ceil(args.sustained_seconds * 1e3 / max(ms / args.steps, 1e-3)))))
+        big = (gemm_ms / max(timed, 1)) > 0.05   # average GEMM launch longer than 50 us
+        dev.reset_counters()
+        dev.set_option("time_gemms", 1 if big else 0)
+        barrier()
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        dev.timer_start()
+        for i in range(n_sus):
+            step(args.warmup + i)
+        ms_sus = max_over_ranks(dev.timer_stop())
+        barrier()
+        clocks_sus = sampler2.stop() if rank == 0 else None
+        _, _, _, timed_s, gemm_ms_s, timed_flops_s = dev.counters_full()
+        dev.set_option("time_gemms", 0)
+        sustained = {"steps": n_sus, "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / n_sus, "value": B * n_sus / (ms_sus * 1e-3),
+                     "unit": "samples/s", "clocks": clocks_sus,
+                     "gemm_tflops": (timed_flops_s / 1e12) / (gemm_ms_s * 1e-3) if (big and gemm_ms_s > 0) else None,
+                     "gemm_launches_timed": timed_s if big else 0}
+
     # ---------------- optional leg: declared stale-1 chains mode (allreduce + update overlapped with the next
     # step's chain advance; statistical parity only)
     overlap = None
@@ -447,6 +518,35 @@ def main():
                "api": f"qb_{'pcd' if pcd else 'cd'}_step_host + qb_set_next_host_batch (pinned-host upload of every mini-batch, "
                       "overlapped with the previous step; step; reconstruction error readback)"}
 
+    # ---------------- the same end-to-end leg on the reference API's own host element type: Vector{Vector{Int}} = Int64 rows
+    # (Float64 for Gaussian data), 8 bytes per element over PCIe instead of 1.  The Julia shim packs x_train to UInt8 ONCE per
+    # train! call (QARBoMB200.jl, `pack_rows`), so `e2e` above is what an epoch loop sees; this is the cost without packing.
+    e2e_i64 = None
+    if e2e is not None and not args.no_e2e_i64:
+        wide = np.float64 if w["gaussian"] else np.int64
+        nbuf = min(nb, 2)
+        xs = [torch.from_numpy(Xl[j * Bl:(j + 1) * Bl].astype(wide)).pin_memory() for j in range(nbuf)]
+        ys = [torch.from_numpy(Yl[j * Bl:(j + 1) * Bl].astype(np.int64)).pin_memory() for j in range(nbuf)] if Yl is not None else None
+
+        def host_step64(i):
+            j, jn = i % nbuf, (i + 1) % nbuf
+            return dev.step_host(w["algo"], xs[j], ys[j] if ys else None, k, lr, lr, next_x=xs[jn], next_y=ys[jn] if ys else None)
+
+        n64 = max(3, min(args.steps, 10))
+        for i in range(3):
+            host_step64(i)
+        barrier()
+        dev.timer_start()
+        for i in range(n64):
+            host_step64(3 + i)
+        ms3 = max_over_ranks(dev.timer_stop())
+        barrier()
+        h2d = int(xs[0].numel() * xs[0].element_size() + (ys[0].numel() * ys[0].element_size() if ys else 0))
+        e2e_i64 = {"value": B * n64 / (ms3 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 8 * world,
+                   "ms_per_step": ms3 / n64, "steps": n64, "host_dtype": "float64" if w["gaussian"] else "int64",
+                   "pcie_gbs": h2d / (ms3 / n64 * 1e-3) / 1e9}
+        del xs, ys
+
     if rank != 0:
         dev.close()
         if world > 1:
@@ -454,20 +554,27 @@ def main():
         return 0
 
     pk = peaks()
-    # which measured bf16 peak bounds the GEMMs of THIS run: the sustained figure when the step ran power-capped (long
-    # runs settle there), the burst figure when the whole timed region was short enough to run at full clocks
+    # Two measured bf16 peaks exist (MEASURED_PEAKS.json): burst (a kernel timed alone at full clocks) and sustained (back to
+    # back for seconds, power-capped clocks).  The K-step timed region is short, so `frac` divides by the BURST peak unless the
+    # clock samples of that region show the power cap; `frac_burst` / `frac_sustained` are always both printed, and the
+    # sustained leg below has its own achieved figure measured in the sustained regime.
     reasons = (clocks or {}).get("reasons") or []
-    capped = ("sw_power_cap" in reasons) or ((clocks or {}).get("sm_mhz") or 0) < 0.97 * ((clocks or {}).get("sm_max_mhz") or 1)
-    if not capped and "tf_burst" in pk:
-        pk = dict(pk, tf=pk["tf_burst"], src=pk["src"].replace("sustained bf16", "burst bf16: no power cap seen during the timed region"))
+    sm_med, sm_max = (clocks or {}).get("sm_mhz") or 0, (clocks or {}).get("sm_max_mhz") or 1
+    capped = ("sw_power_cap" in reasons and sm_med < 0.9 * sm_max) or (sm_med and sm_med < 0.8 * sm_max)
+    tf_burst, tf_sust = pk.get("tf_burst", pk["tf"]), pk["tf"]
+    pk = dict(pk, tf=tf_sust if capped else tf_burst,
+              src=pk["src"].replace("sustained bf16", "sustained bf16: timed region ran power-capped" if capped else
+                                    "burst bf16: timed region ran at >= 90 % of max SM clock"))
     F = flops_per_step(w) / world  # per GPU per step
     achieved = (timed_flops / 1e12) / (gemm_ms * 1e-3) if gemm_ms > 0 else None
     cfg5_bf16 = args.workload == "cfg5" and args.precision == "bf16" and world == 1
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
             "frac": (achieved / pk["tf"]) if achieved else None,
-            "traffic": ncu_traffic("gibbs_gemm_kernel", "r1_ncu_gemm_raw_summary.txt") if cfg5_bf16 else None,
-            "traffic_note": "dram read+write bytes per launch, mean over the GEMM launches of one `ncu --set full` capture "
-                            "of this command (profiles/r1_ncu_gemm_raw_summary.txt)",
+            "frac_burst": (achieved / tf_burst) if achieved else None, "frac_sustained": (achieved / tf_sust) if achieved else None,
+            "peak_burst": tf_burst, "peak_sustained": tf_sust,
+            "traffic": ncu_traffic(NCU_GEMM_SUMMARY, "gibbs_gemm_kernel", mix=gemm_mix(w)) if cfg5_bf16 else None,
+            "traffic_note": "dram read+write bytes per launch from one `ncu --set full` capture of this command (profiles/" + NCU_GEMM_SUMMARY +
+                            "), per-specialisation means weighted by the launch mix of a step (2k sampling : 1 probability : 1 gradient)",
             "kernel": "qb::sm100::gibbs_gemm_kernel (fused Gibbs half-step / gradient GEMMs)" if args.precision == "bf16"
             else "qb::simt_gemm_kernel (fp32 validation path)",
             "gemm_launches_timed": timed, "avg_launch_ms": gemm_ms / max(timed, 1),
@@ -478,21 +585,34 @@ def main():
             "peak_note": "the denominator is a MEASURED cuBLAS bf16 8192^3 throughput (MEASURED_PEAKS.json), not the nominal 2250 TFLOP/s; "
                          "a fraction slightly above 1 means these GEMMs ran faster than cuBLAS did in the same power regime",
             "whole_step_tflops": F * args.steps / (ms * 1e-3) / 1e12}
+    if sustained:
+        ws = F * sustained["steps"] / sustained["seconds"] / 1e12
+        sustained.update({"whole_step_tflops": ws, "whole_step_frac_sustained": ws / tf_sust,
+                          "gemm_frac_sustained": (sustained["gemm_tflops"] / tf_sust) if sustained["gemm_tflops"] else None,
+                          "gemm_frac_burst": (sustained["gemm_tflops"] / tf_burst) if sustained["gemm_tflops"] else None})
+        roof["sustained"] = sustained
     # update kernel (HBM-bound): 12 B/param fp32 read-modify-write + 4 B/param for the two bf16 shadows
+    # (read w, read g, write w); with the NCCL sharded update a rank touches only its H / world hidden rows and writes only the
+    # row-major shadow (the transposed one is rebuilt after the all-gather by transpose_bf16_wide_kernel)
     P_w = (w["V"] + w["L"]) * w["H"]
+    sharded = world > 1 and args.precision == "bf16" and not args.p2p and args.sharded_update != 0 and w["H"] % world == 0
     upd_bytes = (16.0 if args.precision == "bf16" else 12.0) * P_w
+    if sharded:
+        upd_bytes = 14.0 * P_w / world
     upd_gbs = (upd_bytes * upd_n / 1e9) / (upd_ms * 1e-3) if upd_ms > 0 else None
     roof_upd = {"bound": "hbm", "achieved": upd_gbs, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": (upd_gbs / pk["hbm"]) if upd_gbs else None,
-                "traffic": ncu_traffic("update_w_kernel", "r1_ncu_update_raw_summary.txt") if cfg5_bf16 else None,
+                "traffic": ncu_traffic(NCU_UPDATE_SUMMARY, "update_w_kernel") if cfg5_bf16 else None,
+                "bytes_note": "14 B/param x (H/world) rows: sharded update" if sharded else "12 B/param fp32 read-modify-write + 4 B/param bf16 shadows",
                 "kernel": "qb::update_w_kernel",
                 "bytes_per_launch": upd_bytes, "avg_launch_ms": upd_ms / max(upd_n, 1), "launches_timed": upd_n}
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": dict(cfg, l2="inputs cycle over %d resident mini-batches (%.2f GB incl. transposed copies) > 126 MB L2"
-                                    % (nb, 2 * nb * Bl * w["V"] * 2 / 1e9)),
+            "config": cfg,
             "gibbs_steps_per_s": value * k * (w.get("chains", B) / B if pcd else 1.0), "gpu_launches": launches, "roofline": roof, "roofline_update": roof_upd, "clocks": clocks, "e2e": e2e}
+    if e2e_i64:
+        line["e2e_i64"] = e2e_i64
     if overlap:
         line["overlap"] = overlap
     if p2p_t:

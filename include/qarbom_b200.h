@@ -103,6 +103,9 @@ int32_t qb_set_data(qb_handle *h, const void *X, int32_t x_dtype, const void *Y,
  * or NULL to draw the same U[0,1) floats from the device Philox stream. */
 int32_t qb_init_chains(qb_handle *h, int64_t n_chains, const double *v, const double *hid, const double *y);
 int32_t qb_get_chains(qb_handle *h, double *v, double *hid, double *y);
+/* The same for the LOCAL chains [row0, row0 + n_rows): FantasyData[i].v / .h / .y (src/fantasy_data.jl:1-10) of a
+ * few chains without moving all of them (parity checks of row subsets at full problem sizes). */
+int32_t qb_get_chain_rows(qb_handle *h, int64_t row0, int64_t n_rows, double *v, double *hid, double *y);
 
 /* Production RNG: Philox4x32-10 keyed by `seed`, counters keyed by (draw, global row,
  * unit) so results do not depend on the number of GPUs. */
@@ -218,6 +221,17 @@ int32_t qb_get_p2p_timing(qb_handle *h, double *wait_ms, double *work_ms);
  * timed_* report the number of launches timed, their summed duration and flops. */
 int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_launches, double *gemm_flops,
                         int64_t *timed_gemms, double *timed_gemm_ms, double *timed_gemm_flops);
+/* GEMM launches since the last reset by kernel specialisation: counts[(pair * 4 + b) * QB_GEMM_KINDS + kind] with
+ * pair = 1 for the cta_group::2 kernel, b = log2(tile width / 32) (32, 64, 128, 256), kind = QB_GEMM_KIND_*; the
+ * last slot counts launches of the fp32 CUDA-core GEMM.  Tests use it to assert WHICH kernel produced a result. */
+#define QB_GEMM_KINDS 8
+#define QB_GEMM_HIST_SLOTS (2 * 4 * QB_GEMM_KINDS + 1)
+#define QB_GEMM_KIND_GENERIC 0
+#define QB_GEMM_KIND_GRAD 1
+#define QB_GEMM_KIND_FAST_SAMPLE 2
+#define QB_GEMM_KIND_FAST_PROB 3
+#define QB_GEMM_KIND_FAST_SAMPLE_PROB 4
+int32_t qb_get_gemm_histogram(qb_handle *h, int64_t *counts, int32_t n_slots);
 /* with "time_gemms": number and summed CUDA-event duration of the update_w kernel launches */
 int32_t qb_get_update_timing(qb_handle *h, int64_t *timed_updates, double *timed_update_ms);
 int32_t qb_reset_counters(qb_handle *h);

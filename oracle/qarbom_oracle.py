@@ -773,12 +773,14 @@ def serial_normals(Z_v: np.ndarray, order: str) -> np.ndarray:
 # --------------------------------------------------------------------------- batched (BLAS-3) formulation
 def batched_step(m: Model, X: np.ndarray, Y: Optional[np.ndarray], algo: str, k: int, lr: float, llr: float = 0.0, *,
                  cv: Optional[np.ndarray] = None, ch: Optional[np.ndarray] = None, cy: Optional[np.ndarray] = None,
-                 U_h=None, U_v=None, U_y=None, Z_v=None, rng: Optional[np.random.Generator] = None):
+                 U_h=None, U_v=None, U_y=None, Z_v=None, rng: Optional[np.random.Generator] = None, v_store=None):
     """One mini-batch step of PCD (a20/a22) or mini-batch CD (a16/a17 with the batch extension) written with
     matrix-matrix products over the whole batch -- the formulation the device implements, and the BEST CASE for a
     CPU (threaded dgemm instead of the reference's per-sample gemv + outer products).  Used (1) by tests to show it
     equals the per-sample restatement on the same streams and (2) by bench.py as the `value_batched_blas` CPU figure.
-    Random numbers: dense arrays U_h[k][B][H], U_v[k][B][V] (or Z_v), U_y[k][B][L], or a numpy Generator."""
+    Random numbers: dense arrays U_h[k][B][H], U_v[k][B][V] (or Z_v), U_y[k][B][L], or a numpy Generator.
+    `v_store` (tests of the device's bf16 mode only; None = the reference): rounding applied to a real-valued Gaussian
+    visible sample when it is stored, so the oracle follows a device that keeps its states in bf16."""
     clf, B = m.is_classifier, X.shape[0]
 
     def uni(arr, s, shape):
@@ -793,6 +795,8 @@ def batched_step(m: Model, X: np.ndarray, Y: Optional[np.ndarray], algo: str, k:
         mu = m.a + h @ m.W.T
         if m.gaussian:
             v2 = mu + (Z_v[s] if Z_v is not None else rng.standard_normal(mu.shape))
+            if v_store is not None:
+                v2 = v_store(v2)
         else:
             v2 = (uni(U_v, s, mu.shape) < logistic(mu)).astype(np.float64)
         y2 = None

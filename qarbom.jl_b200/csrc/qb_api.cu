@@ -188,6 +188,7 @@ struct qb_handle {
     bool sharded_update = false, master_sharded = false;
     bool exchange_done = false;  // the step already reduced its gradient shard and the bias gradients (state_exchange)
     int64_t launches = 0, gemm_launches = 0;
+    int64_t gemm_hist[QB_GEMM_HIST_SLOTS] = {};
     double gemm_flops = 0.0;
     int force_bn = 0, use_2cta = 1;
     bool async_steps = false;   // step calls return without a stream sync (qb_sync to wait)
@@ -328,7 +329,7 @@ struct GemmScope {
     qb_handle *h; bool timed = false; size_t i = 0;
     GemmScope(qb_handle *h_, double flops) : h(h_) {
         h->launches++; h->gemm_launches++; h->gemm_flops += flops;
-        if (h->time_gemms && h->gemm_ev_used + 2 <= 16384) {
+        if (h->time_gemms && h->gemm_ev_used + 2 <= 65536) {
             while (h->gemm_ev.size() < h->gemm_ev_used + 2) {
                 cudaEvent_t e; QB_CUDA(cudaEventCreate(&e)); h->gemm_ev.push_back(e);
             }
@@ -336,8 +337,19 @@ struct GemmScope {
             h->gemm_timed++; h->gemm_timed_flops += flops;
             QB_CUDA(cudaEventRecord(h->gemm_ev[i], h->stream));
         }
+        sm100::last_shape().kind = -1;
     }
-    ~GemmScope() { if (timed) cudaEventRecord(h->gemm_ev[i + 1], h->stream); }
+    ~GemmScope() {
+        if (timed) cudaEventRecord(h->gemm_ev[i + 1], h->stream);
+        // launch histogram: slot = (pair, log2(bn / 32), kind); the SIMT GEMM of the fp32 path counts in the last slot
+        const sm100::LaunchShape &ls = sm100::last_shape();
+        int slot = QB_GEMM_HIST_SLOTS - 1;
+        if (ls.kind >= 0 && ls.kind < QB_GEMM_KINDS) {
+            const int b = ls.bn == 256 ? 3 : ls.bn == 128 ? 2 : ls.bn == 64 ? 1 : 0;
+            slot = (ls.pair * 4 + b) * QB_GEMM_KINDS + ls.kind;
+        }
+        h->gemm_hist[slot]++;
+    }
 };
 
 void simt_gemm(qb_handle *h, const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbk, int64_t sbn, float *C,
@@ -1300,6 +1312,17 @@ int32_t qb_get_chains(qb_handle *h, double *v, double *hid, double *y) {
     });
 }
 
+int32_t qb_get_chain_rows(qb_handle *h, int64_t row0, int64_t n_rows, double *v, double *hid, double *y) {
+    return guarded([&] {
+        QB_H_KEEP(h);
+        QB_CHECK(h->n_chains > 0, QB_E_STATE, "no chains");
+        QB_CHECK(row0 >= 0 && n_rows >= 1 && row0 + n_rows <= h->n_chains, QB_E_ARG, "chain row range out of bounds");
+        download_rows(h, h->cv, row0, 0, n_rows, h->V, v);
+        download_rows(h, h->ch, row0, 0, n_rows, h->H, hid);
+        if (h->L > 0) download_rows(h, h->cv, row0, h->V, n_rows, h->L, y);
+    });
+}
+
 int32_t qb_seed(qb_handle *h, uint64_t seed) {
     return guarded([&] { QB_H(h); h->seed = seed; h->draw = 0; });
 }
@@ -1869,10 +1892,18 @@ int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_la
         if (timed_gemm_flops) *timed_gemm_flops = h->gemm_timed_flops;
     });
 }
+int32_t qb_get_gemm_histogram(qb_handle *h, int64_t *counts, int32_t n_slots) {
+    return guarded([&] {
+        QB_H_KEEP(h);
+        QB_CHECK(counts != nullptr && n_slots >= 1, QB_E_ARG, "counts is NULL or n_slots < 1");
+        for (int i = 0; i < n_slots; i++) counts[i] = i < QB_GEMM_HIST_SLOTS ? h->gemm_hist[i] : 0;
+    });
+}
 int32_t qb_reset_counters(qb_handle *h) {
     return guarded([&] {
         QB_H_KEEP(h);
         h->launches = 0; h->gemm_launches = 0; h->gemm_flops = 0.0;
+        for (auto &c : h->gemm_hist) c = 0;
         h->gemm_ev_used = 0; h->gemm_timed = 0; h->gemm_timed_flops = 0.0;
         h->upd_ev_used = 0; h->upd_timed = 0;
     });

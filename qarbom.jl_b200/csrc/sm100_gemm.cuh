@@ -962,12 +962,17 @@ inline void pick_shape(long long M, long long N, int num_sms, int force_bn, int 
     }
 }
 
+// which (tile width, pair, specialisation) the last launch() of this thread picked: introspection for tests / bench
+struct LaunchShape { int bn = 0, pair = 0, kind = -1; };
+inline LaunchShape &last_shape() { static thread_local LaunchShape s; return s; }
+
 inline void launch(cudaStream_t st, const Operand &A, const Operand &B, const Operand *A2, const Operand *B2, const EpiParams &ep,
                    int num_sms, int force_bn = 0, int use_2cta = 1) {
     QB_CHECK(A.k == B.k && A.k > 0, -1, "GEMM operands disagree on K");
     QB_CHECK((A2 == nullptr) == (B2 == nullptr), -1, "phase-2 operands must come in pairs");
     int bn; bool pair;
     pick_shape(ep.M, ep.N, num_sms, force_bn, use_2cta, bn, pair);
+    last_shape().bn = bn; last_shape().pair = pair ? 1 : 0; last_shape().kind = pick_kind(ep);
     if (pair) {
         if (bn == 256) launch_bn_2cta<256>(st, A, B, A2, B2, ep, num_sms);
         else launch_bn_2cta<128>(st, A, B, A2, B2, ep, num_sms);

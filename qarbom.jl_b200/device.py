@@ -102,6 +102,12 @@ class DeviceRBM:
         check(lib().qb_get_chains(self._h, ptr(v), ptr(h), ptr(y)))
         return v, h, y
 
+    def get_chain_rows(self, row0: int, n: int):
+        v, h = np.zeros((n, self.V)), np.zeros((n, self.H))
+        y = np.zeros((n, self.L)) if self.L else None
+        check(lib().qb_get_chain_rows(self._h, row0, n, ptr(v), ptr(h), ptr(y)))
+        return v, h, y
+
     def inject_streams(self, U_h, U_v=None, U_y=None, Z_v=None):
         U_h = np.ascontiguousarray(U_h, dtype=np.float64)
         k, B = U_h.shape[0], U_h.shape[1]
@@ -282,6 +288,24 @@ class DeviceRBM:
         check(lib().qb_get_counters(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(f), ctypes.byref(t),
                                     ctypes.byref(ms), ctypes.byref(tf)))
         return a.value, b.value, f.value, t.value, ms.value, tf.value
+
+    GEMM_KINDS = ("generic", "grad", "fast_sample", "fast_prob", "fast_sample_prob", "fast_gauss", "fast_label", "x3")
+
+    def gemm_histogram(self) -> dict:
+        """{(kernel, tile width, kind name): launches} since the last counter reset."""
+        n = 2 * 4 * 8 + 1
+        c = (ctypes.c_int64 * n)()
+        check(lib().qb_get_gemm_histogram(self._h, c, n))
+        out = {}
+        for pair in range(2):
+            for b in range(4):
+                for k in range(8):
+                    v = c[(pair * 4 + b) * 8 + k]
+                    if v:
+                        out[("2cta" if pair else "1cta", 32 << b, self.GEMM_KINDS[k])] = int(v)
+        if c[n - 1]:
+            out[("simt", 64, "fp32")] = int(c[n - 1])
+        return out
 
     def update_timing(self):
         n, ms = ctypes.c_int64(0), ctypes.c_double(0)

@@ -22,9 +22,16 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def uniforms(seed: int, draw: int, rows: int, units: int, row0: int = 0) -> np.ndarray:
+def _row_index(rows, row0):
+    """`rows` is a count (rows row0 .. row0 + rows - 1) or an explicit array of global row indices."""
+    if np.ndim(rows) == 0:
+        return (np.arange(int(rows), dtype=np.uint64) + np.uint64(row0))[:, None]
+    return (np.asarray(rows, dtype=np.uint64) + np.uint64(row0))[:, None]
+
+
+def uniforms(seed: int, draw: int, rows, units: int, row0: int = 0) -> np.ndarray:
     """[rows][units] float64 array of the uniforms the device uses for one sampling half-step."""
-    r = (np.arange(rows, dtype=np.uint64) + np.uint64(row0))[:, None]
+    r = _row_index(rows, row0)
     u = np.arange(units, dtype=np.uint64)[None, :]
     r, u = np.broadcast_arrays(r, u)
     out = philox4x32_10(u, r >> np.uint64(2), draw & 0xFFFFFFFF, (draw >> 32) & 0x7FFFFFFF, seed & 0xFFFFFFFF, seed >> 32)
@@ -33,8 +40,8 @@ def uniforms(seed: int, draw: int, rows: int, units: int, row0: int = 0) -> np.n
     return (x >> np.uint64(9)).astype(np.float64) / float(1 << 23)
 
 
-def normals(seed: int, draw: int, rows: int, units: int, row0: int = 0) -> np.ndarray:
-    r = (np.arange(rows, dtype=np.uint64) + np.uint64(row0))[:, None]
+def normals(seed: int, draw: int, rows, units: int, row0: int = 0) -> np.ndarray:
+    r = _row_index(rows, row0)
     u = np.arange(units, dtype=np.uint64)[None, :]
     r, u = np.broadcast_arrays(r, u)
     out = philox4x32_10(u, r >> np.uint64(1), draw & 0xFFFFFFFF, ((draw >> 32) & 0x7FFFFFFF) | 0x80000000,
