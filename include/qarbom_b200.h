@@ -231,6 +231,8 @@ int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_la
 #define QB_GEMM_KIND_FAST_SAMPLE 2
 #define QB_GEMM_KIND_FAST_PROB 3
 #define QB_GEMM_KIND_FAST_SAMPLE_PROB 4
+#define QB_GEMM_KIND_FAST_GAUSS 5  /* Gaussian visibles: mean + Box-Muller normal in the epilogue */
+#define QB_GEMM_KIND_FAST_LABEL 6  /* Bernoulli visibles + label units (softmax + Bernoulli) in the epilogue */
 int32_t qb_get_gemm_histogram(qb_handle *h, int64_t *counts, int32_t n_slots);
 /* with "time_gemms": number and summed CUDA-event duration of the update_w kernel launches */
 int32_t qb_get_update_timing(qb_handle *h, int64_t *timed_updates, double *timed_update_ms);

@@ -35,7 +35,8 @@ static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
 // ----------------------------------------------------------------------------- Philox4x32-10
 // Counter-based RNG (Salmon et al., SC'11).  The stream contract of this library:
 //   uniform (draw, row, unit)  = u23( philox(ctr = (unit, row >> 2, draw_lo, draw_hi), key = seed)[row & 3] )
-//   normal  (draw, row, unit)  = box_muller( philox(ctr = (unit, row >> 1, draw_lo, draw_hi | 1<<31), key)[2*(row&1) .. +1] )
+//   normal  (draw, row, unit)  = box_muller( philox(ctr = (unit, row >> 2, draw_lo, draw_hi | 1<<31), key) )[row & 3]
+//                                (words x,y -> rows 4g, 4g+1 as r cos, r sin; words z,w -> rows 4g+2, 4g+3)
 // with `row` the GLOBAL row (chain / mini-batch row) so results do not depend on the
 // number of GPUs.  tests/philox_ref.py restates this in numpy.
 struct Philox4 {
@@ -86,21 +87,26 @@ __device__ __forceinline__ float rng_uniform(const RngKey &k, uint32_t unit, uin
     uint32_t v = r == 0 ? p.x : (r == 1 ? p.y : (r == 2 ? p.z : p.w));
     return u23(v);
 }
-__device__ __forceinline__ float box_muller(uint32_t a, uint32_t b) {
-    float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
-    float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);
-    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+// Box-Muller on two 23-bit uniforms built from mantissa bits (exact in fp32 and fp64): u1 = 1 - (a >> 9) 2^-23 in (0, 1],
+// u2 = (b >> 9) 2^-23 in [0, 1);  z0 = r cos(2 pi u2), z1 = r sin(2 pi u2), r = sqrt(-2 ln u1)  (|z| <= 5.65)
+__device__ __forceinline__ void box_muller2(uint32_t a, uint32_t b, float &z0, float &z1) {
+    const float u1 = 1.0f - u23(a), u2 = u23(b);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    z0 = r * cs; z1 = r * sn;
 }
-// two normals for rows (2*pair, 2*pair+1)
-__device__ __forceinline__ void rng_normal2(const RngKey &k, uint32_t unit, uint32_t row_pair, float &z0, float &z1) {
-    Philox4 p = philox4x32_10(unit, row_pair, k.draw_lo, k.draw_hi | 0x80000000u, k.seed_lo, k.seed_hi);
-    z0 = box_muller(p.x, p.y);
-    z1 = box_muller(p.z, p.w);
+// four normals for rows (4*group .. 4*group+3)
+__device__ __forceinline__ void rng_normal4(const RngKey &k, uint32_t unit, uint32_t row_group, float (&z)[4]) {
+    Philox4 p = philox4x32_10(unit, row_group, k.draw_lo, k.draw_hi | 0x80000000u, k.seed_lo, k.seed_hi);
+    box_muller2(p.x, p.y, z[0], z[1]);
+    box_muller2(p.z, p.w, z[2], z[3]);
 }
 __device__ __forceinline__ float rng_normal(const RngKey &k, uint32_t unit, uint64_t row) {
-    float z0, z1;
-    rng_normal2(k, unit, (uint32_t)(row >> 1), z0, z1);
-    return (row & 1) ? z1 : z0;
+    float z[4];
+    rng_normal4(k, unit, (uint32_t)(row >> 2), z);
+    const uint32_t r = (uint32_t)(row & 3);
+    return r == 0 ? z[0] : (r == 1 ? z[1] : (r == 2 ? z[2] : z[3]));
 }
 
 // logistic: exact-ish fp32 (expf + IEEE divide) for the validation path ...

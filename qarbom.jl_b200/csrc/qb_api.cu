@@ -472,7 +472,8 @@ void op_visible(qb_handle *h, const Mat &in, int64_t rows, const VisibleOut &o, 
         GemmScope gs(h, 2.0 * (double)h->VL * (double)rows * (double)h->H);
         sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->gemm_sms, h->force_bn, h->use_2cta);
     }
-    if (h->L > 0 && o.sample && o.state) {
+    // label units: finished inside the GEMM epilogue (K_FAST_LABEL) or, from the raw pre-activations, by a side kernel
+    if (h->L > 0 && o.sample && o.state && sm100::last_shape().kind != sm100::K_FAST_LABEL) {
         label_bf16_kernel<<<grid1d(rows, 128), 128, 0, h->stream>>>(
             h->lab_pre, h->L, (int)rows, (int)h->V, (int)h->L, o.state_rm ? o.state->b : nullptr, o.state->ld,
             o.state_T ? o.state->bT : nullptr, o.state->ldT, rng.inj, rng.ld_inj, rng.key, row0,

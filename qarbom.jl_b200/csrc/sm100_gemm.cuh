@@ -35,7 +35,8 @@ constexpr int SMEM_AB_BUDGET = 192 * 1024;
 
 enum { EPI_SAMPLE = 0, EPI_GRAD = 1 };
 // kernel specialisations: generic epilogue, gradient store, and the two compile-time fast paths
-enum { K_GENERIC = 0, K_GRAD = 1, K_FAST_SAMPLE = 2, K_FAST_PROB = 3, K_FAST_SAMPLE_PROB = 4 };
+// (numbering = QB_GEMM_KIND_* of include/qarbom_b200.h)
+enum { K_GENERIC = 0, K_GRAD = 1, K_FAST_SAMPLE = 2, K_FAST_PROB = 3, K_FAST_SAMPLE_PROB = 4, K_FAST_GAUSS = 5, K_FAST_LABEL = 6 };
 // Epilogue warpgroups per CTA: the lean epilogues are latency-bound with 2 warps per scheduler
 // (ncu: IPC 0.3, epilogue time ~ MMA time), so they run 4 warpgroups (16 warps, 64 columns each at
 // BN = 256); the register-hungry generic epilogue keeps 2.
@@ -205,8 +206,7 @@ __device__ __forceinline__ void epilogue_sample(const EpiParams &ep, uint32_t tm
                     Philox4 ph = rng_uniform4(ep.key, (uint32_t)unit, (uint32_t)(grow >> 2));
                     rnd[0] = ph.x; rnd[1] = ph.y; rnd[2] = ph.z; rnd[3] = ph.w;
                 } else {
-                    rng_normal2(ep.key, (uint32_t)unit, (uint32_t)(grow >> 1), zn[0], zn[1]);
-                    rng_normal2(ep.key, (uint32_t)unit, (uint32_t)(grow >> 1) + 1u, zn[2], zn[3]);
+                    rng_normal4(ep.key, (uint32_t)unit, (uint32_t)(grow >> 2), zn);
                     if (ep.act == ACT_GAUSS_THRESH) {
                         Philox4 ph = rng_uniform4(ep.key, (uint32_t)unit, (uint32_t)(grow >> 2));
                         rnd[0] = ph.x; rnd[1] = ph.y; rnd[2] = ph.z; rnd[3] = ph.w;
@@ -340,9 +340,29 @@ __device__ __forceinline__ float sigmoid_mufu(float x) {
     return r;
 }
 
+// Box-Muller with four MUFU ops for two normals (same formula as box_muller2 in common.cuh; lg2 / sqrt / sin / cos are the
+// approximate hardware functions, |error| < 1e-5 absolute on z): the Gaussian-visible epilogue costs the same two MUFU per
+// element as the sigmoid one.  The angle is taken around zero, 2 pi (u2 - 1/2) in [-pi, pi), where sin/cos.approx are accurate.
+__device__ __forceinline__ void box_muller2_fast(uint32_t a, uint32_t b, float &z0, float &z1) {
+    const float u1 = 1.0f - u23(a);
+    const float ang = (u23(b) - 0.5f) * 6.283185307179586f;
+    float l, r, sn, cs;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u1));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -1.3862943611198906f));  // -2 ln u1 = -2 ln2 lg2 u1
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
+    z0 = -r * cs; z1 = -r * sn;   // cos(x + pi) = -cos x, sin(x + pi) = -sin x
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
 // one 16-column chunk of the fast epilogue; FULL = all 16 rows and the unit are in range (the common
-// case: no per-element predicates at all)
-template <bool SAMPLE, bool PROB, bool FULL>
+// case: no per-element predicates at all).  GAUSS: s = x + z (Gaussian visibles, src/rbm.jl:187) instead of a Bernoulli draw.
+template <bool SAMPLE, bool PROB, bool FULL, bool GAUSS = false>
 __device__ __forceinline__ void fast_chunk(const EpiParams &ep, const uint32_t (&r)[16], int unit, int row_base, int nv, float bias,
                                            bool want_sT, bool want_pT, bool want_prm, float &bg_p, int &bg_s) {
     uint32_t sb[16], pb[16];
@@ -351,22 +371,36 @@ __device__ __forceinline__ void fast_chunk(const EpiParams &ep, const uint32_t (
         uint32_t rnd[4];
         if (SAMPLE) {
             const unsigned long long grow = (unsigned long long)(ep.row0 + row_base + 4 * g);
-            Philox4 ph = rng_uniform4(ep.key, (uint32_t)unit, (uint32_t)(grow >> 2));
+            Philox4 ph = philox4x32_10((uint32_t)unit, (uint32_t)(grow >> 2), ep.key.draw_lo, ep.key.draw_hi | (GAUSS ? 0x80000000u : 0u),
+                                       ep.key.seed_lo, ep.key.seed_hi);
             rnd[0] = ph.x; rnd[1] = ph.y; rnd[2] = ph.z; rnd[3] = ph.w;
         }
+        if (GAUSS) {
+            float z[4];
+            box_muller2_fast(rnd[0], rnd[1], z[0], z[1]);
+            box_muller2_fast(rnd[2], rnd[3], z[2], z[3]);
 #pragma unroll
-        for (int jj = 0; jj < 4; jj++) {
-            const int j = 4 * g + jj;
-            const float p = sigmoid_mufu(__uint_as_float(r[j]) + bias);
-            if (PROB) {
-                const float ps = p * ep.pscale;
-                if (FULL || j < nv) bg_p += ps;
-                pb[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(ps));
+            for (int jj = 0; jj < 4; jj++) {
+                const int j = 4 * g + jj;
+                const float sv = __uint_as_float(r[j]) + bias + z[jj];
+                if (FULL || j < nv) bg_p += sv;
+                sb[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(sv));
             }
-            if (SAMPLE) {
-                const bool on = u23(rnd[jj]) < p;
-                sb[j] = on ? 0x3F80u : 0u;  // bf16(1.0) / bf16(0.0)
-                bg_s += (on && (FULL || j < nv)) ? 1 : 0;
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int j = 4 * g + jj;
+                const float p = sigmoid_mufu(__uint_as_float(r[j]) + bias);
+                if (PROB) {
+                    const float ps = p * ep.pscale;
+                    if (FULL || j < nv) bg_p += ps;
+                    pb[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(ps));
+                }
+                if (SAMPLE) {
+                    const bool on = u23(rnd[jj]) < p;
+                    sb[j] = on ? 0x3F80u : 0u;  // bf16(1.0) / bf16(0.0)
+                    bg_s += (on && (FULL || j < nv)) ? 1 : 0;
+                }
             }
         }
     }
@@ -415,13 +449,62 @@ __device__ __forceinline__ void fast_chunk(const EpiParams &ep, const uint32_t (
 // instruction count and code size, so it hides completely behind the next tile's MMAs.
 //   SAMPLE: s = (u < sigmoid(x)); stores state_rm (required), state_T (optional); bias gradient of s
 //   PROB  : p = sigmoid(x); stores prob_T / prob_rm (optional); bias gradient of p (bg_what == 1)
-template <int BN, int WGS, bool SAMPLE, bool PROB>
+//   MODE 1: Gaussian visibles, s = x + z (bias gradient of s)
+//   MODE 2: Bernoulli visibles followed by label units (RBMClassifier): the one warp whose 32 lanes hold the label units
+//           [split, M) finishes them in place -- softmax over the label lanes by warp shuffles, then independent Bernoulli
+//           draws (gibbs_sample_label, src/gibbs.jl:46-49 + src/rbm.jl:196-205) -- every other warp runs the plain path.
+template <bool FULL>
+__device__ __forceinline__ void label_chunk(const EpiParams &ep, const uint32_t (&r)[16], int unit, bool uvalid, int row_base, int nrows,
+                                            float bias, bool want_sT, int &bg_s) {
+    const bool is_label = uvalid && unit >= ep.split;
+    uint32_t sb[16];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const unsigned long long grow = (unsigned long long)(ep.row0 + row_base + 4 * g);
+        Philox4 ph = rng_uniform4(ep.key, (uint32_t)unit, (uint32_t)(grow >> 2));
+        const uint32_t rnd[4] = {ph.x, ph.y, ph.z, ph.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            const int j = 4 * g + jj;
+            const float x = __uint_as_float(r[j]) + bias;
+            const float mx = warp_max(is_label ? x : -INFINITY);
+            const float e = is_label ? __expf(x - mx) : 0.f;
+            const float den = warp_sum(e);
+            const float p = is_label ? __fdividef(e, den) : sigmoid_mufu(x);
+            const bool on = u23(rnd[jj]) < p;
+            sb[j] = on ? 0x3F80u : 0u;
+            bg_s += (on && (FULL || j < nrows)) ? 1 : 0;
+        }
+    }
+    if (!uvalid) return;
+    unsigned short *dst = reinterpret_cast<unsigned short *>(ep.state_rm) + (long long)row_base * ep.ld_srm + unit;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        if (FULL || j < nrows) *dst = (unsigned short)sb[j];
+        dst += ep.ld_srm;
+    }
+    if (want_sT) {
+        unsigned short *dT = reinterpret_cast<unsigned short *>(ep.state_T) + (long long)unit * ep.ld_sT + row_base;
+        if (FULL) {
+            reinterpret_cast<uint4 *>(dT)[0] = make_uint4(sb[0] | (sb[1] << 16), sb[2] | (sb[3] << 16), sb[4] | (sb[5] << 16), sb[6] | (sb[7] << 16));
+            reinterpret_cast<uint4 *>(dT)[1] = make_uint4(sb[8] | (sb[9] << 16), sb[10] | (sb[11] << 16), sb[12] | (sb[13] << 16), sb[14] | (sb[15] << 16));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (j < nrows) dT[j] = (unsigned short)sb[j];
+        }
+    }
+}
+
+template <int BN, int WGS, bool SAMPLE, bool PROB, int MODE = 0>
 __device__ __forceinline__ void epilogue_fast(const EpiParams &ep, uint32_t tmem_acc, int m_blk, int n_blk, int quarter, int wg,
                                               int lane) {
     const int unit = m_blk * BM + quarter * 32 + lane;
     const bool uvalid = unit < ep.M;
     const float bias = uvalid ? ep.bias[unit] : 0.f;
     const bool want_sT = SAMPLE && ep.state_T != nullptr, want_pT = PROB && ep.prob_T != nullptr, want_prm = PROB && ep.prob_rm != nullptr;
+    // MODE 2: does this warp hold the label units? (warp-uniform; pick_kind guarantees they sit inside ONE 32-lane group)
+    const bool label_warp = MODE == 2 && (unit - lane) + 32 > ep.split && (unit - lane) < ep.M;
     float bg_p = 0.f;
     int bg_s = 0;
     constexpr int COLS_PER_WG = BN / WGS;
@@ -436,10 +519,16 @@ __device__ __forceinline__ void epilogue_fast(const EpiParams &ep, uint32_t tmem
         if (nvalid <= 0) continue;
         nvalid = nvalid > 16 ? 16 : nvalid;
         const int nv = uvalid ? nvalid : 0;
-        if (nv == 16) fast_chunk<SAMPLE, PROB, true>(ep, r, unit, row_base, nv, bias, want_sT, want_pT, want_prm, bg_p, bg_s);
-        else if (nv > 0) fast_chunk<SAMPLE, PROB, false>(ep, r, unit, row_base, nv, bias, want_sT, want_pT, want_prm, bg_p, bg_s);
+        if (label_warp) {   // all 32 lanes take part in the shuffles, stores are predicated per lane
+            if (nvalid == 16) label_chunk<true>(ep, r, unit, uvalid, row_base, nvalid, bias, want_sT, bg_s);
+            else label_chunk<false>(ep, r, unit, uvalid, row_base, nvalid, bias, want_sT, bg_s);
+            continue;
+        }
+        if (nv == 16) fast_chunk<SAMPLE, PROB, true, MODE == 1>(ep, r, unit, row_base, nv, bias, want_sT, want_pT, want_prm, bg_p, bg_s);
+        else if (nv > 0) fast_chunk<SAMPLE, PROB, false, MODE == 1>(ep, r, unit, row_base, nv, bias, want_sT, want_pT, want_prm, bg_p, bg_s);
     }
-    if (ep.bg_what && uvalid) atomicAdd(ep.bias_grad + unit, ep.bg_sign * ((PROB && ep.bg_what == 1) ? bg_p : (float)bg_s));
+    if (ep.bg_what && uvalid)
+        atomicAdd(ep.bias_grad + unit, ep.bg_sign * (((PROB && ep.bg_what == 1) || MODE == 1) ? bg_p : (float)bg_s));
 }
 
 template <int BN, int WGS>
@@ -580,6 +669,8 @@ gibbs_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             else if (KIND == K_GRAD) epilogue_grad<BN, WGS>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else if (KIND == K_FAST_SAMPLE) epilogue_fast<BN, WGS, true, false>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else if (KIND == K_FAST_SAMPLE_PROB) epilogue_fast<BN, WGS, true, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_FAST_GAUSS) epilogue_fast<BN, WGS, true, false, 1>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_FAST_LABEL) epilogue_fast<BN, WGS, true, false, 2>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else epilogue_fast<BN, WGS, false, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             tcgen05_fence_before();
             __syncwarp();
@@ -768,6 +859,8 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ CUtensorMap mapA, const __grid_co
             else if (KIND == K_GRAD) epilogue_grad<BN, WGS>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else if (KIND == K_FAST_SAMPLE) epilogue_fast<BN, WGS, true, false>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else if (KIND == K_FAST_SAMPLE_PROB) epilogue_fast<BN, WGS, true, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_FAST_GAUSS) epilogue_fast<BN, WGS, true, false, 1>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_FAST_LABEL) epilogue_fast<BN, WGS, true, false, 2>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else epilogue_fast<BN, WGS, false, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             tcgen05_fence_before();
             __syncwarp();
@@ -845,10 +938,15 @@ inline CUtensorMap encode_tmap(const Operand &o, int box_rows) {
 // which specialisation serves these epilogue parameters
 inline int pick_kind(const EpiParams &ep) {
     if (ep.mode == EPI_GRAD) return K_GRAD;
-    const bool plain = ep.act == ACT_SIGMOID && ep.split >= ep.M && !ep.inj && !ep.sqerr && !ep.softplus_rows && !ep.prob_f32;
+    const bool lean = !ep.inj && !ep.sqerr && !ep.softplus_rows && !ep.prob_f32;
+    const bool plain = lean && ep.act == ACT_SIGMOID && ep.split >= ep.M;
     if (plain && ep.sample && ep.use_rng && ep.state_rm && !ep.prob_rm)
         return (ep.prob_T || ep.bg_what == 1) ? K_FAST_SAMPLE_PROB : K_FAST_SAMPLE;
     if (plain && !ep.sample && !ep.state_rm && !ep.state_T) return K_FAST_PROB;
+    const bool sample_only = lean && ep.sample && ep.use_rng && ep.state_rm && !ep.prob_rm && !ep.prob_T && ep.bg_what != 1;
+    if (sample_only && ep.act == ACT_GAUSSIAN && ep.split >= ep.M) return K_FAST_GAUSS;
+    // label units fused when they all sit in one 32-lane group of a tile
+    if (sample_only && ep.act == ACT_SIGMOID && ep.split < ep.M && (ep.split % 32) + (ep.M - ep.split) <= 32) return K_FAST_LABEL;
     return K_GENERIC;
 }
 
@@ -891,6 +989,8 @@ inline void launch_bn_2cta(cudaStream_t st, const Operand &A, const Operand &B, 
         case K_FAST_SAMPLE: launch_bn_kind_2cta<BN, K_FAST_SAMPLE>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
         case K_FAST_PROB: launch_bn_kind_2cta<BN, K_FAST_PROB>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
         case K_FAST_SAMPLE_PROB: launch_bn_kind_2cta<BN, K_FAST_SAMPLE_PROB>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
+        case K_FAST_GAUSS: launch_bn_kind_2cta<BN, K_FAST_GAUSS>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
+        case K_FAST_LABEL: launch_bn_kind_2cta<BN, K_FAST_LABEL>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
         default: launch_bn_kind_2cta<BN, K_GENERIC>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
     }
     QB_CUDA(cudaGetLastError());
@@ -909,6 +1009,8 @@ inline void launch_bn(cudaStream_t st, const Operand &A, const Operand &B, const
         case K_FAST_SAMPLE: launch_bn_kind<BN, K_FAST_SAMPLE>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
         case K_FAST_PROB: launch_bn_kind<BN, K_FAST_PROB>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
         case K_FAST_SAMPLE_PROB: launch_bn_kind<BN, K_FAST_SAMPLE_PROB>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
+        case K_FAST_GAUSS: launch_bn_kind<BN, K_FAST_GAUSS>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
+        case K_FAST_LABEL: launch_bn_kind<BN, K_FAST_LABEL>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
         default: launch_bn_kind<BN, K_GENERIC>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
     }
     QB_CUDA(cudaGetLastError());
@@ -922,6 +1024,8 @@ inline void init_bn() {
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_SAMPLE_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_LABEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
 }
 template <int BN>
 inline void init_bn_2cta() {
@@ -931,6 +1035,8 @@ inline void init_bn_2cta() {
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_SAMPLE_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_LABEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
 }
 // once per device (qb_create): opt in to the large dynamic shared-memory carve-out
 inline void init_device() {
