@@ -16,6 +16,7 @@
 #include "p2p_kernels.cuh"
 #include "simt_kernels.cuh"
 #include "sm100_gemm.cuh"
+#include "sm100_chain.cuh"
 
 using namespace qb;
 
@@ -191,6 +192,12 @@ struct qb_handle {
     int64_t gemm_hist[QB_GEMM_HIST_SLOTS] = {};
     double gemm_flops = 0.0;
     int force_bn = 0, use_2cta = 1;
+    // fused chain launches (sm100_chain.cuh): half-steps recorded between chain_begin / chain_end run as ONE persistent kernel
+    bool fused_chain = true; int chain_bn = 0;      // options "fused_chain", "chain_bn" (0 = automatic)
+    int rec_depth = 0; sm100::ChainBuilder *rec = nullptr;
+    unsigned int *chain_cnt = nullptr; int64_t chain_cnt_region = 0, chain_launch_no = 0;
+    unsigned int *chain_err_host = nullptr, *chain_err_dev = nullptr;
+    int64_t chain_launches = 0;
     bool async_steps = false;   // step calls return without a stream sync (qb_sync to wait)
     bool time_gemms = false;    // bracket every GEMM launch with CUDA events on the launching stream
     std::vector<cudaEvent_t> gemm_ev; size_t gemm_ev_used = 0; int64_t gemm_timed = 0; double gemm_timed_flops = 0.0;
@@ -360,6 +367,127 @@ void simt_gemm(qb_handle *h, const float *A, int64_t sam, int64_t sak, const flo
     QB_CUDA(cudaGetLastError());
 }
 
+// ----------------------------------------------------------------------------- fused chains
+constexpr int QB_CHAIN_REGIONS = 32;
+
+void chain_flush(qb_handle *h);
+
+void chain_begin(qb_handle *h) {
+    if (h->rec_depth++ > 0) return;
+    if (!h->rec) h->rec = new sm100::ChainBuilder();
+    h->rec->prog.n_steps = 0;
+}
+void chain_end(qb_handle *h) {
+    if (--h->rec_depth > 0) return;
+    chain_flush(h);
+}
+struct ChainRegion {   // records the half-steps issued inside a scope, launches them when the scope ends
+    qb_handle *h;
+    explicit ChainRegion(qb_handle *h_) : h(h_) { chain_begin(h); }
+    ~ChainRegion() noexcept(false) {
+        if (std::uncaught_exceptions()) { h->rec_depth = 0; if (h->rec) h->rec->prog.n_steps = 0; return; }
+        chain_end(h);
+    }
+};
+
+int chain_tile_width(qb_handle *h, int64_t N) {
+    if (h->chain_bn) return h->chain_bn;
+    if (h->force_bn >= 64) return h->force_bn;
+    return N >= 2048 ? 256 : 128;
+}
+
+void launch_single(qb_handle *h, const sm100::Operand &A, const sm100::Operand &B, const sm100::EpiParams &ep, double flops) {
+    GemmScope gs(h, flops);
+    sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->gemm_sms, h->force_bn, h->use_2cta);
+}
+
+// does step i (about to be appended, reading B and writing the row-major / transposed outputs of ep) only touch buffers of
+// earlier steps that are its ancestors along the dependency chain?  (row-block counters order exactly those)
+bool chain_hazard_free(const sm100::ChainBuilder &cb, const sm100::Operand &B, const sm100::EpiParams &ep, int dep) {
+    bool anc[sm100::CHAIN_MAX_STEPS] = {};
+    for (int a = dep; a >= 0; a = cb.prog.step[a].dep_step) anc[a] = true;
+    const void *outs[4] = {ep.state_rm, ep.prob_rm, ep.state_T, ep.prob_T};
+    for (int j = 0; j < cb.prog.n_steps; j++) {
+        if (anc[j]) continue;
+        const sm100::ChainStep &S = cb.prog.step[j];
+        const void *jouts[4] = {S.ep.state_rm, S.ep.prob_rm, S.ep.state_T, S.ep.prob_T};
+        const void *jin = cb.ops[S.b_map].ptr;
+        for (const void *o : outs) {
+            if (!o) continue;
+            if (o == jin) return false;                      // write after read of a non-ancestor
+            for (const void *q : jouts) if (q == o) return false;   // write after write
+        }
+        for (const void *q : jouts) if (q && q == (const void *)B.ptr) return false;   // read of a non-ancestor's output (cannot happen: dep is the latest writer)
+    }
+    return true;
+}
+
+// one fused half-step GEMM of the bf16 path: recorded into the open chain region, or launched right away
+void gemm_half_step(qb_handle *h, const sm100::Operand &A, const sm100::Operand &B, const sm100::EpiParams &ep, double flops) {
+    const bool can_chain = h->rec_depth > 0 && h->fused_chain && h->use_2cta != 0 && h->force_bn != 32 && sm100::chainable(ep);
+    if (h->rec_depth > 0 && !can_chain) chain_flush(h);
+    if (!can_chain) { launch_single(h, A, B, ep, flops); return; }
+    sm100::ChainBuilder &cb = *h->rec;
+    if (cb.prog.n_steps > 0 && (cb.prog.N != ep.N || cb.full())) chain_flush(h);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (cb.prog.n_steps == 0) cb.begin(ep.N, chain_tile_width(h, ep.N));
+        int dep = -1;
+        for (int j = cb.prog.n_steps - 1; j >= 0; j--) {
+            const sm100::EpiParams &e = cb.prog.step[j].ep;
+            if ((const void *)e.state_rm == (const void *)B.ptr || (const void *)e.prob_rm == (const void *)B.ptr) { dep = j; break; }
+        }
+        if (cb.n_maps + 2 <= sm100::CHAIN_MAX_MAPS && chain_hazard_free(cb, B, ep, dep)) {
+            cb.add(A, B, ep, dep);
+            return;
+        }
+        chain_flush(h);   // start a new program with this step first
+    }
+    launch_single(h, A, B, ep, flops);
+}
+
+void chain_flush(qb_handle *h) {
+    if (!h->rec || h->rec->prog.n_steps == 0) return;
+    sm100::ChainBuilder &cb = *h->rec;
+    const int n = cb.prog.n_steps;
+    cb.prog.n_steps = 0;   // (re-entrancy: launch_single below must not see the program)
+    if (n == 1) {
+        const sm100::ChainStep &S = cb.prog.step[0];
+        launch_single(h, cb.ops[S.a_map], cb.ops[S.b_map], S.ep, cb.flops);
+        return;
+    }
+    cb.prog.n_steps = n;
+    if (!h->chain_cnt) {
+        h->chain_cnt_region = (int64_t)sm100::CHAIN_MAX_STEPS * ceil_div(h->Bmax, 64);
+        h->chain_cnt = dalloc<unsigned int>((size_t)QB_CHAIN_REGIONS * h->chain_cnt_region + 1);   // + the abort flag
+        QB_CUDA(cudaHostAlloc((void **)&h->chain_err_host, sizeof(unsigned int), cudaHostAllocMapped));
+        *h->chain_err_host = 0u;
+        QB_CUDA(cudaHostGetDevicePointer((void **)&h->chain_err_dev, h->chain_err_host, 0));
+    }
+    // arrival counters: a fresh region of a ring per launch, the whole ring is cleared once per lap
+    const int64_t region = h->chain_launch_no % QB_CHAIN_REGIONS;
+    if (region == 0 && h->chain_launch_no > 0)
+        QB_CUDA(cudaMemsetAsync(h->chain_cnt, 0, (size_t)QB_CHAIN_REGIONS * h->chain_cnt_region * sizeof(unsigned int), h->stream));
+    h->chain_launch_no++;
+    cb.prog.counters = h->chain_cnt + region * h->chain_cnt_region;
+    cb.prog.error_flag = h->chain_err_dev;
+    cb.prog.abort_flag = h->chain_cnt + (size_t)QB_CHAIN_REGIONS * h->chain_cnt_region;
+    {
+        GemmScope gs(h, cb.flops);
+        sm100::launch_chain(h->stream, cb, h->gemm_sms);
+        sm100::last_shape().bn = cb.bn; sm100::last_shape().pair = 1; sm100::last_shape().kind = sm100::K_CHAIN;
+    }
+    h->chain_launches++;
+    cb.prog.n_steps = 0;
+}
+
+void chain_check_error(qb_handle *h) {
+    if (h->chain_err_host && *(volatile unsigned int *)h->chain_err_host) {
+        *h->chain_err_host = 0u;
+        cudaMemsetAsync(h->chain_cnt + (size_t)QB_CHAIN_REGIONS * h->chain_cnt_region, 0, sizeof(unsigned int), h->stream);
+        throw Error(QB_E_CUDA, "fused chain kernel: a row-block dependency was not satisfied in time (results of the step are invalid)");
+    }
+}
+
 // ----------------------------------------------------------------------------- the three ops
 struct HiddenOut {
     Mat *prob = nullptr;   // probabilities (fp32 path: .f; bf16 path: .b and/or .bT per flags)
@@ -403,8 +531,7 @@ void op_hidden(qb_handle *h, const Mat &in, int64_t rows, int64_t kdim, const Hi
     ep.softplus_rows = o.softplus_rows;
     ep.pscale = o.pscale;
     QB_CHECK(o.pscale == 1.f || sm100::pick_kind(ep) == sm100::K_FAST_PROB, QB_E_UNSUPPORTED, "pscale needs the fast probability epilogue");
-    GemmScope gs(h, 2.0 * (double)h->H * (double)rows * (double)kdim);
-    sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->gemm_sms, h->force_bn, h->use_2cta);
+    gemm_half_step(h, A, B, ep, 2.0 * (double)h->H * (double)rows * (double)kdim);
 }
 
 struct VisibleOut {
@@ -468,12 +595,9 @@ void op_visible(qb_handle *h, const Mat &in, int64_t rows, const VisibleOut &o, 
     if (o.bg_sign_neg) { ep.bg_what = 2; ep.bg_sign = -1.f; ep.bias_grad = G_a(h); }
     if (o.sqerr) { ep.sqerr = o.sqerr; ep.ref_rm = o.ref->b; ep.ld_ref = o.ref->ld; }
     ep.pscale = 1.f;
-    {
-        GemmScope gs(h, 2.0 * (double)h->VL * (double)rows * (double)h->H);
-        sm100::launch(h->stream, A, B, nullptr, nullptr, ep, h->gemm_sms, h->force_bn, h->use_2cta);
-    }
+    gemm_half_step(h, A, B, ep, 2.0 * (double)h->VL * (double)rows * (double)h->H);
     // label units: finished inside the GEMM epilogue (K_FAST_LABEL) or, from the raw pre-activations, by a side kernel
-    if (h->L > 0 && o.sample && o.state && sm100::last_shape().kind != sm100::K_FAST_LABEL) {
+    if (h->L > 0 && o.sample && o.state && sm100::pick_kind(ep) != sm100::K_FAST_LABEL) {
         label_bf16_kernel<<<grid1d(rows, 128), 128, 0, h->stream>>>(
             h->lab_pre, h->L, (int)rows, (int)h->V, (int)h->L, o.state_rm ? o.state->b : nullptr, o.state->ld,
             o.state_T ? o.state->bT : nullptr, o.state->ldT, rng.inj, rng.ld_inj, rng.key, row0,
@@ -775,6 +899,7 @@ void check_step_args(qb_handle *h, int64_t B, int64_t k, bool allow_k0 = false) 
 // k Gibbs steps on the persistent chains (_update_fantasy_data!, src/fantasy_data.jl:12-29)
 void advance_chains(qb_handle *h, int64_t B, int64_t k, StepRng &sr, bool fold_bias) {
     const int64_t row0 = row0_of(h, B);
+    ChainRegion region(h);   // bf16: the 2k half-steps run as one persistent kernel (sm100_chain.cuh)
     for (int64_t s = 0; s < k; s++) {
         const bool last = (s == k - 1);
         HiddenOut ho; ho.state = &h->ch; ho.state_rm = true; ho.state_T = last;
@@ -928,6 +1053,10 @@ void pcd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT,
     zero_bias_grads(h, ps);
     const bool clf = h->L > 0;
     if (ev) QB_CUDA(cudaEventRecord(ev[0], h->stream));
+    // bf16: the chain advance and the positive phase (independent of each other) are recorded into one fused launch; its tiles
+    // come last in the schedule and fill the tail of the chain.  With phase timing (ev) the phases stay separate launches.
+    const bool fuse_pos = h->bf && !clf && k > 0 && ev == nullptr;
+    if (fuse_pos) chain_begin(h);
     if (!clf && k > 0) advance_chains(h, Nc, k, sr, h->bf);  // chains FIRST: train_pcd.jl:14-16
     else if (h->bf) {
         // classifier: gradient uses the chains as they are (train_pcd.jl:57-86); their transposes and
@@ -943,7 +1072,8 @@ void pcd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT,
     HiddenOut ho; ho.prob = &h->phd; ho.prob_T = true; ho.bg_what = 1; ho.bg_sign = 1.f; ho.pscale = ps;  // conditional_prob_h(v_data[, y_data])
     const bool fused_recon = h->step_recon_wanted && !clf && !h->gaussian && Nc == B;
     if (fused_recon) ho.prob_rm = true;  // the reconstruction below reads p(h | x) row-major
-    op_hidden(h, xb, B, h->VL, ho, Rng(), row0);
+    try { op_hidden(h, xb, B, h->VL, ho, Rng(), row0); } catch (...) { if (fuse_pos) { h->rec_depth = 0; h->rec->prog.n_steps = 0; } throw; }
+    if (fuse_pos) chain_end(h);
     if (fused_recon) {  // reconstruct(x) = sigma(a + W p(h | x)) against x, squared error summed into dscal[0] (src/rbm.jl:220-224)
         QB_CUDA(cudaMemsetAsync(h->dscal, 0, sizeof(double), h->stream));
         VisibleOut vo; vo.state = &h->vm; vo.sample = false; vo.state_rm = !h->bf; vo.ref = &xb; vo.sqerr = h->dscal;
@@ -969,8 +1099,10 @@ void cd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, 
     if (ev) QB_CUDA(cudaEventRecord(ev[0], h->stream));
     // positive phase fused with the first hidden sample of the chain (same p(h | v_data[, y_data]))
     HiddenOut h0; h0.prob = &h->phd; h0.prob_T = true; h0.bg_what = 1; h0.bg_sign = 1.f; h0.state = &h->hs; h0.state_rm = true;
+    {
+    ChainRegion region(h);   // bf16: the 2k+1 forward contractions run as one persistent kernel (with phase timing: per launch)
     op_hidden(h, xb, B, h->VL, h0, sr.hidden(0), row0);
-    if (ev) QB_CUDA(cudaEventRecord(ev[1], h->stream));
+    if (ev) { chain_flush(h); QB_CUDA(cudaEventRecord(ev[1], h->stream)); }
     for (int64_t s = 0; s < k; s++) {
         const bool last = (s == k - 1);
         if (s > 0) {
@@ -983,6 +1115,7 @@ void cd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, 
     // h_model = conditional_prob_h(rbm, v_model): probabilities, 2-arg form (ignores y_model, train_cd.jl:34)
     HiddenOut hm; hm.prob = &h->phm; hm.prob_T = true; hm.bg_what = 1; hm.bg_sign = -1.f;
     op_hidden(h, h->vm, B, h->V, hm, Rng(), row0);
+    }
     if (ev) QB_CUDA(cudaEventRecord(ev[2], h->stream));
     op_grad(h, h->phd, xb, xbT, xb_ldT, h->phm, h->vm, B, B, 1.f);
     op_update(h, lr, llr, B);
@@ -1172,6 +1305,7 @@ int32_t qb_destroy(qb_handle *h) {
                     cudaIpcCloseMemHandle(h->peerG[r]); cudaIpcCloseMemHandle(h->peerWb[r]); cudaIpcCloseMemHandle(h->peerWbT[r]);
                     cudaIpcCloseMemHandle(h->peerFlags[r]); cudaIpcCloseMemHandle(h->peerP[r]);
                 }
+        cudaFree(h->chain_cnt); if (h->chain_err_host) cudaFreeHost(h->chain_err_host); delete h->rec;
         cudaFree(h->p2p_flags); cudaFree(h->p2p_grid_bar); cudaFree(h->p2p_ns);
         cudaFree(h->P); dfree(h->G); cudaFree(h->Vel); cudaFree(h->P_best); cudaFree(h->F); cudaFree(h->F2); cudaFree(h->P_eff); cudaFree(h->W2); cudaFree(h->online_vec); cudaFree(h->online_bar); cudaFree(h->online_ns); dfree(h->Wb); cudaFree(h->WbT);
         cudaFree(h->bits_loc); cudaFree(h->bits_all); cudaFree(h->cvT_all); cudaFree(h->chT_all);
@@ -1370,7 +1504,7 @@ int32_t qb_pcd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, dou
         Mat xb; const bf16 *xbT; int64_t ldT;
         batch_view(h, batch_index, B, xb, xbT, ldT);
         pcd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, nullptr);
-        if (!h->async_steps) QB_CUDA(cudaStreamSynchronize(h->stream));
+        if (!h->async_steps) { QB_CUDA(cudaStreamSynchronize(h->stream)); chain_check_error(h); }
     });
 }
 
@@ -1381,7 +1515,7 @@ int32_t qb_cd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, doub
         Mat xb; const bf16 *xbT; int64_t ldT;
         batch_view(h, batch_index, B, xb, xbT, ldT);
         cd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, nullptr);
-        if (!h->async_steps) QB_CUDA(cudaStreamSynchronize(h->stream));
+        if (!h->async_steps) { QB_CUDA(cudaStreamSynchronize(h->stream)); chain_check_error(h); }
     });
 }
 
@@ -1937,6 +2071,12 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
             h->state_exchange = value != 0.0;
             if (h->state_exchange) ensure_overlap_resources(h);  // collective (communicator split)
             h->gemm_sms = ((h->stale_chains || h->state_exchange) && h->comm_overlap) ? std::max(2, (h->num_sms - QB_OVERLAP_CTAS) & ~1) : h->num_sms;
+        } else if (!strcmp(key, "fused_chain")) {
+            h->fused_chain = value != 0.0;
+        } else if (!strcmp(key, "chain_bn")) {
+            const int bn = (int)value;
+            QB_CHECK(bn == 0 || bn == 64 || bn == 128 || bn == 256, QB_E_ARG, "chain_bn must be 0/64/128/256");
+            h->chain_bn = bn;
         } else if (!strcmp(key, "fast_pcd_pair_chains")) {
             h->fast_pcd_pair_chains = value != 0.0;
         } else if (!strcmp(key, "stale_chains")) {
@@ -1984,7 +2124,7 @@ int32_t qb_get_update_timing(qb_handle *h, int64_t *timed_updates, double *timed
     });
 }
 int32_t qb_sync(qb_handle *h) {
-    return guarded([&] { QB_H_KEEP(h); wait_pending_update(h); QB_CUDA(cudaStreamSynchronize(h->stream)); });
+    return guarded([&] { QB_H_KEEP(h); wait_pending_update(h); QB_CUDA(cudaStreamSynchronize(h->stream)); chain_check_error(h); });
 }
 int32_t qb_timer_start(qb_handle *h) {
     return guarded([&] { QB_H_KEEP(h); QB_CUDA(cudaEventRecord(h->timer_ev[0], h->stream)); });
@@ -1998,6 +2138,7 @@ int32_t qb_timer_stop(qb_handle *h, double *elapsed_ms) {
         float t = 0.f;
         QB_CUDA(cudaEventElapsedTime(&t, h->timer_ev[0], h->timer_ev[1]));
         *elapsed_ms = t;
+        chain_check_error(h);
     });
 }
 

@@ -36,7 +36,8 @@ constexpr int SMEM_AB_BUDGET = 192 * 1024;
 enum { EPI_SAMPLE = 0, EPI_GRAD = 1 };
 // kernel specialisations: generic epilogue, gradient store, and the two compile-time fast paths
 // (numbering = QB_GEMM_KIND_* of include/qarbom_b200.h)
-enum { K_GENERIC = 0, K_GRAD = 1, K_FAST_SAMPLE = 2, K_FAST_PROB = 3, K_FAST_SAMPLE_PROB = 4, K_FAST_GAUSS = 5, K_FAST_LABEL = 6 };
+enum { K_GENERIC = 0, K_GRAD = 1, K_FAST_SAMPLE = 2, K_FAST_PROB = 3, K_FAST_SAMPLE_PROB = 4, K_FAST_GAUSS = 5, K_FAST_LABEL = 6,
+       K_CHAIN = 7 /* histogram slot of the multi-half-step kernel (sm100_chain.cuh), not an epilogue */ };
 // Epilogue warpgroups per CTA: the lean epilogues are latency-bound with 2 warps per scheduler
 // (ncu: IPC 0.3, epilogue time ~ MMA time), so they run 4 warpgroups (16 warps, 64 columns each at
 // BN = 256); the register-hungry generic epilogue keeps 2.

@@ -113,11 +113,24 @@ def _host_rbm(q, m):
     return r
 
 
-def test_cfg5_pcd1_half_steps_and_update_match_oracle(q, cfg5):
+def _assert_kernels(hist, fused, width, per_launch):
+    """Which kernels produced the step: the persistent multi-half-step kernel (+ the gradient GEMM), or -- option
+    fused_chain = 0 -- one launch per contraction with the lean compile-time epilogues."""
+    if fused:
+        assert hist.get(("2cta", width, "chain")) == 1 and hist.get(("2cta", 256, "grad")) == 1 and sum(hist.values()) == 2, hist
+    else:
+        for key, n in per_launch.items():
+            assert hist.get(("2cta", width, key)) == n, hist
+        assert sum(hist.values()) == sum(per_launch.values()), hist
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+def test_cfg5_pcd1_half_steps_and_update_match_oracle(q, cfg5, fused):
     m0, X, cv0, ch0, rows = cfg5
     m = qo.copy_rbm(m0)
     lr = 0.01
     with q.DeviceRBM(_host_rbm(q, m), max_batch=B5, precision="bf16", seed=SEED) as dev:
+        dev.set_option("fused_chain", fused)
         dev.set_data(X)
         dev.init_chains(B5, cv0, ch0)
         eps = _probability_error(dev, m, X[rows].astype(np.float64))
@@ -128,9 +141,8 @@ def test_cfg5_pcd1_half_steps_and_update_match_oracle(q, cfg5):
             dev.reset_counters()
             dev.pcd_step(0, B5, 1, lr)
             hist = dev.gemm_histogram()
-            # the benchmarked specialisations: pair kernel, 256-wide tiles, lean sampling / probability / gradient epilogues
-            assert hist.get(("2cta", 256, "fast_sample")) == 2 and hist.get(("2cta", 256, "fast_prob")) == 1 \
-                and hist.get(("2cta", 256, "grad")) == 1 and sum(hist.values()) == 4, hist
+            # the benchmarked kernels: pair kernel, 256-wide tiles, lean sampling / probability / gradient epilogues
+            _assert_kernels(hist, fused, 256, {"fast_sample": 2, "fast_prob": 1, "grad": 1})
             dv, dh = _rows_of(dev, BLOCKS5)
             # gibbs_sample_hidden (src/gibbs.jl:3-6) from the device's own previous visible states ...
             inband += _check_bernoulli(f"step {t} hidden", dh, _p_hidden(m, v_prev), philox_ref.uniforms(SEED, draw, rows, H5), guard)
@@ -161,10 +173,12 @@ def test_cfg5_pcd1_half_steps_and_update_match_oracle(q, cfg5):
     print(f"cfg5 PCD-1: 3 steps x {rows.size} rows x {V5 + H5} units, guard {guard:.1e}, {inband} in-band disagreements")
 
 
-def test_cfg5_pcd10_single_call_matches_oracle_on_row_subset(q, cfg5):
+@pytest.mark.parametrize("fused", [1, 0])
+def test_cfg5_pcd10_single_call_matches_oracle_on_row_subset(q, cfg5, fused):
     m, X, cv0, ch0, rows = cfg5
     k = 10
     with q.DeviceRBM(_host_rbm(q, m), max_batch=B5, precision="bf16", seed=SEED) as dev:
+        dev.set_option("fused_chain", fused)
         dev.set_data(X)
         dev.init_chains(B5, cv0, ch0)
         eps = _probability_error(dev, m, X[rows].astype(np.float64))
@@ -172,9 +186,7 @@ def test_cfg5_pcd10_single_call_matches_oracle_on_row_subset(q, cfg5):
         guard = max(4 * eps, 2e-6)
         dev.reset_counters()
         dev.pcd_step(0, B5, k, 0.01)      # the chains advance BEFORE the update (train_pcd.jl:14-16): W is m.W throughout
-        hist = dev.gemm_histogram()
-        assert hist.get(("2cta", 256, "fast_sample")) == 2 * k and hist.get(("2cta", 256, "fast_prob")) == 1 \
-            and hist.get(("2cta", 256, "grad")) == 1, hist
+        _assert_kernels(dev.gemm_histogram(), fused, 256, {"fast_sample": 2 * k, "fast_prob": 1, "grad": 1})
         dv, dh = _rows_of(dev, BLOCKS5)
     # _update_fantasy_data! (src/fantasy_data.jl:12-19) for the row subset, remembering how close every draw came to its p
     v = cv0[rows]
@@ -243,7 +255,8 @@ def test_cfg3_gaussian_half_steps_match_oracle(q, cfg3):
             _sync_from_device(m, dev)
 
 
-def test_cfg3_cd5_step_matches_oracle(q, cfg3):
+@pytest.mark.parametrize("fused", [1, 0])
+def test_cfg3_cd5_step_matches_oracle(q, cfg3, fused):
     """Two CD-5 mini-batch steps at the cfg3 shape against the oracle's batched formulation (tested equal to the
     per-sample restatement of src/training/train_cd.jl:2-21) fed the same Philox numbers, with the oracle storing
     Gaussian states in bf16 like the device."""
@@ -251,6 +264,7 @@ def test_cfg3_cd5_step_matches_oracle(q, cfg3):
     m = qo.copy_rbm(m0)
     lr = 0.002
     with q.DeviceRBM(_host_rbm(q, m), max_batch=B3, precision="bf16", seed=SEED) as dev:
+        dev.set_option("fused_chain", fused)
         dev.set_data(X)
         draw = 0
         for t in range(2):
@@ -262,9 +276,11 @@ def test_cfg3_cd5_step_matches_oracle(q, cfg3):
             dev.reset_counters()
             dev.cd_step(t, B3, K3, lr)
             hist = dev.gemm_histogram()
-            assert sum(hist.values()) == 2 * K3 + 2 and all(key[0] != "simt" for key in hist), hist
-            # the Gaussian visible half-steps run the compile-time Box-Muller epilogue, not the generic one
-            assert sum(n for key, n in hist.items() if key[2] == "fast_gauss") == K3 and not any(key[2] == "generic" for key in hist), hist
+            if fused:   # 2k+1 forward contractions in one persistent launch + the gradient GEMM
+                assert sum(n for key, n in hist.items() if key[2] == "chain") == 1 and sum(hist.values()) == 2, hist
+            else:       # the Gaussian visible half-steps run the compile-time Box-Muller epilogue, not the generic one
+                assert sum(hist.values()) == 2 * K3 + 2 and not any(key[2] == "generic" or key[0] == "simt" for key in hist), hist
+                assert sum(n for key, n in hist.items() if key[2] == "fast_gauss") == K3, hist
             Wd0 = dev.rbm.W.copy()      # the device's fp32 master before the step (the oracle restarts from its bf16 rounding)
             dev.pull_params()
             r = dev.rbm
@@ -297,13 +313,15 @@ def _host_clf(q, m):
     return r
 
 
-def test_cfg4_classifier_cd1_step_matches_oracle(q, cfg4):
+@pytest.mark.parametrize("fused", [1, 0])
+def test_cfg4_classifier_cd1_step_matches_oracle(q, cfg4, fused):
     """Two CD-1 steps of the RBMClassifier at the cfg4 shape (src/training/train_cd.jl:23-43 with the mini-batch extension):
     3-arg positive phase, label units sampled as independent Bernoullis of the softmax, 2-arg negative hidden."""
     m0, X, Y = cfg4
     m = qo.copy_rbm(m0)
     lr, llr = 0.01, 0.02
     with q.DeviceRBM(_host_clf(q, m), max_batch=B4, precision="bf16", seed=SEED) as dev:
+        dev.set_option("fused_chain", fused)
         dev.set_data(X, Y)
         draw = 0
         for t in range(2):
@@ -315,9 +333,14 @@ def test_cfg4_classifier_cd1_step_matches_oracle(q, cfg4):
             qo.batched_step(m, X[sl], Y[sl], "CD", 1, lr, llr, U_h=U_h, U_v=U_vy[None, :, :V4], U_y=U_vy[None, :, V4:])
             dev.reset_counters()
             dev.cd_step(t, B4, 1, lr, llr)
-            hist = dev.gemm_histogram()      # label units are finished inside the visible GEMM's epilogue: 4 GEMMs + 1 update
-            assert sum(n for key, n in hist.items() if key[2] == "fast_label") == 1 and not any(key[2] == "generic" for key in hist), hist
-            assert dev.counters()[0] <= 6, dev.counters()   # (+ one accumulator-init launch on the very first step)
+            hist = dev.gemm_histogram()      # label units are finished inside the visible GEMM's epilogue, no side kernel
+            assert not any(key[2] == "generic" for key in hist), hist
+            if fused:
+                assert sum(n for key, n in hist.items() if key[2] == "chain") == 1 and sum(hist.values()) == 2, hist
+                assert t == 0 or dev.counters()[0] <= 3, dev.counters()   # chain + gradient + update
+            else:
+                assert sum(n for key, n in hist.items() if key[2] == "fast_label") == 1 and sum(hist.values()) == 4, hist
+                assert t == 0 or dev.counters()[0] <= 5, dev.counters()   # (the first step also builds the transposed data copies)
             Wd0, Ud0 = dev.rbm.W.copy(), dev.rbm.U.copy()   # the device's fp32 masters before the step
             dev.pull_params()
             r = dev.rbm
