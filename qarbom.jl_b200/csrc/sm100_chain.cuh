@@ -38,7 +38,7 @@ struct ChainStep {
     EpiParams ep;
 };
 struct ChainProgram {
-    int n_steps, N, tiles_n, total_tiles;
+    int n_steps, N, tiles_n, total_tiles, n_maps;
     unsigned int *counters;      // [n_steps][tiles_n], zero at launch
     unsigned int *error_flag;    // mapped host memory: set when a dependency poll expired
     unsigned int *abort_flag;    // device copy of the same: once set, no poll of this or a later launch waits again
@@ -79,7 +79,7 @@ gibbs_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant
     const int total_tiles = prog.total_tiles, tiles_n = prog.tiles_n;
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < CHAIN_MAX_MAPS; i++) prefetch_tmap(&maps.m[i]);
+        for (int i = 0; i < prog.n_maps; i++) prefetch_tmap(&maps.m[i]);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::STAGES; s++) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
@@ -264,6 +264,7 @@ struct ChainBuilder {
         S.ep = ep;
         S.dep_count = dep >= 0 ? prog.step[dep].tiles_m * 2 * 4 * Shape<256, K_FAST_SAMPLE>::WGS : 0;
         prog.total_tiles += S.tiles_m * prog.tiles_n;
+        prog.n_maps = n_maps;
         flops += 2.0 * (double)ep.M * (double)ep.N * (double)A.k;
         return prog.n_steps++;
     }
