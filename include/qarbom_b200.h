@@ -162,8 +162,10 @@ int32_t qb_cd_step_host(qb_handle *h, const void *X, int32_t x_dtype, const void
 
 /* Pipelining hint for the two calls above: X/Y of the NEXT qb_*_step_host call.  Its upload starts on
  * a copy stream inside the next step call and overlaps that step's kernels; the call after that, given
- * the same X pointer and B, consumes it without a fresh copy.  The hinted host buffers (pinned memory
- * for a truly asynchronous copy) must stay valid until the call that consumes them returns. */
+ * the same X / Y pointers, element types and B, consumes it without a fresh copy (any mismatch falls back to a fresh
+ * upload).  The hinted host buffers (pinned memory for a truly asynchronous copy) must stay valid AND UNCHANGED from the
+ * step call that starts their upload until the call that consumes them returns: the copy engine reads them in between,
+ * a buffer refilled in that window trains on a mix of old and new contents. */
 int32_t qb_set_next_host_batch(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype);
 
 /* evaluate + _evaluate(MeanSquaredError) + reconstruct (src/evaluation.jl:16-20,52-70;

@@ -32,6 +32,7 @@ struct P2pParams {
     unsigned int epoch;                 // flag value of the first barrier of this launch (second = epoch + 1)
     unsigned int *grid_bar;
     unsigned long long *phase_ns;       // [2] accumulated ns: waiting for the peers' gradients, reduce + update + push
+    unsigned int *timeout_flag;         // mapped host memory: set when a peer did not show up within the deadline
 };
 
 __device__ __forceinline__ void xgpu_barrier(const P2pParams &p, unsigned int value) {
@@ -41,9 +42,18 @@ __device__ __forceinline__ void xgpu_barrier(const P2pParams &p, unsigned int va
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(value) : "memory");
         const unsigned int *mine = p.flags[p.rank] + threadIdx.x;
         unsigned int seen;
+        // bounded wait: a peer that threw, ran a different number of steps or died must not wedge this GPU.  After the
+        // deadline (~5 s) the rank raises a host-visible flag and carries on; p2p_update turns it into QB_E_CUDA.
+        const unsigned long long t0 = gtimer();
+        unsigned int spins = 0;
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-        } while ((int)(seen - value) < 0);
+            if ((int)(seen - value) >= 0) break;
+            if ((++spins & 1023u) == 0u && gtimer() - t0 > 5000000000ull) {
+                if (p.timeout_flag) *(volatile unsigned int *)p.timeout_flag = 1u;
+                break;
+            }
+        } while (true);
     }
     __syncthreads();
 }

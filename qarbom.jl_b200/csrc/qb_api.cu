@@ -164,7 +164,7 @@ struct qb_handle {
     // host-batch prefetch (qb_set_next_host_batch): second staging matrix filled on copy_stream while a step runs
     Mat hb2; void *staging2 = nullptr; size_t staging2_bytes = 0;
     const void *next_X = nullptr, *next_Y = nullptr; int next_xdt = 0, next_ydt = 0;   // hint for the next step_host call
-    const void *pf_X = nullptr; int64_t pf_B = 0; bool pf_valid = false; cudaEvent_t ev_pf = nullptr;
+    const void *pf_X = nullptr, *pf_Y = nullptr; int pf_xdt = 0, pf_ydt = 0; int64_t pf_B = 0; bool pf_valid = false; cudaEvent_t ev_pf = nullptr;
     float *pre_h = nullptr, *pre_v = nullptr, *lab_pre = nullptr, *softplus_rows = nullptr;
     float *out_f32 = nullptr;  // fp32 [Bmax][max(ldv, ldh)] API output staging
     float *znoise = nullptr;   // fp32 [Bmax][V] injected reconstruct noise (Gaussian visibles)
@@ -182,6 +182,7 @@ struct qb_handle {
     bf16 *peerWb[QB_MAX_PEERS] = {}, *peerWbT[QB_MAX_PEERS] = {};
     unsigned int *peerFlags[QB_MAX_PEERS] = {}, *p2p_flags = nullptr, *p2p_grid_bar = nullptr;
     unsigned int p2p_epoch = 1; unsigned long long *p2p_ns = nullptr; int p2p_blocks_per_sm = 3;
+    unsigned int *p2p_timeout_host = nullptr, *p2p_timeout_dev = nullptr;
     int64_t shard_rows = 0;
     // NCCL variant of the sharded update (option "sharded_update", bf16, H % world == 0): reduce-scatter of the fp32
     // gradient, update of the owned hidden rows only, all-gather of the bf16 shadow, local transpose.  Moves 3/4 of the
@@ -193,7 +194,7 @@ struct qb_handle {
     double gemm_flops = 0.0;
     int force_bn = 0, use_2cta = 1;
     // fused chain launches (sm100_chain.cuh): half-steps recorded between chain_begin / chain_end run as ONE persistent kernel
-    bool fused_chain = true; int chain_bn = 0;      // options "fused_chain", "chain_bn" (0 = automatic)
+    int fused_chain_mode = 1; int chain_bn = 0;     // options "fused_chain" (0 never, 1 automatic, 2 always), "chain_bn" (0 = automatic)
     int rec_depth = 0; sm100::ChainBuilder *rec = nullptr;
     unsigned int *chain_cnt = nullptr; int64_t chain_cnt_region = 0, chain_launch_no = 0;
     unsigned int *chain_err_host = nullptr, *chain_err_dev = nullptr;
@@ -202,6 +203,7 @@ struct qb_handle {
     bool time_gemms = false;    // bracket every GEMM launch with CUDA events on the launching stream
     std::vector<cudaEvent_t> gemm_ev; size_t gemm_ev_used = 0; int64_t gemm_timed = 0; double gemm_timed_flops = 0.0;
     cudaEvent_t timer_ev[2] = {};
+    std::vector<cudaEvent_t> epoch_ev;   // 5 per mini-batch step of a timed epoch, resolved after the epoch
     std::vector<cudaEvent_t> upd_ev; size_t upd_ev_used = 0; int64_t upd_timed = 0;
 };
 
@@ -393,7 +395,14 @@ struct ChainRegion {   // records the half-steps issued inside a scope, launches
 int chain_tile_width(qb_handle *h, int64_t N) {
     if (h->chain_bn) return h->chain_bn;
     if (h->force_bn >= 64) return h->force_bn;
-    return N >= 2048 ? 256 : 128;
+    return N >= 1024 ? 256 : (N > 64 ? 128 : 64);
+}
+// Measured (tools/chain_probe.py, profiles/r2_chain_probe.txt): the pair-tile chain wins where a half-step is more than one wave
+// of 256 x 256 pair tiles (cfg5: 2048 rows -17 %, 8192 rows -1 %), ties at exactly one partial wave (1024 rows) and loses on
+// small models, whose half-steps want many small single-CTA tiles.  Option "fused_chain": 1 = automatic, 2 = always, 0 = never.
+bool chain_pays(qb_handle *h, const sm100::EpiParams &ep) {
+    if (h->fused_chain_mode == 2) return true;
+    return (int64_t)ceil_div(ep.N, 256) * ceil_div(ep.M, 256) >= h->gemm_sms / 2;
 }
 
 void launch_single(qb_handle *h, const sm100::Operand &A, const sm100::Operand &B, const sm100::EpiParams &ep, double flops) {
@@ -424,7 +433,8 @@ bool chain_hazard_free(const sm100::ChainBuilder &cb, const sm100::Operand &B, c
 
 // one fused half-step GEMM of the bf16 path: recorded into the open chain region, or launched right away
 void gemm_half_step(qb_handle *h, const sm100::Operand &A, const sm100::Operand &B, const sm100::EpiParams &ep, double flops) {
-    const bool can_chain = h->rec_depth > 0 && h->fused_chain && h->use_2cta != 0 && h->force_bn != 32 && sm100::chainable(ep);
+    const bool can_chain = h->rec_depth > 0 && h->fused_chain_mode != 0 && h->use_2cta != 0 && h->force_bn != 32 && sm100::chainable(ep) &&
+                           chain_pays(h, ep);
     if (h->rec_depth > 0 && !can_chain) chain_flush(h);
     if (!can_chain) { launch_single(h, A, B, ep, flops); return; }
     sm100::ChainBuilder &cb = *h->rec;
@@ -481,6 +491,10 @@ void chain_flush(qb_handle *h) {
 }
 
 void chain_check_error(qb_handle *h) {
+    if (h->p2p_timeout_host && *(volatile unsigned int *)h->p2p_timeout_host) {
+        *h->p2p_timeout_host = 0u;
+        throw Error(QB_E_CUDA, "peer-memory exchange: a peer rank did not reach the gradient barrier within 5 s (ranks out of step or a rank died); parameters are invalid");
+    }
     if (h->chain_err_host && *(volatile unsigned int *)h->chain_err_host) {
         *h->chain_err_host = 0u;
         cudaMemsetAsync(h->chain_cnt + (size_t)QB_CHAIN_REGIONS * h->chain_cnt_region, 0, sizeof(unsigned int), h->stream);
@@ -757,6 +771,16 @@ void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local) {
     p.lr = (float)(lr / Bg); p.llr = (float)(llr / Bg); p.momentum = (float)h->momentum; p.wd = (float)h->weight_decay;
     p.epoch = h->p2p_epoch; h->p2p_epoch += 2;
     p.grid_bar = h->p2p_grid_bar; p.phase_ns = h->p2p_ns;
+    if (!h->p2p_timeout_host) {
+        QB_CUDA(cudaHostAlloc((void **)&h->p2p_timeout_host, sizeof(unsigned int), cudaHostAllocMapped));
+        *h->p2p_timeout_host = 0u;
+        QB_CUDA(cudaHostGetDevicePointer((void **)&h->p2p_timeout_dev, h->p2p_timeout_host, 0));
+    }
+    if (*(volatile unsigned int *)h->p2p_timeout_host) {   // raised by an earlier launch: the peers are out of step
+        *h->p2p_timeout_host = 0u;
+        throw Error(QB_E_CUDA, "peer-memory exchange: a peer rank did not reach the gradient barrier within 5 s (ranks out of step or a rank died); parameters are invalid");
+    }
+    p.timeout_flag = h->p2p_timeout_dev;
     const int p2p_grid = h->num_sms * h->p2p_blocks_per_sm;
     QB_CUDA(cudaMemsetAsync(h->p2p_grid_bar, 0, sizeof(unsigned int), h->stream));
     size_t ei = 0; bool timed = false;
@@ -1140,7 +1164,9 @@ void batch_view(qb_handle *h, int64_t m, int64_t B, Mat &xb, const bf16 *&xbT, i
 void stage_host_batch(qb_handle *h, const void *X, int xdt, const void *Y, int ydt, int64_t B) {
     QB_CHECK(X != nullptr, QB_E_ARG, "X is NULL");
     QB_CHECK(h->L == 0 || Y != nullptr, QB_E_ARG, "labels required for classifier models");
-    if (h->pf_valid && h->pf_X == X && h->pf_B == B) {
+    const bool hit = h->pf_valid && h->pf_X == X && h->pf_B == B && h->pf_xdt == xdt && (h->L == 0 || (h->pf_Y == Y && h->pf_ydt == ydt));
+    if (h->pf_valid && !hit) QB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pf, 0));   // hb2 / staging2 are still being filled: order the reuse after it
+    if (hit) {
         // this batch was uploaded on copy_stream while the previous step was computing
         QB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_pf, 0));
         std::swap(h->hb, h->hb2);
@@ -1164,7 +1190,7 @@ void stage_host_batch(qb_handle *h, const void *X, int xdt, const void *Y, int y
             h->launches++;
         }
         QB_CUDA(cudaEventRecord(h->ev_pf, h->copy_stream));
-        h->pf_X = h->next_X; h->pf_B = B; h->pf_valid = true;
+        h->pf_X = h->next_X; h->pf_Y = h->next_Y; h->pf_xdt = h->next_xdt; h->pf_ydt = h->next_ydt; h->pf_B = B; h->pf_valid = true;
         h->next_X = nullptr; h->next_Y = nullptr;
     }
 }
@@ -1306,7 +1332,7 @@ int32_t qb_destroy(qb_handle *h) {
                     cudaIpcCloseMemHandle(h->peerFlags[r]); cudaIpcCloseMemHandle(h->peerP[r]);
                 }
         cudaFree(h->chain_cnt); if (h->chain_err_host) cudaFreeHost(h->chain_err_host); delete h->rec;
-        cudaFree(h->p2p_flags); cudaFree(h->p2p_grid_bar); cudaFree(h->p2p_ns);
+        cudaFree(h->p2p_flags); cudaFree(h->p2p_grid_bar); cudaFree(h->p2p_ns); if (h->p2p_timeout_host) cudaFreeHost(h->p2p_timeout_host);
         cudaFree(h->P); dfree(h->G); cudaFree(h->Vel); cudaFree(h->P_best); cudaFree(h->F); cudaFree(h->F2); cudaFree(h->P_eff); cudaFree(h->W2); cudaFree(h->online_vec); cudaFree(h->online_bar); cudaFree(h->online_ns); dfree(h->Wb); cudaFree(h->WbT);
         cudaFree(h->bits_loc); cudaFree(h->bits_all); cudaFree(h->cvT_all); cudaFree(h->chT_all);
         dfree(h->Wb_alt); cudaFree(h->WbT_alt); dfree(h->G_alt); cudaFree(h->bias_buf[0]); cudaFree(h->bias_buf[1]);
@@ -1321,6 +1347,7 @@ int32_t qb_destroy(qb_handle *h) {
         for (auto &e : h->ev) cudaEventDestroy(e);
         for (auto &e : h->timer_ev) cudaEventDestroy(e);
         for (auto &e : h->gemm_ev) cudaEventDestroy(e);
+        for (auto &e : h->epoch_ev) cudaEventDestroy(e);
         for (auto &e : h->upd_ev) cudaEventDestroy(e);
         cudaStreamDestroy(h->stream); cudaStreamDestroy(h->copy_stream);
         delete h;
@@ -1668,27 +1695,53 @@ static void epoch_impl(qb_handle *h, bool pcd, int64_t B, int64_t k, double lr, 
     QB_CHECK(h->N > 0, QB_E_STATE, "qb_set_data has not been called");
     const int64_t nb = h->N / B;  // _set_mini_batches: trailing remainder dropped -- all of it when N < B (src/utils.jl:13-26)
     double t[3] = {0, 0, 0};
-    for (int64_t m = 0; m < nb; m++) {
-        Mat xb; const bf16 *xbT; int64_t ldT;
-        batch_view(h, m, B, xb, xbT, ldT);
-        const bool timed = (times != nullptr) && !(pcd && h->stale_chains);  // the overlapped step has no phase boundaries
-        if (pcd) pcd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, timed ? h->ev : nullptr);
-        else cd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, timed ? h->ev : nullptr);
-        if (timed) {
-            QB_CUDA(cudaStreamSynchronize(h->stream));
+    // Phase times come from CUDA events recorded around the phases of every step and resolved AFTER the epoch (in chunks of
+    // QB_EPOCH_EV_STEPS steps): no host synchronisation between mini-batches, the stream stays full.
+    const bool timed = (times != nullptr) && !(pcd && h->stale_chains);  // the overlapped step has no phase boundaries
+    constexpr int64_t QB_EPOCH_EV_STEPS = 1024;
+    auto resolve = [&](int64_t n_steps) {
+        QB_CUDA(cudaStreamSynchronize(h->stream));
+        for (int64_t i = 0; i < n_steps; i++) {
+            cudaEvent_t *e = h->epoch_ev.data() + 5 * i;
             float a = 0, b = 0, c = 0, d = 0;
-            QB_CUDA(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
-            QB_CUDA(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
-            QB_CUDA(cudaEventElapsedTime(&c, h->ev[2], h->ev[3]));
+            QB_CUDA(cudaEventElapsedTime(&a, e[0], e[1]));
+            QB_CUDA(cudaEventElapsedTime(&b, e[1], e[2]));
+            QB_CUDA(cudaEventElapsedTime(&c, e[2], e[3]));
             if (pcd) {
-                QB_CUDA(cudaEventElapsedTime(&d, h->ev[3], h->ev[4]));
+                QB_CUDA(cudaEventElapsedTime(&d, e[3], e[4]));
                 t[1] += (a + d) * 1e-3; t[0] += b * 1e-3; t[2] += c * 1e-3;  // gibbs, sample, update
             } else {
                 t[0] += a * 1e-3; t[1] += b * 1e-3; t[2] += c * 1e-3;
             }
         }
+    };
+    // long epochs of short steps: the phase split is sampled on every 16th mini-batch (event records between the launches of
+    // a 30 us step cost a tenth of it) and scaled to the event-timed duration of the whole epoch
+    const int64_t stride = nb > 64 ? 16 : 1;
+    if (timed) QB_CUDA(cudaEventRecord(h->ev[6], h->stream));
+    int64_t pending = 0;
+    for (int64_t m = 0; m < nb; m++) {
+        Mat xb; const bf16 *xbT; int64_t ldT;
+        batch_view(h, m, B, xb, xbT, ldT);
+        cudaEvent_t *ev = nullptr;
+        if (timed && m % stride == 0) {
+            while ((int64_t)h->epoch_ev.size() < 5 * (pending + 1)) { cudaEvent_t e; QB_CUDA(cudaEventCreate(&e)); h->epoch_ev.push_back(e); }
+            ev = h->epoch_ev.data() + 5 * pending;
+        }
+        if (pcd) pcd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, ev);
+        else cd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, ev);
+        if (ev && ++pending == QB_EPOCH_EV_STEPS) { resolve(pending); pending = 0; }
     }
+    if (timed) QB_CUDA(cudaEventRecord(h->ev[7], h->stream));
+    if (timed && pending) resolve(pending);
     QB_CUDA(cudaStreamSynchronize(h->stream));
+    chain_check_error(h);
+    if (timed && nb > 0) {
+        float total = 0.f;
+        QB_CUDA(cudaEventElapsedTime(&total, h->ev[6], h->ev[7]));
+        const double sum = t[0] + t[1] + t[2];
+        if (stride > 1 && sum > 0) { const double f = total * 1e-3 / sum; t[0] *= f; t[1] *= f; t[2] *= f; }
+    }
     if (times) { times[0] = t[0]; times[1] = t[1]; times[2] = t[2]; }
 }
 
@@ -2072,7 +2125,8 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
             if (h->state_exchange) ensure_overlap_resources(h);  // collective (communicator split)
             h->gemm_sms = ((h->stale_chains || h->state_exchange) && h->comm_overlap) ? std::max(2, (h->num_sms - QB_OVERLAP_CTAS) & ~1) : h->num_sms;
         } else if (!strcmp(key, "fused_chain")) {
-            h->fused_chain = value != 0.0;
+            QB_CHECK(value == 0.0 || value == 1.0 || value == 2.0, QB_E_ARG, "fused_chain must be 0, 1 or 2");
+            h->fused_chain_mode = (int)value;
         } else if (!strcmp(key, "chain_bn")) {
             const int bn = (int)value;
             QB_CHECK(bn == 0 || bn == 64 || bn == 128 || bn == 256, QB_E_ARG, "chain_bn must be 0/64/128/256");

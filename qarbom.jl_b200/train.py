@@ -70,7 +70,8 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
           fast_label_learning_rate: float = 0.1, metrics=None,
           early_stopping: bool = False, store_best_rbm: bool = True, patience: int = 10,
           stopping_metric=None, x_test_dataset=None, y_test_dataset=None, file_path: Optional[str] = None,
-          # ---- extensions (defaults reproduce the reference)
+          # ---- extensions.  Their defaults reproduce the reference's SEMANTICS; the arithmetic defaults to the bf16 production
+          # mode (increments within 2e-2 of Float64).  precision="fp32" is the validation mode (1e-5 of Float64).
           momentum: float = 0.0, weight_decay: float = 0.0, precision: str = "bf16", seed: int = 0, device: int = 0,
           n_chains: Optional[int] = None,
           verbose: bool = True, chains_init=None) -> dict:

@@ -22,7 +22,7 @@ nb = 4
 for B in [int(a) for a in sys.argv[2:]] or CFG["rows"]:
     X = rng.standard_normal((nb * B, V)).astype(np.float32) if CFG["g"] else (rng.random((nb * B, V), dtype=np.float32) < 0.5).astype(np.uint8)
     Y = np.eye(L, dtype=np.uint8)[np.arange(nb * B) % L] if L else None
-    for fused, bn in [(0, 0), (1, 0), (1, 64), (1, 128), (1, 256)]:
+    for fused, bn in [(0, 0), (1, 0), (2, 64), (2, 128), (2, 256)]:
         dev = q.DeviceRBM(rbm, max_batch=B, precision="bf16", seed=1)
         dev.set_option("fused_chain", fused); dev.set_option("chain_bn", bn)
         dev.set_data(X, Y)
