@@ -45,6 +45,10 @@ extern "C" {
 /* arithmetic mode */
 #define QB_PREC_FP32 0  /* fp32 CUDA-core kernels: validation mode (1e-5 rel. vs Float64) */
 #define QB_PREC_BF16 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate: production */
+#define QB_PREC_FP32X3 2 /* validation mode ON the tensor cores: every fp32 operand is split into three bf16 components
+                          * (x = hi + mid + lo, 24 mantissa bits), the component products that matter (i + j <= 2) accumulate
+                          * into one fp32 TMEM tile; everything around the contractions is the QB_PREC_FP32 path.  Same
+                          * tolerances as QB_PREC_FP32, 3-6x the MMA work of QB_PREC_BF16. */
 
 /* host element types for datasets */
 #define QB_DT_F64 0
@@ -236,6 +240,9 @@ int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_la
 #define QB_GEMM_KIND_FAST_GAUSS 5  /* Gaussian visibles: mean + Box-Muller normal in the epilogue */
 #define QB_GEMM_KIND_FAST_LABEL 6  /* Bernoulli visibles + label units (softmax + Bernoulli) in the epilogue */
 int32_t qb_get_gemm_histogram(qb_handle *h, int64_t *counts, int32_t n_slots);
+/* Tensor-core flops ISSUED since the last reset: equal to the algorithmic gemm_flops of qb_get_counters except in
+ * QB_PREC_FP32X3, where every contraction issues 3..6 bf16 component products (reported separately). */
+int32_t qb_get_issued_flops(qb_handle *h, double *issued_flops);
 /* with "time_gemms": number and summed CUDA-event duration of the update_w kernel launches */
 int32_t qb_get_update_timing(qb_handle *h, int64_t *timed_updates, double *timed_update_ms);
 int32_t qb_reset_counters(qb_handle *h);

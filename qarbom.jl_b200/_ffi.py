@@ -11,13 +11,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libqarbom_b200.so")
 
 QB_VISIBLE_BERNOULLI, QB_VISIBLE_GAUSSIAN = 0, 1
-QB_PREC_FP32, QB_PREC_BF16 = 0, 1
+QB_PREC_FP32, QB_PREC_BF16, QB_PREC_FP32X3 = 0, 1, 2
 QB_DT_F64, QB_DT_I64, QB_DT_F32, QB_DT_U8 = 0, 1, 2, 3
 
 # every symbol declared by include/qarbom_b200.h
 SYMBOLS = [
     "qb_version", "qb_device_count", "qb_last_error", "qb_create", "qb_destroy", "qb_set_params", "qb_get_params", "qb_snapshot_params", "qb_restore_params",
-    "qb_set_optimizer", "qb_set_data", "qb_init_chains", "qb_get_chains", "qb_get_chain_rows", "qb_get_gemm_histogram", "qb_seed", "qb_inject_streams",
+    "qb_set_optimizer", "qb_set_data", "qb_init_chains", "qb_get_chains", "qb_get_chain_rows", "qb_get_gemm_histogram", "qb_get_issued_flops", "qb_seed", "qb_inject_streams",
     "qb_pcd_step", "qb_cd_step", "qb_pcd_epoch", "qb_cd_epoch", "qb_fast_pcd_epoch", "qb_pcd_step_host", "qb_cd_step_host", "qb_set_next_host_batch", "qb_eval_mse",
     "qb_eval_free_energy", "qb_reconstruct", "qb_conditional_prob_h", "qb_sample_hidden", "qb_sample_visible", "qb_conditional_prob_y_given_v", "qb_comm_unique_id", "qb_comm_init", "qb_p2p_export", "qb_p2p_import", "qb_get_p2p_timing",
     "qb_get_counters", "qb_reset_counters", "qb_set_option", "qb_sync", "qb_timer_start", "qb_timer_stop", "qb_get_update_timing",
@@ -69,6 +69,7 @@ def lib():
         "qb_get_chains": [_P, _P, _P, _P],
         "qb_get_chain_rows": [_P, _i64, _i64, _P, _P, _P],
         "qb_get_gemm_histogram": [_P, _P, _i32],
+        "qb_get_issued_flops": [_P, _P],
         "qb_seed": [_P, ctypes.c_uint64],
         "qb_inject_streams": [_P, _P, _P, _P, _P, _i64, _i64],
         "qb_pcd_step": [_P, _i64, _i64, _i64, _f64, _f64],

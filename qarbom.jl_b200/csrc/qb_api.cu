@@ -92,6 +92,7 @@ struct Mat {
     bf16 *b = nullptr;   // bf16 [rows][ld]        (QB_PREC_BF16)
     bf16 *bT = nullptr;  // bf16 [units][ldT]      (QB_PREC_BF16, gradient operand)
     int64_t ld = 0, ldT = 0, rows = 0, units = 0;
+    bool exact = false;  // every element is known to be exactly representable in bf16 (sampled 0/1 states, UInt8 data)
     Mat row_slice(int64_t r0, int64_t n) const {  // rows [r0, r0+n); the transposed view is not sliceable
         Mat m = *this;
         if (m.f) m.f += r0 * ld;
@@ -111,6 +112,10 @@ struct qb_handle {
     qb_config cfg{};
     int64_t V = 0, H = 0, L = 0, VL = 0, ldv = 0, ldh = 0, Bmax = 0, ldb = 0;
     bool bf = false, gaussian = false;
+    // QB_PREC_FP32X3: the fp32 path with its contractions on the tensor cores (operands split into three bf16 components)
+    bool x3 = false;
+    bf16 *W3[3] = {nullptr, nullptr, nullptr}, *W3T[3] = {nullptr, nullptr, nullptr}; bool w3_dirty = true;   // components of W / its transpose
+    bf16 *x3_buf[2][3] = {}; size_t x3_cap[2] = {0, 0};   // components of the operands split on the fly
     bool gauss_threshold = false;  // FastPCD chain advance on Gaussian visibles: v = 1[u < mean + z] (src/gibbs.jl:22-25)
     bool fast_pcd_pair_chains = false;  // classifier FastPCD: pair sample i with chain i instead of the reference's chain 1
     int num_sms = 148;
@@ -191,7 +196,7 @@ struct qb_handle {
     bool exchange_done = false;  // the step already reduced its gradient shard and the bias gradients (state_exchange)
     int64_t launches = 0, gemm_launches = 0;
     int64_t gemm_hist[QB_GEMM_HIST_SLOTS] = {};
-    double gemm_flops = 0.0;
+    double gemm_flops = 0.0, gemm_issued_flops = 0.0;   // algorithmic / extra component-product flops (QB_PREC_FP32X3)
     int force_bn = 0, use_2cta = 1;
     // fused chain launches (sm100_chain.cuh): half-steps recorded between chain_begin / chain_end run as ONE persistent kernel
     int fused_chain_mode = 1; int chain_bn = 0;     // options "fused_chain" (0 never, 1 automatic, 2 always), "chain_bn" (0 = automatic)
@@ -275,6 +280,8 @@ void upload_rows(qb_handle *h, const void *src, int dt, int64_t n, int64_t cols,
 void upload_rows_on(qb_handle *h, cudaStream_t st, void *&staging, size_t &staging_bytes, const void *src, int dt, int64_t n,
                     int64_t cols, Mat &dst, int64_t r0, int64_t col0) {
     if (n == 0 || cols == 0) return;
+    // UInt8 values are exact in bf16; anything else may not be (a later column block can only take exactness away)
+    dst.exact = (dt == QB_DT_U8) && (col0 == 0 || dst.exact);
     const size_t es = dt_size(dt);
     const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)((64u << 20) / (cols * es)));
     for (int64_t r = 0; r < n; r += chunk_rows) {
@@ -361,8 +368,83 @@ struct GemmScope {
     }
 };
 
+// QB_PREC_FP32X3: C = alpha A B + beta C + bias on tcgen05 with fp32-grade accuracy.  Every operand is split into bf16
+// components x = hi + mid + lo (an operand known to be bf16-exact has one), the products (i, j) with i + j <= 2 -- the ones
+// above 2^-24 relative -- accumulate into one fp32 TMEM tile, smallest terms first.  The weights' components (both
+// orientations) are cached and refreshed after every update; states and probabilities are split on the fly.
+void x3_split(qb_handle *h, const float *src, int64_t s_row, int64_t s_k, int64_t rows, int64_t K, bf16 *const c[3], int ncomp, int64_t ldk) {
+    dim3 g((unsigned)ceil_div(ldk, 32), (unsigned)ceil_div(rows, 32));
+    split3_kernel<<<g, 256, 0, h->stream>>>(src, s_row, s_k, (int)rows, (int)K, c[0], ncomp > 1 ? c[1] : nullptr, ncomp > 1 ? c[2] : nullptr, ldk);
+    QB_CUDA(cudaGetLastError());
+    h->launches++;
+}
+
+void x3_ensure_weights(qb_handle *h) {
+    if (!h->w3_dirty) return;
+    for (int i = 0; i < 3; i++) {
+        if (!h->W3[i]) h->W3[i] = dalloc<bf16>(h->H * h->ldv);
+        if (!h->W3T[i]) h->W3T[i] = dalloc<bf16>(h->VL * h->ldh);
+    }
+    x3_split(h, h->P, h->ldv, 1, h->H, h->VL, h->W3, 3, h->ldv);
+    x3_split(h, h->P, 1, h->ldv, h->VL, h->H, h->W3T, 3, h->ldh);
+    h->w3_dirty = false;
+}
+
+// components of one operand, as [rows][K] K-major matrices: the weight cache when `src` views W, else a fresh split
+int x3_operand(qb_handle *h, int slot, const float *src, int64_t s_row, int64_t s_k, int64_t rows, int64_t K, bool exact,
+               sm100::Operand out[3]) {
+    const float *W = h->P;
+    if (src >= W && src < W + h->nW) {
+        x3_ensure_weights(h);
+        const int64_t off = src - W;
+        if (s_k == 1 && s_row == h->ldv) {            // rows of W: (hidden unit, visible column)
+            QB_CHECK(off % 8 == 0, QB_E_UNSUPPORTED, "x3: misaligned view of W");
+            for (int i = 0; i < 3; i++) out[i] = sm100::Operand{h->W3[i] + off, rows, K, h->ldv};
+            return 3;
+        }
+        if (s_row == 1 && s_k == h->ldv) {            // rows of W': (visible column, hidden unit); off = first column
+            QB_CHECK(off < h->ldv, QB_E_UNSUPPORTED, "x3: unsupported view of W");
+            for (int i = 0; i < 3; i++) out[i] = sm100::Operand{h->W3T[i] + off * h->ldh, rows, K, h->ldh};
+            return 3;
+        }
+    }
+    const int ncomp = exact ? 1 : 3;
+    const int64_t ldk = round_up(K, 8);
+    const size_t need = (size_t)rows * ldk;
+    if (h->x3_cap[slot] < need) {
+        for (int i = 0; i < 3; i++) { cudaFree(h->x3_buf[slot][i]); h->x3_buf[slot][i] = dalloc<bf16>(need); }
+        h->x3_cap[slot] = need;
+    }
+    x3_split(h, src, s_row, s_k, rows, K, h->x3_buf[slot], ncomp, ldk);
+    for (int i = 0; i < ncomp; i++) out[i] = sm100::Operand{h->x3_buf[slot][i], rows, K, ldk};
+    return ncomp;
+}
+
+void x3_gemm(qb_handle *h, const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbk, int64_t sbn, float *C, int64_t ldc,
+             int64_t M, int64_t N, int64_t K, float alpha, float beta, const float *bias, bool a_exact, bool b_exact) {
+    sm100::Operand ac[3], bc[3];
+    const int na = x3_operand(h, 0, A, sam, sak, M, K, a_exact, ac);
+    const int nb = x3_operand(h, 1, B, sbn, sbk, N, K, b_exact, bc);
+    sm100::Product prods[sm100::MAX_PHASES];
+    int n = 0;
+    for (int sum = 2; sum >= 0; sum--)          // smallest components first
+        for (int i = std::min(sum, na - 1); i >= 0; i--) {
+            const int j = sum - i;
+            if (j >= nb) continue;
+            prods[n++] = sm100::Product{ac[i], bc[j], false};
+        }
+    sm100::EpiParams ep{};
+    ep.mode = sm100::EPI_GRAD; ep.M = (int)M; ep.N = (int)N; ep.out_f32 = C; ep.ld_out = ldc;
+    ep.g_affine = 1; ep.g_alpha = alpha; ep.g_beta = beta; ep.g_bias = bias;
+    GemmScope gs(h, 2.0 * (double)M * (double)N * (double)K);
+    h->gemm_issued_flops += 2.0 * (double)M * (double)N * (double)K * (double)(n - 1);   // component products beyond the algorithmic one
+    sm100::launch_products(h->stream, prods, n, ep, h->gemm_sms, h->force_bn, h->use_2cta);
+}
+
 void simt_gemm(qb_handle *h, const float *A, int64_t sam, int64_t sak, const float *B, int64_t sbk, int64_t sbn, float *C,
-               int64_t ldc, int64_t M, int64_t N, int64_t K, float alpha, float beta, const float *bias) {
+               int64_t ldc, int64_t M, int64_t N, int64_t K, float alpha, float beta, const float *bias, bool a_exact = false,
+               bool b_exact = false) {
+    if (h->x3) { x3_gemm(h, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, alpha, beta, bias, a_exact, b_exact); return; }
     GemmScope gs(h, 2.0 * (double)M * (double)N * (double)K);
     dim3 g((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64));
     simt_gemm_kernel<<<g, 256, 0, h->stream>>>(A, sam, sak, B, sbk, sbn, C, ldc, (int)M, (int)N, (int)K, alpha, beta, bias);
@@ -516,7 +598,9 @@ struct HiddenOut {
 // conditional_prob_h (+ gibbs_sample_hidden): in = visible-side rows [rows][kdim] (kdim = V or V+L)
 void op_hidden(qb_handle *h, const Mat &in, int64_t rows, int64_t kdim, const HiddenOut &o, const Rng &rng, int64_t row0) {
     if (!h->bf) {
-        simt_gemm(h, in.f, in.ld, 1, Wf(h), 1, h->ldv, h->pre_h, h->ldh, rows, h->H, kdim, 1.f, 0.f, bh(h));
+        simt_gemm(h, in.f, in.ld, 1, Wf(h), 1, h->ldv, h->pre_h, h->ldh, rows, h->H, kdim, 1.f, 0.f, bh(h), in.exact);
+        if (o.state) o.state->exact = true;
+        if (o.prob) o.prob->exact = false;
         if (o.softplus_rows) return;  // fp32 path reads pre_h directly
         act_sample_kernel<<<grid1d(rows * h->H), 256, 0, h->stream>>>(
             h->pre_h, h->ldh, (int)rows, (int)h->H, 0, o.prob ? o.prob->f : nullptr, o.prob ? o.prob->ld : 0,
@@ -563,7 +647,8 @@ void op_visible(qb_handle *h, const Mat &in, int64_t rows, const VisibleOut &o, 
     const int act = h->gaussian ? (h->gauss_threshold ? 2 : 1) : 0;
     QB_CHECK(act != 2 || (!rng.inj && rng.use_rng), QB_E_UNSUPPORTED, "thresholded Gaussian visibles draw from the Philox stream only");
     if (!h->bf) {
-        simt_gemm(h, in.f, in.ld, 1, Wf(h), h->ldv, 1, h->pre_v, h->ldv, rows, h->VL, h->H, 1.f, 0.f, acat(h));
+        simt_gemm(h, in.f, in.ld, 1, Wf(h), h->ldv, 1, h->pre_v, h->ldv, rows, h->VL, h->H, 1.f, 0.f, acat(h), in.exact);
+        if (o.state) o.state->exact = (act != 1) && o.sample;   // Bernoulli (or thresholded) samples are 0/1; means and Gaussian samples are reals
         // value written for each visible unit: sampled state (sample), probability (Bernoulli
         // mean-field) or mean + noise (Gaussian; noise only if the caller supplied a stream)
         float *st = o.state ? o.state->f : nullptr;
@@ -643,8 +728,8 @@ void colsum<bf16>(qb_handle *h, const bf16 *A, int64_t lda, int64_t rows, int64_
 void op_grad(qb_handle *h, const Mat &posH, const Mat &posV, const bf16 *posV_T, int64_t posV_ldT, const Mat &negH,
              const Mat &negV, int64_t rows, int64_t nrows, float pos_scale) {
     if (!h->bf) {
-        simt_gemm(h, posH.f, 1, posH.ld, posV.f, posV.ld, 1, G_W(h), h->ldv, h->H, h->VL, rows, pos_scale, 0.f, nullptr);
-        simt_gemm(h, negH.f, 1, negH.ld, negV.f, negV.ld, 1, G_W(h), h->ldv, h->H, h->VL, nrows, -1.f, 1.f, nullptr);
+        simt_gemm(h, posH.f, 1, posH.ld, posV.f, posV.ld, 1, G_W(h), h->ldv, h->H, h->VL, rows, pos_scale, 0.f, nullptr, posH.exact, posV.exact);
+        simt_gemm(h, negH.f, 1, negH.ld, negV.f, negV.ld, 1, G_W(h), h->ldv, h->H, h->VL, nrows, -1.f, 1.f, nullptr, negH.exact, negV.exact);
         colsum<float>(h, posV.f, posV.ld, rows, h->VL, pos_scale, G_a(h));
         colsum<float>(h, negV.f, negV.ld, nrows, h->VL, -1.f, G_a(h));
         colsum<float>(h, posH.f, posH.ld, rows, h->H, pos_scale, G_b(h));
@@ -741,6 +826,7 @@ void op_update_on(qb_handle *h, double lr, double llr, int64_t B_local, cudaStre
     if (timed) QB_CUDA(cudaEventRecord(h->upd_ev[ei + 1], st));
     QB_CUDA(cudaGetLastError());
     h->launches += 1;
+    h->w3_dirty = true;
     if (sharded) {
         QB_NCCL(nccl().AllGather(Wb_out + hr0 * h->ldv, Wb_out, (size_t)(sr * h->ldv), /*ncclBfloat16*/ 9, comm, st));
         dim3 gt((unsigned)ceil_div(h->VL, 128), (unsigned)ceil_div(h->H, 64));
@@ -878,6 +964,7 @@ void set_stale_mode(qb_handle *h, bool on) {
 }
 
 void refresh_shadows(qb_handle *h) {
+    h->w3_dirty = true;
     if (!h->bf) return;
     dim3 g((unsigned)ceil_div(h->VL, 64), (unsigned)ceil_div(h->H, 64));
     shadow_kernel<<<g, 256, 0, h->stream>>>(Wf(h), (int)h->H, (int)h->VL, h->ldv, h->Wb, h->WbT, h->ldh);
@@ -1173,6 +1260,7 @@ void stage_host_batch(qb_handle *h, const void *X, int xdt, const void *Y, int y
     } else {
         upload_rows(h, X, xdt, B, h->V, h->hb, 0, 0);
         if (h->L > 0) upload_rows(h, Y, ydt, B, h->L, h->hb, 0, h->V);
+        h->hb.exact = xdt == QB_DT_U8 && (h->L == 0 || ydt == QB_DT_U8);
         if (h->bf) transpose_into(h, h->hb.b, h->hb.ld, B, h->VL, h->hb.bT, h->hb.ldT);
     }
     h->pf_valid = false;
@@ -1262,7 +1350,7 @@ int32_t qb_create(qb_handle **out, const qb_config *cfg) {
         QB_CHECK(out && cfg, QB_E_ARG, "NULL argument");
         QB_CHECK(cfg->n_visible > 0 && cfg->n_hidden > 0 && cfg->n_classifiers >= 0, QB_E_ARG, "V, H must be > 0 and L >= 0");
         QB_CHECK(cfg->max_batch > 0, QB_E_ARG, "max_batch must be > 0");
-        QB_CHECK(cfg->precision == QB_PREC_FP32 || cfg->precision == QB_PREC_BF16, QB_E_ARG, "unknown precision");
+        QB_CHECK(cfg->precision == QB_PREC_FP32 || cfg->precision == QB_PREC_BF16 || cfg->precision == QB_PREC_FP32X3, QB_E_ARG, "unknown precision");
         QB_CHECK(cfg->visible_kind == QB_VISIBLE_BERNOULLI || cfg->visible_kind == QB_VISIBLE_GAUSSIAN, QB_E_ARG, "unknown visible kind");
         QB_CHECK(cfg->world >= 1 && cfg->rank >= 0 && cfg->rank < cfg->world, QB_E_ARG, "bad rank/world");
         int ndev = 0;
@@ -1280,6 +1368,7 @@ int32_t qb_create(qb_handle **out, const qb_config *cfg) {
         h->ldv = round_up(h->VL, 8); h->ldh = round_up(h->H, 8);
         h->Bmax = cfg->max_batch; h->ldb = round_up(h->Bmax, 8);
         h->bf = cfg->precision == QB_PREC_BF16;
+        h->x3 = cfg->precision == QB_PREC_FP32X3;
         h->gaussian = cfg->visible_kind == QB_VISIBLE_GAUSSIAN;
         h->num_sms = prop.multiProcessorCount;
         h->gemm_sms = h->num_sms;
@@ -1289,6 +1378,7 @@ int32_t qb_create(qb_handle **out, const qb_config *cfg) {
         for (auto &e : h->timer_ev) QB_CUDA(cudaEventCreate(&e));
         h->nW = h->H * h->ldv; h->nP = h->nW + h->ldv + h->ldh;
         h->P = dalloc<float>(h->nP); h->G = dalloc<float>(h->nP);
+        if (h->x3) sm100::init_device();
         if (h->bf) {
             sm100::init_device();
             h->Wb = dalloc<bf16>(h->H * h->ldv);
@@ -1331,6 +1421,7 @@ int32_t qb_destroy(qb_handle *h) {
                     cudaIpcCloseMemHandle(h->peerG[r]); cudaIpcCloseMemHandle(h->peerWb[r]); cudaIpcCloseMemHandle(h->peerWbT[r]);
                     cudaIpcCloseMemHandle(h->peerFlags[r]); cudaIpcCloseMemHandle(h->peerP[r]);
                 }
+        for (int i = 0; i < 3; i++) { cudaFree(h->W3[i]); cudaFree(h->W3T[i]); cudaFree(h->x3_buf[0][i]); cudaFree(h->x3_buf[1][i]); }
         cudaFree(h->chain_cnt); if (h->chain_err_host) cudaFreeHost(h->chain_err_host); delete h->rec;
         cudaFree(h->p2p_flags); cudaFree(h->p2p_grid_bar); cudaFree(h->p2p_ns); if (h->p2p_timeout_host) cudaFreeHost(h->p2p_timeout_host);
         cudaFree(h->P); dfree(h->G); cudaFree(h->Vel); cudaFree(h->P_best); cudaFree(h->F); cudaFree(h->F2); cudaFree(h->P_eff); cudaFree(h->W2); cudaFree(h->online_vec); cudaFree(h->online_bar); cudaFree(h->online_ns); dfree(h->Wb); cudaFree(h->WbT);
@@ -1437,6 +1528,7 @@ int32_t qb_set_data(qb_handle *h, const void *X, int32_t x_dtype, const void *Y,
         h->N = n_rows;
         upload_rows(h, X, x_dtype, n_rows, h->V, h->data, 0, 0);
         if (h->L > 0) upload_rows(h, Y, y_dtype, n_rows, h->L, h->data, 0, h->V);
+        h->data.exact = x_dtype == QB_DT_U8 && (h->L == 0 || y_dtype == QB_DT_U8);   // 0..255 are exact in bf16
         QB_CUDA(cudaStreamSynchronize(h->stream));
     });
 }
@@ -1446,6 +1538,7 @@ int32_t qb_init_chains(qb_handle *h, int64_t n_chains, const double *v, const do
         QB_H(h);
         QB_CHECK(n_chains >= 1 && n_chains <= h->Bmax, QB_E_ARG, "n_chains must be in [1, max_batch]");
         h->n_chains = n_chains; h->chains_binary = false;
+        h->cv.exact = false; h->ch.exact = false;
         if (v) {
             QB_CHECK(hid != nullptr && (h->L == 0 || y != nullptr), QB_E_ARG, "v, h (and y) must all be given");
             upload_rows(h, v, QB_DT_F64, n_chains, h->V, h->cv, 0, 0);
@@ -2087,10 +2180,17 @@ int32_t qb_get_gemm_histogram(qb_handle *h, int64_t *counts, int32_t n_slots) {
         for (int i = 0; i < n_slots; i++) counts[i] = i < QB_GEMM_HIST_SLOTS ? h->gemm_hist[i] : 0;
     });
 }
+int32_t qb_get_issued_flops(qb_handle *h, double *issued_flops) {
+    return guarded([&] {
+        QB_H_KEEP(h);
+        QB_CHECK(issued_flops != nullptr, QB_E_ARG, "issued_flops is NULL");
+        *issued_flops = h->gemm_flops + h->gemm_issued_flops;
+    });
+}
 int32_t qb_reset_counters(qb_handle *h) {
     return guarded([&] {
         QB_H_KEEP(h);
-        h->launches = 0; h->gemm_launches = 0; h->gemm_flops = 0.0;
+        h->launches = 0; h->gemm_launches = 0; h->gemm_flops = 0.0; h->gemm_issued_flops = 0.0;
         for (auto &c : h->gemm_hist) c = 0;
         h->gemm_ev_used = 0; h->gemm_timed = 0; h->gemm_timed_flops = 0.0;
         h->upd_ev_used = 0; h->upd_timed = 0;

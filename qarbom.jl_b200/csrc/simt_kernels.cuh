@@ -69,6 +69,38 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const float *__restrict_
     }
 }
 
+// ----------------------------------------------------------------------------- fp32 -> three bf16 components (QB_PREC_FP32X3)
+// x = hi + mid + lo with hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid): 3 x 8 significand bits cover fp32's 24.
+// src element (r, k) at src[r * s_row + k * s_k]; components are written K-major, c[i][r * ldk + k], columns [K, ldk) zeroed.
+// 32 x 32 tiles through shared memory so that both the strided read (s_k != 1: a transposed view) and the write coalesce.
+__global__ void __launch_bounds__(256) split3_kernel(const float *__restrict__ src, int64_t s_row, int64_t s_k, int rows, int K,
+                                                     bf16 *__restrict__ c0, bf16 *__restrict__ c1, bf16 *__restrict__ c2, int64_t ldk) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    const bool k_fast = (s_k == 1);   // which source index is contiguous
+    for (int i = ty; i < 32; i += 8) {
+        const int r = k_fast ? r0 + i : r0 + tx, k = k_fast ? k0 + tx : k0 + i;
+        float v = 0.f;
+        if (r < rows && k < K) v = src[(int64_t)r * s_row + (int64_t)k * s_k];
+        if (k_fast) tile[i][tx] = v; else tile[tx][i] = v;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, k = k0 + tx;
+        if (r >= rows || k >= ldk) continue;
+        const float v = tile[i][tx];
+        const bf16 h = __float2bfloat16(v);
+        const float r1 = v - __bfloat162float(h);
+        const bf16 m = __float2bfloat16(r1);
+        const bf16 l = __float2bfloat16(r1 - __bfloat162float(m));
+        const int64_t o = (int64_t)r * ldk + k;
+        c0[o] = h;
+        if (c1) c1[o] = m;
+        if (c2) c2[o] = l;
+    }
+}
+
 // ----------------------------------------------------------------------------- activation + sampling
 // act: 0 = sigmoid (+ Bernoulli sample when `state`), 1 = Gaussian visible (value = pre [+ z])
 // Units in [0, n_units) of every row; label units are finished by label_kernel instead.

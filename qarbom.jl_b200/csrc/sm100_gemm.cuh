@@ -71,7 +71,20 @@ struct EpiParams {
     // ---- EPI_GRAD
     float *out_f32; long long ld_out;
     int grad_sub;  // out = out - acc instead of out = acc (negative statistics subtracted from an already reduced positive part)
+    // affine form (QB_PREC_FP32X3's GEMM): out = g_alpha * acc + g_beta * out + g_bias[n]; active when g_affine != 0
+    int g_affine; float g_alpha, g_beta; const float *g_bias;
     float pscale;  // probabilities are multiplied by this before being stored / summed (n_chains / batch; 1 normally)
+};
+
+// A launch accumulates a LIST of products into one TMEM tile: D = sum_p (+/-) A_p B_p^T.  One phase is a plain GEMM, two
+// (the second negated) the CD / PCD gradient, and the fp32-grade mode (QB_PREC_FP32X3) expands every real-valued operand into
+// bf16 components (x = hi + mid + lo, 24 mantissa bits) and lists the component products that matter (i + j <= 2).
+constexpr int MAX_PHASES = 12;
+struct Phases {
+    int n;
+    int kb_end[MAX_PHASES];   // cumulative 64-deep k-blocks at the end of each phase
+    unsigned int neg_mask;    // bit p: phase p is subtracted (a_negate in the instruction descriptor)
+    CUtensorMap A[MAX_PHASES], B[MAX_PHASES];
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -546,12 +559,22 @@ __device__ __forceinline__ void epilogue_grad(const EpiParams &ep, uint32_t tmem
         const int n0 = n_blk * BN + c0;
         if (n0 >= ep.N || m >= ep.M) continue;
         float *dst = ep.out_f32 + (long long)m * ep.ld_out + n0;
+        if (ep.g_affine) {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (n0 + j < ep.N) {
+                    float v = ep.g_alpha * __uint_as_float(r[j]);
+                    if (ep.g_beta != 0.f) v = fmaf(ep.g_beta, dst[j], v);
+                    if (ep.g_bias) v += ep.g_bias[n0 + j];
+                    r[j] = __float_as_uint(v);
+                }
+        }
         if (ep.grad_sub) {
 #pragma unroll
             for (int j = 0; j < 16; j++)
                 if (n0 + j < ep.N) r[j] = __float_as_uint(dst[j] - __uint_as_float(r[j]));
         }
-        if (n0 + 16 <= ep.N) {
+        if (n0 + 16 <= ep.N && (ep.ld_out & 3) == 0) {
 #pragma unroll
             for (int q = 0; q < 4; q++)
                 reinterpret_cast<uint4 *>(dst)[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
@@ -566,9 +589,7 @@ __device__ __forceinline__ void epilogue_grad(const EpiParams &ep, uint32_t tmem
 // ----------------------------------------------------------------------------- the kernel
 template <int BN, int KIND>
 __global__ void __launch_bounds__((Shape<BN, KIND>::THREADS), 1)
-gibbs_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, int K1, int K2,
-                  const EpiParams ep) {
+gibbs_gemm_kernel(const __grid_constant__ Phases ph, const EpiParams ep) {
     using C = Cfg<BN>;
     constexpr int WGS = Shape<BN, KIND>::WGS;
     extern __shared__ uint8_t smem_raw[];
@@ -584,12 +605,10 @@ gibbs_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (ep.M + BM - 1) / BM, tiles_n = (ep.N + BN - 1) / BN;
     const int num_tiles = tiles_m * tiles_n;
-    const int kb1 = (K1 + BK - 1) / BK, kb2 = (K2 + BK - 1) / BK, kb_total = kb1 + kb2;
+    const int kb_total = ph.kb_end[ph.n - 1];
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&mapA);
-        prefetch_tmap(&mapB);
-        if (kb2) { prefetch_tmap(&mapA2); prefetch_tmap(&mapB2); }
+        for (int p = 0; p < ph.n; p++) { prefetch_tmap(&ph.A[p]); prefetch_tmap(&ph.B[p]); }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -613,17 +632,14 @@ gibbs_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
+                int p = 0, kb0 = 0;
                 for (int kb = 0; kb < kb_total; kb++) {
+                    while (kb >= ph.kb_end[p]) kb0 = ph.kb_end[p++];
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
                     mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                    if (kb < kb1) {
-                        tma_load_2d(sa, &mapA, full_bar(stage), kb * BK, m_blk * BM);
-                        tma_load_2d(sb, &mapB, full_bar(stage), kb * BK, n_blk * BN);
-                    } else {
-                        tma_load_2d(sa, &mapA2, full_bar(stage), (kb - kb1) * BK, m_blk * BM);
-                        tma_load_2d(sb, &mapB2, full_bar(stage), (kb - kb1) * BK, n_blk * BN);
-                    }
+                    tma_load_2d(sa, &ph.A[p], full_bar(stage), (kb - kb0) * BK, m_blk * BM);
+                    tma_load_2d(sb, &ph.B[p], full_bar(stage), (kb - kb0) * BK, n_blk * BN);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -639,12 +655,14 @@ gibbs_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 mbar_wait(tempty_bar(as), aphase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
+                int p = 0;
                 for (int kb = 0; kb < kb_total; kb++) {
+                    while (kb >= ph.kb_end[p]) p++;
                     mbar_wait(full_bar(stage), phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
                     const uint64_t adesc = make_kmajor_sw128_desc(sa), bdesc = make_kmajor_sw128_desc(sb);
-                    const uint32_t idesc = (kb < kb1) ? idesc_pos : idesc_neg;
+                    const uint32_t idesc = ((ph.neg_mask >> p) & 1u) ? idesc_neg : idesc_pos;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++) {
                         // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
@@ -754,9 +772,7 @@ struct Cfg2 {
 
 template <int BN, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Shape<BN, KIND>::THREADS), 1)
-gibbs_gemm_kernel_2cta(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                       const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, int K1, int K2,
-                       const EpiParams ep) {
+gibbs_gemm_kernel_2cta(const __grid_constant__ Phases ph, const EpiParams ep) {
     using C = Cfg2<BN>;
     constexpr int WGS = Shape<BN, KIND>::WGS;
     extern __shared__ uint8_t smem_raw[];
@@ -774,12 +790,10 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ CUtensorMap mapA, const __grid_co
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
     const int tiles_m = (ep.M + 2 * BM - 1) / (2 * BM), tiles_n = (ep.N + BN - 1) / BN;
     const int num_tiles = tiles_m * tiles_n;
-    const int kb1 = (K1 + BK - 1) / BK, kb2 = (K2 + BK - 1) / BK, kb_total = kb1 + kb2;
+    const int kb_total = ph.kb_end[ph.n - 1];
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&mapA);
-        prefetch_tmap(&mapB);
-        if (kb2) { prefetch_tmap(&mapA2); prefetch_tmap(&mapB2); }
+        for (int p = 0; p < ph.n; p++) { prefetch_tmap(&ph.A[p]); prefetch_tmap(&ph.B[p]); }
     }
     if (warp == 1 && lane == 0) {
         // full: leader's arrive.expect_tx + the peer producer's remote arrive; tmem_empty: 8 epilogue warps per CTA
@@ -804,18 +818,15 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ CUtensorMap mapA, const __grid_co
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
                 const int m0 = m_blk * 2 * BM + (int)rank * BM, n0 = n_blk * BN + (int)rank * (BN / 2);
+                int p = 0, kb0 = 0;
                 for (int kb = 0; kb < kb_total; kb++) {
+                    while (kb >= ph.kb_end[p]) kb0 = ph.kb_end[p++];
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
                     else mbar_arrive_remote(full_bar(stage), 0);
-                    if (kb < kb1) {
-                        tma_load_2d_2sm(sa, &mapA, full_bar(stage), kb * BK, m0);
-                        tma_load_2d_2sm(sb, &mapB, full_bar(stage), kb * BK, n0);
-                    } else {
-                        tma_load_2d_2sm(sa, &mapA2, full_bar(stage), (kb - kb1) * BK, m0);
-                        tma_load_2d_2sm(sb, &mapB2, full_bar(stage), (kb - kb1) * BK, n0);
-                    }
+                    tma_load_2d_2sm(sa, &ph.A[p], full_bar(stage), (kb - kb0) * BK, m0);
+                    tma_load_2d_2sm(sb, &ph.B[p], full_bar(stage), (kb - kb0) * BK, n0);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -831,12 +842,14 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ CUtensorMap mapA, const __grid_co
                 mbar_wait(tempty_bar(as), aphase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
+                int p = 0;
                 for (int kb = 0; kb < kb_total; kb++) {
+                    while (kb >= ph.kb_end[p]) p++;
                     mbar_wait(full_bar(stage), phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
                     const uint64_t adesc = make_kmajor_sw128_desc(sa), bdesc = make_kmajor_sw128_desc(sb);
-                    const uint32_t idesc = (kb < kb1) ? idesc_pos : idesc_neg;
+                    const uint32_t idesc = ((ph.neg_mask >> p) & 1u) ? idesc_neg : idesc_pos;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++)
                         umma_bf16_2sm(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
@@ -951,9 +964,30 @@ inline int pick_kind(const EpiParams &ep) {
     return K_GENERIC;
 }
 
+// one product of a launch: D (+/-)= A B^T
+struct Product {
+    Operand A, B;
+    bool negate;
+};
+
+template <int BN, bool PAIR>
+inline void fill_phases(Phases &ph, const Product *prods, int n) {
+    QB_CHECK(n >= 1 && n <= MAX_PHASES, -1, "a launch takes 1.." + std::to_string(MAX_PHASES) + " products");
+    ph.n = n; ph.neg_mask = 0u;
+    int kb = 0;
+    for (int p = 0; p < n; p++) {
+        QB_CHECK(prods[p].A.k == prods[p].B.k && prods[p].A.k > 0, -1, "GEMM operands disagree on K");
+        ph.A[p] = make_tmap(prods[p].A, BM);
+        ph.B[p] = make_tmap(prods[p].B, PAIR ? BN / 2 : BN);
+        kb += (int)ceil_div(prods[p].A.k, BK);
+        ph.kb_end[p] = kb;
+        if (prods[p].negate) ph.neg_mask |= 1u << p;
+    }
+    for (int p = n; p < MAX_PHASES; p++) ph.kb_end[p] = kb;
+}
+
 template <int BN, int KIND>
-inline void launch_bn_kind(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &ma2,
-                           const CUtensorMap &mb2, int K1, int K2, const EpiParams &ep, int grid) {
+inline void launch_bn_kind(cudaStream_t st, const Phases &ph, const EpiParams &ep, int grid) {
     using C = Cfg<BN>;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(Shape<BN, KIND>::THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
@@ -961,12 +995,11 @@ inline void launch_bn_kind(cudaStream_t st, const CUtensorMap &ma, const CUtenso
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    QB_CUDA(cudaLaunchKernelEx(&cfg, gibbs_gemm_kernel<BN, KIND>, ma, mb, ma2, mb2, K1, K2, ep));
+    QB_CUDA(cudaLaunchKernelEx(&cfg, gibbs_gemm_kernel<BN, KIND>, ph, ep));
 }
 
 template <int BN, int KIND>
-inline void launch_bn_kind_2cta(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &ma2,
-                                const CUtensorMap &mb2, int K1, int K2, const EpiParams &ep, int clusters) {
+inline void launch_bn_kind_2cta(cudaStream_t st, const Phases &ph, const EpiParams &ep, int clusters) {
     using C = Cfg2<BN>;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(Shape<BN, KIND>::THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
@@ -974,45 +1007,41 @@ inline void launch_bn_kind_2cta(cudaStream_t st, const CUtensorMap &ma, const CU
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    QB_CUDA(cudaLaunchKernelEx(&cfg, gibbs_gemm_kernel_2cta<BN, KIND>, ma, mb, ma2, mb2, K1, K2, ep));
+    QB_CUDA(cudaLaunchKernelEx(&cfg, gibbs_gemm_kernel_2cta<BN, KIND>, ph, ep));
 }
 
 template <int BN>
-inline void launch_bn_2cta(cudaStream_t st, const Operand &A, const Operand &B, const Operand *A2, const Operand *B2,
-                           const EpiParams &ep, int num_sms) {
-    CUtensorMap ma = make_tmap(A, BM), mb = make_tmap(B, BN / 2);
-    CUtensorMap ma2 = A2 ? make_tmap(*A2, BM) : ma, mb2 = B2 ? make_tmap(*B2, BN / 2) : mb;
+inline void launch_bn_2cta(cudaStream_t st, const Product *prods, int n, const EpiParams &ep, int num_sms) {
+    static thread_local Phases ph;
+    fill_phases<BN, true>(ph, prods, n);
     const int tiles = (int)(ceil_div(ep.M, 2 * BM) * ceil_div(ep.N, BN));
     const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
-    const int K1 = (int)A.k, K2 = A2 ? (int)A2->k : 0;
     switch (pick_kind(ep)) {
-        case K_GRAD: launch_bn_kind_2cta<BN, K_GRAD>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
-        case K_FAST_SAMPLE: launch_bn_kind_2cta<BN, K_FAST_SAMPLE>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
-        case K_FAST_PROB: launch_bn_kind_2cta<BN, K_FAST_PROB>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
-        case K_FAST_SAMPLE_PROB: launch_bn_kind_2cta<BN, K_FAST_SAMPLE_PROB>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
-        case K_FAST_GAUSS: launch_bn_kind_2cta<BN, K_FAST_GAUSS>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
-        case K_FAST_LABEL: launch_bn_kind_2cta<BN, K_FAST_LABEL>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
-        default: launch_bn_kind_2cta<BN, K_GENERIC>(st, ma, mb, ma2, mb2, K1, K2, ep, clusters); break;
+        case K_GRAD: launch_bn_kind_2cta<BN, K_GRAD>(st, ph, ep, clusters); break;
+        case K_FAST_SAMPLE: launch_bn_kind_2cta<BN, K_FAST_SAMPLE>(st, ph, ep, clusters); break;
+        case K_FAST_PROB: launch_bn_kind_2cta<BN, K_FAST_PROB>(st, ph, ep, clusters); break;
+        case K_FAST_SAMPLE_PROB: launch_bn_kind_2cta<BN, K_FAST_SAMPLE_PROB>(st, ph, ep, clusters); break;
+        case K_FAST_GAUSS: launch_bn_kind_2cta<BN, K_FAST_GAUSS>(st, ph, ep, clusters); break;
+        case K_FAST_LABEL: launch_bn_kind_2cta<BN, K_FAST_LABEL>(st, ph, ep, clusters); break;
+        default: launch_bn_kind_2cta<BN, K_GENERIC>(st, ph, ep, clusters); break;
     }
     QB_CUDA(cudaGetLastError());
 }
 
 template <int BN>
-inline void launch_bn(cudaStream_t st, const Operand &A, const Operand &B, const Operand *A2, const Operand *B2,
-                      const EpiParams &ep, int num_sms) {
-    CUtensorMap ma = make_tmap(A, BM), mb = make_tmap(B, BN);
-    CUtensorMap ma2 = A2 ? make_tmap(*A2, BM) : ma, mb2 = B2 ? make_tmap(*B2, BN) : mb;
+inline void launch_bn(cudaStream_t st, const Product *prods, int n, const EpiParams &ep, int num_sms) {
+    static thread_local Phases ph;
+    fill_phases<BN, false>(ph, prods, n);
     const int tiles = (int)(ceil_div(ep.M, BM) * ceil_div(ep.N, BN));
     const int grid = tiles < num_sms ? tiles : num_sms;
-    const int K1 = (int)A.k, K2 = A2 ? (int)A2->k : 0;
     switch (pick_kind(ep)) {
-        case K_GRAD: launch_bn_kind<BN, K_GRAD>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
-        case K_FAST_SAMPLE: launch_bn_kind<BN, K_FAST_SAMPLE>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
-        case K_FAST_PROB: launch_bn_kind<BN, K_FAST_PROB>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
-        case K_FAST_SAMPLE_PROB: launch_bn_kind<BN, K_FAST_SAMPLE_PROB>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
-        case K_FAST_GAUSS: launch_bn_kind<BN, K_FAST_GAUSS>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
-        case K_FAST_LABEL: launch_bn_kind<BN, K_FAST_LABEL>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
-        default: launch_bn_kind<BN, K_GENERIC>(st, ma, mb, ma2, mb2, K1, K2, ep, grid); break;
+        case K_GRAD: launch_bn_kind<BN, K_GRAD>(st, ph, ep, grid); break;
+        case K_FAST_SAMPLE: launch_bn_kind<BN, K_FAST_SAMPLE>(st, ph, ep, grid); break;
+        case K_FAST_PROB: launch_bn_kind<BN, K_FAST_PROB>(st, ph, ep, grid); break;
+        case K_FAST_SAMPLE_PROB: launch_bn_kind<BN, K_FAST_SAMPLE_PROB>(st, ph, ep, grid); break;
+        case K_FAST_GAUSS: launch_bn_kind<BN, K_FAST_GAUSS>(st, ph, ep, grid); break;
+        case K_FAST_LABEL: launch_bn_kind<BN, K_FAST_LABEL>(st, ph, ep, grid); break;
+        default: launch_bn_kind<BN, K_GENERIC>(st, ph, ep, grid); break;
     }
     QB_CUDA(cudaGetLastError());
 }
@@ -1073,24 +1102,31 @@ inline void pick_shape(long long M, long long N, int num_sms, int force_bn, int 
 struct LaunchShape { int bn = 0, pair = 0, kind = -1; };
 inline LaunchShape &last_shape() { static thread_local LaunchShape s; return s; }
 
-inline void launch(cudaStream_t st, const Operand &A, const Operand &B, const Operand *A2, const Operand *B2, const EpiParams &ep,
-                   int num_sms, int force_bn = 0, int use_2cta = 1) {
-    QB_CHECK(A.k == B.k && A.k > 0, -1, "GEMM operands disagree on K");
-    QB_CHECK((A2 == nullptr) == (B2 == nullptr), -1, "phase-2 operands must come in pairs");
+// a list of products accumulated into one tile (see Phases)
+inline void launch_products(cudaStream_t st, const Product *prods, int n, const EpiParams &ep, int num_sms, int force_bn = 0,
+                            int use_2cta = 1) {
     int bn; bool pair;
     pick_shape(ep.M, ep.N, num_sms, force_bn, use_2cta, bn, pair);
     last_shape().bn = bn; last_shape().pair = pair ? 1 : 0; last_shape().kind = pick_kind(ep);
     if (pair) {
-        if (bn == 256) launch_bn_2cta<256>(st, A, B, A2, B2, ep, num_sms);
-        else launch_bn_2cta<128>(st, A, B, A2, B2, ep, num_sms);
+        if (bn == 256) launch_bn_2cta<256>(st, prods, n, ep, num_sms);
+        else launch_bn_2cta<128>(st, prods, n, ep, num_sms);
         return;
     }
     switch (bn) {
-        case 256: launch_bn<256>(st, A, B, A2, B2, ep, num_sms); break;
-        case 128: launch_bn<128>(st, A, B, A2, B2, ep, num_sms); break;
-        case 64: launch_bn<64>(st, A, B, A2, B2, ep, num_sms); break;
-        default: launch_bn<32>(st, A, B, A2, B2, ep, num_sms); break;
+        case 256: launch_bn<256>(st, prods, n, ep, num_sms); break;
+        case 128: launch_bn<128>(st, prods, n, ep, num_sms); break;
+        case 64: launch_bn<64>(st, prods, n, ep, num_sms); break;
+        default: launch_bn<32>(st, prods, n, ep, num_sms); break;
     }
+}
+
+inline void launch(cudaStream_t st, const Operand &A, const Operand &B, const Operand *A2, const Operand *B2, const EpiParams &ep,
+                   int num_sms, int force_bn = 0, int use_2cta = 1) {
+    QB_CHECK((A2 == nullptr) == (B2 == nullptr), -1, "phase-2 operands must come in pairs");
+    Product prods[2] = {{A, B, false}, {A, B, true}};
+    if (A2) { prods[1].A = *A2; prods[1].B = *B2; }
+    launch_products(st, prods, A2 ? 2 : 1, ep, num_sms, force_bn, use_2cta);
 }
 
 }  // namespace sm100

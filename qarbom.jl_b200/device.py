@@ -18,7 +18,7 @@ class DeviceRBM:
         self.V, self.H, self.L = rbm.n_visible, rbm.n_hidden, getattr(rbm, "n_classifiers", 0)
         cfg = QbConfig(self.V, self.H, self.L,
                        _ffi.QB_VISIBLE_GAUSSIAN if rbm.gaussian else _ffi.QB_VISIBLE_BERNOULLI,
-                       {"fp32": _ffi.QB_PREC_FP32, "bf16": _ffi.QB_PREC_BF16}[precision], int(max_batch), device, rank,
+                       {"fp32": _ffi.QB_PREC_FP32, "bf16": _ffi.QB_PREC_BF16, "fp32x3": _ffi.QB_PREC_FP32X3}[precision], int(max_batch), device, rank,
                        world, 0)
         self._h = ctypes.c_void_p()
         check(lib().qb_create(ctypes.byref(self._h), ctypes.byref(cfg)))
@@ -306,6 +306,11 @@ class DeviceRBM:
         if c[n - 1]:
             out[("simt", 64, "fp32")] = int(c[n - 1])
         return out
+
+    def issued_flops(self) -> float:
+        f = ctypes.c_double(0)
+        check(lib().qb_get_issued_flops(self._h, ctypes.byref(f)))
+        return f.value
 
     def update_timing(self):
         n, ms = ctypes.c_int64(0), ctypes.c_double(0)

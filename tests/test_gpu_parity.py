@@ -26,7 +26,8 @@ def q():
     return qarbom_b200
 
 
-TOL = {"fp32": dict(w=1e-5, dw=2e-4, p=2e-6), "bf16": dict(w=None, dw=2e-2, p=2e-6)}
+# "fp32x3" = QB_PREC_FP32X3, the validation mode ON the tensor cores (three bf16 components per fp32 operand): fp32 tolerances
+TOL = {"fp32": dict(w=1e-5, dw=2e-4, p=2e-6), "fp32x3": dict(w=1e-5, dw=2e-4, p=2e-6), "bf16": dict(w=None, dw=2e-2, p=2e-6)}
 
 
 def _resync(m, dev, prec):
@@ -49,7 +50,7 @@ def _data(rng, n, V, L, gaussian, bf16):
 
 
 # ------------------------------------------------------------------------------ conditionals
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp32x3", "bf16"])
 @pytest.mark.parametrize("V,H,L", [(3, 2, 0), (16, 8, 0), (70, 33, 5), (784, 500, 10)])
 def test_conditional_prob_h_and_reconstruct(q, prec, V, H, L):
     rng = np.random.default_rng(V * 1000 + H)
@@ -85,7 +86,7 @@ PCD_CASES = [  # V, H, L, gaussian, B, k, steps
 ]
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp32x3", "bf16"])
 @pytest.mark.parametrize("V,H,L,gaussian,B,k,steps", PCD_CASES)
 def test_pcd_steps_match_oracle(q, prec, V, H, L, gaussian, B, k, steps):
     if prec == "bf16" and gaussian:
@@ -156,7 +157,7 @@ CD_CASES = [  # V, H, L, gaussian, B, k, n_batches
 ]
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp32x3", "bf16"])
 @pytest.mark.parametrize("V,H,L,gaussian,B,k,nb", CD_CASES)
 def test_cd_steps_match_oracle(q, prec, V, H, L, gaussian, B, k, nb):
     if prec == "bf16" and gaussian:
@@ -218,7 +219,7 @@ def test_bf16_grbm_single_step_tolerance(q):
 
 
 # ------------------------------------------------------------------------------ production RNG (Philox)
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp32x3", "bf16"])
 def test_philox_mode_matches_oracle_fed_with_the_same_stream(q, prec):
     """Device Philox == numpy Philox: the oracle, fed the uniforms the stream contract
     defines, must reproduce the device's chain states (outside a 1e-4 guard band)."""
@@ -273,7 +274,7 @@ def test_philox_bernoulli_frequencies(q):
 
 
 # ------------------------------------------------------------------------------ evaluation
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp32x3", "bf16"])
 @pytest.mark.parametrize("V,H,L,gaussian", [(3, 2, 0, False), (70, 33, 0, False), (70, 33, 4, False), (40, 24, 0, True)])
 def test_eval_mse_and_free_energy(q, prec, V, H, L, gaussian):
     bf = prec == "bf16"
@@ -503,7 +504,7 @@ def test_stale_chains_mode_matches_its_definition(q):
 
 
 # ------------------------------------------------------------------------------ classifier evaluation
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp32x3", "bf16"])
 def test_classify_and_accuracy(q, prec):
     bf = prec == "bf16"
     rng = np.random.default_rng(17)
@@ -537,7 +538,7 @@ def test_train_classifier_reference_scenario(q, tmp_path):
 
 
 # ------------------------------------------------------------------------------ host-batch (end-to-end) path
-@pytest.mark.parametrize("prec,L", [("fp32", 0), ("bf16", 0), ("bf16", 4)])
+@pytest.mark.parametrize("prec,L", [("fp32", 0), ("fp32x3", 0), ("fp32x3", 4), ("bf16", 0), ("bf16", 4)])
 def test_step_host_equals_resident_step_with_and_without_prefetch(q, prec, L):
     rng = np.random.default_rng(31)
     V, H, B, k, steps = 72, 40, 24, 2, 4
@@ -572,7 +573,7 @@ def test_step_host_equals_resident_step_with_and_without_prefetch(q, prec, L):
 
 
 # ------------------------------------------------------------------------------ more chains than rows (extension)
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp32x3", "bf16"])
 @pytest.mark.parametrize("V,H,L,B,Nc", [(40, 24, 0, 8, 20), (40, 24, 0, 12, 4), (30, 18, 3, 8, 16)])
 def test_pcd_with_n_chains_different_from_batch(q, prec, V, H, L, B, Nc):
     """BASELINE.json config 2 ("1000 persistent chains, batch 256"): n_chains != batch_size is a declared
@@ -623,7 +624,7 @@ def test_pcd_with_n_chains_different_from_batch(q, prec, V, H, L, B, Nc):
 
 
 # ------------------------------------------------------------------------------ quantum-trainer positive phase
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp32x3", "bf16"])
 @pytest.mark.parametrize("L", [0, 3])
 def test_persistent_qubo_minibatch_with_supplied_model_sample(q, prec, L):
     """persistent_qubo! pairs every sample of the mini-batch with ONE (v~, h~) pair returned by the
@@ -676,7 +677,7 @@ def test_device_side_snapshot_and_restore(q):
 
 
 # ------------------------------------------------------------------------------ online (B = 1) CD: cooperative persistent kernel
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp32x3", "bf16"])
 @pytest.mark.parametrize("V,H,gaussian,k,n", [(3, 2, False, 3, 40), (50, 30, False, 1, 64), (784, 500, False, 2, 24), (24, 16, True, 2, 32)])
 def test_online_cd_epoch_matches_reference_algorithm(q, prec, V, H, gaussian, k, n):
     """train!(rbm, x, CD) with the reference's own batch size 1 (src/training/train_cd.jl:2-21): the one-kernel
@@ -846,7 +847,7 @@ def test_train_fast_pcd_classifier_reference_scenario(q, tmp_path):
         assert dev.classify([[1, 0, 0]]).tolist() == [[1]]
 
 
-@pytest.mark.parametrize("prec,L", [("fp32", 0), ("bf16", 0), ("fp32", 3)])
+@pytest.mark.parametrize("prec,L", [("fp32", 0), ("fp32x3", 0), ("bf16", 0), ("fp32", 3)])
 def test_step_host_reconstruction_error_value(q, prec, L):
     """qb_pcd_step_host returns sum over rows and visible units of (x - reconstruct(x))^2 (src/rbm.jl:220-224): for binary
     models without labels taken inside the step with the weights BEFORE the update (from the positive-phase p(h|x)),
@@ -874,7 +875,7 @@ def test_step_host_reconstruction_error_value(q, prec, L):
 
 
 # ------------------------------------------------------------------------------ single sampling half-steps
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp32x3", "bf16"])
 @pytest.mark.parametrize("V,H,L,gaussian", [(3, 2, 0, False), (70, 33, 0, False), (40, 24, 5, False), (40, 24, 0, True), (30, 18, 3, True)])
 def test_sample_hidden_and_visible_half_steps(q, prec, V, H, L, gaussian):
     """qb_sample_hidden / qb_sample_visible against gibbs_sample_hidden / gibbs_sample_visible / gibbs_sample_label
