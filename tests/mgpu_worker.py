@@ -35,7 +35,7 @@ def main():
             dist.broadcast(uid, 0)
             dev.comm_init(uid.cpu().numpy().tobytes())
             if prec == "bf16":   # "sharded" (the bf16 default): NCCL reduce-scatter + shard update + bf16 all-gather + local transpose
-                dev.set_option("sharded_update", 0 if exchange == "nccl" else 1)
+                dev.set_option("sharded_update", 0 if exchange == "nccl" else 1)   # ("chain" runs on the default sharded exchange)
             if exchange == "state":     # positive product reduce-scattered behind the chains + bit-packed chain-state all-gather
                 dev.set_option("state_exchange", 1)
             if exchange == "p2p":
@@ -43,6 +43,8 @@ def main():
                 allh = torch.empty(320 * world, dtype=torch.uint8, device="cuda")
                 dist.all_gather_into_tensor(allh, mine)
                 dev.p2p_import(allh.cpu().numpy().tobytes())
+        if exchange == "chain" and comm:   # the persistent multi-half-step kernel on the data-parallel side, one launch per half-step on the reference side
+            dev.set_option("fused_chain", 2)
         dev.set_data(Xs)
         dev.init_chains(Brows)
         if exchange == "stale":      # stale-1 chains on both sides: the overlapped exchange (CTA-limited communicator) must not change results

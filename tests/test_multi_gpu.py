@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("prec,exchange", [("fp32", "nccl"), ("bf16", "nccl"), ("bf16", "sharded"), ("bf16", "stale"), ("bf16", "state"), ("bf16", "p2p")])
+@pytest.mark.parametrize("prec,exchange", [("fp32", "nccl"), ("bf16", "nccl"), ("bf16", "sharded"), ("bf16", "stale"), ("bf16", "state"), ("bf16", "p2p"), ("bf16", "chain")])
 def test_two_rank_pcd_matches_single_gpu(prec, exchange):
     import torch
     n = torch.cuda.device_count()
@@ -22,3 +22,4 @@ def test_two_rank_pcd_matches_single_gpu(prec, exchange):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "MGPU" in out.stdout
+    print("\n".join(line for line in out.stdout.splitlines() if line.startswith("MGPU")))   # evidence for profiles/ (run with -s)
