@@ -141,6 +141,12 @@ int32_t qb_cd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, doub
  * returns to train! (src/training/train_pcd.jl:42), measured with CUDA events. */
 int32_t qb_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]);
 int32_t qb_cd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]);
+/* n_steps consecutive mini-batch steps of the same two functions on the resident mini-batches first_batch, first_batch + 1,
+ * ... (wrapping around after the last full mini-batch); an epoch is first_batch = 0, n_steps = N / B.  pcd != 0:
+ * persistent_contrastive_divergence!, else contrastive_divergence!.  On small models (bf16 mode, one GPU, no momentum) all
+ * the steps run inside ONE persistent kernel launch (sm100_epoch.cuh); the results are those of n_steps single-step calls. */
+int32_t qb_train_steps(qb_handle *h, int32_t pcd, int64_t first_batch, int64_t n_steps, int64_t B, int64_t k, double lr,
+                       double llr);
 
 /* One epoch of fast_persistent_contrastive_divergence! (src/training/train_fast_pcd.jl:1-57; classifiers :59-127):
  * inside a mini-batch the slow weights are updated and the fast weights decayed (19/20) after every SAMPLE, then
@@ -230,7 +236,7 @@ int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_la
 /* GEMM launches since the last reset by kernel specialisation: counts[(pair * 4 + b) * QB_GEMM_KINDS + kind] with
  * pair = 1 for the cta_group::2 kernel, b = log2(tile width / 32) (32, 64, 128, 256), kind = QB_GEMM_KIND_*; the
  * last slot counts launches of the fp32 CUDA-core GEMM.  Tests use it to assert WHICH kernel produced a result. */
-#define QB_GEMM_KINDS 8
+#define QB_GEMM_KINDS 10
 #define QB_GEMM_HIST_SLOTS (2 * 4 * QB_GEMM_KINDS + 1)
 #define QB_GEMM_KIND_GENERIC 0
 #define QB_GEMM_KIND_GRAD 1
@@ -239,6 +245,8 @@ int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_la
 #define QB_GEMM_KIND_FAST_SAMPLE_PROB 4
 #define QB_GEMM_KIND_FAST_GAUSS 5  /* Gaussian visibles: mean + Box-Muller normal in the epilogue */
 #define QB_GEMM_KIND_FAST_LABEL 6  /* Bernoulli visibles + label units (softmax + Bernoulli) in the epilogue */
+#define QB_GEMM_KIND_CHAIN 7       /* persistent multi-half-step kernel: all half-steps of a chain advance / CD forward pass */
+#define QB_GEMM_KIND_EPOCH 8       /* persistent multi-mini-batch kernel: whole training steps incl. gradient + update */
 int32_t qb_get_gemm_histogram(qb_handle *h, int64_t *counts, int32_t n_slots);
 /* Tensor-core flops ISSUED since the last reset: equal to the algorithmic gemm_flops of qb_get_counters except in
  * QB_PREC_FP32X3, where every contraction issues 3..6 bf16 component products (reported separately). */

@@ -18,7 +18,7 @@ QB_DT_F64, QB_DT_I64, QB_DT_F32, QB_DT_U8 = 0, 1, 2, 3
 SYMBOLS = [
     "qb_version", "qb_device_count", "qb_last_error", "qb_create", "qb_destroy", "qb_set_params", "qb_get_params", "qb_snapshot_params", "qb_restore_params",
     "qb_set_optimizer", "qb_set_data", "qb_init_chains", "qb_get_chains", "qb_get_chain_rows", "qb_get_gemm_histogram", "qb_get_issued_flops", "qb_seed", "qb_inject_streams",
-    "qb_pcd_step", "qb_cd_step", "qb_pcd_epoch", "qb_cd_epoch", "qb_fast_pcd_epoch", "qb_pcd_step_host", "qb_cd_step_host", "qb_set_next_host_batch", "qb_eval_mse",
+    "qb_pcd_step", "qb_cd_step", "qb_pcd_epoch", "qb_cd_epoch", "qb_train_steps", "qb_fast_pcd_epoch", "qb_pcd_step_host", "qb_cd_step_host", "qb_set_next_host_batch", "qb_eval_mse",
     "qb_eval_free_energy", "qb_reconstruct", "qb_conditional_prob_h", "qb_sample_hidden", "qb_sample_visible", "qb_conditional_prob_y_given_v", "qb_comm_unique_id", "qb_comm_init", "qb_p2p_export", "qb_p2p_import", "qb_get_p2p_timing",
     "qb_get_counters", "qb_reset_counters", "qb_set_option", "qb_sync", "qb_timer_start", "qb_timer_stop", "qb_get_update_timing",
 ]
@@ -76,6 +76,7 @@ def lib():
         "qb_cd_step": [_P, _i64, _i64, _i64, _f64, _f64],
         "qb_pcd_epoch": [_P, _i64, _i64, _f64, _f64, _P],
         "qb_cd_epoch": [_P, _i64, _i64, _f64, _f64, _P],
+        "qb_train_steps": [_P, _i32, _i64, _i64, _i64, _i64, _f64, _f64],
         "qb_fast_pcd_epoch": [_P, _i64, _i64, _f64, _f64, _f64, _f64, _P],
         "qb_pcd_step_host": [_P, _P, _i32, _P, _i32, _i64, _i64, _f64, _f64, _P],
         "qb_cd_step_host": [_P, _P, _i32, _P, _i32, _i64, _i64, _f64, _f64, _P],

@@ -17,6 +17,7 @@
 #include "simt_kernels.cuh"
 #include "sm100_gemm.cuh"
 #include "sm100_chain.cuh"
+#include "sm100_epoch.cuh"
 
 using namespace qb;
 
@@ -83,6 +84,8 @@ struct NcclConfig218 {
                                      (nccl().GetErrorString ? nccl().GetErrorString(_r) : "?")); \
     } while (0)
 }  // namespace
+
+struct HalfCapture { qb::sm100::Operand A, B; qb::sm100::EpiParams ep; double flops; bool set; };
 
 // ----------------------------------------------------------------------------- device matrices
 constexpr int QB_OVERLAP_CTAS = 16;
@@ -204,6 +207,11 @@ struct qb_handle {
     unsigned int *chain_cnt = nullptr; int64_t chain_cnt_region = 0, chain_launch_no = 0;
     unsigned int *chain_err_host = nullptr, *chain_err_dev = nullptr;
     int64_t chain_launches = 0;
+    // persistent multi-mini-batch kernel (sm100_epoch.cuh): option "epoch_kernel" 0 never, 1 automatic (small models), 2 always
+    int epoch_kernel_mode = 1; sm100::EpochBuilder *epoch = nullptr;
+    unsigned int *epoch_cnt = nullptr; size_t epoch_cnt_cap = 0;
+    struct HalfCapture *capture = nullptr;   // describe-only mode of op_hidden / op_visible (program builders)
+    int64_t epoch_launches = 0;
     bool async_steps = false;   // step calls return without a stream sync (qb_sync to wait)
     bool time_gemms = false;    // bracket every GEMM launch with CUDA events on the launching stream
     std::vector<cudaEvent_t> gemm_ev; size_t gemm_ev_used = 0; int64_t gemm_timed = 0; double gemm_timed_flops = 0.0;
@@ -515,6 +523,7 @@ bool chain_hazard_free(const sm100::ChainBuilder &cb, const sm100::Operand &B, c
 
 // one fused half-step GEMM of the bf16 path: recorded into the open chain region, or launched right away
 void gemm_half_step(qb_handle *h, const sm100::Operand &A, const sm100::Operand &B, const sm100::EpiParams &ep, double flops) {
+    if (h->capture) { h->capture->A = A; h->capture->B = B; h->capture->ep = ep; h->capture->flops = flops; h->capture->set = true; return; }
     const bool can_chain = h->rec_depth > 0 && h->fused_chain_mode != 0 && h->use_2cta != 0 && h->force_bn != 32 && sm100::chainable(ep) &&
                            chain_pays(h, ep);
     if (h->rec_depth > 0 && !can_chain) chain_flush(h);
@@ -537,6 +546,15 @@ void gemm_half_step(qb_handle *h, const sm100::Operand &A, const sm100::Operand 
     launch_single(h, A, B, ep, flops);
 }
 
+void ensure_chain_flags(qb_handle *h) {
+    if (h->chain_cnt) return;
+    h->chain_cnt_region = (int64_t)sm100::CHAIN_MAX_STEPS * ceil_div(h->Bmax, 64);
+    h->chain_cnt = dalloc<unsigned int>((size_t)QB_CHAIN_REGIONS * h->chain_cnt_region + 1);   // + the abort flag
+    QB_CUDA(cudaHostAlloc((void **)&h->chain_err_host, sizeof(unsigned int), cudaHostAllocMapped));
+    *h->chain_err_host = 0u;
+    QB_CUDA(cudaHostGetDevicePointer((void **)&h->chain_err_dev, h->chain_err_host, 0));
+}
+
 void chain_flush(qb_handle *h) {
     if (!h->rec || h->rec->prog.n_steps == 0) return;
     sm100::ChainBuilder &cb = *h->rec;
@@ -548,13 +566,7 @@ void chain_flush(qb_handle *h) {
         return;
     }
     cb.prog.n_steps = n;
-    if (!h->chain_cnt) {
-        h->chain_cnt_region = (int64_t)sm100::CHAIN_MAX_STEPS * ceil_div(h->Bmax, 64);
-        h->chain_cnt = dalloc<unsigned int>((size_t)QB_CHAIN_REGIONS * h->chain_cnt_region + 1);   // + the abort flag
-        QB_CUDA(cudaHostAlloc((void **)&h->chain_err_host, sizeof(unsigned int), cudaHostAllocMapped));
-        *h->chain_err_host = 0u;
-        QB_CUDA(cudaHostGetDevicePointer((void **)&h->chain_err_dev, h->chain_err_host, 0));
-    }
+    ensure_chain_flags(h);
     // arrival counters: a fresh region of a ring per launch, the whole ring is cleared once per lap
     const int64_t region = h->chain_launch_no % QB_CHAIN_REGIONS;
     if (region == 0 && h->chain_launch_no > 0)
@@ -696,7 +708,7 @@ void op_visible(qb_handle *h, const Mat &in, int64_t rows, const VisibleOut &o, 
     ep.pscale = 1.f;
     gemm_half_step(h, A, B, ep, 2.0 * (double)h->VL * (double)rows * (double)h->H);
     // label units: finished inside the GEMM epilogue (K_FAST_LABEL) or, from the raw pre-activations, by a side kernel
-    if (h->L > 0 && o.sample && o.state && sm100::pick_kind(ep) != sm100::K_FAST_LABEL) {
+    if (h->L > 0 && o.sample && o.state && sm100::pick_kind(ep) != sm100::K_FAST_LABEL && !h->capture) {
         label_bf16_kernel<<<grid1d(rows, 128), 128, 0, h->stream>>>(
             h->lab_pre, h->L, (int)rows, (int)h->V, (int)h->L, o.state_rm ? o.state->b : nullptr, o.state->ld,
             o.state_T ? o.state->bT : nullptr, o.state->ldT, rng.inj, rng.ld_inj, rng.key, row0,
@@ -1234,6 +1246,149 @@ void cd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, 
     h->inj_active = false;
 }
 
+// ----------------------------------------------------------------------------- persistent multi-mini-batch kernel
+void ensure_dataT(qb_handle *h, int64_t B);
+void ensure_chain_flags(qb_handle *h);
+
+// describe one half-step through the regular op_* code (nothing is launched)
+HalfCapture describe_hidden(qb_handle *h, const Mat &in, int64_t rows, int64_t kdim, const HiddenOut &o, bool sample) {
+    HalfCapture c{}; h->capture = &c;
+    Rng r; if (sample) { r.use_rng = 1; r.key.seed_lo = (uint32_t)h->seed; r.key.seed_hi = (uint32_t)(h->seed >> 32); }
+    try { op_hidden(h, in, rows, kdim, o, r, 0); } catch (...) { h->capture = nullptr; throw; }
+    h->capture = nullptr;
+    return c;
+}
+HalfCapture describe_visible(qb_handle *h, const Mat &in, int64_t rows, const VisibleOut &o) {
+    HalfCapture c{}; h->capture = &c;
+    Rng r; r.use_rng = 1; r.key.seed_lo = (uint32_t)h->seed; r.key.seed_hi = (uint32_t)(h->seed >> 32);
+    try { op_visible(h, in, rows, o, r, 0); } catch (...) { h->capture = nullptr; throw; }
+    h->capture = nullptr;
+    return c;
+}
+
+// n_steps consecutive mini-batch steps on resident batches (first + i) mod nb in ONE launch.  Returns false (nothing done)
+// when the configuration is outside what the kernel covers; the caller then runs the steps one launch sequence at a time.
+int epoch_tile_width(const qb_handle *h, int64_t B) { return h->force_bn ? h->force_bn : (B <= 128 ? 32 : 64); }
+
+// the cheap part of the eligibility test (the per-half-step epilogue check happens while the program is built)
+bool epoch_kernel_eligible(const qb_handle *h, bool pcd, int64_t B, int64_t k) {
+    if (h->epoch_kernel_mode == 0 || !h->bf || h->cfg.world != 1 || h->stale_chains || h->inj_active || h->time_gemms) return false;
+    if (h->momentum != 0.0 || h->weight_decay != 0.0 || h->use_2cta == 2 || (h->force_bn != 0 && h->force_bn != 32 && h->force_bn != 64)) return false;
+    if (h->N < B || k < 1 || 2 * k + 2 > sm100::EPOCH_MAX_STEPS) return false;
+    if (pcd && (h->L > 0 || h->n_chains != B)) return false;
+    if (h->gaussian && h->L > 0) return false;   // Gaussian visibles + label units: generic epilogue only
+    // automatic: models whose half-steps are at most about two waves of 128 x BN tiles (beyond that one launch per GEMM /
+    // the pair-tile chain kernel is the better schedule)
+    const int64_t tiles = ceil_div(std::max(h->H, h->VL), 128) * ceil_div(B, epoch_tile_width(h, B));
+    return h->epoch_kernel_mode == 2 || tiles <= 2 * h->num_sms;
+}
+
+bool epoch_kernel_run(qb_handle *h, bool pcd, int64_t first, int64_t n_steps, int64_t B, int64_t k, double lr, double llr) {
+    if (n_steps < 1 || !epoch_kernel_eligible(h, pcd, B, k)) return false;
+    const int bn = epoch_tile_width(h, B);
+    ensure_dataT(h, B);
+    const int64_t nb = h->dataT_nb;
+    if (nb < 1) return false;
+    if (!h->epoch) h->epoch = new sm100::EpochBuilder();
+    sm100::EpochBuilder &eb = *h->epoch;
+    eb.begin(bn);
+    Mat data_all = h->data;   // the whole dataset: the mini-batch is a row offset (b_row_mb = B rows per batch index)
+    const sm100::Operand dataT_all{h->dataT, nb * h->VL, B, h->dataT_ld};
+    auto half = [&](const HalfCapture &c, int b_row_mb, int dep, int draw_off) -> int {
+        if (!c.set || !sm100::chainable(c.ep)) return -2;
+        sm100::EpiParams ep = c.ep; ep.N = (int)B;
+        sm100::Operand Bop = c.B;
+        if (b_row_mb) Bop.rows = h->N;   // view of the whole dataset
+        return eb.add_half_step(c.A, Bop, b_row_mb, ep, dep, draw_off);
+    };
+    int last = -1, d0 = -1, d1 = -1;
+    const sm100::Operand *negA = nullptr, *negB = nullptr;
+    sm100::Operand phdT{h->phd.bT, h->H, B, h->phd.ldT}, phmT{h->phm.bT, h->H, B, h->phm.ldT}, vmT{h->vm.bT, h->VL, B, h->vm.ldT},
+        chT{h->ch.bT, h->H, B, h->ch.ldT}, cvT{h->cv.bT, h->VL, B, h->cv.ldT};
+    if (!pcd) {
+        HiddenOut h0; h0.prob = &h->phd; h0.prob_T = true; h0.bg_what = 1; h0.bg_sign = 1.f; h0.state = &h->hs; h0.state_rm = true;
+        last = half(describe_hidden(h, data_all, B, h->VL, h0, true), (int)B, -1, 0);
+        if (last < 0) return false;
+        for (int64_t s = 0; s < k; s++) {
+            const bool fin = (s == k - 1);
+            if (s > 0) {
+                HiddenOut hs; hs.state = &h->hs; hs.state_rm = true;
+                last = half(describe_hidden(h, h->vm, B, h->VL, hs, true), 0, last, (int)(2 * s));
+                if (last < 0) return false;
+            }
+            VisibleOut vo; vo.state = &h->vm; vo.sample = true; vo.state_rm = true; vo.state_T = fin; vo.bg_sign_neg = fin ? 1 : 0;
+            last = half(describe_visible(h, h->hs, B, vo), 0, last, (int)(2 * s + 1));
+            if (last < 0) return false;
+        }
+        HiddenOut hm; hm.prob = &h->phm; hm.prob_T = true; hm.bg_what = 1; hm.bg_sign = -1.f;
+        last = half(describe_hidden(h, h->vm, B, h->V, hm, false), 0, last, 0);
+        if (last < 0) return false;
+        d0 = last; negA = &phmT; negB = &vmT;
+    } else {
+        for (int64_t s = 0; s < k; s++) {
+            const bool fin = (s == k - 1);
+            HiddenOut ho; ho.state = &h->ch; ho.state_rm = true; ho.state_T = fin;
+            if (fin) { ho.bg_what = 2; ho.bg_sign = -1.f; }
+            last = half(describe_hidden(h, h->cv, B, h->VL, ho, true), 0, last, (int)(2 * s));
+            if (last < 0) return false;
+            VisibleOut vo; vo.state = &h->cv; vo.sample = true; vo.state_rm = true; vo.state_T = fin; vo.bg_sign_neg = fin ? 1 : 0;
+            last = half(describe_visible(h, h->ch, B, vo), 0, last, (int)(2 * s + 1));
+            if (last < 0) return false;
+        }
+        d1 = last;
+        HiddenOut ho; ho.prob = &h->phd; ho.prob_T = true; ho.bg_what = 1; ho.bg_sign = 1.f;
+        d0 = half(describe_hidden(h, data_all, B, h->VL, ho, false), (int)B, -1, 0);
+        if (d0 < 0) return false;
+        negA = &chT; negB = &cvT;
+    }
+    eb.add_grad_update(phdT, dataT_all, (int)h->VL, *negA, *negB, (int)h->H, (int)h->VL, d0, d1);
+    sm100::EpochProgram &P = eb.prog;
+    P.draws_per_iter = (int)(2 * k);
+    P.n_batches = (int)nb;
+    P.W = h->P; P.Wb = h->Wb; P.WbT = h->WbT; P.ldv = h->ldv; P.ldh = h->ldh; P.V = (int)h->V;
+    P.lr = (float)(lr / (double)B); P.llr = (float)(llr / (double)B);
+    P.bias_P = acat(h); P.bias_G = G_a(h); P.datasum = h->datasum; P.datasum_ld = h->ldv; P.dscale = 1.f;
+    P.n_vis = (int)h->ldv; P.n_bias = (int)(h->ldv + h->ldh);
+    ensure_chain_flags(h);
+    P.error_flag = h->chain_err_dev;
+    P.abort_flag = h->chain_cnt + (size_t)QB_CHAIN_REGIONS * h->chain_cnt_region;
+    // the bias-gradient accumulators must start at zero (the kernel leaves them at zero)
+    if (!h->bias_grads_clean) {
+        const int n = (int)(h->ldv + h->ldh);
+        init_bias_grads_kernel<<<grid1d(n), 256, 0, h->stream>>>(G_a(h), nullptr, 1.f, (int)h->ldv, n);
+        QB_CUDA(cudaGetLastError());
+        h->launches++;
+    }
+    constexpr int64_t MAX_ITERS = 2048;
+    for (int64_t done = 0; done < n_steps; done += MAX_ITERS) {
+        const int64_t it = std::min(MAX_ITERS, n_steps - done);
+        const size_t need = (size_t)it * P.n_steps * (P.max_tiles_n + 1);
+        if (h->epoch_cnt_cap < need) {
+            cudaFree(h->epoch_cnt);
+            h->epoch_cnt = dalloc<unsigned int>(need);
+            h->epoch_cnt_cap = need;
+        } else {
+            QB_CUDA(cudaMemsetAsync(h->epoch_cnt, 0, need * sizeof(unsigned int), h->stream));
+        }
+        P.n_iters = (int)it;
+        P.batch0 = (int)((first + done) % nb);
+        P.draw0 = h->draw;
+        P.rb_cnt = h->epoch_cnt;
+        P.tot_cnt = h->epoch_cnt + (size_t)it * P.n_steps * P.max_tiles_n;
+        {
+            GemmScope gs(h, eb.flops_per_iter * (double)it);
+            sm100::launch_epoch(h->stream, eb, h->gemm_sms);
+            sm100::last_shape().bn = bn; sm100::last_shape().pair = 0; sm100::last_shape().kind = sm100::K_GRAD_UPDATE;
+        }
+        h->draw += (uint64_t)(2 * k) * (uint64_t)it;
+        h->epoch_launches++;
+    }
+    h->bias_grads_clean = true;
+    h->chains_binary = h->chains_binary || pcd;
+    h->cur_datasum = nullptr;
+    return true;
+}
+
 // resident mini-batch `m` of B rows as (row-major view, transposed pointer)
 void batch_view(qb_handle *h, int64_t m, int64_t B, Mat &xb, const bf16 *&xbT, int64_t &ldT) {
     QB_CHECK(h->N > 0, QB_E_STATE, "qb_set_data has not been called");
@@ -1422,6 +1577,7 @@ int32_t qb_destroy(qb_handle *h) {
                     cudaIpcCloseMemHandle(h->peerFlags[r]); cudaIpcCloseMemHandle(h->peerP[r]);
                 }
         for (int i = 0; i < 3; i++) { cudaFree(h->W3[i]); cudaFree(h->W3T[i]); cudaFree(h->x3_buf[0][i]); cudaFree(h->x3_buf[1][i]); }
+        cudaFree(h->epoch_cnt); delete h->epoch;
         cudaFree(h->chain_cnt); if (h->chain_err_host) cudaFreeHost(h->chain_err_host); delete h->rec;
         cudaFree(h->p2p_flags); cudaFree(h->p2p_grid_bar); cudaFree(h->p2p_ns); if (h->p2p_timeout_host) cudaFreeHost(h->p2p_timeout_host);
         cudaFree(h->P); dfree(h->G); cudaFree(h->Vel); cudaFree(h->P_best); cudaFree(h->F); cudaFree(h->F2); cudaFree(h->P_eff); cudaFree(h->W2); cudaFree(h->online_vec); cudaFree(h->online_bar); cudaFree(h->online_ns); dfree(h->Wb); cudaFree(h->WbT);
@@ -1788,6 +1944,61 @@ static void epoch_impl(qb_handle *h, bool pcd, int64_t B, int64_t k, double lr, 
     QB_CHECK(h->N > 0, QB_E_STATE, "qb_set_data has not been called");
     const int64_t nb = h->N / B;  // _set_mini_batches: trailing remainder dropped -- all of it when N < B (src/utils.jl:13-26)
     double t[3] = {0, 0, 0};
+    // Small models: the epoch is one launch of the persistent multi-mini-batch kernel.  When phase times are wanted the
+    // first mini-batches run one launch sequence at a time with phase events (same arithmetic, same results) and their
+    // split is scaled to the event-timed duration of the whole epoch.
+    if (nb > 0 && h->epoch_kernel_mode != 0) {
+        const int64_t probe = (times != nullptr && !(pcd && h->stale_chains)) ? std::min<int64_t>(4, nb) : 0;
+        if (epoch_kernel_eligible(h, pcd, B, k)) {
+            QB_CUDA(cudaEventRecord(h->ev[6], h->stream));
+            cudaEvent_t pe[5];
+            double f[3] = {0, 0, 0};
+            for (int64_t m = 0; m < probe; m++) {
+                Mat xb; const bf16 *xbT; int64_t ldT;
+                batch_view(h, m, B, xb, xbT, ldT);
+                while ((int64_t)h->epoch_ev.size() < 5 * (m + 1)) { cudaEvent_t e; QB_CUDA(cudaEventCreate(&e)); h->epoch_ev.push_back(e); }
+                for (int i = 0; i < 5; i++) pe[i] = h->epoch_ev[5 * m + i];
+                if (pcd) pcd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, pe);
+                else cd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, pe);
+            }
+            if (epoch_kernel_run(h, pcd, probe, nb - probe, B, k, lr, llr) || nb == probe) {
+                QB_CUDA(cudaEventRecord(h->ev[7], h->stream));
+                QB_CUDA(cudaStreamSynchronize(h->stream));
+                chain_check_error(h);
+                if (times) {
+                    for (int64_t m = 0; m < probe; m++) {
+                        cudaEvent_t *e = h->epoch_ev.data() + 5 * m;
+                        float a = 0, b = 0, c = 0, d = 0;
+                        QB_CUDA(cudaEventElapsedTime(&a, e[0], e[1])); QB_CUDA(cudaEventElapsedTime(&b, e[1], e[2]));
+                        QB_CUDA(cudaEventElapsedTime(&c, e[2], e[3]));
+                        if (pcd) { QB_CUDA(cudaEventElapsedTime(&d, e[3], e[4])); f[1] += a + d; f[0] += b; f[2] += c; }
+                        else { f[0] += a; f[1] += b; f[2] += c; }
+                    }
+                    float total = 0.f;
+                    QB_CUDA(cudaEventElapsedTime(&total, h->ev[6], h->ev[7]));
+                    const double sum = f[0] + f[1] + f[2];
+                    for (int i = 0; i < 3; i++) times[i] = sum > 0 ? total * 1e-3 * f[i] / sum : 0.0;
+                }
+                return;
+            }
+            // not covered after all: the probe steps are done, continue with the remaining mini-batches below
+            for (int64_t m = probe; m < nb; m++) {
+                Mat xb; const bf16 *xbT; int64_t ldT;
+                batch_view(h, m, B, xb, xbT, ldT);
+                if (pcd) pcd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, nullptr);
+                else cd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, nullptr);
+            }
+            QB_CUDA(cudaEventRecord(h->ev[7], h->stream));
+            QB_CUDA(cudaStreamSynchronize(h->stream));
+            chain_check_error(h);
+            if (times) {
+                float total = 0.f;
+                QB_CUDA(cudaEventElapsedTime(&total, h->ev[6], h->ev[7]));
+                times[0] = 0.0; times[1] = total * 1e-3; times[2] = 0.0;
+            }
+            return;
+        }
+    }
     // Phase times come from CUDA events recorded around the phases of every step and resolved AFTER the epoch (in chunks of
     // QB_EPOCH_EV_STEPS steps): no host synchronisation between mini-batches, the stream stays full.
     const bool timed = (times != nullptr) && !(pcd && h->stale_chains);  // the overlapped step has no phase boundaries
@@ -1836,6 +2047,27 @@ static void epoch_impl(qb_handle *h, bool pcd, int64_t B, int64_t k, double lr, 
         if (stride > 1 && sum > 0) { const double f = total * 1e-3 / sum; t[0] *= f; t[1] *= f; t[2] *= f; }
     }
     if (times) { times[0] = t[0]; times[1] = t[1]; times[2] = t[2]; }
+}
+
+int32_t qb_train_steps(qb_handle *h, int32_t pcd, int64_t first_batch, int64_t n_steps, int64_t B, int64_t k, double lr, double llr) {
+    return guarded([&] {
+        if (pcd) { QB_H_KEEP(h); } else { QB_H(h); }
+        check_step_args(h, B, k);
+        QB_CHECK(!h->inj_active, QB_E_STATE, "injected streams are per step: use qb_pcd_step / qb_cd_step");
+        QB_CHECK(h->N >= B, QB_E_STATE, "the resident dataset holds no full mini-batch");
+        QB_CHECK(first_batch >= 0 && n_steps >= 0, QB_E_ARG, "first_batch and n_steps must be >= 0");
+        QB_CHECK(!pcd || h->n_chains >= 1, QB_E_STATE, "qb_init_chains has not been called");
+        const int64_t nb = h->N / B;
+        if (n_steps > 0 && !epoch_kernel_run(h, pcd != 0, first_batch % nb, n_steps, B, k, lr, llr)) {
+            for (int64_t i = 0; i < n_steps; i++) {
+                Mat xb; const bf16 *xbT; int64_t ldT;
+                batch_view(h, (first_batch + i) % nb, B, xb, xbT, ldT);
+                if (pcd) pcd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, nullptr);
+                else cd_step_impl(h, xb, xbT, ldT, B, k, lr, llr, nullptr);
+            }
+        }
+        if (!h->async_steps) { QB_CUDA(cudaStreamSynchronize(h->stream)); chain_check_error(h); }
+    });
 }
 
 int32_t qb_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double llr, double times[3]) {
@@ -2227,6 +2459,9 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
         } else if (!strcmp(key, "fused_chain")) {
             QB_CHECK(value == 0.0 || value == 1.0 || value == 2.0, QB_E_ARG, "fused_chain must be 0, 1 or 2");
             h->fused_chain_mode = (int)value;
+        } else if (!strcmp(key, "epoch_kernel")) {
+            QB_CHECK(value == 0.0 || value == 1.0 || value == 2.0, QB_E_ARG, "epoch_kernel must be 0, 1 or 2");
+            h->epoch_kernel_mode = (int)value;
         } else if (!strcmp(key, "chain_bn")) {
             const int bn = (int)value;
             QB_CHECK(bn == 0 || bn == 64 || bn == 128 || bn == 256, QB_E_ARG, "chain_bn must be 0/64/128/256");

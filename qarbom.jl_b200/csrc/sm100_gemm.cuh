@@ -515,7 +515,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiParams &ep, uint32_t tmem
                                               int lane) {
     const int unit = m_blk * BM + quarter * 32 + lane;
     const bool uvalid = unit < ep.M;
-    const float bias = uvalid ? ep.bias[unit] : 0.f;
+    const float bias = uvalid ? __ldcg(ep.bias + unit) : 0.f;   // L2: sm100_epoch.cuh rewrites the biases between iterations
     const bool want_sT = SAMPLE && ep.state_T != nullptr, want_pT = PROB && ep.prob_T != nullptr, want_prm = PROB && ep.prob_rm != nullptr;
     // MODE 2: does this warp hold the label units? (warp-uniform; pick_kind guarantees they sit inside ONE 32-lane group)
     const bool label_warp = MODE == 2 && (unit - lane) + 32 > ep.split && (unit - lane) < ep.M;

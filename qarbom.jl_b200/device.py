@@ -143,6 +143,10 @@ class DeviceRBM:
         check(lib().qb_fast_pcd_epoch(self._h, B, k, lr, fast_lr, llr, fast_llr, t if timed else None))
         return tuple(t)
 
+    def train_steps(self, method: str, first_batch: int, n_steps: int, B: int, k: int, lr: float, llr: float = 0.0):
+        """n_steps consecutive mini-batch steps on resident batches first_batch, first_batch + 1, ... (qb_train_steps)."""
+        check(lib().qb_train_steps(self._h, 1 if method.upper() == "PCD" else 0, first_batch, n_steps, B, k, lr, llr))
+
     def cd_epoch(self, B: int, k: int, lr: float, llr: float = 0.0, timed: bool = True):
         t = (ctypes.c_double * 3)()
         check(lib().qb_cd_epoch(self._h, B, k, lr, llr, t if timed else None))
@@ -289,18 +293,19 @@ class DeviceRBM:
                                     ctypes.byref(ms), ctypes.byref(tf)))
         return a.value, b.value, f.value, t.value, ms.value, tf.value
 
-    GEMM_KINDS = ("generic", "grad", "fast_sample", "fast_prob", "fast_sample_prob", "fast_gauss", "fast_label", "chain")
+    GEMM_KINDS = ("generic", "grad", "fast_sample", "fast_prob", "fast_sample_prob", "fast_gauss", "fast_label", "chain", "epoch", "-")
 
     def gemm_histogram(self) -> dict:
         """{(kernel, tile width, kind name): launches} since the last counter reset."""
-        n = 2 * 4 * 8 + 1
+        nk = len(self.GEMM_KINDS)
+        n = 2 * 4 * nk + 1
         c = (ctypes.c_int64 * n)()
         check(lib().qb_get_gemm_histogram(self._h, c, n))
         out = {}
         for pair in range(2):
             for b in range(4):
-                for k in range(8):
-                    v = c[(pair * 4 + b) * 8 + k]
+                for k in range(nk):
+                    v = c[(pair * 4 + b) * nk + k]
                     if v:
                         out[("2cta" if pair else "1cta", 32 << b, self.GEMM_KINDS[k])] = int(v)
         if c[n - 1]:
