@@ -1268,7 +1268,8 @@ HalfCapture describe_visible(qb_handle *h, const Mat &in, int64_t rows, const Vi
 
 // n_steps consecutive mini-batch steps on resident batches (first + i) mod nb in ONE launch.  Returns false (nothing done)
 // when the configuration is outside what the kernel covers; the caller then runs the steps one launch sequence at a time.
-int epoch_tile_width(const qb_handle *h, int64_t B) { return h->force_bn ? h->force_bn : (B <= 128 ? 32 : 64); }
+// (measured, tools/epoch_probe.py: 32-row tiles beat 64-row tiles at 256 rows -- 25.7 vs 31.6 us per cfg2 step)
+int epoch_tile_width(const qb_handle *h, int64_t B) { return h->force_bn ? h->force_bn : (B <= 256 ? 32 : 64); }
 
 // the cheap part of the eligibility test (the per-half-step epilogue check happens while the program is built)
 bool epoch_kernel_eligible(const qb_handle *h, bool pcd, int64_t B, int64_t k) {
@@ -1277,10 +1278,11 @@ bool epoch_kernel_eligible(const qb_handle *h, bool pcd, int64_t B, int64_t k) {
     if (h->N < B || k < 1 || 2 * k + 2 > sm100::EPOCH_MAX_STEPS) return false;
     if (pcd && (h->L > 0 || h->n_chains != B)) return false;
     if (h->gaussian && h->L > 0) return false;   // Gaussian visibles + label units: generic epilogue only
-    // automatic: models whose half-steps are at most about two waves of 128 x BN tiles (beyond that one launch per GEMM /
-    // the pair-tile chain kernel is the better schedule)
+    // automatic: models whose half-steps are a fraction of one wave of 128 x BN tiles -- there the launch latencies of the
+    // step-by-step path dominate.  Measured (tools/epoch_probe.py, profiles/r2_epoch_probe.txt): cfg2 -19 %, cfg1 tie; from
+    // about one wave on (cfg4 +18 %, cfg3 +8 %) one launch per GEMM is the better schedule.
     const int64_t tiles = ceil_div(std::max(h->H, h->VL), 128) * ceil_div(B, epoch_tile_width(h, B));
-    return h->epoch_kernel_mode == 2 || tiles <= 2 * h->num_sms;
+    return h->epoch_kernel_mode == 2 || 2 * tiles <= h->num_sms;
 }
 
 bool epoch_kernel_run(qb_handle *h, bool pcd, int64_t first, int64_t n_steps, int64_t B, int64_t k, double lr, double llr) {

@@ -198,8 +198,11 @@ gibbs_epoch_kernel(const __grid_constant__ EpochMaps maps, const __grid_constant
                 const unsigned int *rb = prog.rb_cnt + ((long long)iter * prog.n_steps) * prog.max_tiles_n;
                 const unsigned int *tot = prog.tot_cnt + (long long)iter * prog.n_steps;
                 // whole-step dependencies gate BOTH operands (new weights / operands produced by every row of the batch)
+                // EVERY tile of iteration iter waits for the update of iteration iter - 1 before its first load: the weights of
+                // a row-block-dependent step are fetched ahead of its row-block wait, and this CTA need not have run any of
+                // the iteration's earlier steps (dep_prev steps need it by construction).  tot - 1: last step of iteration iter - 1
                 bool waited = false;
-                if (S.dep_prev && iter > 0) { epoch_wait(tot - 1, (unsigned int)prog.last_step_total, prog); waited = true; }   // tot - 1: last step of iteration iter - 1
+                if (iter > 0) { epoch_wait(tot - 1, (unsigned int)prog.last_step_total, prog); waited = true; }
                 for (int d = 0; d < 2; d++)
                     if (S.dep_all[d] >= 0) { epoch_wait(tot + S.dep_all[d], (unsigned int)S.dep_all_count[d], prog); waited = true; }
                 if (waited) fence_proxy_async_global();

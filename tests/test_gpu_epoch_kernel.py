@@ -73,11 +73,14 @@ def test_persistent_kernel_equals_step_by_step(q, V, H, L, gaussian, B, k, algo,
     if algo == "PCD":
         assert np.array_equal(ref[5][0], got[5][0]) and np.array_equal(ref[5][1], got[5][1]), "chain states differ"
     # same GEMMs, same epilogue arithmetic; only the order of the float atomics of the bias sums differs (and feeds back
-    # into later probabilities at the 1e-7 level)
-    assert np.max(np.abs(ref[0] - got[0])) < 2e-6, np.max(np.abs(ref[0] - got[0]))
-    assert np.max(np.abs(ref[1] - got[1])) < 2e-6 and np.max(np.abs(ref[2] - got[2])) < 2e-6
+    # into later probabilities at the 1e-7 level): a few fp32 ulps of the parameter's magnitude (the GRBM case grows |a| to
+    # ~1e2 within these steps; two runs of the step-by-step path differ from each other by the same amount)
+    def close(r, g):
+        return np.max(np.abs(r - g)) <= 2e-6 * max(1.0, float(np.max(np.abs(r))))
+    assert close(ref[0], got[0]), np.max(np.abs(ref[0] - got[0]))
+    assert close(ref[1], got[1]) and close(ref[2], got[2]), (np.max(np.abs(ref[1] - got[1])), np.max(np.abs(ref[2] - got[2])))
     if L:
-        assert np.max(np.abs(ref[3] - got[3])) < 2e-6 and np.max(np.abs(ref[4] - got[4])) < 2e-6
+        assert close(ref[3], got[3]) and close(ref[4], got[4])
 
 
 def test_cfg1_epoch_kernel_matches_oracle(q):
