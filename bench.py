@@ -305,6 +305,9 @@ def main():
     ap.add_argument("--p2p", action="store_true",
                     help="multi-GPU: fused NVLink peer-memory reduce-scatter + update + all-gather kernel instead of ncclAllReduce + "
                          "update (measured slower at 8 GPUs this round, see profiles/README.md)")
+    ap.add_argument("--nvls", type=int, default=1,
+                    help="multi-GPU, bf16: 1 = fused reduce-scatter + update + all-gather kernel over NVSwitch multicast (multimem.ld_reduce / "
+                         "multimem.st) when the box supports it, else the NCCL exchange; 0 = NCCL exchange")
     ap.add_argument("--sharded-update", type=int, default=-1,
                     help="multi-GPU exchange: 1 = NCCL reduce-scatter + shard update + bf16 all-gather, 0 = allreduce + full update, -1 = library default")
     ap.add_argument("--state-exchange", type=int, default=-1,
@@ -332,10 +335,11 @@ def main():
                  "inputs cycle over %d resident mini-batches (%.3f GB): smaller than the 126 MB L2, which is the steady state of "
                  "training on this dataset (every epoch re-reads it); no flush between steps" % (w["nb"], 2 * w["nb"] * Bl_cfg * w["V"] * 2 / 1e9),
            "gibbs_steps": w["k"], "algorithm": w["algo"], "rng": "philox4x32-10", "persistent_chains": w.get("chains", w["B"]) if w["algo"] == "PCD" else None,
-           "parallelism": (f"dp{world} (rows/chains sharded; gradient exchange: " +
-                           ("fused NVLink peer-memory reduce-scatter + update + bf16 all-gather kernel" if (args.p2p and args.precision == "bf16") else
-                            "ncclReduceScatter + shard update + bf16 ncclAllGather + local transpose" if (args.sharded_update != 0 and args.precision == "bf16" and w["H"] % world == 0) else
-                            "ncclAllReduce + update") + ")") if world > 1 else "single GPU"}
+           "parallelism": f"dp{world} (rows/chains of every mini-batch sharded by rank, one gradient exchange per step)" if world > 1 else "single GPU"}
+    # how the gradient exchange is done is a property of THIS arm (decided at run time), reported next to `config`, not inside it
+    exchange_mode = ("fused NVLink peer-memory reduce-scatter + update + bf16 all-gather kernel (unicast, CUDA IPC)" if (args.p2p and args.precision == "bf16") else
+                     "ncclReduceScatter + shard update + bf16 ncclAllGather + local transpose" if (args.sharded_update != 0 and args.precision == "bf16" and w["H"] % world == 0) else
+                     "ncclAllReduce + update") if world > 1 else None
 
     if args.impl == "reference":
         if rank != 0:
@@ -373,6 +377,7 @@ def main():
     else:
         rbm = (q.GRBM if w["gaussian"] else q.RBM)(w["V"], w["H"], W=W0)
     chains_l = w.get("chains", B) // world
+    args.p2p_like = False
     dev = q.DeviceRBM(rbm, max_batch=max(Bl, chains_l), precision=args.precision, device=local_rank, rank=rank, world=world, seed=1234)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -390,7 +395,18 @@ def main():
                 dev.set_option("p2p_blocks_per_sm", args.p2p_blocks)
         elif args.precision == "bf16" and args.sharded_update >= 0 and w["H"] % world == 0:
             dev.set_option("sharded_update", args.sharded_update)
-        if args.precision == "bf16" and args.state_exchange >= 0 and not args.p2p and args.sharded_update != 0 and w["H"] % world == 0:
+        nvls_on = False
+        if args.precision == "bf16" and args.nvls and not args.p2p and args.sharded_update != 0 and args.state_exchange <= 0 and w["H"] % world == 0:
+            why = dev.enable_nvls_exchange()      # collective; "" = switched on
+            nvls_on = why == ""
+            if nvls_on:
+                exchange_mode = ("ONE fused kernel per rank over NVSwitch multicast: multimem.ld_reduce of the fp32 gradient shard (reduce-scatter in "
+                                 "the switch) + update of the owned hidden rows + multimem.st of the new bf16 shadow (all-gather by the switch); "
+                                 "transposed shadow rebuilt locally")
+            elif rank == 0:
+                print(f"[bench] NVSwitch multicast exchange not available, using the NCCL exchange: {why}", file=sys.stderr)
+        args.p2p_like = args.p2p or nvls_on
+        if args.precision == "bf16" and args.state_exchange >= 0 and not args.p2p_like and args.sharded_update != 0 and w["H"] % world == 0:
             dev.set_option("state_exchange", args.state_exchange)
     dev.set_data(Xl, Yl)
     pcd = w["algo"] == "PCD"
@@ -423,7 +439,7 @@ def main():
         sampler.start()
     barrier()
     dev.reset_counters()
-    if world > 1 and args.precision == "bf16" and args.p2p:
+    if world > 1 and args.precision == "bf16" and args.p2p_like:
         dev.p2p_timing()  # reset the in-kernel phase timers
     dev.timer_start()
     for i in range(args.steps):
@@ -434,7 +450,7 @@ def main():
     ms = max_over_ranks(ms)
     launches = dev.counters_full()[0]
     value = B * args.steps / (ms * 1e-3)
-    p2p_t = dev.p2p_timing() if (world > 1 and args.precision == "bf16" and args.p2p) else None
+    p2p_t = dev.p2p_timing() if (world > 1 and args.precision == "bf16" and args.p2p_like) else None
     dev.reset_counters()
     dev.set_option("time_gemms", 1)
     barrier()
@@ -477,7 +493,7 @@ def main():
     # ---------------- optional leg: declared stale-1 chains mode (allreduce + update overlapped with the next
     # step's chain advance; statistical parity only)
     overlap = None
-    if pcd and args.precision == "bf16" and w["L"] == 0 and ((world > 1 and (not args.p2p)) or args.stale_chains):
+    if pcd and args.precision == "bf16" and w["L"] == 0 and ((world > 1 and (not args.p2p_like)) or args.stale_chains):
         dev.set_option("stale_chains", 1)
         for i in range(args.warmup):
             step(i)
@@ -595,7 +611,7 @@ def main():
     # (read w, read g, write w); with the NCCL sharded update a rank touches only its H / world hidden rows and writes only the
     # row-major shadow (the transposed one is rebuilt after the all-gather by transpose_bf16_wide_kernel)
     P_w = (w["V"] + w["L"]) * w["H"]
-    sharded = world > 1 and args.precision == "bf16" and not args.p2p and args.sharded_update != 0 and w["H"] % world == 0
+    sharded = world > 1 and args.precision == "bf16" and not args.p2p_like and args.sharded_update != 0 and w["H"] % world == 0
     upd_bytes = (16.0 if args.precision == "bf16" else 12.0) * P_w
     if sharded:
         upd_bytes = 14.0 * P_w / world
@@ -611,6 +627,8 @@ def main():
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": cfg,
             "gibbs_steps_per_s": value * k * (w.get("chains", B) / B if pcd else 1.0), "gpu_launches": launches, "roofline": roof, "roofline_update": roof_upd, "clocks": clocks, "e2e": e2e}
+    if exchange_mode:
+        line["exchange_mode"] = exchange_mode
     if e2e_i64:
         line["e2e_i64"] = e2e_i64
     if overlap:

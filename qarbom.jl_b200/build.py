@@ -19,6 +19,38 @@ def _sources():
     return out
 
 
+def _nccl_device_api_flags():
+    """nvls_setup.cu is compiled against NCCL's own headers when the device API (NCCL >= 2.28: nccl_device/*.h, shipped in
+    the nvidia-nccl wheel next to the library torch loads) is present; without them the NVSwitch-multicast exchange reports
+    itself unavailable at run time and the NCCL collectives are used."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        roots = list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []
+    except (ImportError, ValueError):
+        roots = []
+    for r in roots:
+        inc = os.path.join(r, "include")
+        if os.path.isfile(os.path.join(inc, "nccl_device", "impl", "comm__types.h")) and os.path.isfile(os.path.join(inc, "nccl.h")):
+            return ["-DQB_HAVE_NCCL_DEVICE_API", "-I" + inc, "-diag-suppress", "821"]
+    return []
+
+
+def nccl_runtime_library():
+    """Path of the libnccl.so.2 that matches those headers (None when the wheel is absent)."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        roots = list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []
+    except (ImportError, ValueError):
+        roots = []
+    for r in roots:
+        p = os.path.join(r, "lib", "libnccl.so.2")
+        if os.path.isfile(p):
+            return p
+    return None
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
@@ -30,7 +62,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = ["nvcc", *NVCC_FLAGS, os.path.join(SRC, "qb_api.cu"), "-o", LIB, "-lcudart", "-ldl"]
+    cmd = ["nvcc", *NVCC_FLAGS, *_nccl_device_api_flags(), os.path.join(SRC, "qb_api.cu"), os.path.join(SRC, "nvls_setup.cu"),
+           "-o", LIB, "-lcudart", "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -11,6 +11,15 @@
 // system-scope flag barriers bracket the kernel: "every G is complete" and "every push has landed".
 // The kernel is launched cooperatively (grid barrier between the flag barriers and the tile loop); each GPU
 // runs its own kernel, ranks never share a GPU.
+//
+// NVLS variant (template parameter NVLS; addresses from nvls_setup.cu): the same kernel over NVSwitch MULTICAST addresses.
+//     reduce-scatter : ONE multimem.ld_reduce.add.v4.f32 per 16 bytes -- the switch sums the ranks' gradients in flight, the
+//                      owner receives 4 B/param instead of 4 B/param from every peer
+//     all-gather     : ONE multimem.st per 8 bytes of the new row-major bf16 shadow -- the switch replicates it into every
+//                      rank's buffer (2 B/param out per shard instead of 2 B/param to every peer)
+// The transposed shadow is NOT pushed in this variant (it would double the inbound NVLink bytes of every GPU); each rank
+// rebuilds it from the complete row-major shadow with a local transpose kernel, HBM-bound and 5x cheaper than the link.
+// Biases are reduced over unicast peer addresses in rank order by every rank, so the replicas stay bit-identical.
 #pragma once
 #include "common.cuh"
 #include "online_kernels.cuh"  // grid_barrier
@@ -22,6 +31,8 @@ constexpr int QB_MAX_PEERS = 8;
 struct P2pParams {
     int rank, world;
     const float *G[QB_MAX_PEERS];       // every rank's gradient buffer [W | a | b]
+    const float *G_mc;                  // NVLS: multicast address of the gradient buffers (multimem.ld_reduce = sum over ranks)
+    bf16 *Wb_mc;                        // NVLS: multicast address of the row-major shadows (multimem.st = store to all ranks)
     bf16 *Wb[QB_MAX_PEERS], *WbT[QB_MAX_PEERS];
     unsigned int *flags[QB_MAX_PEERS];  // flags[p][r]: written by rank r, polled by rank p
     float *W, *Vel;                     // local fp32 master / velocity ([H][ldv] + biases)
@@ -58,9 +69,19 @@ __device__ __forceinline__ void xgpu_barrier(const P2pParams &p, unsigned int va
     __syncthreads();
 }
 
-template <bool VEL>
+__device__ __forceinline__ float4 multimem_ld_reduce_add_f32x4(const float *mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st_b32x2(void *mc, uint2 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)) : "memory");
+}
+
+template <bool VEL, bool NVLS = false>
 __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(const P2pParams p) {
-    constexpr int TH = 64, TC = 128, PITCH = TC + 8, ROWS = 2;
+    constexpr int TH = 64, TC = 128, PITCH = TC + 8, ROWS = NVLS ? 4 : 2;   // NVLS: one 16-byte load per row, so more rows in flight
     __shared__ __align__(16) unsigned short tile[TH][PITCH];
     unsigned int gepoch = 0;
     const bool timer = blockIdx.x == 0 && threadIdx.x == 0 && p.phase_ns != nullptr;
@@ -81,7 +102,7 @@ __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(const P2pParams 
         for (int i = 0; i < 4; i++) lrc[i] = (c + i < p.V) ? p.lr : p.llr;
 #pragma unroll 1
         for (int pass = 0; pass < TH / (8 * ROWS); pass++) {
-            float4 w[ROWS], g[ROWS], v[ROWS], q[ROWS][QB_MAX_PEERS];
+            float4 w[ROWS], g[ROWS], v[ROWS], q[ROWS][NVLS ? 1 : QB_MAX_PEERS];
             // issue every load first (fully unrolled, predicated on the rank count): a remote 128-bit load takes
             // ~2-3 us over NVLink, so ROWS x world of them must be in flight per thread, not one after the other
 #pragma unroll
@@ -91,10 +112,15 @@ __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(const P2pParams 
                 const long long o = (long long)h * p.ldv + c;  // ldv % 8 == 0, padding columns are zero: 128-bit loads stay in bounds
                 w[it] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (VEL) v[it] = w[it];
+                if (NVLS) {
+                    q[it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) q[it][0] = multimem_ld_reduce_add_f32x4(p.G_mc + o);   // summed over the ranks inside the switch
+                } else {
 #pragma unroll
-                for (int r = 0; r < QB_MAX_PEERS; r++) {
-                    q[it][r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok && r < p.world) q[it][r] = __ldcg(reinterpret_cast<const float4 *>(p.G[r] + o));
+                    for (int r = 0; r < (NVLS ? 1 : QB_MAX_PEERS); r++) {
+                        q[it][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok && r < p.world) q[it][r] = __ldcg(reinterpret_cast<const float4 *>(p.G[r] + o));
+                    }
                 }
                 if (ok) {
                     w[it] = *reinterpret_cast<const float4 *>(p.W + o);
@@ -105,7 +131,7 @@ __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(const P2pParams 
             for (int it = 0; it < ROWS; it++) {
                 g[it] = q[it][0];
 #pragma unroll
-                for (int r = 1; r < QB_MAX_PEERS; r++) { g[it].x += q[it][r].x; g[it].y += q[it][r].y; g[it].z += q[it][r].z; g[it].w += q[it][r].w; }
+                for (int r = 1; r < (NVLS ? 1 : QB_MAX_PEERS); r++) { g[it].x += q[it][r].x; g[it].y += q[it][r].y; g[it].z += q[it][r].z; g[it].w += q[it][r].w; }
             }
 #pragma unroll
             for (int it = 0; it < ROWS; it++) {
@@ -124,15 +150,17 @@ __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(const P2pParams 
                 }
                 __nv_bfloat162 b01 = __floats2bfloat162_rn(wp[0], wp[1]), b23 = __floats2bfloat162_rn(wp[2], wp[3]);
                 const uint2 packed = make_uint2(*reinterpret_cast<uint32_t *>(&b01), *reinterpret_cast<uint32_t *>(&b23));
-                *reinterpret_cast<uint2 *>(&tile[hl][4 * tx]) = packed;
+                if (!NVLS) *reinterpret_cast<uint2 *>(&tile[hl][4 * tx]) = packed;
                 if (h < p.h_end && c < p.VL) {
                     const long long o = (long long)h * p.ldv + c;
                     *reinterpret_cast<float4 *>(p.W + o) = w[it];
                     if (VEL) *reinterpret_cast<float4 *>(p.Vel + o) = v[it];
-                    for (int r = 0; r < p.world; r++) *reinterpret_cast<uint2 *>(p.Wb[r] + o) = packed;  // all-gather, row-major shadow
+                    if (NVLS) multimem_st_b32x2(p.Wb_mc + o, packed);   // all-gather by the switch: one store, every rank's shadow
+                    else for (int r = 0; r < p.world; r++) *reinterpret_cast<uint2 *>(p.Wb[r] + o) = packed;  // all-gather, row-major shadow
                 }
             }
         }
+        if (NVLS) continue;   // the transposed shadow is rebuilt locally after the kernel
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < 2; q++) {  // all-gather, transposed shadow: 32 B per (column, 16-row chunk)

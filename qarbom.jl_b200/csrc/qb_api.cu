@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "online_kernels.cuh"
 #include "p2p_kernels.cuh"
+#include "nvls_setup.h"
 #include "simt_kernels.cuh"
 #include "sm100_gemm.cuh"
 #include "sm100_chain.cuh"
@@ -47,8 +48,12 @@ struct Nccl {
 Nccl &nccl() {
     static Nccl n;
     if (!n.lib) {
-        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        // QB_NCCL_LIB: an explicit library (the host layer points it at the nvidia-nccl wheel torch uses, whose version matches
+        // the device-API headers nvls_setup.cu was built against); else whatever "libnccl.so.2" resolves to -- the copy already
+        // loaded into the process (torch.distributed) wins by SONAME
+        const char *names[] = {getenv("QB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
         for (const char *nm : names) {
+            if (!nm || !*nm) continue;
             n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
             if (n.lib) break;
         }
@@ -192,6 +197,9 @@ struct qb_handle {
     unsigned int p2p_epoch = 1; unsigned long long *p2p_ns = nullptr; int p2p_blocks_per_sm = 3;
     unsigned int *p2p_timeout_host = nullptr, *p2p_timeout_dev = nullptr;
     int64_t shard_rows = 0;
+    // NVLS variant of that kernel (option "nvls_exchange"): G, the row-major shadow and the barrier flags live in NCCL
+    // symmetric windows; the kernel reduces through the switch (multimem.ld_reduce) and pushes through it (multimem.st)
+    bool nvls = false; void *nvls_state = nullptr; const float *G_mc = nullptr; bf16 *Wb_mc = nullptr;
     // NCCL variant of the sharded update (option "sharded_update", bf16, H % world == 0): reduce-scatter of the fp32
     // gradient, update of the owned hidden rows only, all-gather of the bf16 shadow, local transpose.  Moves 3/4 of the
     // allreduce bytes and does 1/world of the update work; the fp32 master is then sharded like in the p2p path.
@@ -862,6 +870,7 @@ void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local) {
     for (int r = 0; r < p.world; r++) {
         p.G[r] = h->peerG[r]; p.Wb[r] = h->peerWb[r]; p.WbT[r] = h->peerWbT[r]; p.flags[r] = h->peerFlags[r];
     }
+    p.G_mc = h->G_mc; p.Wb_mc = h->Wb_mc;
     p.W = h->P; p.Vel = use_vel ? h->Vel : nullptr; p.bias_rd = h->bias_rd;
     p.H = (int)h->H; p.VL = (int)h->VL; p.V = (int)h->V; p.ldv = h->ldv; p.ldh = h->ldh; p.nW = h->nW;
     p.h_begin = (int)std::min<int64_t>(h->H, (int64_t)p.rank * h->shard_rows);
@@ -888,23 +897,70 @@ void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local) {
         QB_CUDA(cudaEventRecord(h->upd_ev[ei], h->stream));
     }
     void *args[] = {(void *)&p};
-    if (use_vel) QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<true>, dim3(p2p_grid), dim3(256), args, 0, h->stream));
+    if (h->nvls) {
+        if (use_vel) QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<true, true>, dim3(p2p_grid), dim3(256), args, 0, h->stream));
+        else QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<false, true>, dim3(p2p_grid), dim3(256), args, 0, h->stream));
+        // every rank's rows of the row-major shadow have landed (second barrier of the kernel): rebuild the transposed one
+        dim3 gt((unsigned)ceil_div(h->VL, 128), (unsigned)ceil_div(h->H, 64));
+        transpose_bf16_wide_kernel<<<gt, 256, 0, h->stream>>>(h->Wb, h->ldv, (int)h->H, (int)h->VL, h->WbT, h->ldh);
+        QB_CUDA(cudaGetLastError());
+        h->launches += 1;
+        h->master_sharded = true;
+    } else if (use_vel) QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<true>, dim3(p2p_grid), dim3(256), args, 0, h->stream));
     else QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<false>, dim3(p2p_grid), dim3(256), args, 0, h->stream));
     if (timed) QB_CUDA(cudaEventRecord(h->upd_ev[ei + 1], h->stream));
     h->launches += 1;
+    h->w3_dirty = true;
+}
+
+// Option "nvls_exchange" = 1 (COLLECTIVE: every rank, after qb_comm_init, between steps): move the gradient, the row-major
+// bf16 shadow and the barrier flags into NCCL symmetric windows and switch the data-parallel exchange to the NVLS variant of
+// p2p_reduce_update_kernel.  Throws QB_E_UNSUPPORTED with the reason when multicast is not available (nothing changes then).
+void nvls_enable(qb_handle *h) {
+    if (h->nvls) return;
+    QB_CHECK(h->comm != nullptr, QB_E_STATE, "nvls_exchange needs a communicator: call qb_comm_init first");
+    QB_CHECK(h->bf && h->cfg.world > 1 && h->cfg.world <= QB_MAX_PEERS, QB_E_UNSUPPORTED, "nvls_exchange needs bf16 precision and 2..8 ranks");
+    QB_CHECK(!h->p2p && !h->stale_chains && !h->state_exchange, QB_E_UNSUPPORTED, "nvls_exchange excludes qb_p2p_import, stale_chains and state_exchange");
+    QB_CHECK((h->H % h->cfg.world) == 0, QB_E_UNSUPPORTED, "nvls_exchange needs n_hidden to be a multiple of the number of ranks (equal shards of hidden rows)");
+    QB_CHECK(h->nccl_mem.empty(), QB_E_UNSUPPORTED, "nvls_exchange and QB_NCCL_REGISTER are mutually exclusive");
+    QB_CUDA(cudaStreamSynchronize(h->stream));
+    QbNvlsBuffers io{};
+    io.n = 3;
+    io.bytes[0] = (size_t)h->nP * sizeof(float);
+    io.bytes[1] = (size_t)h->H * h->ldv * sizeof(bf16);
+    io.bytes[2] = 4096;
+    const char *why = qb_nvls_setup(nccl().lib, h->comm, &io);
+    if (why) throw Error(QB_E_UNSUPPORTED, std::string("NVSwitch multicast exchange unavailable: ") + why);
+    QB_CHECK(io.lsa_rank == h->cfg.rank && io.lsa_size == h->cfg.world, QB_E_NCCL, "NCCL's load/store team does not match the ranks of this job");
+    if (cudaMemcpy(io.local[1], h->Wb, io.bytes[1], cudaMemcpyDeviceToDevice) != cudaSuccess) {
+        qb_nvls_teardown(io.state);
+        throw Error(QB_E_CUDA, "copying the shadow into the symmetric window failed");
+    }
+    cudaFree(h->G); cudaFree(h->Wb);
+    h->G = (float *)io.local[0]; h->Wb = (bf16 *)io.local[1];
+    h->G_mc = (const float *)io.mc[0]; h->Wb_mc = (bf16 *)io.mc[1];
+    for (int r = 0; r < h->cfg.world; r++) {
+        h->peerG[r] = (float *)io.peer[0][r]; h->peerWb[r] = (bf16 *)io.peer[1][r]; h->peerWbT[r] = nullptr;
+        h->peerFlags[r] = (unsigned int *)io.peer[2][r]; h->peerP[r] = nullptr;
+    }
+    if (!h->p2p_grid_bar) { h->p2p_grid_bar = dalloc<unsigned int>(1); h->p2p_ns = dalloc<unsigned long long>(2); }
+    h->shard_rows = h->H / h->cfg.world;
+    h->bias_grads_clean = false;   // the fresh gradient buffer is zero everywhere, but the flag's other invariants (datasum) are per step
+    h->nvls_state = io.state;
+    h->nvls = true; h->p2p = true; h->sharded_update = true;
 }
 
 // p2p mode: the fp32 master is sharded by hidden rows; pull the other ranks' shards (collective by convention:
 // every rank is between steps when any rank calls this)
 void p2p_gather_master(qb_handle *h) {
-    if (h->master_sharded && h->comm && !h->p2p) {  // NCCL sharded update: in-place all-gather of the owned hidden rows
+    if (h->master_sharded && h->comm && (!h->p2p || h->nvls)) {  // NCCL sharded update / NVLS kernel (equal shards): in-place all-gather of the owned hidden rows
         const int64_t sr = h->H / h->cfg.world;
         QB_NCCL(nccl().AllGather(h->P + sr * h->cfg.rank * h->ldv, h->P, (size_t)(sr * h->ldv), /*ncclFloat32*/ 7, h->comm, h->stream));
         QB_CUDA(cudaStreamSynchronize(h->stream));
         h->master_sharded = false;
         return;
     }
-    if (!h->p2p) return;
+    if (!h->p2p || h->nvls) return;
     QB_CUDA(cudaStreamSynchronize(h->stream));
     for (int r = 0; r < h->cfg.world; r++) {
         if (r == h->cfg.rank) continue;
@@ -1569,10 +1625,11 @@ int32_t qb_destroy(qb_handle *h) {
             if (p && std::find(h->nccl_mem.begin(), h->nccl_mem.end(), p) != h->nccl_mem.end()) nccl().MemFree(p);
             else cudaFree(p);
         };
+        if (h->nvls_state) { qb_nvls_teardown(h->nvls_state); h->nvls_state = nullptr; h->G = nullptr; h->Wb = nullptr; }   // (frees G / Wb / flags windows)
         if (h->comm) for (void *r : h->nccl_reg) nccl().CommDeregister(h->comm, r);
         if (h->comm_overlap) nccl().CommDestroy(h->comm_overlap);
         if (h->comm) nccl().CommDestroy(h->comm);
-        if (h->p2p)
+        if (h->p2p && !h->nvls)
             for (int r = 0; r < h->cfg.world; r++)
                 if (r != h->cfg.rank) {
                     cudaIpcCloseMemHandle(h->peerG[r]); cudaIpcCloseMemHandle(h->peerWb[r]); cudaIpcCloseMemHandle(h->peerWbT[r]);
@@ -2438,6 +2495,9 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
             int bn = (int)value;
             QB_CHECK(bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 256, QB_E_ARG, "force_bn must be 0/32/64/128/256");
             h->force_bn = bn;
+        } else if (!strcmp(key, "nvls_exchange")) {
+            QB_CHECK(value == 1.0, QB_E_ARG, "nvls_exchange can only be switched on (1)");
+            nvls_enable(h);
         } else if (!strcmp(key, "p2p_blocks_per_sm")) {
             QB_CHECK(value >= 1 && value <= 4, QB_E_ARG, "p2p_blocks_per_sm must be 1..4");
             h->p2p_blocks_per_sm = (int)value;

@@ -3,12 +3,13 @@ Julia shim, which cannot be executed in this image -- see INTEGRATION.md)."""
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Sequence
 
 import numpy as np
 
 from . import _ffi
-from ._ffi import QbConfig, as_rows, check, lib, ptr
+from ._ffi import QbConfig, QbError, as_rows, check, lib, ptr
 
 
 class DeviceRBM:
@@ -265,8 +266,27 @@ class DeviceRBM:
         return buf.raw
 
     def comm_init(self, uid: bytes):
+        # the library dlopens NCCL itself: point it at the nvidia-nccl wheel (the copy torch.distributed uses, and the one whose
+        # device-API headers the NVSwitch-multicast exchange was built against) unless the caller chose a library
+        if not os.environ.get("QB_NCCL_LIB"):
+            from .build import nccl_runtime_library
+            path = nccl_runtime_library()
+            if path:
+                os.environ["QB_NCCL_LIB"] = path
         buf = ctypes.create_string_buffer(uid, 128)
         check(lib().qb_comm_init(self._h, buf))
+
+    def enable_nvls_exchange(self) -> str:
+        """COLLECTIVE (every rank, after comm_init, between steps): switch the gradient exchange to the fused kernel over
+        NVSwitch multicast (multimem.ld_reduce / multimem.st).  Returns "" on success, else the reason why multicast is
+        unavailable -- the NCCL reduce-scatter / all-gather exchange stays in place then."""
+        try:
+            self.set_option("nvls_exchange", 1)
+            return ""
+        except QbError as e:
+            if e.code != -5:   # QB_E_UNSUPPORTED
+                raise
+            return str(e)
 
     def p2p_export(self) -> bytes:
         buf = ctypes.create_string_buffer(320)
