@@ -11,6 +11,12 @@
 //   * the rank-2 update  W += lr (v h_d' - v~ h~')  (src/rbm.jl:138-150) is applied by the owners to both
 //     layouts right away -- the next sample's products read only rows the CTA itself updated.
 //
+// Classifier models (src/training/train_cd.jl:23-43 -- the classifier DEFAULT): the label units are the last L of the V rows
+// ([v | y] data rows, [W | U] columns, [a | c] biases).  The chain runs on the 3-argument conditional_prob_h, the visible
+// half-step leaves the label PRE-activations in the exchange vector and every CTA finishes them identically (softmax over the
+// L units, then independent Bernoulli draws: gibbs_sample_label, src/gibbs.jl:46-49), h_model comes from the 2-argument form
+// that ignores the sampled labels (train_cd.jl:34), and label columns move with label_learning_rate (src/rbm.jl:101-118).
+//
 // fp32 arithmetic (a matrix-vector product is bandwidth/latency-bound: tensor cores do not apply).
 // Random numbers follow the library contract with row = 0 and two draw ids per Gibbs step, i.e. exactly
 // what a sequence of qb_cd_step(B = 1) calls consumes.
@@ -24,8 +30,9 @@ struct OnlineCdParams {
     float *W2; long long ldh;     // [V][ldh]   (fp32 transposed copy, updated in place)
     float *a, *b;                 // biases (updated in place)
     const float *Xf; const bf16 *Xb; long long ldx;  // dataset rows (one of the two is set)
-    int V, H, n_samples, k, gaussian;
-    float lr;
+    int V, H, n_samples, k, gaussian;   // V counts the label units too ([v | y] rows)
+    int Vx;                             // visible units proper: rows / columns >= Vx are label units
+    float lr, llr;
     float *vec;                   // scratch: 2 (parity) x [hd | hs | hm | vm]
     unsigned int *barrier;        // grid barrier counter (zeroed before launch)
     const float *injUh, *injUv;   // optional injected streams [k][n_samples][H] / [k][n_samples][V] (uniforms or normals)
@@ -72,6 +79,21 @@ __device__ __forceinline__ void owned_rows(int n_rows, const float *__restrict__
         const float *w = cache ? cache + (long long)m * n_cols : W + (long long)r * ld;
         float acc = 0.f;
         for (int c = lane; c < n_cols; c += 32) acc = fmaf(w[c], x_smem[c], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) finish(r, acc);
+    }
+}
+
+// same with a dot product over the first n_dot of the row's n_cols columns
+template <typename F>
+__device__ __forceinline__ void owned_rows_pitch(int n_rows, const float *__restrict__ W, long long ld, int n_cols, int n_dot,
+                                                 const float *__restrict__ x_smem, const float *cache, F &&finish) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    int m = 0;
+    for (int r = blockIdx.x * wpb + warp; r < n_rows; r += gridDim.x * wpb, m++) {
+        const float *w = cache ? cache + (long long)m * n_cols : W + (long long)r * ld;
+        float acc = 0.f;
+        for (int c = lane; c < n_dot; c += 32) acc = fmaf(w[c], x_smem[c], acc);
         acc = warp_sum(acc);
         if (lane == 0) finish(r, acc);
     }
@@ -135,7 +157,9 @@ __global__ void __launch_bounds__(1024) online_cd_kernel(const OnlineCdParams p)
             owned_rows(V, p.W2, p.ldh, H, sh, c2, [&](int i, float acc) {
                 const float x = acc + p.a[i];
                 const long long io = ((long long)s * p.n_samples + n) * V + i;
-                if (p.gaussian) {
+                if (i >= p.Vx) {
+                    g_vm[i] = x;   // label unit: pre-activation c_l + U_l . h, finished after the barrier
+                } else if (p.gaussian) {
                     const float z = p.injUv ? p.injUv[io] : rng_normal(kv, (uint32_t)i, 0ull);
                     g_vm[i] = x + z;
                 } else {
@@ -145,7 +169,24 @@ __global__ void __launch_bounds__(1024) online_cd_kernel(const OnlineCdParams p)
                 }
             });
             grid_barrier(p.barrier, epoch, nb);
-            for (int i = threadIdx.x; i < V; i += blockDim.x) sv[i] = g_vm[i];
+            for (int i = threadIdx.x; i < p.Vx; i += blockDim.x) sv[i] = g_vm[i];
+            if (p.Vx < V) {
+                // ---- gibbs_sample_label: every warp reduces the L pre-activations (same numbers in every CTA), then each thread
+                // draws its label units -- p_l = exp(x_l - logsumexp(x)) (src/rbm.jl:196-205), y_l = 1[u_l < p_l]
+                float mx = -INFINITY;
+                for (int l = p.Vx + lane_; l < V; l += 32) mx = fmaxf(mx, g_vm[l]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                float den = 0.f;
+                for (int l = p.Vx + lane_; l < V; l += 32) den += expf(g_vm[l] - mx);
+                den = warp_sum(den);
+                const float lse = mx + logf(den);
+                for (int l = p.Vx + threadIdx.x; l < V; l += blockDim.x) {
+                    const float pr = expf(g_vm[l] - lse);
+                    const float u = p.injUv ? p.injUv[((long long)s * p.n_samples + n) * V + l] : rng_uniform(kv, (uint32_t)l, 0ull);
+                    sv[l] = (u < pr) ? 1.f : 0.f;
+                }
+            }
             __syncthreads();
             if (s + 1 < p.k) {
                 // ---- next hidden sample of the chain
@@ -160,7 +201,9 @@ __global__ void __launch_bounds__(1024) online_cd_kernel(const OnlineCdParams p)
             }
         }
         // ---- h_model = conditional_prob_h(v_model): probabilities
-        owned_rows(H, p.W1, p.ldv, V, sv, c1, [&](int j, float acc) { g_hm[j] = sigmoid_exact(acc + p.b[j]); });
+        // (2-argument form: only the Vx visible columns -- the sampled labels are ignored, train_cd.jl:34; a cached row keeps its
+        // pitch V, the dot product just stops at Vx)
+        owned_rows_pitch(H, p.W1, p.ldv, V, p.Vx, sv, c1, [&](int j, float acc) { g_hm[j] = sigmoid_exact(acc + p.b[j]); });
         grid_barrier(p.barrier, epoch, nb);
         if (timer) { unsigned long long t1 = gtimer(); acc_ns[1] += t1 - t0; t0 = t1; }
         // ---- update_rbm!(rbm, v_data, h_data, v_model, h_model, lr): owners update both layouts
@@ -172,15 +215,16 @@ __global__ void __launch_bounds__(1024) online_cd_kernel(const OnlineCdParams p)
             for (int j = blockIdx.x * wpb + warp; j < H; j += gridDim.x * wpb, m++) {
                 float *w = CACHE ? c1 + (long long)m * V : p.W1 + (long long)j * p.ldv;
                 const float hd = sh[j], hm = sh2[j];
-                for (int c = lane; c < V; c += 32) w[c] += p.lr * (sx[c] * hd - sv[c] * hm);
+                for (int c = lane; c < V; c += 32) w[c] += (c < p.Vx ? p.lr : p.llr) * (sx[c] * hd - sv[c] * hm);
                 if (lane == 0) p.b[j] += p.lr * (hd - hm);
             }
             m = 0;
             for (int i = blockIdx.x * wpb + warp; i < V; i += gridDim.x * wpb, m++) {
                 float *w = CACHE ? c2 + (long long)m * H : p.W2 + (long long)i * p.ldh;
                 const float xd = sx[i], xm = sv[i];
-                for (int c = lane; c < H; c += 32) w[c] += p.lr * (xd * sh[c] - xm * sh2[c]);
-                if (lane == 0) p.a[i] += p.lr * (xd - xm);
+                const float lr_i = i < p.Vx ? p.lr : p.llr;
+                for (int c = lane; c < H; c += 32) w[c] += lr_i * (xd * sh[c] - xm * sh2[c]);
+                if (lane == 0) p.a[i] += lr_i * (xd - xm);
             }
         }
         __syncthreads();  // sx / sv / sh are rewritten by the next sample

@@ -1856,40 +1856,40 @@ int32_t qb_cd_step(qb_handle *h, int64_t batch_index, int64_t B, int64_t k, doub
 
 // contrastive_divergence! with the reference's own batch size 1 (src/training/train_cd.jl:2-21): one cooperative
 // persistent kernel for the whole epoch (online_kernels.cuh) instead of 2k+3 launches per sample
-static bool online_cd_epoch(qb_handle *h, int64_t k, double lr, double times[3]) {
-    if (!h->online_kernel || h->L > 0 || h->cfg.world > 1 || h->momentum != 0.0 || h->weight_decay != 0.0) return false;
+static bool online_cd_epoch(qb_handle *h, int64_t k, double lr, double llr, double times[3]) {
+    if (!h->online_kernel || h->cfg.world > 1 || h->momentum != 0.0 || h->weight_decay != 0.0) return false;
     const int64_t N = h->N;
     if (h->inj_active) QB_CHECK(h->inj_B == N && h->inj_k >= k, QB_E_ARG, "injected streams must cover every sample of the epoch");
     if (!h->W2) {
-        h->W2 = dalloc<float>(h->V * h->ldh);
-        h->online_vec = dalloc<float>(2 * (3 * h->H + h->V));
+        h->W2 = dalloc<float>(h->VL * h->ldh);
+        h->online_vec = dalloc<float>(2 * (3 * h->H + h->VL));
         h->online_bar = dalloc<unsigned int>(1);
         h->online_ns = dalloc<unsigned long long>(3);
     }
     {
-        dim3 g((unsigned)ceil_div(h->V, 32), (unsigned)ceil_div(h->H, 32));
-        transpose_f32_kernel<<<g, 256, 0, h->stream>>>(Wf(h), h->ldv, (int)h->H, (int)h->V, h->W2, h->ldh);
+        dim3 g((unsigned)ceil_div(h->VL, 32), (unsigned)ceil_div(h->H, 32));
+        transpose_f32_kernel<<<g, 256, 0, h->stream>>>(Wf(h), h->ldv, (int)h->H, (int)h->VL, h->W2, h->ldh);
         QB_CUDA(cudaGetLastError());
     }
     QB_CUDA(cudaMemsetAsync(h->online_bar, 0, sizeof(unsigned int), h->stream));
     OnlineCdParams p{};
     p.W1 = Wf(h); p.ldv = h->ldv; p.W2 = h->W2; p.ldh = h->ldh; p.a = acat(h); p.b = bh(h);
     p.Xf = h->data.f; p.Xb = h->data.b; p.ldx = h->data.ld;
-    p.V = (int)h->V; p.H = (int)h->H; p.n_samples = (int)N; p.k = (int)k; p.gaussian = h->gaussian ? 1 : 0;
-    p.lr = (float)lr;
+    p.V = (int)h->VL; p.Vx = (int)h->V; p.H = (int)h->H; p.n_samples = (int)N; p.k = (int)k; p.gaussian = h->gaussian ? 1 : 0;
+    p.lr = (float)lr; p.llr = (float)llr;
     p.vec = h->online_vec; p.barrier = h->online_bar; p.phase_ns = h->online_ns;
-    if (h->inj_active) { p.injUh = h->injUh; p.injUv = h->gaussian ? h->injZv : h->injUv; }
+    if (h->inj_active) { p.injUh = h->injUh; p.injUv = (h->gaussian && h->L == 0) ? h->injZv : h->injUv; }   // classifier streams: one [k][N][V + L] array
     p.key0.seed_lo = (uint32_t)h->seed; p.key0.seed_hi = (uint32_t)(h->seed >> 32);
     p.key0.draw_lo = (uint32_t)h->draw; p.key0.draw_hi = (uint32_t)(h->draw >> 32) & 0x7FFFFFFFu;
     // fewer, fatter CTAs make the grid barrier cheaper: one row per warp, up to 32 warps per CTA
-    const int64_t rows = std::max(h->H, h->V);
+    const int64_t rows = std::max(h->H, h->VL);
     const int wpb = h->online_wpb > 0 ? h->online_wpb : (rows >= 148 * 16 ? 32 : (rows >= 148 * 4 ? 16 : 8));
     int grid = (int)std::min<int64_t>(h->num_sms, std::max<int64_t>(1, ceil_div(rows, wpb)));
-    const size_t smem_vec = (size_t)(2 * h->V + 2 * h->H) * sizeof(float);
+    const size_t smem_vec = (size_t)(2 * h->VL + 2 * h->H) * sizeof(float);
     QB_CHECK(smem_vec <= 200 * 1024, QB_E_UNSUPPORTED, "model too large for the online kernel's shared-memory vectors");
     // rows owned by a warp stay in shared memory for the whole epoch when they fit
     const int64_t warps = (int64_t)grid * wpb;
-    const size_t smem_rows = (size_t)wpb * (size_t)(ceil_div(h->H, warps) * h->V + ceil_div(h->V, warps) * h->H) * sizeof(float);
+    const size_t smem_rows = (size_t)wpb * (size_t)(ceil_div(h->H, warps) * h->VL + ceil_div(h->VL, warps) * h->H) * sizeof(float);
     const bool cache = smem_vec + smem_rows <= 200 * 1024;
     const size_t smem = smem_vec + (cache ? smem_rows : 0);
     void *args[] = {(void *)&p};
@@ -1998,7 +1998,7 @@ static void fast_pcd_epoch(qb_handle *h, int64_t B, int64_t k, double lr, double
 
 static void epoch_impl(qb_handle *h, bool pcd, int64_t B, int64_t k, double lr, double llr, double times[3]) {
     check_step_args(h, B, k);
-    if (!pcd && B == 1 && h->N >= 1 && online_cd_epoch(h, k, lr, times)) return;
+    if (!pcd && B == 1 && h->N >= 1 && online_cd_epoch(h, k, lr, llr, times)) return;
     QB_CHECK(!h->inj_active, QB_E_STATE, "injected streams are per step (or per online CD epoch); use qb_pcd_step / qb_cd_step");
     QB_CHECK(h->N > 0, QB_E_STATE, "qb_set_data has not been called");
     const int64_t nb = h->N / B;  // _set_mini_batches: trailing remainder dropped -- all of it when N < B (src/utils.jl:13-26)

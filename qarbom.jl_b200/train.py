@@ -176,10 +176,12 @@ def train(rbm: AbstractRBM, x_train, method, label_train=None, *, n_epochs: int,
         dev.pull_params()
         merged = {k: [initial[k]] + hist[k] for k in keys}                # merge_metrics
         if file_path:
+            # CSV.write(file_path, DataFrame(metrics_dict)), train_cd.jl:113-115: a DataFrame built from a Dict sorts its columns by name
+            cols = sorted(keys)
             with open(file_path, "w", newline="") as f:
                 w = csv.writer(f)
-                w.writerow(keys)
-                for row in zip(*[merged[k] for k in keys]):
+                w.writerow(cols)
+                for row in zip(*[merged[k] for k in cols]):
                     w.writerow(row)
         if verbose:
             _log_finish(epochs_run, *tot)

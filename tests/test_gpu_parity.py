@@ -702,6 +702,56 @@ def test_online_cd_epoch_matches_reference_algorithm(q, prec, V, H, gaussian, k,
         assert np.max(np.abs(dev.rbm.a - m.a)) < 2e-6 and np.max(np.abs(dev.rbm.b - m.b)) < 2e-6
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("V,H,L,gaussian,k,n", [(3, 2, 1, False, 3, 40), (50, 30, 4, False, 1, 64), (784, 1000, 10, False, 1, 12),
+                                                 (24, 16, 3, True, 2, 32)])
+def test_online_cd_epoch_classifier_matches_reference_algorithm(q, prec, V, H, L, gaussian, k, n):
+    """train!(rbm, x, y, CD) for classifier models (src/training/train_cd.jl:23-43, the classifier default: batch size 1):
+    3-argument h_data, chain over (h, v, y) with softmax + independent Bernoulli label draws, h_model from the 2-argument form
+    that ignores the sampled labels, W / a / b with learning_rate and U / c with label_learning_rate -- one kernel per epoch
+    against the oracle's per-sample algorithm fed the same injected streams."""
+    rng = np.random.default_rng(97 + V + k + L)
+    m = make_oracle_model(rng, V, H, L, gaussian, scale=0.2)
+    X, Y = _data(rng, n, V, L, gaussian, prec == "bf16")
+    ds = DenseStreams(rng, k, n, V, H, L, gaussian)
+    su, sz = ds.serial("cd")
+    st = qo.GuardedStream(su, sz)
+    m0 = qo.copy_rbm(m)
+    qo.contrastive_divergence(m, X, steps=k, learning_rate=0.02, stream=st, y=Y, label_learning_rate=0.03, batch_size=1)
+    ds.absorb(st.u, "cd")
+    with q.DeviceRBM(to_host_rbm(q, m0), max_batch=4, precision=prec) as dev:
+        dev.set_data(X, Y)
+        dev.inject_streams(ds.U_h, ds.U_v, ds.U_y, ds.Z_v)
+        dev.reset_counters()
+        t = dev.cd_epoch(1, k, 0.02, 0.03)
+        assert dev.counters()[0] <= 4, "the epoch must be ONE cooperative launch (+ transposes), not a launch sequence per sample"
+        assert all(x >= 0 for x in t) and sum(t) > 0
+        dev.pull_params()
+        assert rel_err(dev.rbm.W, m.W) < 2e-5 and rel_err(dev.rbm.W - m0.W, m.W - m0.W) < 2e-4
+        assert rel_err(dev.rbm.U, m.U) < 2e-5 and rel_err(dev.rbm.U - m0.U, m.U - m0.U) < 2e-4
+        assert np.max(np.abs(dev.rbm.a - m.a)) < 2e-6 and np.max(np.abs(dev.rbm.b - m.b)) < 2e-6 and np.max(np.abs(dev.rbm.c - m.c)) < 2e-6
+
+
+def test_online_cd_classifier_kernel_equals_per_sample_steps(q):
+    """... and, with the production Philox stream, the classifier epoch equals a sequence of qb_cd_step(B = 1) calls."""
+    rng = np.random.default_rng(94)
+    V, H, L, k, n = 64, 40, 5, 2, 48
+    m = make_oracle_model(rng, V, H, L, scale=0.2)
+    X, Y = _data(rng, n, V, L, False, False)
+    out = []
+    for online in (1, 0):
+        rbm = to_host_rbm(q, m)
+        with q.DeviceRBM(rbm, max_batch=4, precision="fp32", seed=23) as dev:
+            dev.set_option("online_kernel", online)
+            dev.set_data(X, Y)
+            dev.cd_epoch(1, k, 0.02, 0.03, timed=False)
+            dev.pull_params()
+            out.append((rbm.W.copy(), rbm.U.copy(), rbm.a.copy(), rbm.b.copy(), rbm.c.copy()))
+    for a, b in zip(*out):
+        assert np.max(np.abs(a - b)) < 2e-6
+    assert np.max(np.abs(out[0][1] - m.U)) > 1e-3
+
+
 def test_online_cd_kernel_equals_per_sample_steps(q):
     """... and, with the production Philox stream, equal a sequence of qb_cd_step(B = 1) calls."""
     rng = np.random.default_rng(93)
