@@ -55,10 +55,13 @@ NCU_UPDATE_SUMMARY = "r2_ncu_update_raw_summary.txt"
 
 def gemm_mix(w):
     """Launches per step by kernel specialisation (template argument text of the ncu kernel name)."""
+    # With the persistent chain kernel (the default where a half-step is at least one wave of pair tiles, e.g. cfg5) a step is
+    # ONE gibbs_chain_kernel launch (all 2k + 1 forward contractions) + the gradient GEMM; the per-half-step kernels appear in a
+    # capture only when that kernel is off.  Keys absent from the capture drop out of the weighted mean.
     k = w["k"]
     if w["algo"] == "PCD":
-        return {", 2>": 2 * k, ", 3>": 1, ", 1>": 1}      # K_FAST_SAMPLE, K_FAST_PROB, K_GRAD
-    return {", 2>": 2 * k - 1, ", 4>": 1, ", 3>": 1, ", 1>": 1}
+        return {"gibbs_chain_kernel": 1, ", 2>": 2 * k, ", 3>": 1, ", 1>": 1}      # chain | K_FAST_SAMPLE, K_FAST_PROB, K_GRAD
+    return {"gibbs_chain_kernel": 1, ", 2>": 2 * k - 1, ", 4>": 1, ", 3>": 1, ", 1>": 1}
 
 
 def peaks():
@@ -588,10 +591,11 @@ def main():
             "frac": (achieved / pk["tf"]) if achieved else None,
             "frac_burst": (achieved / tf_burst) if achieved else None, "frac_sustained": (achieved / tf_sust) if achieved else None,
             "peak_burst": tf_burst, "peak_sustained": tf_sust,
-            "traffic": ncu_traffic(NCU_GEMM_SUMMARY, "gibbs_gemm_kernel", mix=gemm_mix(w)) if cfg5_bf16 else None,
+            "traffic": ncu_traffic(NCU_GEMM_SUMMARY, "gibbs_", mix=gemm_mix(w)) if cfg5_bf16 else None,
             "traffic_note": "dram read+write bytes per launch from one `ncu --set full` capture of this command (profiles/" + NCU_GEMM_SUMMARY +
-                            "), per-specialisation means weighted by the launch mix of a step (2k sampling : 1 probability : 1 gradient)",
-            "kernel": "qb::sm100::gibbs_gemm_kernel (fused Gibbs half-step / gradient GEMMs)" if args.precision == "bf16"
+                            "), per-kernel means weighted by the launch mix of a step (1 chain launch = the 2k + 1 forward contractions : 1 gradient GEMM)",
+            "kernel": "qb::sm100::gibbs_chain_kernel (persistent: all fused Gibbs half-steps of the step) + gibbs_gemm_kernel_2cta<., K_GRAD> (gradient); "
+                      "gibbs_gemm_kernel* per half-step where the chain kernel does not pay" if args.precision == "bf16"
             else "qb::simt_gemm_kernel (fp32 validation path)",
             "gemm_launches_timed": timed, "avg_launch_ms": gemm_ms / max(timed, 1),
             "gemm_share_of_step": gemm_ms / ms_instr if ms_instr > 0 else None,

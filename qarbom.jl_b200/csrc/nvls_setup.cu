@@ -114,11 +114,11 @@ extern "C" const char *qb_nvls_setup(void *nccl_lib, void *comm_, QbNvlsBuffers 
         if (cudaMemcpy(&w, st->win[i], sizeof(w), cudaMemcpyDeviceToHost) != cudaSuccess) { qb_nvls_teardown(st); return "reading a window descriptor failed"; }
         io->local[i] = st->mem[i];
         io->mc[i] = (char *)st->devComm.lsaMultimem.mcBasePtr + (uint64_t)w.mcOffset4K * 4096;
+        // rank p's buffer as seen from this GPU; slot lsaRank is a second mapping of my own buffer (an alias of st->mem[i],
+        // same physical memory), so the local pointer handed out is the allocation itself
         for (int p = 0; p < io->lsa_size; p++) io->peer[i][p] = add4g(w.lsaFlatBase, (uint32_t)p * w.stride4G);
-        if (io->peer[i][w.lsaRank] != st->mem[i]) {   // the window must map my own buffer at my own slot
-            qb_nvls_teardown(st);
-            return "symmetric window does not map the local buffer where expected (window layout mismatch)";
-        }
+        if (w.lsaRank != st->devComm.lsaRank || w.stride4G == 0) { qb_nvls_teardown(st); return "unexpected symmetric window descriptor"; }
+        io->peer[i][w.lsaRank] = st->mem[i];
     }
     io->state = st;
     return nullptr;
