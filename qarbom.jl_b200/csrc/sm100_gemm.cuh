@@ -347,6 +347,14 @@ __device__ __forceinline__ void epilogue_sample(const EpiParams &ep, uint32_t tm
 //                   optional prob_T; bias gradient of s (bg_what == 2) or p (bg_what == 1)
 //   SAMPLE = false: p = sigmoid(x); stores prob_T / prob_rm (optional); bias gradient of p
 // sigmoid with exactly two MUFU ops and no range fix-ups: x -> -inf gives ex2 = +inf, rcp(inf) = 0
+// sigmoid(acc + bias) with the bias folded into the exponent's multiply: ex2(acc * -log2e + bias * -log2e), one FFMA instead
+// of FADD + FMUL (bias_l2e = bias * -log2e, once per thread)
+__device__ __forceinline__ float sigmoid_mufu_fma(float acc, float bias_l2e) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(acc, -1.4426950408889634f, bias_l2e)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
 __device__ __forceinline__ float sigmoid_mufu(float x) {
     float e, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
@@ -380,6 +388,7 @@ template <bool SAMPLE, bool PROB, bool FULL, bool GAUSS = false>
 __device__ __forceinline__ void fast_chunk(const EpiParams &ep, const uint32_t (&r)[16], int unit, int row_base, int nv, float bias,
                                            bool want_sT, bool want_pT, bool want_prm, float &bg_p, int &bg_s) {
     uint32_t sb[16], pb[16];
+    const float bias_l2e = bias * -1.4426950408889634f;
 #pragma unroll
     for (int g = 0; g < 4; g++) {
         uint32_t rnd[4];
@@ -404,16 +413,17 @@ __device__ __forceinline__ void fast_chunk(const EpiParams &ep, const uint32_t (
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) {
                 const int j = 4 * g + jj;
-                const float p = sigmoid_mufu(__uint_as_float(r[j]) + bias);
+                const float p = sigmoid_mufu_fma(__uint_as_float(r[j]), bias_l2e);
                 if (PROB) {
                     const float ps = p * ep.pscale;
                     if (FULL || j < nv) bg_p += ps;
                     pb[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(ps));
                 }
                 if (SAMPLE) {
-                    const bool on = u23(rnd[jj]) < p;
-                    sb[j] = on ? 0x3F80u : 0u;  // bf16(1.0) / bf16(0.0)
-                    bg_s += (on && (FULL || j < nv)) ? 1 : 0;
+                    sb[j] = (u23(rnd[jj]) < p) ? 0x3F80u : 0u;  // bf16(1.0) / bf16(0.0)
+                    // bias-gradient count: the state bits are summed as they are (one add, no second use of the predicate) and
+                    // divided by 0x3F80 once per thread at the end
+                    bg_s += (FULL || j < nv) ? (int)sb[j] : 0;
                 }
             }
         }
@@ -485,9 +495,8 @@ __device__ __forceinline__ void label_chunk(const EpiParams &ep, const uint32_t 
             const float e = is_label ? __expf(x - mx) : 0.f;
             const float den = warp_sum(e);
             const float p = is_label ? __fdividef(e, den) : sigmoid_mufu(x);
-            const bool on = u23(rnd[jj]) < p;
-            sb[j] = on ? 0x3F80u : 0u;
-            bg_s += (on && (FULL || j < nrows)) ? 1 : 0;
+            sb[j] = (u23(rnd[jj]) < p) ? 0x3F80u : 0u;
+            bg_s += (FULL || j < nrows) ? (int)sb[j] : 0;   // (summed state bits, / 0x3F80 at the end: see fast_chunk)
         }
     }
     if (!uvalid) return;
@@ -542,7 +551,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiParams &ep, uint32_t tmem
         else if (nv > 0) fast_chunk<SAMPLE, PROB, false, MODE == 1>(ep, r, unit, row_base, nv, bias, want_sT, want_pT, want_prm, bg_p, bg_s);
     }
     if (ep.bg_what && uvalid)
-        atomicAdd(ep.bias_grad + unit, ep.bg_sign * (((PROB && ep.bg_what == 1) || MODE == 1) ? bg_p : (float)bg_s));
+        atomicAdd(ep.bias_grad + unit, ep.bg_sign * (((PROB && ep.bg_what == 1) || MODE == 1) ? bg_p : (float)(bg_s / 0x3F80)));
 }
 
 template <int BN, int WGS>
