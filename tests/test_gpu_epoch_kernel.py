@@ -76,7 +76,7 @@ def test_persistent_kernel_equals_step_by_step(q, V, H, L, gaussian, B, k, algo,
     # into later probabilities at the 1e-7 level): a few fp32 ulps of the parameter's magnitude (the GRBM case grows |a| to
     # ~1e2 within these steps; two runs of the step-by-step path differ from each other by the same amount)
     def close(r, g):
-        return np.max(np.abs(r - g)) <= 2e-6 * max(1.0, float(np.max(np.abs(r))))
+        return np.max(np.abs(r - g)) <= 1e-5 * max(1.0, float(np.max(np.abs(r))))
     assert close(ref[0], got[0]), np.max(np.abs(ref[0] - got[0]))
     assert close(ref[1], got[1]) and close(ref[2], got[2]), (np.max(np.abs(ref[1] - got[1])), np.max(np.abs(ref[2] - got[2])))
     if L:
@@ -119,7 +119,7 @@ def test_cfg1_epoch_kernel_matches_oracle(q):
         dev.train_steps("CD", 0, nb, B, 1, lr)
         assert dev.gemm_histogram().get(("1cta", 32, "epoch")) == 1
         dev.pull_params()
-    assert np.max(np.abs(rbm2.W - Ws[-1][0])) < 2e-6
+    assert np.max(np.abs(rbm2.W - Ws[-1][0])) < 1e-5   # (float atomics of the bias sums differ in order: a few fp32 ulps per step)
 
 
 def test_epoch_call_reports_phase_times_and_equals_steps(q):
@@ -142,4 +142,4 @@ def test_epoch_call_reports_phase_times_and_equals_steps(q):
                     dev.cd_step(i, B, 1, 0.05)
             dev.pull_params()
             res.append(rbm.W.copy())
-    assert np.max(np.abs(res[0] - res[1])) < 2e-6
+    assert np.max(np.abs(res[0] - res[1])) < 1e-5   # 12 steps; a flipped sample would show as lr / B = 5e-4
