@@ -211,6 +211,7 @@ struct qb_handle {
     int force_bn = 0, use_2cta = 1;
     // fused chain launches (sm100_chain.cuh): half-steps recorded between chain_begin / chain_end run as ONE persistent kernel
     int fused_chain_mode = 1; int chain_bn = 0;     // options "fused_chain" (0 never, 1 automatic, 2 always), "chain_bn" (0 = automatic)
+    int chain_quad_mode = 1;                        // option "chain_quad": 4-CTA-cluster chain kernel with multicast weights (0 never, 1 automatic, 2 whenever possible)
     int rec_depth = 0; sm100::ChainBuilder *rec = nullptr;
     unsigned int *chain_cnt = nullptr; int64_t chain_cnt_region = 0, chain_launch_no = 0;
     unsigned int *chain_err_host = nullptr, *chain_err_dev = nullptr;
@@ -502,6 +503,16 @@ bool chain_pays(qb_handle *h, const sm100::EpiParams &ep) {
     if (h->fused_chain_mode == 2) return true;
     return (int64_t)ceil_div(ep.N, 256) * ceil_div(ep.M, 256) >= h->gemm_sms / 2;
 }
+// The quad variant (gibbs_chain_kernel_quad) is for half-steps of about one wave of 256 x 256 pair tiles -- there each pair
+// holds a single tile per half-step and its epilogue is exposed; with 128-row blocks per pair and the weights multicast inside
+// a 4-CTA cluster every pair alternates between two independent tiles.
+bool chain_quad_wanted(qb_handle *h, const sm100::EpiParams &ep) {
+    if (h->chain_quad_mode == 0 || h->fused_chain_mode == 0 || h->chain_bn != 0 || h->force_bn != 0 || (ep.N % 256) != 0) return false;
+    if (h->gemm_sms < h->num_sms) return false;   // (stale-chains mode reserves SMs for the exchange: pair kernels only)
+    if (h->chain_quad_mode == 2) return true;
+    const int64_t tiles = (int64_t)(ep.N / 256) * ceil_div(ep.M, 256);
+    return tiles >= h->num_sms / 8 && tiles < h->gemm_sms / 2 + h->gemm_sms / 4;
+}
 
 void launch_single(qb_handle *h, const sm100::Operand &A, const sm100::Operand &B, const sm100::EpiParams &ep, double flops) {
     GemmScope gs(h, flops);
@@ -532,14 +543,15 @@ bool chain_hazard_free(const sm100::ChainBuilder &cb, const sm100::Operand &B, c
 // one fused half-step GEMM of the bf16 path: recorded into the open chain region, or launched right away
 void gemm_half_step(qb_handle *h, const sm100::Operand &A, const sm100::Operand &B, const sm100::EpiParams &ep, double flops) {
     if (h->capture) { h->capture->A = A; h->capture->B = B; h->capture->ep = ep; h->capture->flops = flops; h->capture->set = true; return; }
+    const bool quad = h->rec_depth > 0 && h->use_2cta != 0 && sm100::chainable(ep) && chain_quad_wanted(h, ep);
     const bool can_chain = h->rec_depth > 0 && h->fused_chain_mode != 0 && h->use_2cta != 0 && h->force_bn != 32 && sm100::chainable(ep) &&
-                           chain_pays(h, ep);
+                           (quad || chain_pays(h, ep));
     if (h->rec_depth > 0 && !can_chain) chain_flush(h);
     if (!can_chain) { launch_single(h, A, B, ep, flops); return; }
     sm100::ChainBuilder &cb = *h->rec;
-    if (cb.prog.n_steps > 0 && (cb.prog.N != ep.N || cb.full())) chain_flush(h);
+    if (cb.prog.n_steps > 0 && (cb.prog.N != ep.N || cb.full() || cb.quad != quad)) chain_flush(h);
     for (int attempt = 0; attempt < 2; attempt++) {
-        if (cb.prog.n_steps == 0) cb.begin(ep.N, chain_tile_width(h, ep.N));
+        if (cb.prog.n_steps == 0) cb.begin(ep.N, quad ? sm100::QUAD_BN : chain_tile_width(h, ep.N), quad);
         int dep = -1;
         for (int j = cb.prog.n_steps - 1; j >= 0; j--) {
             const sm100::EpiParams &e = cb.prog.step[j].ep;
@@ -2495,6 +2507,9 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
             int bn = (int)value;
             QB_CHECK(bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 256, QB_E_ARG, "force_bn must be 0/32/64/128/256");
             h->force_bn = bn;
+        } else if (!strcmp(key, "chain_quad")) {
+            QB_CHECK(value == 0.0 || value == 1.0 || value == 2.0, QB_E_ARG, "chain_quad must be 0, 1 or 2");
+            h->chain_quad_mode = (int)value;
         } else if (!strcmp(key, "nvls_exchange")) {
             QB_CHECK(value == 1.0, QB_E_ARG, "nvls_exchange can only be switched on (1)");
             nvls_enable(h);

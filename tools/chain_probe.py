@@ -22,9 +22,13 @@ nb = 4
 for B in [int(a) for a in sys.argv[2:]] or CFG["rows"]:
     X = rng.standard_normal((nb * B, V)).astype(np.float32) if CFG["g"] else (rng.random((nb * B, V), dtype=np.float32) < 0.5).astype(np.uint8)
     Y = np.eye(L, dtype=np.uint8)[np.arange(nb * B) % L] if L else None
-    for fused, bn in [(0, 0), (1, 0), (2, 64), (2, 128), (2, 256)]:
+    modes = [(0, 0, 0), (1, 0, 0), (2, 128, 0), (2, 256, 0), (2, 0, 2)] if os.environ.get("CHAIN_PROBE_SHORT") else \
+            [(0, 0, 0), (1, 0, 0), (1, 0, 1), (2, 64, 0), (2, 128, 0), (2, 256, 0), (2, 0, 2)]
+    for fused, bn, quad in modes:   # quad: 4-CTA-cluster chain kernel with multicast weights (0 never, 1 automatic, 2 whenever possible)
+        if quad == 2 and B % 256:
+            continue
         dev = q.DeviceRBM(rbm, max_batch=B, precision="bf16", seed=1)
-        dev.set_option("fused_chain", fused); dev.set_option("chain_bn", bn)
+        dev.set_option("fused_chain", fused); dev.set_option("chain_bn", bn); dev.set_option("chain_quad", quad)
         dev.set_data(X, Y)
         if CFG["pcd"]:
             dev.init_chains(B)
@@ -40,5 +44,5 @@ for B in [int(a) for a in sys.argv[2:]] or CFG["rows"]:
             step(i)
         ms = dev.timer_stop()
         launches = dev.counters()[0] / n
-        print(f"{wl} B={B:5d} fused={fused} chain_bn={bn:3d}: {ms / n * 1e3:9.1f} us/step  {launches:4.1f} launches/step  hist={dev.gemm_histogram()}", flush=True)
+        print(f"{wl} B={B:5d} fused={fused} chain_bn={bn:3d} quad={quad}: {ms / n * 1e3:9.1f} us/step  {launches:4.1f} launches/step  hist={dev.gemm_histogram()}", flush=True)
         dev.close()
