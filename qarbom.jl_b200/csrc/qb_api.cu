@@ -211,7 +211,7 @@ struct qb_handle {
     int force_bn = 0, use_2cta = 1;
     // fused chain launches (sm100_chain.cuh): half-steps recorded between chain_begin / chain_end run as ONE persistent kernel
     int fused_chain_mode = 1; int chain_bn = 0;     // options "fused_chain" (0 never, 1 automatic, 2 always), "chain_bn" (0 = automatic)
-    int chain_quad_mode = 1;                        // option "chain_quad": 4-CTA-cluster chain kernel with multicast weights (0 never, 1 automatic, 2 whenever possible)
+    int chain_quad_mode = 0;                        // option "chain_quad": 4-CTA-cluster chain kernel with multicast weights (0 never -- the default: measured slower --, 1 one-wave shapes, 2 whenever possible)
     int rec_depth = 0; sm100::ChainBuilder *rec = nullptr;
     unsigned int *chain_cnt = nullptr; int64_t chain_cnt_region = 0, chain_launch_no = 0;
     unsigned int *chain_err_host = nullptr, *chain_err_dev = nullptr;
@@ -505,7 +505,12 @@ bool chain_pays(qb_handle *h, const sm100::EpiParams &ep) {
 }
 // The quad variant (gibbs_chain_kernel_quad) is for half-steps of about one wave of 256 x 256 pair tiles -- there each pair
 // holds a single tile per half-step and its epilogue is exposed; with 128-row blocks per pair and the weights multicast inside
-// a 4-CTA cluster every pair alternates between two independent tiles.
+// a 4-CTA cluster every pair alternates between two independent tiles.  MEASURED NEGATIVE (profiles/r2_chain_probe_quad.txt):
+// bit-identical results, but 1028 us per cfg5 step at 1024 rows against 723 us for the 256 x 256 pair chain -- a 256 x 128 tile
+// takes as long as a 256 x 256 one (24 us) with or without the multicast, i.e. the k-loop is bound by the rate at which ONE SM's
+// shared memory can be filled (about 85-90 GB/s per SM: 192 KB in flight per CTA over the TMA round trip), not by L2
+// bandwidth: halving the L2 reads does not help, the bytes that land in each SM per flop are what counts, and those are 1.5x
+// those of the wide tile.  Off by default; kept as an option with its parity test.
 bool chain_quad_wanted(qb_handle *h, const sm100::EpiParams &ep) {
     if (h->chain_quad_mode == 0 || h->fused_chain_mode == 0 || h->chain_bn != 0 || h->force_bn != 0 || (ep.N % 256) != 0) return false;
     if (h->gemm_sms < h->num_sms) return false;   // (stale-chains mode reserves SMs for the exchange: pair kernels only)
