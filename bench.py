@@ -626,6 +626,18 @@ def main():
                 "bytes_note": "14 B/param x (H/world) rows: sharded update" if sharded else "12 B/param fp32 read-modify-write + 4 B/param bf16 shadows",
                 "kernel": "qb::update_w_kernel",
                 "bytes_per_launch": upd_bytes, "avg_launch_ms": upd_ms / max(upd_n, 1), "launches_timed": upd_n}
+    if world > 1 and args.p2p_like and not args.p2p:
+        # the "update" launch of this mode is the fused exchange kernel (reduce-scatter + shard update + all-gather over NVLink)
+        # plus the local transpose: bound by the link, not by HBM.  Bytes a GPU sends per step: its whole fp32 gradient leaves it
+        # once (every shard is summed elsewhere -- through the switch also its own) + its shard of the new bf16 shadow.
+        nvl_out = 4.0 * P_w + 2.0 * P_w / world
+        gbs = (nvl_out * upd_n / 1e9) / (upd_ms * 1e-3) if upd_ms > 0 else None
+        roof_upd = {"bound": "nvlink", "achieved": gbs, "peak": 900.0, "unit": "GB/s", "frac": (gbs / 900.0) if gbs else None,
+                    "traffic": None, "peak_source": "nominal NVLink 5 bandwidth per direction per GPU (no measured figure in MEASURED_PEAKS.json)",
+                    "bytes_note": "outbound NVLink bytes per GPU per step: 4 B/param (fp32 gradient, read by the switch) + 2 B/param / world (bf16 shard pushed); "
+                                  "inbound is smaller (4 B/param / world + 2 B/param)",
+                    "kernel": "qb::p2p_reduce_update_kernel<., NVLS> + transpose_bf16_wide_kernel",
+                    "bytes_per_launch": nvl_out, "avg_launch_ms": upd_ms / max(upd_n, 1), "launches_timed": upd_n}
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
