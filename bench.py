@@ -434,8 +434,18 @@ def main():
     # ---------------- device-resident leg: pass A (clean, for `value`), pass B (GEMM/update launches
     # bracketed by CUDA events, for the rooflines; the event records perturb tiny kernels and PDL)
     dev.set_option("async_steps", 1)
-    for i in range(args.warmup):
-        step(i)
+
+    def run_steps(first, n):
+        """n consecutive mini-batch steps on the resident batches first, first + 1, ... (mod nb).  On one GPU this is ONE call of
+        qb_train_steps -- what the epoch calls of the API do: small models then run as one persistent launch
+        (sm100_epoch.cuh), everything else as the same per-step launch sequence as qb_pcd_step / qb_cd_step."""
+        if world == 1:
+            dev.train_steps(w["algo"], first % nb, n, Bl, k, lr, lr)
+        else:
+            for i in range(n):
+                step(first + i)
+
+    run_steps(0, args.warmup)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -445,8 +455,7 @@ def main():
     if world > 1 and args.precision == "bf16" and args.p2p_like:
         dev.p2p_timing()  # reset the in-kernel phase timers
     dev.timer_start()
-    for i in range(args.steps):
-        step(args.warmup + i)
+    run_steps(args.warmup, args.steps)
     ms = dev.timer_stop()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -481,8 +490,7 @@ def main():
         if rank == 0:
             sampler2.start()
         dev.timer_start()
-        for i in range(n_sus):
-            step(args.warmup + i)
+        run_steps(args.warmup, n_sus)
         ms_sus = max_over_ranks(dev.timer_stop())
         barrier()
         clocks_sus = sampler2.stop() if rank == 0 else None
