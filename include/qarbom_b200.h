@@ -262,8 +262,16 @@ int32_t qb_reset_counters(qb_handle *h);
  * chain advance + bit-packed chain-state all-gather; collective, measured neutral, off by default),
  * "online_kernel" (0: batch-size-1 CD through per-sample launches instead of the cooperative epoch kernel),
  * "online_wpb" (warps per block of the cooperative kernels), "fast_pcd_pair_chains" (classifier FastPCD pairs
- * sample i with chain i instead of the reference's chain 1), "p2p_blocks_per_sm", and for experiments / tests
- * "force_bn" (GEMM tile width) and "use_2cta" (0 never, 1 automatic, 2 always). */
+ * sample i with chain i instead of the reference's chain 1), "p2p_blocks_per_sm",
+ * "nvls_exchange" (= 1, COLLECTIVE, after qb_comm_init: the gradient exchange becomes ONE kernel per rank over NVSwitch
+ * multicast addresses -- multimem.ld_reduce of the fp32 gradient shard, update of the owned hidden rows, multimem.st of the
+ * new bf16 shadow; needs NCCL >= 2.28 at run time (symmetric windows) and multicast-capable GPUs, else QB_E_UNSUPPORTED with
+ * the reason and the NCCL exchange stays),
+ * "fused_chain" (the half-steps of a step as one persistent launch: 0 never, 1 automatic, 2 always), "chain_bn" (its tile
+ * width, 0 = automatic), "chain_quad" (its 4-CTA-cluster variant with multicast weights: 0 never (default: measured slower),
+ * 1 one-wave shapes, 2 whenever possible), "epoch_kernel" (many mini-batch steps of a small model as one persistent launch
+ * in qb_train_steps / the epoch calls: 0 never, 1 automatic, 2 always),
+ * and for experiments / tests "force_bn" (GEMM tile width) and "use_2cta" (0 never, 1 automatic, 2 always). */
 int32_t qb_set_option(qb_handle *h, const char *key, double value);
 int32_t qb_sync(qb_handle *h);
 /* CUDA-event stopwatch on the handle's stream (the stream every kernel is launched on). */

@@ -1355,7 +1355,7 @@ bool epoch_kernel_eligible(const qb_handle *h, bool pcd, int64_t B, int64_t k) {
     // step-by-step path dominate.  Measured (tools/epoch_probe.py, profiles/r2_epoch_probe.txt): cfg2 -19 %, cfg1 tie; from
     // about one wave on (cfg4 +18 %, cfg3 +8 %) one launch per GEMM is the better schedule.
     const int64_t tiles = ceil_div(std::max(h->H, h->VL), 128) * ceil_div(B, epoch_tile_width(h, B));
-    return h->epoch_kernel_mode == 2 || 2 * tiles <= h->num_sms;
+    return h->epoch_kernel_mode == 2 || (B <= 256 && 2 * tiles <= h->num_sms);   // (cfg4: 512 rows, 64 tiles: 48.7 vs 41.5 us)
 }
 
 bool epoch_kernel_run(qb_handle *h, bool pcd, int64_t first, int64_t n_steps, int64_t B, int64_t k, double lr, double llr) {
