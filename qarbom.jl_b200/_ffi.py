@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libqarbom_b200.so")
+# QARBOM_B200_LIB: an explicit build of the same library (experiment builds of tools/, the Julia shim uses the same variable)
+LIB_PATH = os.environ.get("QARBOM_B200_LIB") or os.path.join(HERE, "lib", "libqarbom_b200.so")
 
 QB_VISIBLE_BERNOULLI, QB_VISIBLE_GAUSSIAN = 0, 1
 QB_PREC_FP32, QB_PREC_BF16, QB_PREC_FP32X3 = 0, 1, 2

@@ -62,6 +62,11 @@ template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Shape<BN, K_FAST_SAMPLE>::THREADS), 1)
 gibbs_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainProgram prog) {
     using C = Cfg2<BN>;
+#ifdef QB_EXP_BFRAC
+    constexpr int EXP_TX = 2 * (C::A_BYTES + C::B_BYTES / QB_EXP_BFRAC);
+#else
+    constexpr int EXP_TX = 2 * C::STAGE_BYTES;
+#endif
     constexpr int WGS = Shape<BN, K_FAST_SAMPLE>::WGS;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -121,7 +126,7 @@ gibbs_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant
                     int st = stage; uint32_t ph = phase;
                     for (int i = 0; i < pre; i++) {
                         mbar_wait(empty_bar(st), ph ^ 1);
-                        if (leader) mbar_expect_tx(full_bar(st), 2 * C::STAGE_BYTES);
+                        if (leader) mbar_expect_tx(full_bar(st), EXP_TX);
                         else mbar_arrive_remote(full_bar(st), 0);
                         tma_load_2d_2sm(smem_base + st * C::STAGE_BYTES, mA, full_bar(st), i * BK, m0);
                         if (++st == C::STAGES) { st = 0; ph ^= 1; }
@@ -154,7 +159,7 @@ gibbs_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant
                 for (; kb < kb_total; kb++) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-                    if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+                    if (leader) mbar_expect_tx(full_bar(stage), EXP_TX);
                     else mbar_arrive_remote(full_bar(stage), 0);
                     tma_load_2d_2sm(sa, mA, full_bar(stage), kb * BK, m0);
                     tma_load_2d_2sm(sb, mB, full_bar(stage), kb * BK, n0);
@@ -457,7 +462,11 @@ struct ChainBuilder {
         const int kind = pick_kind(ep);
         QB_CHECK(kind >= K_FAST_SAMPLE && kind <= K_FAST_LABEL, -5, "half-step has no compile-time epilogue: not chainable");
         ChainStep &S = prog.step[prog.n_steps];
+#ifdef QB_EXP_BFRAC
+        S.a_map = map_index(A, quad ? BM / 2 : BM); S.b_map = map_index(B, quad ? bn / 2 : bn / 2 / QB_EXP_BFRAC);
+#else
         S.a_map = map_index(A, quad ? BM / 2 : BM); S.b_map = map_index(B, bn / 2);
+#endif
         S.M = ep.M; S.K = (int)A.k; S.kind = kind; S.dep_step = dep;
         S.tiles_m = (int)ceil_div(ep.M, 2 * BM);
         S.tile_base = prog.total_tiles;
