@@ -779,6 +779,26 @@ struct Cfg2 {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
+// Tile number -> (pair row block, column block) of the persistent schedule.  Half-steps: unit tiles fastest (a wave shares few
+// row blocks of states and every weight panel once).  Gradient GEMM (K = the whole batch, twice): a wave of the plain order
+// touches all 16 A panels plus 5 B panels of 4-8 MiB each -- more than L2 holds, so every wave re-reads every A panel from HBM
+// (ncu: 696 MB read for 268 MB of operands at cfg5).  Groups of 8 row blocks x all column blocks halve the A panels a wave
+// keeps live at the price of reading B once per group.
+template <int KIND>
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int &m_blk, int &n_blk) {
+    if (KIND == K_GRAD && tiles_m > 8) {
+        constexpr int GM = 8;
+        const int per_group = GM * tiles_n;
+        const int g = tile / per_group, within = tile - g * per_group;
+        const int gm = (tiles_m - g * GM) < GM ? (tiles_m - g * GM) : GM;
+        m_blk = g * GM + within % gm;
+        n_blk = within / gm;
+    } else {
+        m_blk = tile % tiles_m;
+        n_blk = tile / tiles_m;
+    }
+}
+
 template <int BN, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Shape<BN, KIND>::THREADS), 1)
 gibbs_gemm_kernel_2cta(const __grid_constant__ Phases ph, const EpiParams ep) {
@@ -825,7 +845,8 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ Phases ph, const EpiParams ep) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
+                int m_blk, n_blk;
+                tile_coords<KIND>(tile, tiles_m, tiles_n, m_blk, n_blk);
                 const int m0 = m_blk * 2 * BM + (int)rank * BM, n0 = n_blk * BN + (int)rank * (BN / 2);
                 int p = 0, kb0 = 0;
                 for (int kb = 0; kb < kb_total; kb++) {
@@ -873,7 +894,9 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ Phases ph, const EpiParams ep) {
         const int quarter = warp & 3, wg = (warp - EPI_WARP0) >> 2;
         int iter = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, iter++) {
-            const int m_blk = (tile % tiles_m) * 2 + (int)rank, n_blk = tile / tiles_m;  // in units of 128 rows
+            int m_pair, n_blk;
+            tile_coords<KIND>(tile, tiles_m, tiles_n, m_pair, n_blk);
+            const int m_blk = m_pair * 2 + (int)rank;  // in units of 128 rows
             const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
             mbar_wait(tfull_bar(as), aphase);
             tcgen05_fence_after();
