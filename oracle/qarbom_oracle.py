@@ -125,6 +125,9 @@ class Model:
     U: Optional[np.ndarray] = None
     c: Optional[np.ndarray] = None
     gaussian: bool = False
+    # NOT part of the reference (None = the reference): rounding applied to a real-valued Gaussian visible sample when a Gibbs
+    # step stores it -- lets tests of the device's bf16 mode follow a device that keeps its chain states in bf16
+    v_store: Optional[object] = None
 
     @property
     def n_visible(self) -> int:
@@ -244,7 +247,8 @@ def gibbs_sample_hidden(m: Model, v, stream: Stream, y=None) -> np.ndarray:
 def gibbs_sample_visible(m: Model, h, stream: Stream) -> np.ndarray:
     """src/gibbs.jl:13-16 (V uniforms) / :18-20 (GRBM: V normals, real-valued)."""
     if m.gaussian:
-        return conditional_prob_v(m, h, stream)
+        v = conditional_prob_v(m, h, stream)
+        return v if m.v_store is None else m.v_store(v)
     p = conditional_prob_v(m, h)
     return stream.bernoulli(p)
 
