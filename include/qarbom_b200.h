@@ -178,6 +178,47 @@ int32_t qb_cd_step_host(qb_handle *h, const void *X, int32_t x_dtype, const void
  * a buffer refilled in that window trains on a mix of old and new contents. */
 int32_t qb_set_next_host_batch(qb_handle *h, const void *X, int32_t x_dtype, const void *Y, int32_t y_dtype);
 
+/* The epoch loop of train! inside the library (src/training/train_cd.jl:60-115, train_pcd.jl:149-213,
+ * train_fast_pcd.jl:185-250 and the classifier variants): initial_evaluation, then per epoch the
+ * training epoch with learning_rate[epoch], evaluate on every requested metric, _diverged on the stopping metric
+ * (src/evaluation.jl:132-168), patience / early stopping, best-model snapshot in HBM (copy_rbm!), and at the end
+ * copy_rbm!(best_rbm, rbm) -- no host round trip of the parameters and no caller-side loop.  The resident dataset
+ * (qb_set_data) is the training set; chains are initialised here for PCD / FastPCD (_init_fantasy_data(rbm, batch_size)).
+ * history[(n_epochs + 1) x n_metrics], row-major: row 0 = initial_evaluation, row e = after epoch e (rows after an early
+ * stop stay untouched) -- merge_metrics' columns.  times[3] = totals of (sample, gibbs, update) seconds.
+ * Metrics: MeanSquaredError / FreeEnergy work on every model; Accuracy and CrossEntropy (reference-literal: computed from the
+ * rounded prediction, hence NaN) need label units and the labels of the evaluated rows in Y_eval.  X_eval == NULL evaluates
+ * the resident training set (Y_eval then holds the training labels); the reference uses the test set for classifiers only
+ * when both arrays are given (train_cd.jl:143-147) -- that rule is the caller's.
+ * on_epoch (optional) is called after every epoch from the calling thread with the epoch number, that epoch's metric row,
+ * its (sample, gibbs, update) seconds and QB_EPOCH_* flags: the place for _log_epoch / _log_metrics. */
+#define QB_METHOD_CD 0
+#define QB_METHOD_PCD 1
+#define QB_METHOD_FAST_PCD 2
+#define QB_METRIC_MSE 0
+#define QB_METRIC_ACCURACY 1
+#define QB_METRIC_CROSS_ENTROPY 2
+#define QB_METRIC_FREE_ENERGY 3
+#define QB_EPOCH_DIVERGED 1      /* _diverged(metrics_dict, stopping_metric) was true */
+#define QB_EPOCH_EARLY_STOP 2    /* ... and patience ran out: this was the last epoch */
+#define QB_EPOCH_NEW_BEST 4      /* best_rbm was replaced by the current parameters */
+typedef struct qb_train_config {
+    int32_t method;                     /* QB_METHOD_* */
+    int32_t n_epochs;
+    int64_t batch_size, gibbs_steps;
+    const double *learning_rate;        /* [n_epochs] */
+    const double *label_learning_rate;  /* [n_epochs]; NULL for models without label units */
+    double fast_learning_rate, fast_label_learning_rate;   /* FastPCD only */
+    int32_t n_metrics; const int32_t *metrics;              /* QB_METRIC_*, in reporting order */
+    int32_t stopping_metric;            /* must be one of `metrics` (the reference indexes metrics_dict with it) */
+    int32_t early_stopping, store_best_rbm, patience;
+    const void *X_eval; int32_t x_dtype; int64_t n_eval;    /* NULL / 0: evaluate the resident training set */
+    const void *Y_eval; int32_t y_dtype;                    /* labels of the evaluated rows (Accuracy / CrossEntropy) */
+    void (*on_epoch)(void *user, int32_t epoch, const double *metrics, const double times[3], int32_t flags);
+    void *user;
+} qb_train_config;
+int32_t qb_train(qb_handle *h, const qb_train_config *cfg, double *history, double times[3], int32_t *epochs_run);
+
 /* evaluate + _evaluate(MeanSquaredError) + reconstruct (src/evaluation.jl:16-20,52-70;
  * src/rbm.jl:220-224): sum over samples of sum_units (x - reconstruct(x))^2 / n_rows.
  * X == NULL evaluates the resident dataset. Z (n_rows x V standard normals) optionally

@@ -21,7 +21,7 @@ SYMBOLS = [
     "qb_set_optimizer", "qb_set_data", "qb_init_chains", "qb_get_chains", "qb_get_chain_rows", "qb_get_gemm_histogram", "qb_get_issued_flops", "qb_seed", "qb_inject_streams",
     "qb_pcd_step", "qb_cd_step", "qb_pcd_epoch", "qb_cd_epoch", "qb_train_steps", "qb_fast_pcd_epoch", "qb_pcd_step_host", "qb_cd_step_host", "qb_set_next_host_batch", "qb_eval_mse",
     "qb_eval_free_energy", "qb_reconstruct", "qb_conditional_prob_h", "qb_sample_hidden", "qb_sample_visible", "qb_conditional_prob_y_given_v", "qb_comm_unique_id", "qb_comm_init", "qb_p2p_export", "qb_p2p_import", "qb_get_p2p_timing",
-    "qb_get_counters", "qb_reset_counters", "qb_set_option", "qb_sync", "qb_timer_start", "qb_timer_stop", "qb_get_update_timing",
+    "qb_get_counters", "qb_reset_counters", "qb_set_option", "qb_sync", "qb_timer_start", "qb_timer_stop", "qb_get_update_timing", "qb_train",
 ]
 
 
@@ -30,6 +30,20 @@ class QbConfig(ctypes.Structure):
                 ("visible_kind", ctypes.c_int32), ("precision", ctypes.c_int32), ("max_batch", ctypes.c_int64),
                 ("device", ctypes.c_int32), ("rank", ctypes.c_int32), ("world", ctypes.c_int32),
                 ("reserved", ctypes.c_int32)]
+
+
+ON_EPOCH = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_int32)
+
+
+class QbTrainConfig(ctypes.Structure):   # mirrors `qb_train_config`
+    _fields_ = [("method", ctypes.c_int32), ("n_epochs", ctypes.c_int32), ("batch_size", ctypes.c_int64), ("gibbs_steps", ctypes.c_int64),
+                ("learning_rate", ctypes.c_void_p), ("label_learning_rate", ctypes.c_void_p),
+                ("fast_learning_rate", ctypes.c_double), ("fast_label_learning_rate", ctypes.c_double),
+                ("n_metrics", ctypes.c_int32), ("metrics", ctypes.c_void_p),
+                ("stopping_metric", ctypes.c_int32), ("early_stopping", ctypes.c_int32), ("store_best_rbm", ctypes.c_int32), ("patience", ctypes.c_int32),
+                ("X_eval", ctypes.c_void_p), ("x_dtype", ctypes.c_int32), ("n_eval", ctypes.c_int64),
+                ("Y_eval", ctypes.c_void_p), ("y_dtype", ctypes.c_int32),
+                ("on_epoch", ON_EPOCH), ("user", ctypes.c_void_p)]
 
 
 class QbError(RuntimeError):
@@ -100,6 +114,7 @@ def lib():
         "qb_timer_start": [_P],
         "qb_timer_stop": [_P, _P],
         "qb_reset_counters": [_P],
+        "qb_train": [_P, ctypes.POINTER(QbTrainConfig), _P, _P, _P],
         "qb_set_option": [_P, ctypes.c_char_p, _f64],
     }
     for name, args in sig.items():

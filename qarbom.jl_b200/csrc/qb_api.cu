@@ -2398,6 +2398,142 @@ int32_t qb_conditional_prob_y_given_v(qb_handle *h, const void *X, int32_t x_dty
     });
 }
 
+// ----------------------------------------------------------------------------- train!'s epoch loop
+// _diverged (src/evaluation.jl:132-168): Accuracy must not decrease / fall below its maximum, every other metric must not
+// increase / exceed its minimum.  NaN compares false, as in Julia.
+static bool metric_diverged(const std::vector<double> &hist, int metric) {
+    if (hist.size() <= 1) return false;
+    const double last = hist.back(), prev = hist[hist.size() - 2];
+    if (metric == QB_METRIC_ACCURACY) {
+        if (last < prev) return true;
+        double mx = hist[0];
+        for (double v : hist) if (v > mx) mx = v;   // maximum(): NaN-free by construction (accuracy is a count / N)
+        return last < mx;
+    }
+    if (last > prev) return true;
+    double mn = hist[0];
+    bool any_nan = false;
+    for (double v : hist) { if (v != v) any_nan = true; else if (mn != mn || v < mn) mn = v; }
+    if (any_nan) return false;   // minimum() of a vector holding NaN is NaN in Julia, and x > NaN is false
+    return last > mn;
+}
+
+int32_t qb_train(qb_handle *h, const qb_train_config *c, double *history, double times[3], int32_t *epochs_run) {
+    // plain C++ over the entry points above (each of them is guarded): status codes are passed through, nothing throws here
+    if (!h || !c || !history) { g_last_error = "qb_train: NULL argument"; return QB_E_ARG; }
+    auto fail = [&](int32_t code, const char *msg) { g_last_error = msg; return code; };
+    if (c->n_epochs < 0 || c->batch_size < 1 || c->gibbs_steps < 1 || !c->learning_rate) return fail(QB_E_ARG, "qb_train: n_epochs >= 0, batch_size >= 1, gibbs_steps >= 1 and learning_rate are required");
+    if (c->method < QB_METHOD_CD || c->method > QB_METHOD_FAST_PCD) return fail(QB_E_ARG, "qb_train: unknown method");
+    if (c->n_metrics < 1 || c->n_metrics > 8 || !c->metrics) return fail(QB_E_ARG, "qb_train: 1..8 metrics required");
+    const bool clf = h->L > 0;
+    if (clf && !c->label_learning_rate) return fail(QB_E_ARG, "qb_train: label_learning_rate is required for classifier models");
+    int stop_col = -1;
+    for (int i = 0; i < c->n_metrics; i++) {
+        const int m = c->metrics[i];
+        if (m < QB_METRIC_MSE || m > QB_METRIC_FREE_ENERGY) return fail(QB_E_ARG, "qb_train: unknown metric");
+        if ((m == QB_METRIC_ACCURACY || m == QB_METRIC_CROSS_ENTROPY) && (!clf || !c->Y_eval))
+            return fail(QB_E_ARG, "qb_train: Accuracy / CrossEntropy need a classifier model and Y_eval");
+        if (m == c->stopping_metric && stop_col < 0) stop_col = i;
+    }
+    if (stop_col < 0) return fail(QB_E_ARG, "qb_train: stopping_metric is not among the metrics (the reference raises KeyError)");
+    const bool test = c->X_eval != nullptr;
+    if (test && c->n_eval < 1) return fail(QB_E_ARG, "qb_train: n_eval must be >= 1 with X_eval");
+    const int64_t n_eval = test ? c->n_eval : h->N;
+    if (n_eval < 1) return fail(QB_E_STATE, "qb_train: no resident dataset (qb_set_data)");
+    const int L = (int)h->L, nm = c->n_metrics;
+    std::vector<double> prob;   // p(y | v) of the evaluated rows, shared by Accuracy and CrossEntropy
+
+    auto label_at = [&](int64_t row, int l) -> double {
+        const char *p = (const char *)c->Y_eval + ((size_t)row * L + l) * dt_size(c->y_dtype);
+        switch (c->y_dtype) {
+            case QB_DT_F64: return *(const double *)p;
+            case QB_DT_I64: return (double)*(const int64_t *)p;
+            case QB_DT_F32: return (double)*(const float *)p;
+            default: return (double)*(const uint8_t *)p;
+        }
+    };
+    auto evaluate = [&](double *row) -> int32_t {
+        bool have_prob = false;
+        for (int i = 0; i < nm; i++) {
+            const int m = c->metrics[i];
+            int32_t rc = QB_OK;
+            if (m == QB_METRIC_MSE) rc = qb_eval_mse(h, test ? c->X_eval : nullptr, c->x_dtype, test ? n_eval : 0, nullptr, &row[i]);
+            else if (m == QB_METRIC_FREE_ENERGY) rc = qb_eval_free_energy(h, test ? c->X_eval : nullptr, c->x_dtype, nullptr, 0, test ? n_eval : 0, &row[i]);
+            else {
+                if (!have_prob) {
+                    prob.resize((size_t)n_eval * L);
+                    rc = qb_conditional_prob_y_given_v(h, test ? c->X_eval : nullptr, c->x_dtype, test ? n_eval : 0, prob.data());
+                    have_prob = rc == QB_OK;
+                }
+                if (rc == QB_OK) {
+                    // evaluate(rbm::RBMClassifiers, ...) (src/evaluation.jl:28-50): rounded_y_pred = 1 where p equals the row maximum
+                    double acc = 0.0, ce = 0.0;
+                    for (int64_t r = 0; r < n_eval; r++) {
+                        const double *p = prob.data() + (size_t)r * L;
+                        double mx = p[0];
+                        for (int l = 1; l < L; l++) if (p[l] > mx) mx = p[l];
+                        bool all_eq = true;
+                        double s = 0.0;
+                        for (int l = 0; l < L; l++) {
+                            const double pred = (p[l] == mx) ? 1.0 : 0.0, y = label_at(r, l);
+                            if (std::llround(y) != (long long)pred) all_eq = false;
+                            s += y * std::log(pred) + (1.0 - y) * std::log(1.0 - pred);   // literally: 0 * -Inf = NaN
+                        }
+                        acc += (all_eq ? 1.0 : 0.0) / (double)n_eval;
+                        ce += s / (double)n_eval;
+                    }
+                    row[i] = (m == QB_METRIC_ACCURACY) ? acc : ce;
+                }
+            }
+            if (rc != QB_OK) return rc;
+        }
+        return QB_OK;
+    };
+
+    int32_t rc = qb_snapshot_params(h);                 // best_rbm = copy_rbm(rbm)
+    if (rc != QB_OK) return rc;
+    if ((rc = evaluate(history)) != QB_OK) return rc;   // initial_evaluation
+    if (c->method != QB_METHOD_CD && (rc = qb_init_chains(h, c->batch_size, nullptr, nullptr, nullptr)) != QB_OK) return rc;
+    std::vector<double> stop_hist;
+    int patience = c->patience, ran = c->n_epochs;
+    double tot[3] = {0, 0, 0};
+    for (int e = 1; e <= c->n_epochs; e++) {
+        double t[3] = {0, 0, 0};
+        const double lr = c->learning_rate[e - 1], llr = clf ? c->label_learning_rate[e - 1] : 0.0;
+        if (c->method == QB_METHOD_FAST_PCD) rc = qb_fast_pcd_epoch(h, c->batch_size, c->gibbs_steps, lr, c->fast_learning_rate, llr, c->fast_label_learning_rate, t);
+        else if (c->method == QB_METHOD_PCD) rc = qb_pcd_epoch(h, c->batch_size, c->gibbs_steps, lr, llr, t);
+        else rc = qb_cd_epoch(h, c->batch_size, c->gibbs_steps, lr, llr, t);
+        if (rc != QB_OK) return rc;
+        for (int i = 0; i < 3; i++) tot[i] += t[i];
+        double *row = history + (size_t)e * nm;
+        if ((rc = evaluate(row)) != QB_OK) return rc;
+        stop_hist.push_back(row[stop_col]);
+        int flags = 0;
+        bool stop = false;
+        if (metric_diverged(stop_hist, c->stopping_metric)) {
+            flags |= QB_EPOCH_DIVERGED;
+            if (c->early_stopping) {
+                if (patience == 0) { flags |= QB_EPOCH_EARLY_STOP; stop = true; }
+                else patience -= 1;
+            }
+        } else {
+            patience = c->patience;
+            if (c->store_best_rbm) {
+                if ((rc = qb_snapshot_params(h)) != QB_OK) return rc;   // copy_rbm!(rbm, best_rbm)
+                flags |= QB_EPOCH_NEW_BEST;
+            }
+        }
+        if (stop) ran = e;
+        // the reference breaks out BEFORE logging the epoch it stops at (train_cd.jl:91-96): the callback still sees it, flagged
+        if (c->on_epoch) c->on_epoch(c->user, e, row, t, flags);
+        if (stop) break;
+    }
+    if (c->store_best_rbm && (rc = qb_restore_params(h)) != QB_OK) return rc;   // copy_rbm!(best_rbm, rbm)
+    if (times) for (int i = 0; i < 3; i++) times[i] = tot[i];
+    if (epochs_run) *epochs_run = ran;
+    return QB_OK;
+}
+
 int32_t qb_comm_unique_id(void *id128) {
     return guarded([&] {
         QB_CHECK(id128 != nullptr, QB_E_ARG, "id buffer is NULL");

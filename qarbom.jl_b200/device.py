@@ -148,6 +148,37 @@ class DeviceRBM:
         """n_steps consecutive mini-batch steps on resident batches first_batch, first_batch + 1, ... (qb_train_steps)."""
         check(lib().qb_train_steps(self._h, 1 if method.upper() == "PCD" else 0, first_batch, n_steps, B, k, lr, llr))
 
+    METHODS = {"CD": 0, "PCD": 1, "FASTPCD": 2}
+    METRICS = {"mse": 0, "accuracy": 1, "cross_entropy": 2, "free_energy": 3}
+
+    def train_epochs(self, method: str, n_epochs: int, B: int, k: int, learning_rate, label_learning_rate=None, *,
+                     metrics=("mse",), stopping_metric=None, early_stopping=False, store_best_rbm=True, patience=10,
+                     fast_learning_rate=0.1, fast_label_learning_rate=0.1, x_eval=None, y_eval=None, on_epoch=None):
+        """train!'s whole epoch loop inside the library (qb_train): initial evaluation, epochs, evaluate, _diverged, patience,
+        best-model snapshot / restore in HBM.  Returns (history[(epochs_run + 1)][n_metrics], (t_sample, t_gibbs, t_update),
+        epochs_run); on_epoch(epoch, metrics_row, times, flags) is called after every epoch."""
+        lr = np.ascontiguousarray(learning_rate, dtype=np.float64)
+        llr = None if label_learning_rate is None else np.ascontiguousarray(label_learning_rate, dtype=np.float64)
+        ids = np.ascontiguousarray([self.METRICS[m] for m in metrics], dtype=np.int32)
+        stop = self.METRICS[stopping_metric if stopping_metric is not None else metrics[0]]
+        X, xdt = as_rows(x_eval, self.V) if x_eval is not None else (None, 0)
+        Y, ydt = as_rows(y_eval, self.L) if y_eval is not None else (None, 0)
+        hist = np.full((n_epochs + 1, len(ids)), np.nan)
+        times = np.zeros(3)
+        ran = ctypes.c_int32(0)
+
+        def _cb(user, epoch, mrow, trow, flags):
+            on_epoch(int(epoch), [mrow[i] for i in range(len(ids))], [trow[i] for i in range(3)], int(flags))
+
+        cb = _ffi.ON_EPOCH(_cb) if on_epoch is not None else ctypes.cast(None, _ffi.ON_EPOCH)
+        cfg = _ffi.QbTrainConfig(self.METHODS[method.upper()], n_epochs, B, k, lr.ctypes.data, None if llr is None else llr.ctypes.data,
+                                 fast_learning_rate, fast_label_learning_rate, len(ids), ids.ctypes.data, stop,
+                                 int(early_stopping), int(store_best_rbm), patience,
+                                 None if X is None else X.ctypes.data, xdt, 0 if X is None else X.shape[0],
+                                 None if Y is None else Y.ctypes.data, ydt, cb, None)
+        check(lib().qb_train(self._h, ctypes.byref(cfg), ptr(hist), ptr(times), ctypes.byref(ran)))
+        return hist[:ran.value + 1], tuple(times), ran.value
+
     def cd_epoch(self, B: int, k: int, lr: float, llr: float = 0.0, timed: bool = True):
         t = (ctypes.c_double * 3)()
         check(lib().qb_cd_epoch(self._h, B, k, lr, llr, t if timed else None))
