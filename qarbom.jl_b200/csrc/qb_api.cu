@@ -496,12 +496,13 @@ int chain_tile_width(qb_handle *h, int64_t N) {
     if (h->force_bn >= 64) return h->force_bn;
     return N >= 1024 ? 256 : (N > 64 ? 128 : 64);
 }
-// Measured (tools/chain_probe.py, profiles/r2_chain_probe.txt): the pair-tile chain wins where a half-step is more than one wave
-// of 256 x 256 pair tiles (cfg5: 2048 rows -17 %, 8192 rows -1 %), ties at exactly one partial wave (1024 rows) and loses on
-// small models, whose half-steps want many small single-CTA tiles.  Option "fused_chain": 1 = automatic, 2 = always, 0 = never.
+// Measured (tools/chain_probe.py, profiles/r2_chain_probe.txt, r2_chain_probe_quad.txt): the pair-tile chain wins from about
+// one wave of 256 x 256 pair tiles per half-step on (cfg5: 1024 rows, 64 tiles: 724 vs 793 us per step; 2048 rows -17 %; 8192
+// rows -1 %) and loses on small models, whose half-steps want many small single-CTA tiles.
+// Option "fused_chain": 1 = automatic, 2 = always, 0 = never.
 bool chain_pays(qb_handle *h, const sm100::EpiParams &ep) {
     if (h->fused_chain_mode == 2) return true;
-    return (int64_t)ceil_div(ep.N, 256) * ceil_div(ep.M, 256) >= h->gemm_sms / 2;
+    return (int64_t)ceil_div(ep.N, 256) * ceil_div(ep.M, 256) >= (h->gemm_sms * 3) / 8;
 }
 // The quad variant (gibbs_chain_kernel_quad) is for half-steps of about one wave of 256 x 256 pair tiles -- there each pair
 // holds a single tile per half-step and its epilogue is exposed; with 128-row blocks per pair and the weights multicast inside
