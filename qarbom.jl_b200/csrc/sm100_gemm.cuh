@@ -641,15 +641,32 @@ gibbs_gemm_kernel(const __grid_constant__ Phases ph, const EpiParams ep) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
-                int p = 0, kb0 = 0;
-                for (int kb = 0; kb < kb_total; kb++) {
-                    while (kb >= ph.kb_end[p]) kb0 = ph.kb_end[p++];
-                    mbar_wait(empty_bar(stage), phase ^ 1);
-                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-                    mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                    tma_load_2d(sa, &ph.A[p], full_bar(stage), (kb - kb0) * BK, m_blk * BM);
-                    tma_load_2d(sb, &ph.B[p], full_bar(stage), (kb - kb0) * BK, n_blk * BN);
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                if (KIND != K_GRAD || ph.n <= 2) {   // constant tensor-map indices on the production paths (see gibbs_gemm_kernel_2cta)
+                    const int kb1 = ph.kb_end[0];
+                    for (int kb = 0; kb < kb_total; kb++) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+                        mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                        if (kb < kb1) {
+                            tma_load_2d(sa, &ph.A[0], full_bar(stage), kb * BK, m_blk * BM);
+                            tma_load_2d(sb, &ph.B[0], full_bar(stage), kb * BK, n_blk * BN);
+                        } else {
+                            tma_load_2d(sa, &ph.A[1], full_bar(stage), (kb - kb1) * BK, m_blk * BM);
+                            tma_load_2d(sb, &ph.B[1], full_bar(stage), (kb - kb1) * BK, n_blk * BN);
+                        }
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                } else {
+                    int p = 0, kb0 = 0;
+                    for (int kb = 0; kb < kb_total; kb++) {
+                        while (kb >= ph.kb_end[p]) kb0 = ph.kb_end[p++];
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+                        mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                        tma_load_2d(sa, &ph.A[p], full_bar(stage), (kb - kb0) * BK, m_blk * BM);
+                        tma_load_2d(sb, &ph.B[p], full_bar(stage), (kb - kb0) * BK, n_blk * BN);
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -665,13 +682,16 @@ gibbs_gemm_kernel(const __grid_constant__ Phases ph, const EpiParams ep) {
                 tcgen05_fence_after();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
                 int p = 0;
+                const bool short_list = KIND != K_GRAD || ph.n <= 2;
+                const int kb1m = ph.kb_end[0];
+                const uint32_t idesc0 = (ph.neg_mask & 1u) ? idesc_neg : idesc_pos, idesc1 = (ph.neg_mask & 2u) ? idesc_neg : idesc_pos;
                 for (int kb = 0; kb < kb_total; kb++) {
-                    while (kb >= ph.kb_end[p]) p++;
+                    if (!short_list) while (kb >= ph.kb_end[p]) p++;
                     mbar_wait(full_bar(stage), phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
                     const uint64_t adesc = make_kmajor_sw128_desc(sa), bdesc = make_kmajor_sw128_desc(sb);
-                    const uint32_t idesc = ((ph.neg_mask >> p) & 1u) ? idesc_neg : idesc_pos;
+                    const uint32_t idesc = short_list ? ((kb < kb1m) ? idesc0 : idesc1) : (((ph.neg_mask >> p) & 1u) ? idesc_neg : idesc_pos);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++) {
                         // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
@@ -848,16 +868,38 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ Phases ph, const EpiParams ep) {
                 int m_blk, n_blk;
                 tile_coords<KIND>(tile, tiles_m, tiles_n, m_blk, n_blk);
                 const int m0 = m_blk * 2 * BM + (int)rank * BM, n0 = n_blk * BN + (int)rank * (BN / 2);
-                int p = 0, kb0 = 0;
-                for (int kb = 0; kb < kb_total; kb++) {
-                    while (kb >= ph.kb_end[p]) kb0 = ph.kb_end[p++];
-                    mbar_wait(empty_bar(stage), phase ^ 1);
-                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-                    if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-                    else mbar_arrive_remote(full_bar(stage), 0);
-                    tma_load_2d_2sm(sa, &ph.A[p], full_bar(stage), (kb - kb0) * BK, m0);
-                    tma_load_2d_2sm(sb, &ph.B[p], full_bar(stage), (kb - kb0) * BK, n0);
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                // One or two products (every production path): the tensor maps are addressed with CONSTANT indices.  A run-time
+                // index into the kernel parameter makes the compiler keep a local copy of the whole product list, and TMA then
+                // fetches its descriptors from local memory -- measured 6 % slower per GEMM.  Longer lists (QB_PREC_FP32X3's
+                // component products) take the general loop.
+                if (KIND != K_GRAD || ph.n <= 2) {   // (only EPI_GRAD launches ever carry longer lists: folded away elsewhere)
+                    const int kb1 = ph.kb_end[0];
+                    for (int kb = 0; kb < kb_total; kb++) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+                        if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+                        else mbar_arrive_remote(full_bar(stage), 0);
+                        if (kb < kb1) {
+                            tma_load_2d_2sm(sa, &ph.A[0], full_bar(stage), kb * BK, m0);
+                            tma_load_2d_2sm(sb, &ph.B[0], full_bar(stage), kb * BK, n0);
+                        } else {
+                            tma_load_2d_2sm(sa, &ph.A[1], full_bar(stage), (kb - kb1) * BK, m0);
+                            tma_load_2d_2sm(sb, &ph.B[1], full_bar(stage), (kb - kb1) * BK, n0);
+                        }
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                } else {
+                    int p = 0, kb0 = 0;
+                    for (int kb = 0; kb < kb_total; kb++) {
+                        while (kb >= ph.kb_end[p]) kb0 = ph.kb_end[p++];
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+                        if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+                        else mbar_arrive_remote(full_bar(stage), 0);
+                        tma_load_2d_2sm(sa, &ph.A[p], full_bar(stage), (kb - kb0) * BK, m0);
+                        tma_load_2d_2sm(sb, &ph.B[p], full_bar(stage), (kb - kb0) * BK, n0);
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -873,13 +915,16 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ Phases ph, const EpiParams ep) {
                 tcgen05_fence_after();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
                 int p = 0;
+                const bool short_list = KIND != K_GRAD || ph.n <= 2;
+                const int kb1m = ph.kb_end[0];
+                const uint32_t idesc0 = (ph.neg_mask & 1u) ? idesc_neg : idesc_pos, idesc1 = (ph.neg_mask & 2u) ? idesc_neg : idesc_pos;
                 for (int kb = 0; kb < kb_total; kb++) {
-                    while (kb >= ph.kb_end[p]) p++;
+                    if (!short_list) while (kb >= ph.kb_end[p]) p++;
                     mbar_wait(full_bar(stage), phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
                     const uint64_t adesc = make_kmajor_sw128_desc(sa), bdesc = make_kmajor_sw128_desc(sb);
-                    const uint32_t idesc = ((ph.neg_mask >> p) & 1u) ? idesc_neg : idesc_pos;
+                    const uint32_t idesc = short_list ? ((kb < kb1m) ? idesc0 : idesc1) : (((ph.neg_mask >> p) & 1u) ? idesc_neg : idesc_pos);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++)
                         umma_bf16_2sm(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
