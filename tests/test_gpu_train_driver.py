@@ -82,3 +82,24 @@ def test_device_epoch_driver_equals_host_loop(q, tmp_path, method, V, H, L, B, k
     assert all(t >= 0 for t in times) and sum(times) > 0
     for a, b in ((ra.W, rb.W), (ra.a, rb.a), (ra.b, rb.b)) + (((ra.U, rb.U), (ra.c, rb.c)) if L else ()):
         assert np.max(np.abs(a - b)) < 1e-6, float(np.max(np.abs(a - b)))
+
+
+def test_device_epoch_driver_argument_errors(q):
+    rng = np.random.default_rng(0)
+    X, _ = _data(rng, 16, 8, 0)
+    with q.DeviceRBM(q.RBM(8, 4), max_batch=8, precision="fp32") as dev:
+        with pytest.raises(q.QbError):
+            dev.train_epochs("PCD", 2, 4, 1, [0.1, 0.1])                                    # no resident dataset
+        dev.set_data(X)
+        with pytest.raises(q.QbError):
+            dev.train_epochs("PCD", 2, 4, 1, [0.1, 0.1], metrics=("mse",), stopping_metric="free_energy")   # KeyError in the reference
+        with pytest.raises(q.QbError):
+            dev.train_epochs("PCD", 2, 4, 1, [0.1, 0.1], metrics=("accuracy",))             # no label units
+        with pytest.raises(q.QbError):
+            dev.train_epochs("PCD", 2, 32, 1, [0.1, 0.1])                                   # batch larger than max_batch
+        hist, _, ran = dev.train_epochs("PCD", 2, 4, 1, [0.1, 0.1])                         # the failed calls left the handle usable
+        assert ran == 2 and hist.shape == (3, 1) and np.all(np.isfinite(hist))
+        with pytest.raises(q.QbError):
+            dev.set_option("nvls_exchange", 1)                                              # needs a communicator (world > 1)
+        with pytest.raises(q.QbError):
+            dev.set_option("chain_quad", 3)
