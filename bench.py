@@ -381,8 +381,12 @@ def main():
         rbm = (q.GRBM if w["gaussian"] else q.RBM)(w["V"], w["H"], W=W0)
     chains_l = w.get("chains", B) // world
     args.p2p_like = False
-    dev = q.DeviceRBM(rbm, max_batch=max(Bl, chains_l), precision=args.precision, device=local_rank, rank=rank, world=world, seed=1234)
-    if world > 1:
+    want_nvls = (world > 1 and args.precision == "bf16" and bool(args.nvls) and not args.p2p and args.sharded_update != 0 and
+                 args.state_exchange <= 0 and w["H"] % world == 0)
+    for try_nvls in ((True, False) if want_nvls else (False,)):
+        dev = q.DeviceRBM(rbm, max_batch=max(Bl, chains_l), precision=args.precision, device=local_rank, rank=rank, world=world, seed=1234)
+        if world == 1:
+            break
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             uid.copy_(torch.frombuffer(bytearray(q.DeviceRBM.comm_unique_id()), dtype=torch.uint8))
@@ -399,18 +403,28 @@ def main():
         elif args.precision == "bf16" and args.sharded_update >= 0 and w["H"] % world == 0:
             dev.set_option("sharded_update", args.sharded_update)
         nvls_on = False
-        if args.precision == "bf16" and args.nvls and not args.p2p and args.sharded_update != 0 and args.state_exchange <= 0 and w["H"] % world == 0:
-            why = dev.enable_nvls_exchange()      # collective; "" = switched on
-            nvls_on = why == ""
+        if try_nvls:
+            try:
+                why = dev.enable_nvls_exchange()      # collective; "" = switched on
+            except q.QbError as e:                    # anything but "unsupported": still only a reason not to use it
+                why = str(e)
+            # every rank must have switched, or none: agree, and start over on the NCCL exchange otherwise
+            ok = torch.tensor([1 if why == "" else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            nvls_on = bool(ok.item())
             if nvls_on:
                 exchange_mode = ("ONE fused kernel per rank over NVSwitch multicast: multimem.ld_reduce of the fp32 gradient shard (reduce-scatter in "
                                  "the switch) + update of the owned hidden rows + multimem.st of the new bf16 shadow (all-gather by the switch); "
                                  "transposed shadow rebuilt locally")
-            elif rank == 0:
-                print(f"[bench] NVSwitch multicast exchange not available, using the NCCL exchange: {why}", file=sys.stderr)
+            else:
+                if why:
+                    print(f"[bench] rank {rank}: NVSwitch multicast exchange not available, using the NCCL exchange: {why}", file=sys.stderr)
+                dev.close()
+                continue
         args.p2p_like = args.p2p or nvls_on
         if args.precision == "bf16" and args.state_exchange >= 0 and not args.p2p_like and args.sharded_update != 0 and w["H"] % world == 0:
             dev.set_option("state_exchange", args.state_exchange)
+        break
     dev.set_data(Xl, Yl)
     pcd = w["algo"] == "PCD"
     if pcd:
