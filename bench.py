@@ -665,6 +665,12 @@ def main():
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": cfg,
             "gibbs_steps_per_s": value * k * (w.get("chains", B) / B if pcd else 1.0), "gpu_launches": launches, "roofline": roof, "roofline_update": roof_upd, "clocks": clocks, "e2e": e2e}
+    # latency floor of the step: its dependent stages (the 2k (+1) forward contractions of the chain, then gradient + update) --
+    # on the small configurations a stage is a fraction of a microsecond of MMA and the step time is stages x stage latency
+    stages = 2 * k + 2
+    line["latency"] = {"dependent_stages_per_step": stages, "us_per_stage": ms / args.steps * 1e3 / stages,
+                       "mma_floor_us_per_step": F / (tf_burst * 1e12) * 1e6,
+                       "note": "stages = 2k + 1 forward contractions on the critical path (PCD: the positive phase runs beside the chain) + gradient/update"}
     if exchange_mode:
         line["exchange_mode"] = exchange_mode
     if e2e_i64:
