@@ -288,6 +288,7 @@ int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_la
 #define QB_GEMM_KIND_FAST_LABEL 6  /* Bernoulli visibles + label units (softmax + Bernoulli) in the epilogue */
 #define QB_GEMM_KIND_CHAIN 7       /* persistent multi-half-step kernel: all half-steps of a chain advance / CD forward pass */
 #define QB_GEMM_KIND_EPOCH 8       /* persistent multi-mini-batch kernel: whole training steps incl. gradient + update */
+#define QB_GEMM_KIND_GRAD_X3 9     /* gradient-store kernel with more than two products (the component products of QB_PREC_FP32X3) */
 int32_t qb_get_gemm_histogram(qb_handle *h, int64_t *counts, int32_t n_slots);
 /* Tensor-core flops ISSUED since the last reset: equal to the algorithmic gemm_flops of qb_get_counters except in
  * QB_PREC_FP32X3, where every contraction issues 3..6 bf16 component products (reported separately). */

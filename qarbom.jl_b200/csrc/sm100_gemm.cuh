@@ -37,7 +37,9 @@ enum { EPI_SAMPLE = 0, EPI_GRAD = 1 };
 // kernel specialisations: generic epilogue, gradient store, and the two compile-time fast paths
 // (numbering = QB_GEMM_KIND_* of include/qarbom_b200.h)
 enum { K_GENERIC = 0, K_GRAD = 1, K_FAST_SAMPLE = 2, K_FAST_PROB = 3, K_FAST_SAMPLE_PROB = 4, K_FAST_GAUSS = 5, K_FAST_LABEL = 6,
-       K_CHAIN = 7 /* histogram slot of the multi-half-step kernel (sm100_chain.cuh), not an epilogue */ };
+       K_CHAIN = 7 /* histogram slot of the multi-half-step kernel (sm100_chain.cuh), not an epilogue */,
+       K_GRAD_LONG = 9 /* gradient-store epilogue with a product list longer than two (QB_PREC_FP32X3's component products): the
+                          only kernels that index the list at run time (slot 8 is the multi-mini-batch kernel's) */ };
 // Epilogue warpgroups per CTA: the lean epilogues are latency-bound with 2 warps per scheduler
 // (ncu: IPC 0.3, epilogue time ~ MMA time), so they run 4 warpgroups (16 warps, 64 columns each at
 // BN = 256); the register-hungry generic epilogue keeps 2.
@@ -641,7 +643,7 @@ gibbs_gemm_kernel(const __grid_constant__ Phases ph, const EpiParams ep) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
-                if (KIND != K_GRAD || ph.n <= 2) {   // constant tensor-map indices on the production paths (see gibbs_gemm_kernel_2cta)
+                if (KIND != K_GRAD_LONG) {   // constant tensor-map indices on the production paths (see gibbs_gemm_kernel_2cta)
                     const int kb1 = ph.kb_end[0];
                     for (int kb = 0; kb < kb_total; kb++) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
@@ -682,7 +684,7 @@ gibbs_gemm_kernel(const __grid_constant__ Phases ph, const EpiParams ep) {
                 tcgen05_fence_after();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
                 int p = 0;
-                const bool short_list = KIND != K_GRAD || ph.n <= 2;
+                constexpr bool short_list = KIND != K_GRAD_LONG;
                 const int kb1m = ph.kb_end[0];
                 const uint32_t idesc0 = (ph.neg_mask & 1u) ? idesc_neg : idesc_pos, idesc1 = (ph.neg_mask & 2u) ? idesc_neg : idesc_pos;
                 for (int kb = 0; kb < kb_total; kb++) {
@@ -714,7 +716,7 @@ gibbs_gemm_kernel(const __grid_constant__ Phases ph, const EpiParams ep) {
             tcgen05_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
             if (KIND == K_GENERIC) epilogue_sample<BN, WGS>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
-            else if (KIND == K_GRAD) epilogue_grad<BN, WGS>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_GRAD || KIND == K_GRAD_LONG) epilogue_grad<BN, WGS>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else if (KIND == K_FAST_SAMPLE) epilogue_fast<BN, WGS, true, false>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else if (KIND == K_FAST_SAMPLE_PROB) epilogue_fast<BN, WGS, true, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else if (KIND == K_FAST_GAUSS) epilogue_fast<BN, WGS, true, false, 1>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
@@ -806,7 +808,7 @@ struct Cfg2 {
 // keeps live at the price of reading B once per group.
 template <int KIND>
 __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int &m_blk, int &n_blk) {
-    if (KIND == K_GRAD && tiles_m > 8) {
+    if ((KIND == K_GRAD || KIND == K_GRAD_LONG) && tiles_m > 8) {
         constexpr int GM = 8;
         const int per_group = GM * tiles_n;
         const int g = tile / per_group, within = tile - g * per_group;
@@ -872,7 +874,7 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ Phases ph, const EpiParams ep) {
                 // index into the kernel parameter makes the compiler keep a local copy of the whole product list, and TMA then
                 // fetches its descriptors from local memory -- measured 6 % slower per GEMM.  Longer lists (QB_PREC_FP32X3's
                 // component products) take the general loop.
-                if (KIND != K_GRAD || ph.n <= 2) {   // (only EPI_GRAD launches ever carry longer lists: folded away elsewhere)
+                if (KIND != K_GRAD_LONG) {   // (lists longer than two products run the K_GRAD_LONG instantiation)
                     const int kb1 = ph.kb_end[0];
                     for (int kb = 0; kb < kb_total; kb++) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
@@ -915,7 +917,7 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ Phases ph, const EpiParams ep) {
                 tcgen05_fence_after();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
                 int p = 0;
-                const bool short_list = KIND != K_GRAD || ph.n <= 2;
+                constexpr bool short_list = KIND != K_GRAD_LONG;
                 const int kb1m = ph.kb_end[0];
                 const uint32_t idesc0 = (ph.neg_mask & 1u) ? idesc_neg : idesc_pos, idesc1 = (ph.neg_mask & 2u) ? idesc_neg : idesc_pos;
                 for (int kb = 0; kb < kb_total; kb++) {
@@ -947,7 +949,7 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ Phases ph, const EpiParams ep) {
             tcgen05_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
             if (KIND == K_GENERIC) epilogue_sample<BN, WGS>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
-            else if (KIND == K_GRAD) epilogue_grad<BN, WGS>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_GRAD || KIND == K_GRAD_LONG) epilogue_grad<BN, WGS>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else if (KIND == K_FAST_SAMPLE) epilogue_fast<BN, WGS, true, false>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else if (KIND == K_FAST_SAMPLE_PROB) epilogue_fast<BN, WGS, true, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else if (KIND == K_FAST_GAUSS) epilogue_fast<BN, WGS, true, false, 1>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
@@ -1094,7 +1096,10 @@ inline void launch_bn_2cta(cudaStream_t st, const Product *prods, int n, const E
     const int tiles = (int)(ceil_div(ep.M, 2 * BM) * ceil_div(ep.N, BN));
     const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
     switch (pick_kind(ep)) {
-        case K_GRAD: launch_bn_kind_2cta<BN, K_GRAD>(st, ph, ep, clusters); break;
+        case K_GRAD:
+            if (n > 2) launch_bn_kind_2cta<BN, K_GRAD_LONG>(st, ph, ep, clusters);
+            else launch_bn_kind_2cta<BN, K_GRAD>(st, ph, ep, clusters);
+            break;
         case K_FAST_SAMPLE: launch_bn_kind_2cta<BN, K_FAST_SAMPLE>(st, ph, ep, clusters); break;
         case K_FAST_PROB: launch_bn_kind_2cta<BN, K_FAST_PROB>(st, ph, ep, clusters); break;
         case K_FAST_SAMPLE_PROB: launch_bn_kind_2cta<BN, K_FAST_SAMPLE_PROB>(st, ph, ep, clusters); break;
@@ -1112,7 +1117,10 @@ inline void launch_bn(cudaStream_t st, const Product *prods, int n, const EpiPar
     const int tiles = (int)(ceil_div(ep.M, BM) * ceil_div(ep.N, BN));
     const int grid = tiles < num_sms ? tiles : num_sms;
     switch (pick_kind(ep)) {
-        case K_GRAD: launch_bn_kind<BN, K_GRAD>(st, ph, ep, grid); break;
+        case K_GRAD:
+            if (n > 2) launch_bn_kind<BN, K_GRAD_LONG>(st, ph, ep, grid);
+            else launch_bn_kind<BN, K_GRAD>(st, ph, ep, grid);
+            break;
         case K_FAST_SAMPLE: launch_bn_kind<BN, K_FAST_SAMPLE>(st, ph, ep, grid); break;
         case K_FAST_PROB: launch_bn_kind<BN, K_FAST_PROB>(st, ph, ep, grid); break;
         case K_FAST_SAMPLE_PROB: launch_bn_kind<BN, K_FAST_SAMPLE_PROB>(st, ph, ep, grid); break;
@@ -1128,6 +1136,7 @@ inline void init_bn() {
     const int b = Cfg<BN>::SMEM_BYTES;
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_GRAD_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_SAMPLE_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
@@ -1139,6 +1148,7 @@ inline void init_bn_2cta() {
     const int b = Cfg2<BN>::SMEM_BYTES;
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_GRAD_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_SAMPLE_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
@@ -1184,7 +1194,7 @@ inline void launch_products(cudaStream_t st, const Product *prods, int n, const 
                             int use_2cta = 1) {
     int bn; bool pair;
     pick_shape(ep.M, ep.N, num_sms, force_bn, use_2cta, bn, pair);
-    last_shape().bn = bn; last_shape().pair = pair ? 1 : 0; last_shape().kind = pick_kind(ep);
+    last_shape().bn = bn; last_shape().pair = pair ? 1 : 0; last_shape().kind = (pick_kind(ep) == K_GRAD && n > 2) ? K_GRAD_LONG : pick_kind(ep);
     if (pair) {
         if (bn == 256) launch_bn_2cta<256>(st, prods, n, ep, num_sms);
         else launch_bn_2cta<128>(st, prods, n, ep, num_sms);
