@@ -277,7 +277,7 @@ int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_la
 /* GEMM launches since the last reset by kernel specialisation: counts[(pair * 4 + b) * QB_GEMM_KINDS + kind] with
  * pair = 1 for the cta_group::2 kernel, b = log2(tile width / 32) (32, 64, 128, 256), kind = QB_GEMM_KIND_*; the
  * last slot counts launches of the fp32 CUDA-core GEMM.  Tests use it to assert WHICH kernel produced a result. */
-#define QB_GEMM_KINDS 10
+#define QB_GEMM_KINDS 11
 #define QB_GEMM_HIST_SLOTS (2 * 4 * QB_GEMM_KINDS + 1)
 #define QB_GEMM_KIND_GENERIC 0
 #define QB_GEMM_KIND_GRAD 1
@@ -289,6 +289,7 @@ int32_t qb_get_counters(qb_handle *h, int64_t *kernel_launches, int64_t *gemm_la
 #define QB_GEMM_KIND_CHAIN 7       /* persistent multi-half-step kernel: all half-steps of a chain advance / CD forward pass */
 #define QB_GEMM_KIND_EPOCH 8       /* persistent multi-mini-batch kernel: whole training steps incl. gradient + update */
 #define QB_GEMM_KIND_GRAD_X3 9     /* gradient-store kernel with more than two products (the component products of QB_PREC_FP32X3) */
+#define QB_GEMM_KIND_FAST_SQERR 10 /* reconstruction error reduced in the epilogue, nothing stored (qb_eval_mse, qb_*_step_host) */
 int32_t qb_get_gemm_histogram(qb_handle *h, int64_t *counts, int32_t n_slots);
 /* Tensor-core flops ISSUED since the last reset: equal to the algorithmic gemm_flops of qb_get_counters except in
  * QB_PREC_FP32X3, where every contraction issues 3..6 bf16 component products (reported separately). */

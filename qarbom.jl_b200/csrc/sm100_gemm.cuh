@@ -39,7 +39,9 @@ enum { EPI_SAMPLE = 0, EPI_GRAD = 1 };
 enum { K_GENERIC = 0, K_GRAD = 1, K_FAST_SAMPLE = 2, K_FAST_PROB = 3, K_FAST_SAMPLE_PROB = 4, K_FAST_GAUSS = 5, K_FAST_LABEL = 6,
        K_CHAIN = 7 /* histogram slot of the multi-half-step kernel (sm100_chain.cuh), not an epilogue */,
        K_GRAD_LONG = 9 /* gradient-store epilogue with a product list longer than two (QB_PREC_FP32X3's component products): the
-                          only kernels that index the list at run time (slot 8 is the multi-mini-batch kernel's) */ };
+                          only kernels that index the list at run time (slot 8 is the multi-mini-batch kernel's) */,
+       K_FAST_SQERR = 10 /* reconstruction error: p = sigmoid(x), sum of (ref - p)^2 -- nothing is stored (evaluate /
+                            _evaluate(MeanSquaredError), src/evaluation.jl:16-20, and the per-step error of qb_*_step_host) */ };
 // Epilogue warpgroups per CTA: the lean epilogues are latency-bound with 2 warps per scheduler
 // (ncu: IPC 0.3, epilogue time ~ MMA time), so they run 4 warpgroups (16 warps, 64 columns each at
 // BN = 256); the register-hungry generic epilogue keeps 2.
@@ -521,6 +523,21 @@ __device__ __forceinline__ void label_chunk(const EpiParams &ep, const uint32_t 
     }
 }
 
+//   MODE 3: reconstruction error only: p = sigmoid(x), acc += (ref - p)^2, no stores
+template <bool FULL>
+__device__ __forceinline__ void sqerr_chunk(const EpiParams &ep, const uint32_t (&r)[16], int unit, int row_base, int nv, float bias, float &acc) {
+    const float bias_l2e = bias * -1.4426950408889634f;
+    const unsigned short *ref = reinterpret_cast<const unsigned short *>(ep.ref_rm) + (long long)row_base * ep.ld_ref + unit;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const float p = sigmoid_mufu_fma(__uint_as_float(r[j]), bias_l2e);
+        if (FULL || j < nv) {
+            const float d = __uint_as_float((uint32_t)ref[(long long)j * ep.ld_ref] << 16) - p;   // bf16 -> fp32
+            acc = fmaf(d, d, acc);
+        }
+    }
+}
+
 template <int BN, int WGS, bool SAMPLE, bool PROB, int MODE = 0>
 __device__ __forceinline__ void epilogue_fast(const EpiParams &ep, uint32_t tmem_acc, int m_blk, int n_blk, int quarter, int wg,
                                               int lane) {
@@ -549,8 +566,18 @@ __device__ __forceinline__ void epilogue_fast(const EpiParams &ep, uint32_t tmem
             else label_chunk<false>(ep, r, unit, uvalid, row_base, nvalid, bias, want_sT, bg_s);
             continue;
         }
+        if (MODE == 3) {
+            if (nv == 16) sqerr_chunk<true>(ep, r, unit, row_base, nv, bias, bg_p);
+            else if (nv > 0) sqerr_chunk<false>(ep, r, unit, row_base, nv, bias, bg_p);
+            continue;
+        }
         if (nv == 16) fast_chunk<SAMPLE, PROB, true, MODE == 1>(ep, r, unit, row_base, nv, bias, want_sT, want_pT, want_prm, bg_p, bg_s);
         else if (nv > 0) fast_chunk<SAMPLE, PROB, false, MODE == 1>(ep, r, unit, row_base, nv, bias, want_sT, want_pT, want_prm, bg_p, bg_s);
+    }
+    if (MODE == 3) {   // one double atomic per warp and tile
+        const float sq = warp_sum(bg_p);
+        if (lane == 0) atomicAdd(ep.sqerr, (double)sq);
+        return;
     }
     if (ep.bg_what && uvalid)
         atomicAdd(ep.bias_grad + unit, ep.bg_sign * (((PROB && ep.bg_what == 1) || MODE == 1) ? bg_p : (float)(bg_s / 0x3F80)));
@@ -721,6 +748,7 @@ gibbs_gemm_kernel(const __grid_constant__ Phases ph, const EpiParams ep) {
             else if (KIND == K_FAST_SAMPLE_PROB) epilogue_fast<BN, WGS, true, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else if (KIND == K_FAST_GAUSS) epilogue_fast<BN, WGS, true, false, 1>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else if (KIND == K_FAST_LABEL) epilogue_fast<BN, WGS, true, false, 2>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_FAST_SQERR) epilogue_fast<BN, WGS, false, true, 3>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else epilogue_fast<BN, WGS, false, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             tcgen05_fence_before();
             __syncwarp();
@@ -954,6 +982,7 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ Phases ph, const EpiParams ep) {
             else if (KIND == K_FAST_SAMPLE_PROB) epilogue_fast<BN, WGS, true, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else if (KIND == K_FAST_GAUSS) epilogue_fast<BN, WGS, true, false, 1>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else if (KIND == K_FAST_LABEL) epilogue_fast<BN, WGS, true, false, 2>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
+            else if (KIND == K_FAST_SQERR) epilogue_fast<BN, WGS, false, true, 3>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             else epilogue_fast<BN, WGS, false, true>(ep, tmem_acc, m_blk, n_blk, quarter, wg, lane);
             tcgen05_fence_before();
             __syncwarp();
@@ -1031,6 +1060,9 @@ inline CUtensorMap encode_tmap(const Operand &o, int box_rows) {
 // which specialisation serves these epilogue parameters
 inline int pick_kind(const EpiParams &ep) {
     if (ep.mode == EPI_GRAD) return K_GRAD;
+    if (ep.sqerr && !ep.inj && !ep.softplus_rows && !ep.prob_f32 && ep.act == ACT_SIGMOID && ep.split >= ep.M && !ep.sample && !ep.state_rm &&
+        !ep.state_T && !ep.prob_rm && !ep.prob_T && !ep.bg_what && ep.pscale == 1.f)
+        return K_FAST_SQERR;
     const bool lean = !ep.inj && !ep.sqerr && !ep.softplus_rows && !ep.prob_f32;
     const bool plain = lean && ep.act == ACT_SIGMOID && ep.split >= ep.M;
     if (plain && ep.sample && ep.use_rng && ep.state_rm && !ep.prob_rm)
@@ -1105,6 +1137,7 @@ inline void launch_bn_2cta(cudaStream_t st, const Product *prods, int n, const E
         case K_FAST_SAMPLE_PROB: launch_bn_kind_2cta<BN, K_FAST_SAMPLE_PROB>(st, ph, ep, clusters); break;
         case K_FAST_GAUSS: launch_bn_kind_2cta<BN, K_FAST_GAUSS>(st, ph, ep, clusters); break;
         case K_FAST_LABEL: launch_bn_kind_2cta<BN, K_FAST_LABEL>(st, ph, ep, clusters); break;
+        case K_FAST_SQERR: launch_bn_kind_2cta<BN, K_FAST_SQERR>(st, ph, ep, clusters); break;
         default: launch_bn_kind_2cta<BN, K_GENERIC>(st, ph, ep, clusters); break;
     }
     QB_CUDA(cudaGetLastError());
@@ -1126,6 +1159,7 @@ inline void launch_bn(cudaStream_t st, const Product *prods, int n, const EpiPar
         case K_FAST_SAMPLE_PROB: launch_bn_kind<BN, K_FAST_SAMPLE_PROB>(st, ph, ep, grid); break;
         case K_FAST_GAUSS: launch_bn_kind<BN, K_FAST_GAUSS>(st, ph, ep, grid); break;
         case K_FAST_LABEL: launch_bn_kind<BN, K_FAST_LABEL>(st, ph, ep, grid); break;
+        case K_FAST_SQERR: launch_bn_kind<BN, K_FAST_SQERR>(st, ph, ep, grid); break;
         default: launch_bn_kind<BN, K_GENERIC>(st, ph, ep, grid); break;
     }
     QB_CUDA(cudaGetLastError());
@@ -1142,6 +1176,7 @@ inline void init_bn() {
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_SAMPLE_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_LABEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel<BN, K_FAST_SQERR>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
 }
 template <int BN>
 inline void init_bn_2cta() {
@@ -1154,6 +1189,7 @@ inline void init_bn_2cta() {
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_SAMPLE_PROB>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_GAUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_LABEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    QB_CUDA(cudaFuncSetAttribute(gibbs_gemm_kernel_2cta<BN, K_FAST_SQERR>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
 }
 // once per device (qb_create): opt in to the large dynamic shared-memory carve-out
 inline void init_device() {

@@ -344,7 +344,7 @@ class DeviceRBM:
                                     ctypes.byref(ms), ctypes.byref(tf)))
         return a.value, b.value, f.value, t.value, ms.value, tf.value
 
-    GEMM_KINDS = ("generic", "grad", "fast_sample", "fast_prob", "fast_sample_prob", "fast_gauss", "fast_label", "chain", "epoch", "grad_x3")
+    GEMM_KINDS = ("generic", "grad", "fast_sample", "fast_prob", "fast_sample_prob", "fast_gauss", "fast_label", "chain", "epoch", "grad_x3", "fast_sqerr")
 
     def gemm_histogram(self) -> dict:
         """{(kernel, tile width, kind name): launches} since the last counter reset."""
