@@ -313,7 +313,15 @@ void upload_rows_on(qb_handle *h, cudaStream_t st, void *&staging, size_t &stagi
         float *df = dst.f ? dst.f + (r0 + r) * dst.ld : nullptr;
         bf16 *db = dst.b ? dst.b + (r0 + r) * dst.ld : nullptr;
         const int64_t tot = nr * cols;
-        switch (dt) {
+        if ((cols % 8) == 0 && (col0 % 8) == 0 && (dst.ld % 8) == 0) {   // eight elements per thread, 16-byte stores
+            const int64_t groups = tot / 8;
+            switch (dt) {
+                case QB_DT_F64: convert_rows8_kernel<double><<<grid1d(groups), 256, 0, st>>>((const double *)staging, cols, nr, df, db, dst.ld, col0); break;
+                case QB_DT_I64: convert_rows8_kernel<long long><<<grid1d(groups), 256, 0, st>>>((const long long *)staging, cols, nr, df, db, dst.ld, col0); break;
+                case QB_DT_F32: convert_rows8_kernel<float><<<grid1d(groups), 256, 0, st>>>((const float *)staging, cols, nr, df, db, dst.ld, col0); break;
+                default: convert_rows8_kernel<unsigned char><<<grid1d(groups), 256, 0, st>>>((const unsigned char *)staging, cols, nr, df, db, dst.ld, col0); break;
+            }
+        } else switch (dt) {
             case QB_DT_F64: convert_rows_kernel<double><<<grid1d(tot), 256, 0, st>>>((const double *)staging, cols, nr, df, db, dst.ld, col0); break;
             case QB_DT_I64: convert_rows_kernel<long long><<<grid1d(tot), 256, 0, st>>>((const long long *)staging, cols, nr, df, db, dst.ld, col0); break;
             case QB_DT_F32: convert_rows_kernel<float><<<grid1d(tot), 256, 0, st>>>((const float *)staging, cols, nr, df, db, dst.ld, col0); break;
@@ -338,11 +346,21 @@ void download_rows(qb_handle *h, const Mat &src, int64_t r0, int64_t col0, int64
     QB_CUDA(cudaStreamSynchronize(h->stream));
 }
 
-void transpose_into(qb_handle *h, const bf16 *src, int64_t lds, int64_t rows, int64_t cols, bf16 *dst, int64_t ldd) {
-    dim3 g((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
-    transpose_bf16_kernel<<<g, 256, 0, h->stream>>>(src, lds, (int)rows, (int)cols, dst, ldd);
+// dst[c][r] = src[r][c] on stream st: 128-bit loads / stores when the leading dimensions and bases allow (they do for every
+// buffer this library allocates: ld % 8 == 0, 256-byte aligned bases; row slices keep 16-byte alignment)
+void transpose_on(qb_handle *h, cudaStream_t st, const bf16 *src, int64_t lds, int64_t rows, int64_t cols, bf16 *dst, int64_t ldd) {
+    if ((lds % 8) == 0 && (ldd % 8) == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0) {
+        dim3 g((unsigned)ceil_div(cols, 128), (unsigned)ceil_div(rows, 64));
+        transpose_bf16_wide_kernel<<<g, 256, 0, st>>>(src, lds, (int)rows, (int)cols, dst, ldd);
+    } else {
+        dim3 g((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+        transpose_bf16_kernel<<<g, 256, 0, st>>>(src, lds, (int)rows, (int)cols, dst, ldd);
+    }
     QB_CUDA(cudaGetLastError());
     h->launches++;
+}
+void transpose_into(qb_handle *h, const bf16 *src, int64_t lds, int64_t rows, int64_t cols, bf16 *dst, int64_t ldd) {
+    transpose_on(h, h->stream, src, lds, rows, cols, dst, ldd);
 }
 
 RngKey make_key(qb_handle *h) {
@@ -1502,12 +1520,7 @@ void stage_host_batch(qb_handle *h, const void *X, int xdt, const void *Y, int y
         }
         upload_rows_on(h, h->copy_stream, h->staging2, h->staging2_bytes, h->next_X, h->next_xdt, B, h->V, h->hb2, 0, 0);
         if (h->L > 0) upload_rows_on(h, h->copy_stream, h->staging2, h->staging2_bytes, h->next_Y, h->next_ydt, B, h->L, h->hb2, 0, h->V);
-        if (h->bf) {
-            dim3 g((unsigned)ceil_div(h->VL, 32), (unsigned)ceil_div(B, 32));
-            transpose_bf16_kernel<<<g, 256, 0, h->copy_stream>>>(h->hb2.b, h->hb2.ld, (int)B, (int)h->VL, h->hb2.bT, h->hb2.ldT);
-            QB_CUDA(cudaGetLastError());
-            h->launches++;
-        }
+        if (h->bf) transpose_on(h, h->copy_stream, h->hb2.b, h->hb2.ld, B, h->VL, h->hb2.bT, h->hb2.ldT);
         QB_CUDA(cudaEventRecord(h->ev_pf, h->copy_stream));
         h->pf_X = h->next_X; h->pf_Y = h->next_Y; h->pf_xdt = h->next_xdt; h->pf_ydt = h->next_ydt; h->pf_B = B; h->pf_valid = true;
         h->next_X = nullptr; h->next_Y = nullptr;

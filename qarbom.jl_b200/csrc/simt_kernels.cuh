@@ -376,6 +376,42 @@ __global__ void convert_rows_kernel(const T *__restrict__ src, int64_t src_cols,
     if (dstb) dstb[r * ld + col0 + c] = __float2bfloat16(v);
 }
 
+// Same conversion, eight consecutive elements of a row per thread (src_cols % 8 == 0, col0 % 8 == 0, ld % 8 == 0, bases 16-byte
+// aligned): one index division per eight elements, one 16-byte bf16 store (two float4 stores) -- the upload of a host mini-batch
+// sits on the critical path of qb_*_step_host (its kernels cannot share an SM with the persistent GEMM CTAs).
+template <typename T>
+__global__ void __launch_bounds__(256) convert_rows8_kernel(const T *__restrict__ src, int64_t src_cols, int64_t rows, float *__restrict__ dstf,
+                                                            bf16 *__restrict__ dstb, int64_t ld, int64_t col0) {
+    const int64_t gpr = src_cols >> 3;   // groups of eight per row
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * gpr) return;
+    const int64_t r = i / gpr, g = i - r * gpr;
+    const T *s = src + r * src_cols + 8 * g;
+    float v[8];
+    if (sizeof(T) == 1) {
+        const uint2 w = *reinterpret_cast<const uint2 *>(s);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { v[j] = (float)((w.x >> (8 * j)) & 0xFFu); v[4 + j] = (float)((w.y >> (8 * j)) & 0xFFu); }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = (float)s[j];
+    }
+    const int64_t o = r * ld + col0 + 8 * g;
+    if (dstf) {
+        reinterpret_cast<float4 *>(dstf + o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4 *>(dstf + o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (dstb) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[j] = *reinterpret_cast<const uint32_t *>(&b);
+        }
+        *reinterpret_cast<uint4 *>(dstb + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
 template <typename T>
 __global__ void export_rows_kernel(const T *__restrict__ src, int64_t ld, int64_t col0, int64_t rows, int64_t cols,
                                    double *__restrict__ dst) {
