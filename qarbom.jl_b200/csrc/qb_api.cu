@@ -316,10 +316,10 @@ void upload_rows_on(qb_handle *h, cudaStream_t st, void *&staging, size_t &stagi
         if ((cols % 8) == 0 && (col0 % 8) == 0 && (dst.ld % 8) == 0) {   // eight elements per thread, 16-byte stores
             const int64_t groups = tot / 8;
             switch (dt) {
-                case QB_DT_F64: convert_rows8_kernel<double><<<grid1d(groups), 256, 0, st>>>((const double *)staging, cols, nr, df, db, dst.ld, col0); break;
-                case QB_DT_I64: convert_rows8_kernel<long long><<<grid1d(groups), 256, 0, st>>>((const long long *)staging, cols, nr, df, db, dst.ld, col0); break;
-                case QB_DT_F32: convert_rows8_kernel<float><<<grid1d(groups), 256, 0, st>>>((const float *)staging, cols, nr, df, db, dst.ld, col0); break;
-                default: convert_rows8_kernel<unsigned char><<<grid1d(groups), 256, 0, st>>>((const unsigned char *)staging, cols, nr, df, db, dst.ld, col0); break;
+                case QB_DT_F64: convert_rows8_kernel<double><<<grid1d(groups, 128), 128, 0, st>>>((const double *)staging, cols, nr, df, db, dst.ld, col0); break;
+                case QB_DT_I64: convert_rows8_kernel<long long><<<grid1d(groups, 128), 128, 0, st>>>((const long long *)staging, cols, nr, df, db, dst.ld, col0); break;
+                case QB_DT_F32: convert_rows8_kernel<float><<<grid1d(groups, 128), 128, 0, st>>>((const float *)staging, cols, nr, df, db, dst.ld, col0); break;
+                default: convert_rows8_kernel<unsigned char><<<grid1d(groups, 128), 128, 0, st>>>((const unsigned char *)staging, cols, nr, df, db, dst.ld, col0); break;
             }
         } else switch (dt) {
             case QB_DT_F64: convert_rows_kernel<double><<<grid1d(tot), 256, 0, st>>>((const double *)staging, cols, nr, df, db, dst.ld, col0); break;

@@ -379,8 +379,11 @@ __global__ void convert_rows_kernel(const T *__restrict__ src, int64_t src_cols,
 // Same conversion, eight consecutive elements of a row per thread (src_cols % 8 == 0, col0 % 8 == 0, ld % 8 == 0, bases 16-byte
 // aligned): one index division per eight elements, one 16-byte bf16 store (two float4 stores) -- the upload of a host mini-batch
 // sits on the critical path of qb_*_step_host (its kernels cannot share an SM with the persistent GEMM CTAs).
+// Blocks of 128 threads at <= 32 registers: ONE such block fits beside a persistent GEMM CTA (640 threads x 96 registers leave
+// 4096 registers per SM), so the conversion of the next host batch proceeds on the copy stream WHILE the chain kernel runs --
+// a fatter kernel would wait for it to end (measured: Int64 rows 5.5 -> 7.1 ms per step with 256-thread blocks).
 template <typename T>
-__global__ void __launch_bounds__(256) convert_rows8_kernel(const T *__restrict__ src, int64_t src_cols, int64_t rows, float *__restrict__ dstf,
+__global__ void __launch_bounds__(128, 16) convert_rows8_kernel(const T *__restrict__ src, int64_t src_cols, int64_t rows, float *__restrict__ dstf,
                                                             bf16 *__restrict__ dstb, int64_t ld, int64_t col0) {
     const int64_t gpr = src_cols >> 3;   // groups of eight per row
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
