@@ -351,7 +351,8 @@ void download_rows(qb_handle *h, const Mat &src, int64_t r0, int64_t col0, int64
 void transpose_on(qb_handle *h, cudaStream_t st, const bf16 *src, int64_t lds, int64_t rows, int64_t cols, bf16 *dst, int64_t ldd) {
     if ((lds % 8) == 0 && (ldd % 8) == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0) {
         dim3 g((unsigned)ceil_div(cols, 128), (unsigned)ceil_div(rows, 64));
-        transpose_bf16_wide_kernel<<<g, 256, 0, st>>>(src, lds, (int)rows, (int)cols, dst, ldd);
+        if (st == h->copy_stream) transpose_bf16_wide_t_kernel<128><<<g, 128, 0, st>>>(src, lds, (int)rows, (int)cols, dst, ldd);   // runs beside the GEMM CTAs
+        else transpose_bf16_wide_kernel<<<g, 256, 0, st>>>(src, lds, (int)rows, (int)cols, dst, ldd);
     } else {
         dim3 g((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
         transpose_bf16_kernel<<<g, 256, 0, st>>>(src, lds, (int)rows, (int)cols, dst, ldd);

@@ -476,6 +476,42 @@ __global__ void __launch_bounds__(256) transpose_bf16_wide_kernel(const bf16 *__
     }
 }
 
+// The same transpose as a template on the block size: THREADS = 128 at <= 32 registers (17 KB of shared memory) fits beside a
+// persistent GEMM CTA, so the transposed copy of the NEXT host batch is built on the copy stream while the chain kernel runs.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2048 / THREADS) transpose_bf16_wide_t_kernel(const bf16 *__restrict__ src, int64_t lds, int rows, int cols,
+                                                                  bf16 *__restrict__ dst, int64_t ldd) {
+    constexpr int TR = 64, TC = 128, PITCH = TC + 8;
+    __shared__ __align__(16) unsigned short tile[TR][PITCH];
+    const int c0 = blockIdx.x * TC, r0 = blockIdx.y * TR;
+#pragma unroll
+    for (int q = 0; q < 1024 / THREADS; q++) {
+        const int idx = threadIdx.x + THREADS * q, r = idx >> 4, cv = (idx & 15) * 8;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r0 + r < rows && c0 + cv < cols) v = *reinterpret_cast<const uint4 *>(src + (int64_t)(r0 + r) * lds + c0 + cv);  // row padding (ld % 8 == 0) is readable
+        *reinterpret_cast<uint4 *>(&tile[r][cv]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 512 / THREADS; q++) {
+        const int task = threadIdx.x + THREADS * q;
+        const int cl = task & (TC - 1), hc = task >> 7;
+        const int cc = c0 + cl, hb = r0 + 16 * hc;
+        if (cc >= cols || hb >= rows) continue;
+        unsigned short *d = reinterpret_cast<unsigned short *>(dst) + (int64_t)cc * ldd + hb;
+        if (hb + 16 <= rows) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) pk[i] = (uint32_t)tile[16 * hc + 2 * i][cl] | ((uint32_t)tile[16 * hc + 2 * i + 1][cl] << 16);
+            reinterpret_cast<uint4 *>(d)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            reinterpret_cast<uint4 *>(d)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else {
+            for (int i = 0; i < 16; i++)
+                if (hb + i < rows) d[i] = tile[16 * hc + i][cl];
+        }
+    }
+}
+
 // Binary states as bits for the multi-GPU state exchange.  src: transposed bf16 states [units][ld] (0 / 1), `rows` a multiple
 // of 8; bits[u][j] bit i = (src[u][8 j + i] != 0).
 __global__ void pack_state_bits_kernel(const bf16 *__restrict__ src, int64_t ld, int units, int rows, uint8_t *__restrict__ bits) {
