@@ -316,10 +316,10 @@ void upload_rows_on(qb_handle *h, cudaStream_t st, void *&staging, size_t &stagi
         if ((cols % 8) == 0 && (col0 % 8) == 0 && (dst.ld % 8) == 0) {   // eight elements per thread, 16-byte stores
             const int64_t groups = tot / 8;
             switch (dt) {
-                case QB_DT_F64: convert_rows8_kernel<double><<<grid1d(groups, 128), 128, 0, st>>>((const double *)staging, cols, nr, df, db, dst.ld, col0); break;
-                case QB_DT_I64: convert_rows8_kernel<long long><<<grid1d(groups, 128), 128, 0, st>>>((const long long *)staging, cols, nr, df, db, dst.ld, col0); break;
-                case QB_DT_F32: convert_rows8_kernel<float><<<grid1d(groups, 128), 128, 0, st>>>((const float *)staging, cols, nr, df, db, dst.ld, col0); break;
-                default: convert_rows8_kernel<unsigned char><<<grid1d(groups, 128), 128, 0, st>>>((const unsigned char *)staging, cols, nr, df, db, dst.ld, col0); break;
+                case QB_DT_F64: convert_rows8_kernel<double, 128><<<grid1d(groups, 128), 128, 0, st>>>((const double *)staging, cols, nr, df, db, dst.ld, col0); break;
+                case QB_DT_I64: convert_rows8_kernel<long long, 128><<<grid1d(groups, 128), 128, 0, st>>>((const long long *)staging, cols, nr, df, db, dst.ld, col0); break;
+                case QB_DT_F32: convert_rows8_kernel<float, 128><<<grid1d(groups, 128), 128, 0, st>>>((const float *)staging, cols, nr, df, db, dst.ld, col0); break;
+                default: convert_rows8_kernel<unsigned char, 256><<<grid1d(groups, 256), 256, 0, st>>>((const unsigned char *)staging, cols, nr, df, db, dst.ld, col0); break;
             }
         } else switch (dt) {
             case QB_DT_F64: convert_rows_kernel<double><<<grid1d(tot), 256, 0, st>>>((const double *)staging, cols, nr, df, db, dst.ld, col0); break;
@@ -351,7 +351,8 @@ void download_rows(qb_handle *h, const Mat &src, int64_t r0, int64_t col0, int64
 void transpose_on(qb_handle *h, cudaStream_t st, const bf16 *src, int64_t lds, int64_t rows, int64_t cols, bf16 *dst, int64_t ldd) {
     if ((lds % 8) == 0 && (ldd % 8) == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0) {
         dim3 g((unsigned)ceil_div(cols, 128), (unsigned)ceil_div(rows, 64));
-        if (st == h->copy_stream) transpose_bf16_wide_t_kernel<128><<<g, 128, 0, st>>>(src, lds, (int)rows, (int)cols, dst, ldd);   // runs beside the GEMM CTAs
+        if (st == h->copy_stream && h->next_xdt != QB_DT_U8)   // wide element types: keep the copy stream moving beside the GEMM CTAs
+            transpose_bf16_wide_t_kernel<128><<<g, 128, 0, st>>>(src, lds, (int)rows, (int)cols, dst, ldd);
         else transpose_bf16_wide_kernel<<<g, 256, 0, st>>>(src, lds, (int)rows, (int)cols, dst, ldd);
     } else {
         dim3 g((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));

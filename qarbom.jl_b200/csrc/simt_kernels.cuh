@@ -382,8 +382,11 @@ __global__ void convert_rows_kernel(const T *__restrict__ src, int64_t src_cols,
 // Blocks of 128 threads at <= 32 registers: ONE such block fits beside a persistent GEMM CTA (640 threads x 96 registers leave
 // 4096 registers per SM), so the conversion of the next host batch proceeds on the copy stream WHILE the chain kernel runs --
 // a fatter kernel would wait for it to end (measured: Int64 rows 5.5 -> 7.1 ms per step with 256-thread blocks).
-template <typename T>
-__global__ void __launch_bounds__(128, 16) convert_rows8_kernel(const T *__restrict__ src, int64_t src_cols, int64_t rows, float *__restrict__ dstf,
+// One-byte elements are the exception: their conversion is a few tens of microseconds when it has the machine to itself, and
+// running beside the GEMM CTAs costs the chain kernel more than that (measured 4.75 vs 4.84 ms per end-to-end step), so they
+// use 256-thread blocks that wait for free SMs.
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2048 / THREADS) convert_rows8_kernel(const T *__restrict__ src, int64_t src_cols, int64_t rows, float *__restrict__ dstf,
                                                             bf16 *__restrict__ dstb, int64_t ld, int64_t col0) {
     const int64_t gpr = src_cols >> 3;   // groups of eight per row
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
