@@ -311,6 +311,10 @@ def main():
     ap.add_argument("--nvls", type=int, default=1,
                     help="multi-GPU, bf16: 1 = fused reduce-scatter + update + all-gather kernel over NVSwitch multicast (multimem.ld_reduce / "
                          "multimem.st) when the box supports it, else the NCCL exchange; 0 = NCCL exchange")
+    ap.add_argument("--split-exchange", type=int, default=-1,
+                    help="NVLS path, binary PCD: 0 = never split the gradient exchange, 2 = always, -1 = library default (automatic: "
+                         "positive product reduced behind the chain advance + negative product as packed uint16 counts when a "
+                         "half-step leaves SMs idle)")
     ap.add_argument("--sharded-update", type=int, default=-1,
                     help="multi-GPU exchange: 1 = NCCL reduce-scatter + shard update + bf16 all-gather, 0 = allreduce + full update, -1 = library default")
     ap.add_argument("--state-exchange", type=int, default=-1,
@@ -422,6 +426,8 @@ def main():
                 dev.close()
                 continue
         args.p2p_like = args.p2p or nvls_on
+        if nvls_on and args.split_exchange >= 0:
+            dev.set_option("split_exchange", args.split_exchange)
         if args.precision == "bf16" and args.state_exchange >= 0 and not args.p2p_like and args.sharded_update != 0 and w["H"] % world == 0:
             dev.set_option("state_exchange", args.state_exchange)
         break

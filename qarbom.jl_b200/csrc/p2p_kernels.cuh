@@ -20,6 +20,14 @@
 // The transposed shadow is NOT pushed in this variant (it would double the inbound NVLink bytes of every GPU); each rank
 // rebuilds it from the complete row-major shadow with a local transpose kernel, HBM-bound and 5x cheaper than the link.
 // Biases are reduced over unicast peer addresses in rank order by every rank, so the replicas stay bit-identical.
+//
+// SPLIT variant (binary PCD, option "split_exchange"): the gradient is exchanged as its two products.  The positive product
+// P_h' X depends only on W_t and the data, so it is computed BEFORE the chain advance and reduced behind it by a small kernel
+// (nvls_reduce_shard_kernel: blocks of 128 threads at <= 32 registers run beside the persistent GEMM CTAs and on the SMs a
+// one-wave half-step leaves idle).  The negative product H~' V~ of binary chains is a matrix of integer counts <= rows per
+// rank: the gradient GEMM stores it as uint16, and ONE multimem.ld_reduce.add.u64 sums four packed counts of every rank
+// without carry (global batch < 65536) -- exact, at half the bytes of the fp32 reduction.  What stays exposed after the chain
+// advance is 2 B/param instead of 4.
 #pragma once
 #include "common.cuh"
 #include "online_kernels.cuh"  // grid_barrier
@@ -33,6 +41,7 @@ struct P2pParams {
     const float *G[QB_MAX_PEERS];       // every rank's gradient buffer [W | a | b]
     const float *G_mc;                  // NVLS: multicast address of the gradient buffers (multimem.ld_reduce = sum over ranks)
     bf16 *Wb_mc;                        // NVLS: multicast address of the row-major shadows (multimem.st = store to all ranks)
+    const unsigned short *Gn16_mc;      // SPLIT: multicast address of the uint16 negative products; G[rank] then holds the REDUCED positive product of the owned rows
     bf16 *Wb[QB_MAX_PEERS], *WbT[QB_MAX_PEERS];
     unsigned int *flags[QB_MAX_PEERS];  // flags[p][r]: written by rank r, polled by rank p
     float *W, *Vel;                     // local fp32 master / velocity ([H][ldv] + biases)
@@ -79,7 +88,53 @@ __device__ __forceinline__ void multimem_st_b32x2(void *mc, uint2 v) {
     asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)) : "memory");
 }
 
-template <bool VEL, bool NVLS = false>
+__device__ __forceinline__ unsigned long long multimem_ld_reduce_add_u64(const void *mc) {
+    unsigned long long v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(v) : "l"(mc) : "memory");
+    return v;
+}
+
+// ---- SPLIT, part 1: "my positive product is complete" to every peer (one block, after the positive-product GEMM in stream order)
+__global__ void nvls_signal_kernel(const P2pParams p) {
+    if (threadIdx.x < (unsigned)p.world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flags[threadIdx.x] + p.rank), "r"(p.epoch) : "memory");
+    }
+}
+// ---- SPLIT, part 2: G[rank][owned rows] <- sum over ranks of G_r[owned rows], in place, through the switch.  No block depends
+// on another block of this grid (each waits for the peers' flags itself), so it is safe to launch beside a persistent kernel
+// that leaves only a few block slots free.
+__global__ void __launch_bounds__(128, 16) nvls_reduce_shard_kernel(const P2pParams p, float *G_local) {
+    if (threadIdx.x < (unsigned)p.world) {
+        const unsigned int *mine = p.flags[p.rank] + threadIdx.x;
+        unsigned int seen;
+        const unsigned long long t0 = gtimer();
+        unsigned int spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+            if ((int)(seen - p.epoch) >= 0) break;
+            if ((++spins & 1023u) == 0u && gtimer() - t0 > 5000000000ull) {
+                if (p.timeout_flag) *(volatile unsigned int *)p.timeout_flag = 1u;
+                break;
+            }
+        } while (true);
+    }
+    __syncthreads();
+    const long long base = (long long)p.h_begin * p.ldv;
+    const long long n4 = ((long long)(p.h_end - p.h_begin) * p.ldv) >> 2;   // ldv % 8 == 0
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i + u * stride < n4) v[u] = multimem_ld_reduce_add_f32x4(p.G_mc + base + 4 * (i + u * stride));
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i + u * stride < n4) *reinterpret_cast<float4 *>(G_local + base + 4 * (i + u * stride)) = v[u];
+    }
+}
+
+template <bool VEL, bool NVLS = false, bool SPLIT = false>
 __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(const P2pParams p) {
     constexpr int TH = 64, TC = 128, PITCH = TC + 8, ROWS = NVLS ? 4 : 2;   // NVLS: one 16-byte load per row, so more rows in flight
     __shared__ __align__(16) unsigned short tile[TH][PITCH];
@@ -112,7 +167,17 @@ __global__ void __launch_bounds__(256) p2p_reduce_update_kernel(const P2pParams 
                 const long long o = (long long)h * p.ldv + c;  // ldv % 8 == 0, padding columns are zero: 128-bit loads stay in bounds
                 w[it] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (VEL) v[it] = w[it];
-                if (NVLS) {
+                if (NVLS && SPLIT) {
+                    q[it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) {
+                        // reduced positive product (this rank's own buffer) minus the negative counts of every rank: four uint16
+                        // per 8 bytes, summed by the switch as ONE u64 (no carry between the fields: global batch < 65536)
+                        const float4 gp = *reinterpret_cast<const float4 *>(p.G[p.rank] + o);
+                        const unsigned long long c = multimem_ld_reduce_add_u64(p.Gn16_mc + o);
+                        q[it][0] = make_float4(gp.x - (float)(unsigned)(c & 0xFFFFull), gp.y - (float)(unsigned)((c >> 16) & 0xFFFFull),
+                                               gp.z - (float)(unsigned)((c >> 32) & 0xFFFFull), gp.w - (float)(unsigned)(c >> 48));
+                    }
+                } else if (NVLS) {
                     q[it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (ok) q[it][0] = multimem_ld_reduce_add_f32x4(p.G_mc + o);   // summed over the ranks inside the switch
                 } else {

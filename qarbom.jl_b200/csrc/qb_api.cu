@@ -200,6 +200,9 @@ struct qb_handle {
     // NVLS variant of that kernel (option "nvls_exchange"): G, the row-major shadow and the barrier flags live in NCCL
     // symmetric windows; the kernel reduces through the switch (multimem.ld_reduce) and pushes through it (multimem.st)
     bool nvls = false; void *nvls_state = nullptr; const float *G_mc = nullptr; bf16 *Wb_mc = nullptr;
+    // split exchange (binary PCD on the NVLS path): uint16 negative products in a fourth window; option "split_exchange"
+    // 0 never, 1 automatic (half-steps of at most one wave minus the SMs the background reduction needs), 2 whenever possible
+    unsigned short *Gn16 = nullptr; const unsigned short *Gn16_mc = nullptr; int split_exchange_mode = 1;
     // NCCL variant of the sharded update (option "sharded_update", bf16, H % world == 0): reduce-scatter of the fp32
     // gradient, update of the owned hidden rows only, all-gather of the bf16 shadow, local transpose.  Moves 3/4 of the
     // allreduce bytes and does 1/world of the update work; the fp32 master is then sharded like in the p2p path.
@@ -899,7 +902,42 @@ void op_update(qb_handle *h, double lr, double llr, int64_t B_local) {
 }
 
 // reduce-scatter + update + all-gather of the bf16 shadows in one kernel over NVLink peer memory
-void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local) {
+// fills the launch parameters shared by the exchange kernels
+void p2p_fill(qb_handle *h, P2pParams &p) {
+    p.rank = h->cfg.rank; p.world = h->cfg.world;
+    for (int r = 0; r < p.world; r++) {
+        p.G[r] = h->peerG[r]; p.Wb[r] = h->peerWb[r]; p.WbT[r] = h->peerWbT[r]; p.flags[r] = h->peerFlags[r];
+    }
+    p.G_mc = h->G_mc; p.Wb_mc = h->Wb_mc; p.Gn16_mc = h->Gn16_mc;
+    p.H = (int)h->H; p.VL = (int)h->VL; p.V = (int)h->V; p.ldv = h->ldv; p.ldh = h->ldh; p.nW = h->nW;
+    p.h_begin = (int)std::min<int64_t>(h->H, (int64_t)p.rank * h->shard_rows);
+    p.h_end = (int)std::min<int64_t>(h->H, (int64_t)(p.rank + 1) * h->shard_rows);
+    if (!h->p2p_timeout_host) {
+        QB_CUDA(cudaHostAlloc((void **)&h->p2p_timeout_host, sizeof(unsigned int), cudaHostAllocMapped));
+        *h->p2p_timeout_host = 0u;
+        QB_CUDA(cudaHostGetDevicePointer((void **)&h->p2p_timeout_dev, h->p2p_timeout_host, 0));
+    }
+    p.timeout_flag = h->p2p_timeout_dev;
+}
+
+// split exchange, background part: after the positive product is in G (stream order on `st`), tell the peers and reduce the
+// owned rows in place through the switch.  Runs on the communication stream beside the chain advance.
+void split_reduce_positive(qb_handle *h, cudaStream_t st) {
+    P2pParams p{};
+    p2p_fill(h, p);
+    p.epoch = h->p2p_epoch; h->p2p_epoch += 1;
+    nvls_signal_kernel<<<1, 32, 0, st>>>(p);
+    QB_CUDA(cudaGetLastError());
+    const int64_t n4 = (int64_t)(p.h_end - p.h_begin) * h->ldv / 4;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(2 * h->num_sms, ceil_div(n4, 4 * 128)));
+    nvls_reduce_shard_kernel<<<blocks, 128, 0, st>>>(p, h->G);
+    QB_CUDA(cudaGetLastError());
+    h->launches += 2;
+}
+
+void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local, bool split);
+void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local) { p2p_update(h, lr, llr, B_local, false); }
+void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local, bool split) {
     const double Bg = (double)B_local * (double)h->cfg.world;
     const bool use_vel = (h->momentum != 0.0 || h->weight_decay != 0.0);
     if (use_vel && !h->Vel) h->Vel = dalloc<float>(h->nP);
@@ -908,7 +946,7 @@ void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local) {
     for (int r = 0; r < p.world; r++) {
         p.G[r] = h->peerG[r]; p.Wb[r] = h->peerWb[r]; p.WbT[r] = h->peerWbT[r]; p.flags[r] = h->peerFlags[r];
     }
-    p.G_mc = h->G_mc; p.Wb_mc = h->Wb_mc;
+    p.G_mc = h->G_mc; p.Wb_mc = h->Wb_mc; p.Gn16_mc = h->Gn16_mc;
     p.W = h->P; p.Vel = use_vel ? h->Vel : nullptr; p.bias_rd = h->bias_rd;
     p.H = (int)h->H; p.VL = (int)h->VL; p.V = (int)h->V; p.ldv = h->ldv; p.ldh = h->ldh; p.nW = h->nW;
     p.h_begin = (int)std::min<int64_t>(h->H, (int64_t)p.rank * h->shard_rows);
@@ -936,7 +974,10 @@ void p2p_update(qb_handle *h, double lr, double llr, int64_t B_local) {
     }
     void *args[] = {(void *)&p};
     if (h->nvls) {
-        if (use_vel) QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<true, true>, dim3(p2p_grid), dim3(256), args, 0, h->stream));
+        if (split) {
+            if (use_vel) QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<true, true, true>, dim3(p2p_grid), dim3(256), args, 0, h->stream));
+            else QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<false, true, true>, dim3(p2p_grid), dim3(256), args, 0, h->stream));
+        } else if (use_vel) QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<true, true>, dim3(p2p_grid), dim3(256), args, 0, h->stream));
         else QB_CUDA(cudaLaunchCooperativeKernel((void *)p2p_reduce_update_kernel<false, true>, dim3(p2p_grid), dim3(256), args, 0, h->stream));
         // every rank's rows of the row-major shadow have landed (second barrier of the kernel): rebuild the transposed one
         dim3 gt((unsigned)ceil_div(h->VL, 128), (unsigned)ceil_div(h->H, 64));
@@ -963,10 +1004,11 @@ void nvls_enable(qb_handle *h) {
     QB_CHECK(h->nccl_mem.empty(), QB_E_UNSUPPORTED, "nvls_exchange and QB_NCCL_REGISTER are mutually exclusive");
     QB_CUDA(cudaStreamSynchronize(h->stream));
     QbNvlsBuffers io{};
-    io.n = 3;
+    io.n = 4;
     io.bytes[0] = (size_t)h->nP * sizeof(float);
     io.bytes[1] = (size_t)h->H * h->ldv * sizeof(bf16);
     io.bytes[2] = 4096;
+    io.bytes[3] = (size_t)h->H * h->ldv * sizeof(unsigned short);   // negative products of the split exchange
     const char *why = qb_nvls_setup(nccl().lib, h->comm, &io);
     if (why) throw Error(QB_E_UNSUPPORTED, std::string("NVSwitch multicast exchange unavailable: ") + why);
     QB_CHECK(io.lsa_rank == h->cfg.rank && io.lsa_size == h->cfg.world, QB_E_NCCL, "NCCL's load/store team does not match the ranks of this job");
@@ -977,6 +1019,7 @@ void nvls_enable(qb_handle *h) {
     cudaFree(h->G); cudaFree(h->Wb);
     h->G = (float *)io.local[0]; h->Wb = (bf16 *)io.local[1];
     h->G_mc = (const float *)io.mc[0]; h->Wb_mc = (bf16 *)io.mc[1];
+    h->Gn16 = (unsigned short *)io.local[3]; h->Gn16_mc = (const unsigned short *)io.mc[3];
     for (int r = 0; r < h->cfg.world; r++) {
         h->peerG[r] = (float *)io.peer[0][r]; h->peerWb[r] = (bf16 *)io.peer[1][r]; h->peerWbT[r] = nullptr;
         h->peerFlags[r] = (unsigned int *)io.peer[2][r]; h->peerP[r] = nullptr;
@@ -1249,11 +1292,15 @@ void pcd_step_state_exchange(qb_handle *h, const Mat &xb, const bf16 *xbT, int64
     h->inj_active = false;
 }
 
+bool split_exchange_wanted(qb_handle *h, int64_t B, int64_t k, const bf16 *xbT, cudaEvent_t *ev);
+void pcd_step_split(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr);
+
 void pcd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr,
                    cudaEvent_t *ev) {
     QB_CHECK(h->n_chains >= 1, QB_E_STATE, "qb_init_chains has not been called");
     maybe_register_exchange_buffers(h);
     if (h->stale_chains) { pcd_step_stale(h, xb, xbT, xb_ldT, B, k, lr, llr); return; }
+    if (split_exchange_wanted(h, B, k, xbT, ev)) { pcd_step_split(h, xb, xbT, xb_ldT, B, k, lr, llr); return; }
     if (h->state_exchange && h->comm && h->sharded_update && !h->p2p && h->L == 0 && !h->gaussian && k > 0 && h->n_chains == B &&
         (B % 8) == 0 && xbT != nullptr && ev == nullptr) {
         pcd_step_state_exchange(h, xb, xbT, xb_ldT, B, k, lr, llr);
@@ -1303,6 +1350,56 @@ void pcd_step_impl(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT,
     if (ev) QB_CUDA(cudaEventRecord(ev[3], h->stream));
     if (clf && k > 0) advance_chains(h, Nc, k, sr, false);  // classifier: chains AFTER the update, train_pcd.jl:89-92
     if (ev) QB_CUDA(cudaEventRecord(ev[4], h->stream));
+    h->inj_active = false;
+}
+
+// Split gradient exchange (see p2p_kernels.cuh): same arithmetic as pcd_step_impl on a binary model without label units --
+// every GEMM of the step uses W_t, so the positive phase and its product may run before the chain advance.
+bool split_exchange_wanted(qb_handle *h, int64_t B, int64_t k, const bf16 *xbT, cudaEvent_t *ev) {
+    if (!h->nvls || h->split_exchange_mode == 0 || !h->bf || h->L > 0 || h->gaussian || k < 1 || h->n_chains != B || xbT == nullptr || ev != nullptr ||
+        h->step_recon_wanted || h->inj_active || h->stale_chains || (int64_t)h->cfg.world * B >= 65536)
+        return false;
+    if (h->split_exchange_mode == 2) return true;
+    // automatic: the background reduction needs block slots beside the chain kernel -- plenty when a half-step is at most one
+    // wave of pair tiles minus a few pairs (1024 rows of cfg5: 64 tiles on 74 pairs); a fuller machine would only delay it
+    const int64_t tiles = ceil_div(B, 256) * ceil_div(std::max(h->H, h->VL), 256);
+    return tiles <= h->num_sms / 2 - 8;
+}
+void pcd_step_split(qb_handle *h, const Mat &xb, const bf16 *xbT, int64_t xb_ldT, int64_t B, int64_t k, double lr, double llr) {
+    if (!h->comm_stream) {   // second stream + events for the background reduction
+        QB_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        QB_CUDA(cudaEventCreateWithFlags(&h->ev_grad, cudaEventDisableTiming));
+        QB_CUDA(cudaEventCreateWithFlags(&h->ev_upd, cudaEventDisableTiming));
+    }
+    StepRng sr{h, B, false};
+    const int64_t row0 = row0_of(h, B);
+    zero_bias_grads(h, 1.f);
+    // positive phase and positive product first ...
+    HiddenOut ho; ho.prob = &h->phd; ho.prob_T = true; ho.bg_what = 1; ho.bg_sign = 1.f;
+    op_hidden(h, xb, B, h->VL, ho, Rng(), row0);
+    {
+        sm100::Operand A{h->phd.bT, h->H, B, h->phd.ldT}, Bo{xbT, h->VL, B, xb_ldT};
+        sm100::EpiParams ep{};
+        ep.mode = sm100::EPI_GRAD; ep.M = (int)h->H; ep.N = (int)h->VL; ep.out_f32 = G_W(h); ep.ld_out = h->ldv;
+        GemmScope gs(h, 2.0 * (double)h->H * (double)h->VL * (double)B);
+        sm100::launch(h->stream, A, Bo, nullptr, nullptr, ep, h->gemm_sms, h->force_bn, h->use_2cta);
+    }
+    if (!h->cur_datasum) colsum<bf16>(h, xb.b, xb.ld, B, h->VL, 1.f, G_a(h));
+    // ... its reduction runs behind the chain advance
+    QB_CUDA(cudaEventRecord(h->ev_grad, h->stream));
+    QB_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_grad, 0));
+    split_reduce_positive(h, h->comm_stream);
+    QB_CUDA(cudaEventRecord(h->ev_upd, h->comm_stream));
+    advance_chains(h, B, k, sr, true);
+    {   // negative product of this rank's chains: exact integer counts, stored as uint16
+        sm100::Operand A{h->ch.bT, h->H, B, h->ch.ldT}, Bo{h->cv.bT, h->VL, B, h->cv.ldT};
+        sm100::EpiParams ep{};
+        ep.mode = sm100::EPI_GRAD; ep.M = (int)h->H; ep.N = (int)h->VL; ep.out_u16 = h->Gn16; ep.ld_out = h->ldv;
+        GemmScope gs(h, 2.0 * (double)h->H * (double)h->VL * (double)B);
+        sm100::launch(h->stream, A, Bo, nullptr, nullptr, ep, h->gemm_sms, h->force_bn, h->use_2cta);
+    }
+    QB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_upd, 0));   // the reduced positive product of the owned rows is in place
+    p2p_update(h, lr, llr, B, /*split*/ true);
     h->inj_active = false;
 }
 
@@ -2664,6 +2761,9 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
             int bn = (int)value;
             QB_CHECK(bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 256, QB_E_ARG, "force_bn must be 0/32/64/128/256");
             h->force_bn = bn;
+        } else if (!strcmp(key, "split_exchange")) {
+            QB_CHECK(value == 0.0 || value == 1.0 || value == 2.0, QB_E_ARG, "split_exchange must be 0, 1 or 2");
+            h->split_exchange_mode = (int)value;
         } else if (!strcmp(key, "chain_quad")) {
             QB_CHECK(value == 0.0 || value == 1.0 || value == 2.0, QB_E_ARG, "chain_quad must be 0, 1 or 2");
             h->chain_quad_mode = (int)value;

@@ -75,6 +75,9 @@ struct EpiParams {
     // ---- EPI_GRAD
     float *out_f32; long long ld_out;
     int grad_sub;  // out = out - acc instead of out = acc (negative statistics subtracted from an already reduced positive part)
+    // EPI_GRAD, integer form: the accumulators are exact small integers (a product of binary states) and are stored as uint16
+    // [M][ld_out] instead of fp32 (the negative product of the split gradient exchange, p2p_kernels.cuh)
+    unsigned short *out_u16;
     // affine form (QB_PREC_FP32X3's GEMM): out = g_alpha * acc + g_beta * out + g_bias[n]; active when g_affine != 0
     int g_affine; float g_alpha, g_beta; const float *g_bias;
     float pscale;  // probabilities are multiplied by this before being stored / summed (n_chains / batch; 1 normally)
@@ -596,6 +599,22 @@ __device__ __forceinline__ void epilogue_grad(const EpiParams &ep, uint32_t tmem
         tmem_wait_ld(r);
         const int n0 = n_blk * BN + c0;
         if (n0 >= ep.N || m >= ep.M) continue;
+        if (ep.out_u16) {
+            unsigned short *d16 = ep.out_u16 + (long long)m * ep.ld_out + n0;
+            if (n0 + 16 <= ep.N) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    pk[j] = __float2uint_rn(__uint_as_float(r[2 * j])) | (__float2uint_rn(__uint_as_float(r[2 * j + 1])) << 16);
+                reinterpret_cast<uint4 *>(d16)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);   // (ld_out % 8 == 0, n0 % 16 == 0: 16-byte aligned)
+                reinterpret_cast<uint4 *>(d16)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (n0 + j < ep.N) d16[j] = (unsigned short)__float2uint_rn(__uint_as_float(r[j]));
+            }
+            continue;
+        }
         float *dst = ep.out_f32 + (long long)m * ep.ld_out + n0;
         if (ep.g_affine) {
 #pragma unroll

@@ -38,12 +38,14 @@ def main():
                 dev.set_option("sharded_update", 0 if exchange == "nccl" else 1)   # ("chain" runs on the default sharded exchange)
             if exchange == "state":     # positive product reduce-scattered behind the chains + bit-packed chain-state all-gather
                 dev.set_option("state_exchange", 1)
-            if exchange == "nvls":     # the same fused kernel over NVSwitch multicast addresses (NCCL symmetric windows)
+            if exchange in ("nvls", "split"):   # the fused kernel over NVSwitch multicast addresses (NCCL symmetric windows); "split":
+                                                # positive product reduced behind the chain advance, negative product as packed uint16 counts
                 why = dev.enable_nvls_exchange()
                 if why:
                     print(f"MGPU-SKIP nvls: {why}")
                     dev.close()
                     dist.barrier(); dist.destroy_process_group(); sys.exit(77)
+                dev.set_option("split_exchange", 2 if exchange == "split" else 0)
             if exchange == "p2p":
                 mine = torch.frombuffer(bytearray(dev.p2p_export()), dtype=torch.uint8).cuda()
                 allh = torch.empty(320 * world, dtype=torch.uint8, device="cuda")

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("prec,exchange", [("fp32", "nccl"), ("bf16", "nccl"), ("bf16", "sharded"), ("bf16", "stale"), ("bf16", "state"), ("bf16", "p2p"), ("bf16", "chain"), ("bf16", "nvls")])
+@pytest.mark.parametrize("prec,exchange", [("fp32", "nccl"), ("bf16", "nccl"), ("bf16", "sharded"), ("bf16", "stale"), ("bf16", "state"), ("bf16", "p2p"), ("bf16", "chain"), ("bf16", "nvls"), ("bf16", "split")])
 def test_two_rank_pcd_matches_single_gpu(prec, exchange):
     import torch
     n = torch.cuda.device_count()
