@@ -202,7 +202,7 @@ struct qb_handle {
     bool nvls = false; void *nvls_state = nullptr; const float *G_mc = nullptr; bf16 *Wb_mc = nullptr;
     // split exchange (binary PCD on the NVLS path): uint16 negative products in a fourth window; option "split_exchange"
     // 0 never, 1 automatic (half-steps of at most one wave minus the SMs the background reduction needs), 2 whenever possible
-    unsigned short *Gn16 = nullptr; const unsigned short *Gn16_mc = nullptr; int split_exchange_mode = 1;
+    unsigned short *Gn16 = nullptr; const unsigned short *Gn16_mc = nullptr; int split_exchange_mode = 0;
     // NCCL variant of the sharded update (option "sharded_update", bf16, H % world == 0): reduce-scatter of the fp32
     // gradient, update of the owned hidden rows only, all-gather of the bf16 shadow, local transpose.  Moves 3/4 of the
     // allreduce bytes and does 1/world of the update work; the fp32 master is then sharded like in the p2p path.
