@@ -311,6 +311,9 @@ def main():
     ap.add_argument("--nvls", type=int, default=1,
                     help="multi-GPU, bf16: 1 = fused reduce-scatter + update + all-gather kernel over NVSwitch multicast (multimem.ld_reduce / "
                          "multimem.st) when the box supports it, else the NCCL exchange; 0 = NCCL exchange")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="experiment: override the workload's global batch (e.g. 2048 on 2 GPUs reproduces the 1024-rows-per-rank regime "
+                         "of the 8-GPU run); the line's config then names it")
     ap.add_argument("--split-exchange", type=int, default=-1,
                     help="NVLS path, binary PCD: 0 = never split the gradient exchange, 2 = always, -1 = library default (automatic: "
                          "positive product reduced behind the chain advance + negative product as packed uint16 counts when a "
@@ -332,6 +335,9 @@ def main():
     w = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.global_batch:
+        w["B"] = args.global_batch
+        w["desc"] += f" [global batch overridden: {args.global_batch}]"
     if args.scaling == "weak":
         w["B"] *= world
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
