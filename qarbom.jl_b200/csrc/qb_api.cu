@@ -929,7 +929,10 @@ void split_reduce_positive(qb_handle *h, cudaStream_t st) {
     nvls_signal_kernel<<<1, 32, 0, st>>>(p);
     QB_CUDA(cudaGetLastError());
     const int64_t n4 = (int64_t)(p.h_end - p.h_begin) * h->ldv / 4;
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(2 * h->num_sms, ceil_div(n4, 4 * 128)));
+    // at most ONE block per SM: a persistent GEMM CTA (61440 registers) and one of these blocks (4096) fill the register file
+    // exactly -- two of them on an SM would keep the chain kernel, launched right after, from starting there until they finish
+    // (measured: the whole reduction then serialises in front of the chain advance)
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(h->num_sms, ceil_div(n4, 4 * 128)));
     nvls_reduce_shard_kernel<<<blocks, 128, 0, st>>>(p, h->G);
     QB_CUDA(cudaGetLastError());
     h->launches += 2;
