@@ -312,8 +312,8 @@ int32_t qb_reset_counters(qb_handle *h);
  * the reason and the NCCL exchange stays),
  * "split_exchange" (on the NVLS path, binary PCD without label units: the gradient is exchanged as its two products -- the
  * positive product is computed before the chain advance and reduced behind it, the negative product travels as exact uint16
- * counts summed as packed u64 by the switch; 0 never, 1 automatic (default: when a half-step leaves SMs idle), 2 whenever
- * possible; same results as the unsplit exchange up to fp32 summation order),
+ * counts summed as packed u64 by the switch; 0 never (default: measured slower), 1 when a half-step
+ * leaves SMs idle, 2 whenever possible; same results as the unsplit exchange up to fp32 summation order),
  * "fused_chain" (the half-steps of a step as one persistent launch: 0 never, 1 automatic, 2 always), "chain_bn" (its tile
  * width, 0 = automatic), "chain_quad" (its 4-CTA-cluster variant with multicast weights: 0 never (default: measured slower),
  * 1 one-wave shapes, 2 whenever possible), "epoch_kernel" (many mini-batch steps of a small model as one persistent launch
