@@ -1571,11 +1571,33 @@ bool epoch_kernel_run(qb_handle *h, bool pcd, int64_t first, int64_t n_steps, in
         P.draw0 = h->draw;
         P.rb_cnt = h->epoch_cnt;
         P.tot_cnt = h->epoch_cnt + (size_t)it * P.n_steps * P.max_tiles_n;
+#ifdef QB_EPOCH_TRACE
+        // development builds: per-tile %globaltimer stamps of the first launch that finds QB_EPOCH_TRACE=<file> set
+        const char *trace_path = getenv("QB_EPOCH_TRACE");
+        const size_t trace_n = (size_t)it * P.tiles_per_iter * 32;
+        P.trace = nullptr;
+        if (trace_path && it <= 256) { P.trace = dalloc<unsigned long long>(trace_n); QB_CUDA(cudaMemsetAsync(P.trace, 0, trace_n * 8, h->stream)); }
+#endif
         {
             GemmScope gs(h, eb.flops_per_iter * (double)it);
             sm100::launch_epoch(h->stream, eb, h->gemm_sms);
             sm100::last_shape().bn = bn; sm100::last_shape().pair = 0; sm100::last_shape().kind = sm100::K_GRAD_UPDATE;
         }
+#ifdef QB_EPOCH_TRACE
+        if (P.trace) {
+            std::vector<unsigned long long> host(trace_n);
+            QB_CUDA(cudaStreamSynchronize(h->stream));
+            QB_CUDA(cudaMemcpy(host.data(), P.trace, trace_n * 8, cudaMemcpyDeviceToHost));
+            if (FILE *f = fopen(trace_path, "wb")) {
+                long long hdr[4 + sm100::EPOCH_MAX_STEPS] = {it, P.tiles_per_iter, P.n_steps, std::min(h->gemm_sms, 1 << 30)};
+                for (int s2 = 0; s2 < P.n_steps; s2++) hdr[4 + s2] = P.step[s2].tile_base;
+                fwrite(hdr, sizeof(hdr), 1, f);
+                fwrite(host.data(), 8, trace_n, f);
+                fclose(f);
+            }
+            cudaFree(P.trace); P.trace = nullptr;
+        }
+#endif
         h->draw += (uint64_t)(2 * k) * (uint64_t)it;
         h->epoch_launches++;
     }

@@ -56,6 +56,11 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
 __device__ __forceinline__ void red_release_gpu_add(unsigned int *p, unsigned int v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// after a gpu-scope fence by every contributing lane and a warp barrier, the relaxed add completes a release pattern
+// (fence.acq_rel + relaxed atomic); red.release would run a second fence of ~0.7 us behind the first one
+__device__ __forceinline__ void red_relaxed_gpu_add(unsigned int *p, unsigned int v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 template <int BN>
@@ -107,8 +112,10 @@ gibbs_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant
     };
 
     if (warp == 0) {
-        // ===== TMA producer (both CTAs: own 128 weight rows, own half of the state tile; bytes land on the leader's barrier)
-        if (lane == 0) {
+        // ===== TMA producer (both CTAs: own 128 weight rows, own half of the state tile; bytes land on the leader's barrier);
+        // warp-uniform loop, one elected lane issues (see elect_one)
+        {
+            const bool issuer = elect_one();
             int stage = 0; uint32_t phase = 0;
             int si = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
@@ -126,9 +133,12 @@ gibbs_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant
                     int st = stage; uint32_t ph = phase;
                     for (int i = 0; i < pre; i++) {
                         mbar_wait(empty_bar(st), ph ^ 1);
-                        if (leader) mbar_expect_tx(full_bar(st), EXP_TX);
-                        else mbar_arrive_remote(full_bar(st), 0);
-                        tma_load_2d_2sm(smem_base + st * C::STAGE_BYTES, mA, full_bar(st), i * BK, m0);
+                        if (issuer) {
+                            if (leader) mbar_expect_tx(full_bar(st), EXP_TX);
+                            else mbar_arrive_remote(full_bar(st), 0);
+                            tma_load_2d_2sm(smem_base + st * C::STAGE_BYTES, mA, full_bar(st), i * BK, m0);
+                        }
+                        __syncwarp();
                         if (++st == C::STAGES) { st = 0; ph ^= 1; }
                     }
                     // ... then wait until every unit tile of (dep_step, this row block) has been stored
@@ -150,26 +160,36 @@ gibbs_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant
                         }
                     }
                     fence_proxy_async_global();   // the states were written through the generic proxy, TMA reads through the async one
-                    for (int i = 0; i < pre; i++) {
-                        tma_load_2d_2sm(smem_base + stage * C::STAGE_BYTES + C::A_BYTES, mB, full_bar(stage), i * BK, n0);
-                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (issuer) {
+                        int st2 = stage;
+                        for (int i = 0; i < pre; i++) {
+                            tma_load_2d_2sm(smem_base + st2 * C::STAGE_BYTES + C::A_BYTES, mB, full_bar(st2), i * BK, n0);
+                            if (++st2 == C::STAGES) st2 = 0;
+                        }
                     }
+                    __syncwarp();
+                    stage = st; phase = ph;
                     kb = pre;
                 }
                 for (; kb < kb_total; kb++) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-                    if (leader) mbar_expect_tx(full_bar(stage), EXP_TX);
-                    else mbar_arrive_remote(full_bar(stage), 0);
-                    tma_load_2d_2sm(sa, mA, full_bar(stage), kb * BK, m0);
-                    tma_load_2d_2sm(sb, mB, full_bar(stage), kb * BK, n0);
+                    if (issuer) {
+                        if (leader) mbar_expect_tx(full_bar(stage), EXP_TX);
+                        else mbar_arrive_remote(full_bar(stage), 0);
+                        tma_load_2d_2sm(sa, mA, full_bar(stage), kb * BK, m0);
+                        tma_load_2d_2sm(sb, mB, full_bar(stage), kb * BK, n0);
+                    }
+                    __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread of the leader CTA drives both tensor cores
-        if (leader && lane == 0) {
+        // ===== MMA issuer: one elected lane of the leader CTA's (warp-uniform) loop drives both tensor cores; the next k-step's
+        // barrier is tested while this one's MMAs are issued (see mbar_test)
+        if (leader) {
+            const bool issuer = elect_one();
             constexpr uint32_t idesc = make_idesc_m256(BN, false);
             int stage = 0; uint32_t phase = 0;
             int iter = 0, si = 0;
@@ -180,17 +200,23 @@ gibbs_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant
                 mbar_wait(tempty_bar(as), aphase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
+                uint32_t ready = mbar_test(full_bar(stage), phase);
                 for (int kb = 0; kb < kb_total; kb++) {
-                    mbar_wait(full_bar(stage), phase);
+                    if (!ready) mbar_wait(full_bar(stage), phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
                     const uint64_t adesc = make_kmajor_sw128_desc(sa), bdesc = make_kmajor_sw128_desc(sb);
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; k++)
-                        umma_bf16_2sm(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                    umma_commit_2sm(empty_bar(stage));
-                    if (kb == kb_total - 1) umma_commit_2sm(tfull_bar(as));
+                    const int cur = stage;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    ready = (kb + 1 < kb_total) ? mbar_test(full_bar(stage), phase) : 0u;
+                    if (issuer) {
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; k++)
+                            umma_bf16_2sm(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        umma_commit_2sm(empty_bar(cur));
+                        if (kb == kb_total - 1) umma_commit_2sm(tfull_bar(as));
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -222,7 +248,7 @@ gibbs_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant
             if (lane == 0) {
                 if (leader) mbar_arrive(tempty_bar(as));
                 else mbar_arrive_remote(tempty_bar(as), 0);
-                red_release_gpu_add(prog.counters + si * tiles_n + n_blk, 1u);
+                red_relaxed_gpu_add(prog.counters + si * tiles_n + n_blk, 1u);
             }
         }
     }
@@ -306,8 +332,9 @@ gibbs_chain_kernel_quad(const __grid_constant__ ChainMaps maps, const __grid_con
     };
 
     if (warp == 0) {
-        // ===== TMA producer (all four CTAs)
-        if (lane == 0) {
+        // ===== TMA producer (all four CTAs); warp-uniform loop, one elected lane issues
+        {
+            const bool issuer = elect_one();
             int stage = 0; uint32_t phase = 0;
             int si = 0;
             for (int tile = quad_id; tile < total_tiles; tile += num_quads) {
@@ -328,9 +355,12 @@ gibbs_chain_kernel_quad(const __grid_constant__ ChainMaps maps, const __grid_con
                     int st = stage; uint32_t ph = phase;
                     for (int i = 0; i < pre; i++) {
                         mbar_wait(empty_bar(st), ph ^ 1);
-                        if (leader) mbar_expect_tx(full_bar(st), 2 * C::STAGE_BYTES);
-                        else mbar_arrive_remote(full_bar(st), lead_rank);
-                        load_a(st, i);
+                        if (issuer) {
+                            if (leader) mbar_expect_tx(full_bar(st), 2 * C::STAGE_BYTES);
+                            else mbar_arrive_remote(full_bar(st), lead_rank);
+                            load_a(st, i);
+                        }
+                        __syncwarp();
                         if (++st == C::STAGES) { st = 0; ph ^= 1; }
                     }
                     const unsigned int *cnt = prog.counters + S.dep_step * tiles_n + n_blk;
@@ -351,25 +381,34 @@ gibbs_chain_kernel_quad(const __grid_constant__ ChainMaps maps, const __grid_con
                         }
                     }
                     fence_proxy_async_global();
-                    for (int i = 0; i < pre; i++) {
-                        tma_load_2d_2sm(smem_base + stage * C::STAGE_BYTES + C::A_BYTES, mB, full_bar(stage), i * BK, n0);
-                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (issuer) {
+                        int st2 = stage;
+                        for (int i = 0; i < pre; i++) {
+                            tma_load_2d_2sm(smem_base + st2 * C::STAGE_BYTES + C::A_BYTES, mB, full_bar(st2), i * BK, n0);
+                            if (++st2 == C::STAGES) st2 = 0;
+                        }
                     }
+                    __syncwarp();
+                    stage = st; phase = ph;
                     kb = pre;
                 }
                 for (; kb < kb_total; kb++) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
-                    if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-                    else mbar_arrive_remote(full_bar(stage), lead_rank);
-                    load_a(stage, kb);
-                    tma_load_2d_2sm(smem_base + stage * C::STAGE_BYTES + C::A_BYTES, mB, full_bar(stage), kb * BK, n0);
+                    if (issuer) {
+                        if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+                        else mbar_arrive_remote(full_bar(stage), lead_rank);
+                        load_a(stage, kb);
+                        tma_load_2d_2sm(smem_base + stage * C::STAGE_BYTES + C::A_BYTES, mB, full_bar(stage), kb * BK, n0);
+                    }
+                    __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread of each pair's leader CTA
-        if (leader && lane == 0) {
+        // ===== MMA issuer: one elected lane of each pair's leader CTA
+        if (leader) {
+            const bool issuer = elect_one();
             constexpr uint32_t idesc = make_idesc_m256(BN, false);
             int stage = 0; uint32_t phase = 0;
             int iter = 0, si = 0;
@@ -380,17 +419,23 @@ gibbs_chain_kernel_quad(const __grid_constant__ ChainMaps maps, const __grid_con
                 mbar_wait(tempty_bar(as), aphase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
+                uint32_t ready = mbar_test(full_bar(stage), phase);
                 for (int kb = 0; kb < kb_total; kb++) {
-                    mbar_wait(full_bar(stage), phase);
+                    if (!ready) mbar_wait(full_bar(stage), phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
                     const uint64_t adesc = make_kmajor_sw128_desc(sa), bdesc = make_kmajor_sw128_desc(sb);
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; k++)
-                        umma_bf16_2sm(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                    umma_commit_2sm_mask(empty_bar(stage), (unsigned short)0xF);   // this pair is done with the stage: tell all four producers
-                    if (kb == kb_total - 1) umma_commit_2sm_mask(tfull_bar(as), pair_mask);
+                    const int cur = stage;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    ready = (kb + 1 < kb_total) ? mbar_test(full_bar(stage), phase) : 0u;
+                    if (issuer) {
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; k++)
+                            umma_bf16_2sm(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        umma_commit_2sm_mask(empty_bar(cur), (unsigned short)0xF);   // this pair is done with the stage: tell all four producers
+                        if (kb == kb_total - 1) umma_commit_2sm_mask(tfull_bar(as), pair_mask);
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -421,7 +466,7 @@ gibbs_chain_kernel_quad(const __grid_constant__ ChainMaps maps, const __grid_con
             if (lane == 0) {
                 if (leader) mbar_arrive(tempty_bar(as));
                 else mbar_arrive_remote(tempty_bar(as), lead_rank);
-                red_release_gpu_add(prog.counters + si * tiles_n + n_blk, 1u);
+                red_relaxed_gpu_add(prog.counters + si * tiles_n + n_blk, 1u);
             }
         }
     }

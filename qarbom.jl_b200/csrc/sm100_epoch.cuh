@@ -53,8 +53,21 @@ struct EpochProgram {
     // update_rbm! fused into the gradient epilogue
     float *W; bf16 *Wb, *WbT; long long ldv, ldh; float lr, llr; int V;
     float *bias_P, *bias_G; const float *datasum; long long datasum_ld; float dscale; int n_vis, n_bias;
+#ifdef QB_EPOCH_TRACE
+    unsigned long long *trace;     // [tile][32] %globaltimer stamps (tools/epoch_trace.py); development builds only
+#endif
     EpochStep step[EPOCH_MAX_STEPS];
 };
+#ifdef QB_EPOCH_TRACE
+__device__ __forceinline__ void epoch_stamp(const EpochProgram &P, long long tile, int slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (P.trace && (threadIdx.x & 31) == 0) P.trace[tile * 32 + slot] = t;
+}
+#define QB_STAMP(tile, slot) epoch_stamp(prog, tile, slot)
+#else
+#define QB_STAMP(tile, slot) ((void)0)
+#endif
 struct EpochMaps {
     CUtensorMap m[EPOCH_MAX_MAPS];
 };
@@ -186,8 +199,9 @@ gibbs_epoch_kernel(const __grid_constant__ EpochMaps maps, const __grid_constant
     };
 
     if (warp == 0) {
-        // ===== TMA producer
-        if (lane == 0) {
+        // ===== TMA producer: the whole warp runs the loop, one elected lane issues (see elect_one)
+        {
+            const bool issuer = elect_one();
             int stage = 0; uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int iter, si, local;
@@ -202,10 +216,12 @@ gibbs_epoch_kernel(const __grid_constant__ EpochMaps maps, const __grid_constant
                 // a row-block-dependent step are fetched ahead of its row-block wait, and this CTA need not have run any of
                 // the iteration's earlier steps (dep_prev steps need it by construction).  tot - 1: last step of iteration iter - 1
                 bool waited = false;
+                QB_STAMP(tile, 0);
                 if (iter > 0) { epoch_wait(tot - 1, (unsigned int)prog.last_step_total, prog); waited = true; }
                 for (int d = 0; d < 2; d++)
                     if (S.dep_all[d] >= 0) { epoch_wait(tot + S.dep_all[d], (unsigned int)S.dep_all_count[d], prog); waited = true; }
                 if (waited) fence_proxy_async_global();
+                QB_STAMP(tile, 1);
                 int kb_total = 0;
                 for (int p = 0; p < S.n_prod; p++) kb_total += (S.K[p] + BK - 1) / BK;
                 const int kb_first = (S.K[0] + BK - 1) / BK;
@@ -216,33 +232,53 @@ gibbs_epoch_kernel(const __grid_constant__ EpochMaps maps, const __grid_constant
                     int st = stage; uint32_t ph = phase;
                     for (int i = 0; i < pre; i++) {
                         mbar_wait(empty_bar(st), ph ^ 1);
-                        mbar_expect_tx(full_bar(st), C::STAGE_BYTES);
-                        tma_load_2d(smem_base + st * C::STAGE_BYTES, &maps.m[S.a_map[0]], full_bar(st), i * BK, m_blk * BM + mb * S.a_row_mb[0]);
+                        if (issuer) {
+                            mbar_expect_tx(full_bar(st), C::STAGE_BYTES);
+                            tma_load_2d(smem_base + st * C::STAGE_BYTES, &maps.m[S.a_map[0]], full_bar(st), i * BK, m_blk * BM + mb * S.a_row_mb[0]);
+                        }
+                        __syncwarp();
                         if (++st == C::STAGES) { st = 0; ph ^= 1; }
                     }
                     epoch_wait(rb + S.dep_rb * prog.max_tiles_n + n_blk, (unsigned int)S.dep_rb_count, prog);
                     fence_proxy_async_global();
-                    for (int i = 0; i < pre; i++) {
-                        tma_load_2d(smem_base + stage * C::STAGE_BYTES + C::A_BYTES, &maps.m[S.b_map[0]], full_bar(stage), i * BK,
-                                    n_blk * BN + mb * S.b_row_mb[0]);
-                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    QB_STAMP(tile, 2);
+#ifdef QB_EPOCH_TRACE
+                    const long long c_tma0 = clock64();
+#endif
+                    if (issuer) {
+                        int st2 = stage;
+                        for (int i = 0; i < pre; i++) {
+                            tma_load_2d(smem_base + st2 * C::STAGE_BYTES + C::A_BYTES, &maps.m[S.b_map[0]], full_bar(st2), i * BK,
+                                        n_blk * BN + mb * S.b_row_mb[0]);
+                            if (++st2 == C::STAGES) st2 = 0;
+                        }
                     }
+                    __syncwarp();
+                    stage = st; phase = ph;
+#ifdef QB_EPOCH_TRACE
+                    if (prog.trace && lane == 0) prog.trace[tile * 32 + 28] = (unsigned long long)(clock64() - c_tma0);
+#endif
                     kb = pre;
                 }
                 for (; kb < kb_total; kb++) {
                     const int p = kb < kb_first ? 0 : 1, kk = kb < kb_first ? kb : kb - kb_first;
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-                    mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                    tma_load_2d(sa, &maps.m[S.a_map[p]], full_bar(stage), kk * BK, m_blk * BM + mb * S.a_row_mb[p]);
-                    tma_load_2d(sb, &maps.m[S.b_map[p]], full_bar(stage), kk * BK, n_blk * BN + mb * S.b_row_mb[p]);
+                    if (issuer) {
+                        mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                        tma_load_2d(sa, &maps.m[S.a_map[p]], full_bar(stage), kk * BK, m_blk * BM + mb * S.a_row_mb[p]);
+                        tma_load_2d(sb, &maps.m[S.b_map[p]], full_bar(stage), kk * BK, n_blk * BN + mb * S.b_row_mb[p]);
+                    }
+                    __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer
-        if (lane == 0) {
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues; the next k-step's barrier is tested while this one's
+        // MMAs are issued (see mbar_test)
+        {
+            const bool issuer = elect_one();
             constexpr uint32_t idesc_pos = make_idesc(BN, false), idesc_neg = make_idesc(BN, true);
             int stage = 0; uint32_t phase = 0;
             long long it = 0;
@@ -257,18 +293,33 @@ gibbs_epoch_kernel(const __grid_constant__ EpochMaps maps, const __grid_constant
                 mbar_wait(tempty_bar(as), aphase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
+                uint32_t ready = mbar_test(full_bar(stage), phase);
                 for (int kb = 0; kb < kb_total; kb++) {
-                    mbar_wait(full_bar(stage), phase);
+                    if (!ready) mbar_wait(full_bar(stage), phase);
                     tcgen05_fence_after();
+                    if (kb == 0) QB_STAMP(tile, 3);
+                    if (kb == kb_total - 1) QB_STAMP(tile, 4);
+#ifdef QB_EPOCH_TRACE
+                    const long long c_issue0 = clock64();   // SM clock: k-step kb's operands are in shared memory
+#endif
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
                     const uint64_t adesc = make_kmajor_sw128_desc(sa), bdesc = make_kmajor_sw128_desc(sb);
                     const uint32_t idesc = kb < kb_first ? idesc_pos : idesc_neg;
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; k++)
-                        umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                    umma_commit(empty_bar(stage));
-                    if (kb == kb_total - 1) umma_commit(tfull_bar(as));
+                    const int cur = stage;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    ready = (kb + 1 < kb_total) ? mbar_test(full_bar(stage), phase) : 0u;
+                    if (issuer) {
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; k++)
+                            umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        umma_commit(empty_bar(cur));
+                        if (kb == kb_total - 1) umma_commit(tfull_bar(as));
+                    }
+                    __syncwarp();
+#ifdef QB_EPOCH_TRACE
+                    if (prog.trace && lane == 0 && kb < 20)   // low words: (clock after the MMAs were issued, clock when the operands had landed)
+                        prog.trace[tile * 32 + 8 + kb] = ((unsigned long long)(uint32_t)clock64() << 32) | (unsigned long long)(uint32_t)c_issue0;
+#endif
                 }
             }
         }
@@ -285,6 +336,7 @@ gibbs_epoch_kernel(const __grid_constant__ EpochMaps maps, const __grid_constant
             const int as = (int)(it & 1); const uint32_t aphase = (uint32_t)((it >> 1) & 1);
             mbar_wait(tfull_bar(as), aphase);
             tcgen05_fence_after();
+            if (warp == EPI_WARP0 && lane == 0) QB_STAMP(tile, 5);
             const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
             if (S.kind == K_GRAD_UPDATE) {
                 epilogue_grad_update<BN, WGS>(prog, S, tmem_acc, m_blk, n_blk, quarter, wg, lane, mb);
@@ -300,15 +352,18 @@ gibbs_epoch_kernel(const __grid_constant__ EpochMaps maps, const __grid_constant
                     default: epilogue_fast<BN, WGS, false, true>(e, tmem_acc, m_blk, n_blk, quarter, wg, lane); break;
                 }
             }
+            if (warp == EPI_WARP0 && lane == 0) QB_STAMP(tile, 6);
             tcgen05_fence_before();
             fence_proxy_async_global();
             __threadfence();
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(tempty_bar(as));
-                red_release_gpu_add(prog.rb_cnt + ((long long)iter * prog.n_steps + si) * prog.max_tiles_n + n_blk, 1u);
-                red_release_gpu_add(prog.tot_cnt + (long long)iter * prog.n_steps + si, 1u);
+                // (every lane has run a gpu-scope fence above: the relaxed adds complete the release)
+                red_relaxed_gpu_add(prog.rb_cnt + ((long long)iter * prog.n_steps + si) * prog.max_tiles_n + n_blk, 1u);
+                red_relaxed_gpu_add(prog.tot_cnt + (long long)iter * prog.n_steps + si, 1u);
             }
+            if (warp == EPI_WARP0 && lane == 0) QB_STAMP(tile, 7);
         }
     }
     __syncwarp();

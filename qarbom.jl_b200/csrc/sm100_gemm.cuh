@@ -118,6 +118,34 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+// One lane of a CONVERGED warp.  The TMA and MMA warps run their loops with all 32 lanes (uniform control flow, operands in
+// uniform registers) and predicate only the tcgen05 / TMA instructions on this: inside an `if (lane == 0)` region the
+// compiler has to broadcast every descriptor into uniform registers with an ELECT / R2UR.BROADCAST loop per instruction,
+// which costs ~100 clocks per tcgen05.mma (393 clocks per k-step of four, measured with tools/epoch_trace.py) -- more than
+// the MMA itself for tiles narrower than 256.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// Non-blocking look at a barrier phase.  The MMA warp tests the NEXT k-step's barrier before it issues the current k-step's MMAs,
+// so the ~170-clock round trip of a wait overlaps the issue instead of preceding it (tools/mma_issue_probe.cu: 326 -> 256
+// clocks per k-step of four 128 x N x 16 MMAs for N <= 128, against 432 with a single-lane issuer).
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -684,8 +712,9 @@ gibbs_gemm_kernel(const __grid_constant__ Phases ph, const EpiParams ep) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
-        // ===== TMA producer
-        if (lane == 0) {
+        // ===== TMA producer: the whole warp runs the loop (uniform control flow), one elected lane issues (see elect_one)
+        {
+            const bool issuer = elect_one();
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
@@ -694,14 +723,17 @@ gibbs_gemm_kernel(const __grid_constant__ Phases ph, const EpiParams ep) {
                     for (int kb = 0; kb < kb_total; kb++) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
                         const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-                        mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                        if (kb < kb1) {
-                            tma_load_2d(sa, &ph.A[0], full_bar(stage), kb * BK, m_blk * BM);
-                            tma_load_2d(sb, &ph.B[0], full_bar(stage), kb * BK, n_blk * BN);
-                        } else {
-                            tma_load_2d(sa, &ph.A[1], full_bar(stage), (kb - kb1) * BK, m_blk * BM);
-                            tma_load_2d(sb, &ph.B[1], full_bar(stage), (kb - kb1) * BK, n_blk * BN);
+                        if (issuer) {
+                            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                            if (kb < kb1) {
+                                tma_load_2d(sa, &ph.A[0], full_bar(stage), kb * BK, m_blk * BM);
+                                tma_load_2d(sb, &ph.B[0], full_bar(stage), kb * BK, n_blk * BN);
+                            } else {
+                                tma_load_2d(sa, &ph.A[1], full_bar(stage), (kb - kb1) * BK, m_blk * BM);
+                                tma_load_2d(sb, &ph.B[1], full_bar(stage), (kb - kb1) * BK, n_blk * BN);
+                            }
                         }
+                        __syncwarp();
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
                 } else {
@@ -710,17 +742,22 @@ gibbs_gemm_kernel(const __grid_constant__ Phases ph, const EpiParams ep) {
                         while (kb >= ph.kb_end[p]) kb0 = ph.kb_end[p++];
                         mbar_wait(empty_bar(stage), phase ^ 1);
                         const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-                        mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                        tma_load_2d(sa, &ph.A[p], full_bar(stage), (kb - kb0) * BK, m_blk * BM);
-                        tma_load_2d(sb, &ph.B[p], full_bar(stage), (kb - kb0) * BK, n_blk * BN);
+                        if (issuer) {
+                            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                            tma_load_2d(sa, &ph.A[p], full_bar(stage), (kb - kb0) * BK, m_blk * BM);
+                            tma_load_2d(sb, &ph.B[p], full_bar(stage), (kb - kb0) * BK, n_blk * BN);
+                        }
+                        __syncwarp();
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread)
-        if (lane == 0) {
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues; the next k-step's barrier is tested while this one's
+        // MMAs are issued (see mbar_test)
+        {
+            const bool issuer = elect_one();
             constexpr uint32_t idesc_pos = make_idesc(BN, false), idesc_neg = make_idesc(BN, true);
             int stage = 0; uint32_t phase = 0;
             int iter = 0;
@@ -733,21 +770,27 @@ gibbs_gemm_kernel(const __grid_constant__ Phases ph, const EpiParams ep) {
                 constexpr bool short_list = KIND != K_GRAD_LONG;
                 const int kb1m = ph.kb_end[0];
                 const uint32_t idesc0 = (ph.neg_mask & 1u) ? idesc_neg : idesc_pos, idesc1 = (ph.neg_mask & 2u) ? idesc_neg : idesc_pos;
+                uint32_t ready = mbar_test(full_bar(stage), phase);
                 for (int kb = 0; kb < kb_total; kb++) {
                     if (!short_list) while (kb >= ph.kb_end[p]) p++;
-                    mbar_wait(full_bar(stage), phase);
+                    if (!ready) mbar_wait(full_bar(stage), phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
                     const uint64_t adesc = make_kmajor_sw128_desc(sa), bdesc = make_kmajor_sw128_desc(sb);
                     const uint32_t idesc = short_list ? ((kb < kb1m) ? idesc0 : idesc1) : (((ph.neg_mask >> p) & 1u) ? idesc_neg : idesc_pos);
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; k++) {
-                        // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-                        umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                    }
-                    umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
-                    if (kb == kb_total - 1) umma_commit(tfull_bar(as));
+                    const int cur = stage;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    ready = (kb + 1 < kb_total) ? mbar_test(full_bar(stage), phase) : 0u;
+                    if (issuer) {
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; k++) {
+                            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                            umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        }
+                        umma_commit(empty_bar(cur));  // frees the smem slot once these MMAs retire
+                        if (kb == kb_total - 1) umma_commit(tfull_bar(as));
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -910,8 +953,10 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ Phases ph, const EpiParams ep) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
-        // ===== TMA producer (both CTAs: own A rows, own half of B; bytes land on the leader's barrier)
-        if (lane == 0) {
+        // ===== TMA producer (both CTAs: own A rows, own half of B; bytes land on the leader's barrier); warp-uniform loop, one
+        // elected lane issues
+        {
+            const bool issuer = elect_one();
             int stage = 0; uint32_t phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 int m_blk, n_blk;
@@ -926,15 +971,18 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ Phases ph, const EpiParams ep) {
                     for (int kb = 0; kb < kb_total; kb++) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
                         const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-                        if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-                        else mbar_arrive_remote(full_bar(stage), 0);
-                        if (kb < kb1) {
-                            tma_load_2d_2sm(sa, &ph.A[0], full_bar(stage), kb * BK, m0);
-                            tma_load_2d_2sm(sb, &ph.B[0], full_bar(stage), kb * BK, n0);
-                        } else {
-                            tma_load_2d_2sm(sa, &ph.A[1], full_bar(stage), (kb - kb1) * BK, m0);
-                            tma_load_2d_2sm(sb, &ph.B[1], full_bar(stage), (kb - kb1) * BK, n0);
+                        if (issuer) {
+                            if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+                            else mbar_arrive_remote(full_bar(stage), 0);
+                            if (kb < kb1) {
+                                tma_load_2d_2sm(sa, &ph.A[0], full_bar(stage), kb * BK, m0);
+                                tma_load_2d_2sm(sb, &ph.B[0], full_bar(stage), kb * BK, n0);
+                            } else {
+                                tma_load_2d_2sm(sa, &ph.A[1], full_bar(stage), (kb - kb1) * BK, m0);
+                                tma_load_2d_2sm(sb, &ph.B[1], full_bar(stage), (kb - kb1) * BK, n0);
+                            }
                         }
+                        __syncwarp();
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
                 } else {
@@ -943,18 +991,22 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ Phases ph, const EpiParams ep) {
                         while (kb >= ph.kb_end[p]) kb0 = ph.kb_end[p++];
                         mbar_wait(empty_bar(stage), phase ^ 1);
                         const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-                        if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-                        else mbar_arrive_remote(full_bar(stage), 0);
-                        tma_load_2d_2sm(sa, &ph.A[p], full_bar(stage), (kb - kb0) * BK, m0);
-                        tma_load_2d_2sm(sb, &ph.B[p], full_bar(stage), (kb - kb0) * BK, n0);
+                        if (issuer) {
+                            if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+                            else mbar_arrive_remote(full_bar(stage), 0);
+                            tma_load_2d_2sm(sa, &ph.A[p], full_bar(stage), (kb - kb0) * BK, m0);
+                            tma_load_2d_2sm(sb, &ph.B[p], full_bar(stage), (kb - kb0) * BK, n0);
+                        }
+                        __syncwarp();
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread of the leader CTA drives both tensor cores
-        if (leader && lane == 0) {
+        // ===== MMA issuer: one elected lane of the leader CTA's (warp-uniform) loop drives both tensor cores
+        if (leader) {
+            const bool issuer = elect_one();
             constexpr uint32_t idesc_pos = make_idesc_m256(BN, false), idesc_neg = make_idesc_m256(BN, true);
             int stage = 0; uint32_t phase = 0;
             int iter = 0;
@@ -967,19 +1019,25 @@ gibbs_gemm_kernel_2cta(const __grid_constant__ Phases ph, const EpiParams ep) {
                 constexpr bool short_list = KIND != K_GRAD_LONG;
                 const int kb1m = ph.kb_end[0];
                 const uint32_t idesc0 = (ph.neg_mask & 1u) ? idesc_neg : idesc_pos, idesc1 = (ph.neg_mask & 2u) ? idesc_neg : idesc_pos;
+                uint32_t ready = mbar_test(full_bar(stage), phase);
                 for (int kb = 0; kb < kb_total; kb++) {
                     if (!short_list) while (kb >= ph.kb_end[p]) p++;
-                    mbar_wait(full_bar(stage), phase);
+                    if (!ready) mbar_wait(full_bar(stage), phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
                     const uint64_t adesc = make_kmajor_sw128_desc(sa), bdesc = make_kmajor_sw128_desc(sb);
                     const uint32_t idesc = short_list ? ((kb < kb1m) ? idesc0 : idesc1) : (((ph.neg_mask >> p) & 1u) ? idesc_neg : idesc_pos);
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; k++)
-                        umma_bf16_2sm(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                    umma_commit_2sm(empty_bar(stage));
-                    if (kb == kb_total - 1) umma_commit_2sm(tfull_bar(as));
+                    const int cur = stage;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    ready = (kb + 1 < kb_total) ? mbar_test(full_bar(stage), phase) : 0u;
+                    if (issuer) {
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; k++)
+                            umma_bf16_2sm(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        umma_commit_2sm(empty_bar(cur));
+                        if (kb == kb_total - 1) umma_commit_2sm(tfull_bar(as));
+                    }
+                    __syncwarp();
                 }
             }
         }
