@@ -49,8 +49,8 @@ WORKLOADS = {
 }
 METRIC = "PCD/CD-k training samples/sec"
 # `ncu --set full` summaries of this round (tools/ncu_summary.py raw <rep>), committed under profiles/
-NCU_GEMM_SUMMARY = "r2_ncu_gemm_raw_summary.txt"
-NCU_UPDATE_SUMMARY = "r2_ncu_update_raw_summary.txt"
+NCU_GEMM_SUMMARY = "r2b_ncu_gemm_raw_summary.txt"
+NCU_UPDATE_SUMMARY = "r2b_ncu_update_raw_summary.txt"
 
 
 def gemm_mix(w):

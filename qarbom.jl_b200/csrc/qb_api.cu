@@ -514,18 +514,24 @@ struct ChainRegion {   // records the half-steps issued inside a scope, launches
     }
 };
 
-int chain_tile_width(qb_handle *h, int64_t N) {
+// Width (batch rows) of the chain kernel's 256-unit pair tiles.  Measured (tools/chain_probe.py, profiles/r2_chain_probe_v2.txt):
+// up to ONE wave of 256 x 256 tiles per half-step every pair would hold a single tile whose epilogue is exposed, and 256 x 128
+// tiles win (cfg5 at 1024 rows: 607 vs 677 us per step; 512 rows: 448 vs 635); from there on the wide tile wins (2048 rows:
+// 959 vs 1124; 8192 rows: 3868 vs 4936).
+int chain_tile_width(qb_handle *h, int64_t M, int64_t N) {
     if (h->chain_bn) return h->chain_bn;
     if (h->force_bn >= 64) return h->force_bn;
-    return N >= 1024 ? 256 : (N > 64 ? 128 : 64);
+    if (N <= 64) return 64;
+    return (int64_t)ceil_div(N, 256) * ceil_div(M, 256) > h->gemm_sms / 2 ? 256 : 128;
 }
-// Measured (tools/chain_probe.py, profiles/r2_chain_probe.txt, r2_chain_probe_quad.txt): the pair-tile chain wins from about
-// one wave of 256 x 256 pair tiles per half-step on (cfg5: 1024 rows, 64 tiles: 724 vs 793 us per step; 2048 rows -17 %; 8192
-// rows -1 %) and loses on small models, whose half-steps want many small single-CTA tiles.
+// The pair-tile chain wins from about three quarters of a wave of its tiles per half-step on (cfg5: 512 rows, 64 tiles of
+// 256 x 128: 448 vs 473 us per step; 1024 rows: 607 vs 696; 2048 rows: 959 vs 1118; 8192 rows -1 %) and loses on small
+// models, whose half-steps want many small single-CTA tiles.
 // Option "fused_chain": 1 = automatic, 2 = always, 0 = never.
-bool chain_pays(qb_handle *h, const sm100::EpiParams &ep) {
+// `units`: the larger layer of the model, so that the hidden and the visible half-steps of one chain get the same answer.
+bool chain_pays(qb_handle *h, int64_t units, int64_t N) {
     if (h->fused_chain_mode == 2) return true;
-    return (int64_t)ceil_div(ep.N, 256) * ceil_div(ep.M, 256) >= (h->gemm_sms * 3) / 8;
+    return (int64_t)ceil_div(N, chain_tile_width(h, units, N)) * ceil_div(units, 256) >= (h->gemm_sms * 3) / 8;
 }
 // The quad variant (gibbs_chain_kernel_quad) is for half-steps of about one wave of 256 x 256 pair tiles -- there each pair
 // holds a single tile per half-step and its epilogue is exposed; with 128-row blocks per pair and the weights multicast inside
@@ -574,13 +580,13 @@ void gemm_half_step(qb_handle *h, const sm100::Operand &A, const sm100::Operand 
     if (h->capture) { h->capture->A = A; h->capture->B = B; h->capture->ep = ep; h->capture->flops = flops; h->capture->set = true; return; }
     const bool quad = h->rec_depth > 0 && h->use_2cta != 0 && sm100::chainable(ep) && chain_quad_wanted(h, ep);
     const bool can_chain = h->rec_depth > 0 && h->fused_chain_mode != 0 && h->use_2cta != 0 && h->force_bn != 32 && sm100::chainable(ep) &&
-                           (quad || chain_pays(h, ep));
+                           (quad || chain_pays(h, std::max<int64_t>(ep.M, A.k), ep.N));
     if (h->rec_depth > 0 && !can_chain) chain_flush(h);
     if (!can_chain) { launch_single(h, A, B, ep, flops); return; }
     sm100::ChainBuilder &cb = *h->rec;
     if (cb.prog.n_steps > 0 && (cb.prog.N != ep.N || cb.full() || cb.quad != quad)) chain_flush(h);
     for (int attempt = 0; attempt < 2; attempt++) {
-        if (cb.prog.n_steps == 0) cb.begin(ep.N, quad ? sm100::QUAD_BN : chain_tile_width(h, ep.N), quad);
+        if (cb.prog.n_steps == 0) cb.begin(ep.N, quad ? sm100::QUAD_BN : chain_tile_width(h, std::max<int64_t>(ep.M, A.k), ep.N), quad);
         int dep = -1;
         for (int j = cb.prog.n_steps - 1; j >= 0; j--) {
             const sm100::EpiParams &e = cb.prog.step[j].ep;
