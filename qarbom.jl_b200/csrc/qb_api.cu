@@ -514,10 +514,10 @@ struct ChainRegion {   // records the half-steps issued inside a scope, launches
     }
 };
 
-// Width (batch rows) of the chain kernel's 256-unit pair tiles.  Measured (tools/chain_probe.py, profiles/r2_chain_probe_v2.txt):
+// Width (batch rows) of the chain kernel's 256-unit pair tiles.  Measured (tools/chain_probe.py, profiles/r2b_chain_probe.txt):
 // up to ONE wave of 256 x 256 tiles per half-step every pair would hold a single tile whose epilogue is exposed, and 256 x 128
-// tiles win (cfg5 at 1024 rows: 607 vs 677 us per step; 512 rows: 448 vs 635); from there on the wide tile wins (2048 rows:
-// 959 vs 1124; 8192 rows: 3868 vs 4936).
+// tiles win (cfg5 at 1024 rows: 625 vs 679 us per step; 512 rows: 449 vs 637); from there on the wide tile wins (2048 rows:
+// 991 vs 1159; 8192 rows: 3962 vs 4911).
 int chain_tile_width(qb_handle *h, int64_t M, int64_t N) {
     if (h->chain_bn) return h->chain_bn;
     if (h->force_bn >= 64) return h->force_bn;
@@ -525,7 +525,7 @@ int chain_tile_width(qb_handle *h, int64_t M, int64_t N) {
     return (int64_t)ceil_div(N, 256) * ceil_div(M, 256) > h->gemm_sms / 2 ? 256 : 128;
 }
 // The pair-tile chain wins from about three quarters of a wave of its tiles per half-step on (cfg5: 512 rows, 64 tiles of
-// 256 x 128: 448 vs 473 us per step; 1024 rows: 607 vs 696; 2048 rows: 959 vs 1118; 8192 rows -1 %) and loses on small
+// 256 x 128: 449 vs 474 us per step; 1024 rows: 625 vs 699; 2048 rows: 991 vs 1122; 8192 rows: a tie) and loses on small
 // models, whose half-steps want many small single-CTA tiles.
 // Option "fused_chain": 1 = automatic, 2 = always, 0 = never.
 // `units`: the larger layer of the model, so that the hidden and the visible half-steps of one chain get the same answer.
@@ -533,14 +533,12 @@ bool chain_pays(qb_handle *h, int64_t units, int64_t N) {
     if (h->fused_chain_mode == 2) return true;
     return (int64_t)ceil_div(N, chain_tile_width(h, units, N)) * ceil_div(units, 256) >= (h->gemm_sms * 3) / 8;
 }
-// The quad variant (gibbs_chain_kernel_quad) is for half-steps of about one wave of 256 x 256 pair tiles -- there each pair
-// holds a single tile per half-step and its epilogue is exposed; with 128-row blocks per pair and the weights multicast inside
-// a 4-CTA cluster every pair alternates between two independent tiles.  MEASURED NEGATIVE (profiles/r2_chain_probe_quad.txt):
-// bit-identical results, but 1028 us per cfg5 step at 1024 rows against 723 us for the 256 x 256 pair chain -- a 256 x 128 tile
-// takes as long as a 256 x 256 one (24 us) with or without the multicast, i.e. the k-loop is bound by the rate at which ONE SM's
-// shared memory can be filled (about 85-90 GB/s per SM: 192 KB in flight per CTA over the TMA round trip), not by L2
-// bandwidth: halving the L2 reads does not help, the bytes that land in each SM per flop are what counts, and those are 1.5x
-// those of the wide tile.  Off by default; kept as an option with its parity test.
+// The quad variant (gibbs_chain_kernel_quad): two CTA pairs in a 4-CTA cluster share a 256-unit x 256-row tile (128-row blocks
+// per pair, weights multicast between the pairs), so every pair alternates between two independent tiles at one wave.  Bit-
+// identical results; with the warp-uniform issue loops it is level with the plain 256 x 128 pair chain (624 vs 625 us per cfg5
+// step at 1024 rows, profiles/r2b_chain_probe.txt), which gets the same alternation without clusters of four -- the multicast
+// buys nothing measurable.  (Its first measurement, 1028 vs 723 us, was taken when every narrow tile was bound by the
+// single-lane issue loop)  Off by default; kept as an option with its parity test.
 bool chain_quad_wanted(qb_handle *h, const sm100::EpiParams &ep) {
     if (h->chain_quad_mode == 0 || h->fused_chain_mode == 0 || h->chain_bn != 0 || h->force_bn != 0 || (ep.N % 256) != 0) return false;
     if (h->gemm_sms < h->num_sms) return false;   // (stale-chains mode reserves SMs for the exchange: pair kernels only)

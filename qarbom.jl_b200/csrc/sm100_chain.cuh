@@ -264,12 +264,12 @@ gibbs_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant
 // ----------------------------------------------------------------------------- quad variant: 4-CTA clusters, weights multicast
 // When a half-step is about ONE wave of 256 x 256 pair tiles (e.g. cfg5 on 8 GPUs: 1024 rows per rank = 64 tiles on 74 pairs),
 // every pair holds one tile per half-step, all tiles of a row block finish together and the epilogue of the only tile is fully
-// exposed (measured 35 us per half-step against 24 us of MMA).  Halving the tile width gives every pair two independent tiles
-// per half-step -- one's epilogue hides under the other's MMAs -- but 256 x 128 tiles re-stream the weights twice and are bound
-// by L2 -> SM bandwidth (measured 43 us).  Here two CTA pairs form a cluster of FOUR CTAs that works on one 256-unit x 256-row
-// tile: pair q takes the 128-row block 2R + q, and every 128 x 64 weight slab is loaded ONCE per cluster -- each CTA fetches 64
-// of its 128 weight rows and TMA-multicasts them to the CTA of the other pair that needs the same rows.  L2 traffic is that of
-// the 256 x 256 pair tile, dependencies and epilogues are per 128-row block.
+// exposed.  Halving the tile width gives every pair two independent tiles per half-step -- one's epilogue hides under the
+// other's MMAs -- at the price of streaming the weights twice.  Here two CTA pairs form a cluster of FOUR CTAs that works on
+// one 256-unit x 256-row tile: pair q takes the 128-row block 2R + q, and every 128 x 64 weight slab is loaded ONCE per cluster
+// -- each CTA fetches 64 of its 128 weight rows and TMA-multicasts them to the CTA of the other pair that needs the same rows.
+// L2 traffic is that of the 256 x 256 pair tile, dependencies and epilogues are per 128-row block.  Measured level with the
+// plain 256 x 128 pair chain (the weights' second pass comes out of L2 at no visible cost), so it is an option, not the default.
 //   barriers: full (per pair leader) = leader's arrive.expect_tx + peer's arrive + 48 KB of bytes (half of the A bytes come
 //   from the other pair's multicasts); empty (every CTA) = 2 arrivals, the tcgen05.commit of BOTH pair leaders multicast to all
 //   four CTAs -- a stage may be refilled only when both pairs have consumed it, because every load writes into two CTAs.
