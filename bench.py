@@ -620,11 +620,14 @@ def main():
                                     "burst bf16: timed region ran at >= 90 % of max SM clock"))
     F = flops_per_step(w) / world  # per GPU per step
     achieved = (timed_flops / 1e12) / (gemm_ms * 1e-3) if gemm_ms > 0 else None
+    n_sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
     cfg5_bf16 = args.workload == "cfg5" and args.precision == "bf16" and world == 1
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
             "frac": (achieved / pk["tf"]) if achieved else None,
             "frac_burst": (achieved / tf_burst) if achieved else None, "frac_sustained": (achieved / tf_sust) if achieved else None,
             "peak_burst": tf_burst, "peak_sustained": tf_sust,
+            # against the hardware instead of a library: 148 SMs x 8192 dense bf16 flop per clock x the median SM clock of the region
+            "frac_of_pipe_at_clock": (achieved / (n_sms * 8192 * sm_med * 1e6 / 1e12)) if (achieved and sm_med) else None,
             "traffic": ncu_traffic(NCU_GEMM_SUMMARY, "gibbs_", mix=gemm_mix(w)) if cfg5_bf16 else None,
             "traffic_note": "dram read+write bytes per launch from one `ncu --set full` capture of this command (profiles/" + NCU_GEMM_SUMMARY +
                             "), per-kernel means weighted by the launch mix of a step (1 chain launch = the 2k + 1 forward contractions : 1 gradient GEMM)",
