@@ -315,7 +315,7 @@ int32_t qb_reset_counters(qb_handle *h);
  * counts summed as packed u64 by the switch; 0 never (default: measured slower), 1 when a half-step
  * leaves SMs idle, 2 whenever possible; same results as the unsplit exchange up to fp32 summation order),
  * "fused_chain" (the half-steps of a step as one persistent launch: 0 never, 1 automatic, 2 always), "chain_bn" (its tile
- * width, 0 = automatic), "chain_quad" (its 4-CTA-cluster variant with multicast weights: 0 never (default: measured no faster),
+ * width, 0 = automatic), "chain_pairs" (experiments: CTA pairs it may use, 0 = all), "chain_quad" (its 4-CTA-cluster variant with multicast weights: 0 never (default: measured no faster),
  * 1 one-wave shapes, 2 whenever possible), "epoch_kernel" (many mini-batch steps of a small model as one persistent launch
  * in qb_train_steps / the epoch calls: 0 never, 1 automatic, 2 always),
  * and for experiments / tests "force_bn" (GEMM tile width) and "use_2cta" (0 never, 1 automatic, 2 always). */

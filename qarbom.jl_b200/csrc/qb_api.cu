@@ -213,6 +213,7 @@ struct qb_handle {
     double gemm_flops = 0.0, gemm_issued_flops = 0.0;   // algorithmic / extra component-product flops (QB_PREC_FP32X3)
     int force_bn = 0, use_2cta = 1;
     // fused chain launches (sm100_chain.cuh): half-steps recorded between chain_begin / chain_end run as ONE persistent kernel
+    int chain_pairs = 0;                            // option "chain_pairs" (experiments): CTA pairs of the chain kernel (0 = all)
     int fused_chain_mode = 1; int chain_bn = 0;     // options "fused_chain" (0 never, 1 automatic, 2 always), "chain_bn" (0 = automatic)
     int chain_quad_mode = 0;                        // option "chain_quad": 4-CTA-cluster chain kernel with multicast weights (0 never -- the default: measured slower --, 1 one-wave shapes, 2 whenever possible)
     int rec_depth = 0; sm100::ChainBuilder *rec = nullptr;
@@ -599,6 +600,16 @@ void gemm_half_step(qb_handle *h, const sm100::Operand &A, const sm100::Operand 
     launch_single(h, A, B, ep, flops);
 }
 
+// CTA pairs the chain kernel runs on: all of them.  Option "chain_pairs" (experiments) limits the count.  Tried: tiles are dealt
+// to the pairs round-robin in program order and a tile of half-step t + 1 depends on tiles one half-step's count T earlier, so
+// with T a whole number of rounds (128 tiles on 64 pairs instead of 1.73 rounds on 74) no dependency is in flight when its
+// consumer comes up -- measured slower (cfg5 at 1024 rows: 664 vs 634 us per step; 2048 rows: 1046 vs 1008): the schedule is
+// not stall-bound, the ten extra pairs are worth more.
+int chain_pairs_for(qb_handle *h, const sm100::ChainBuilder &) {
+    const int pairs = h->gemm_sms / 2;
+    return h->chain_pairs > 0 ? std::min(pairs, h->chain_pairs) : pairs;
+}
+
 void ensure_chain_flags(qb_handle *h) {
     if (h->chain_cnt) return;
     h->chain_cnt_region = (int64_t)sm100::CHAIN_MAX_STEPS * ceil_div(h->Bmax, 64);
@@ -628,6 +639,7 @@ void chain_flush(qb_handle *h) {
     cb.prog.counters = h->chain_cnt + region * h->chain_cnt_region;
     cb.prog.error_flag = h->chain_err_dev;
     cb.prog.abort_flag = h->chain_cnt + (size_t)QB_CHAIN_REGIONS * h->chain_cnt_region;
+    cb.pairs_limit = chain_pairs_for(h, cb);
     {
         GemmScope gs(h, cb.flops);
         sm100::launch_chain(h->stream, cb, h->gemm_sms);
@@ -2825,6 +2837,9 @@ int32_t qb_set_option(qb_handle *h, const char *key, double value) {
         } else if (!strcmp(key, "epoch_kernel")) {
             QB_CHECK(value == 0.0 || value == 1.0 || value == 2.0, QB_E_ARG, "epoch_kernel must be 0, 1 or 2");
             h->epoch_kernel_mode = (int)value;
+        } else if (!strcmp(key, "chain_pairs")) {
+            QB_CHECK(value >= -1.0 && value <= 1024.0, QB_E_ARG, "chain_pairs must be 0 (all) or a count");
+            h->chain_pairs = (int)value;
         } else if (!strcmp(key, "chain_bn")) {
             const int bn = (int)value;
             QB_CHECK(bn == 0 || bn == 64 || bn == 128 || bn == 256, QB_E_ARG, "chain_bn must be 0/64/128/256");

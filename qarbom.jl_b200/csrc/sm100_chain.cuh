@@ -487,6 +487,7 @@ struct ChainBuilder {
     Operand ops[CHAIN_MAX_MAPS];
     int op_box[CHAIN_MAX_MAPS];
     int n_maps = 0, bn = 0;
+    int pairs_limit = 0;   // CTA pairs the launch may use (0 = all): see chain_pairs_for in qb_api.cu
     bool quad = false;   // gibbs_chain_kernel_quad: bn = QUAD_BN rows per pair, tiles are 256 units x (2 x bn) rows
     double flops = 0.0;
     ChainBuilder() { memset(&maps, 0, sizeof(maps)); memset(&prog, 0, sizeof(prog)); }
@@ -555,7 +556,7 @@ inline void launch_chain_bn(cudaStream_t st, const ChainBuilder &cb, int num_sms
         QB_CUDA(cudaFuncSetAttribute(gibbs_chain_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
-    const int pairs = num_sms / 2;
+    const int pairs = (cb.pairs_limit > 0 && cb.pairs_limit < num_sms / 2) ? cb.pairs_limit : num_sms / 2;
     const int clusters = cb.prog.total_tiles < pairs ? cb.prog.total_tiles : pairs;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(Shape<BN, K_FAST_SAMPLE>::THREADS);

@@ -24,11 +24,13 @@ for B in [int(a) for a in sys.argv[2:]] or CFG["rows"]:
     Y = np.eye(L, dtype=np.uint8)[np.arange(nb * B) % L] if L else None
     modes = [(0, 0, 0), (1, 0, 0), (2, 128, 0), (2, 256, 0), (2, 0, 2)] if os.environ.get("CHAIN_PROBE_SHORT") else \
             [(0, 0, 0), (1, 0, 0), (1, 0, 1), (2, 64, 0), (2, 128, 0), (2, 256, 0), (2, 0, 2)]
-    for fused, bn, quad in modes:   # quad: 4-CTA-cluster chain kernel with multicast weights (0 never, 1 automatic, 2 whenever possible)
+    pairs_list = [int(x) for x in os.environ.get("CHAIN_PAIRS", "0").split(",")]   # option "chain_pairs": 0 = all CTA pairs
+    modes = [(f, b, qd, p) for (f, b, qd) in modes for p in (pairs_list if f else [0])]
+    for fused, bn, quad, pairs in modes:   # quad: 4-CTA-cluster chain kernel with multicast weights (0 never, 1 automatic, 2 whenever possible)
         if quad == 2 and B % 256:
             continue
         dev = q.DeviceRBM(rbm, max_batch=B, precision="bf16", seed=1)
-        dev.set_option("fused_chain", fused); dev.set_option("chain_bn", bn); dev.set_option("chain_quad", quad)
+        dev.set_option("fused_chain", fused); dev.set_option("chain_bn", bn); dev.set_option("chain_quad", quad); dev.set_option("chain_pairs", pairs)
         dev.set_data(X, Y)
         if CFG["pcd"]:
             dev.init_chains(B)
@@ -44,5 +46,5 @@ for B in [int(a) for a in sys.argv[2:]] or CFG["rows"]:
             step(i)
         ms = dev.timer_stop()
         launches = dev.counters()[0] / n
-        print(f"{wl} B={B:5d} fused={fused} chain_bn={bn:3d} quad={quad}: {ms / n * 1e3:9.1f} us/step  {launches:4.1f} launches/step  hist={dev.gemm_histogram()}", flush=True)
+        print(f"{wl} B={B:5d} fused={fused} chain_bn={bn:3d} quad={quad} pairs={pairs:3d}: {ms / n * 1e3:9.1f} us/step  {launches:4.1f} launches/step  hist={dev.gemm_histogram()}", flush=True)
         dev.close()
