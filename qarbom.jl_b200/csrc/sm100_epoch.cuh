@@ -199,9 +199,9 @@ gibbs_epoch_kernel(const __grid_constant__ EpochMaps maps, const __grid_constant
     };
 
     if (warp == 0) {
-        // ===== TMA producer: the whole warp runs the loop, one elected lane issues (see elect_one)
+        // ===== TMA producer: the whole warp runs the loop, the instructions are predicated on one elected lane (elect_one, *_if)
         {
-            const bool issuer = elect_one();
+            const uint32_t issue = elect_one() ? 1u : 0u;
             int stage = 0; uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int iter, si, local;
@@ -232,11 +232,8 @@ gibbs_epoch_kernel(const __grid_constant__ EpochMaps maps, const __grid_constant
                     int st = stage; uint32_t ph = phase;
                     for (int i = 0; i < pre; i++) {
                         mbar_wait(empty_bar(st), ph ^ 1);
-                        if (issuer) {
-                            mbar_expect_tx(full_bar(st), C::STAGE_BYTES);
-                            tma_load_2d(smem_base + st * C::STAGE_BYTES, &maps.m[S.a_map[0]], full_bar(st), i * BK, m_blk * BM + mb * S.a_row_mb[0]);
-                        }
-                        __syncwarp();
+                        mbar_expect_tx_if(issue, full_bar(st), C::STAGE_BYTES);
+                        tma_load_2d_if(issue, smem_base + st * C::STAGE_BYTES, &maps.m[S.a_map[0]], full_bar(st), i * BK, m_blk * BM + mb * S.a_row_mb[0]);
                         if (++st == C::STAGES) { st = 0; ph ^= 1; }
                     }
                     epoch_wait(rb + S.dep_rb * prog.max_tiles_n + n_blk, (unsigned int)S.dep_rb_count, prog);
@@ -245,32 +242,26 @@ gibbs_epoch_kernel(const __grid_constant__ EpochMaps maps, const __grid_constant
 #ifdef QB_EPOCH_TRACE
                     const long long c_tma0 = clock64();
 #endif
-                    if (issuer) {
-                        int st2 = stage;
-                        for (int i = 0; i < pre; i++) {
-                            tma_load_2d(smem_base + st2 * C::STAGE_BYTES + C::A_BYTES, &maps.m[S.b_map[0]], full_bar(st2), i * BK,
-                                        n_blk * BN + mb * S.b_row_mb[0]);
-                            if (++st2 == C::STAGES) st2 = 0;
-                        }
+                    for (int i = 0; i < pre; i++) {
+                        tma_load_2d_if(issue, smem_base + stage * C::STAGE_BYTES + C::A_BYTES, &maps.m[S.b_map[0]], full_bar(stage), i * BK,
+                                       n_blk * BN + mb * S.b_row_mb[0]);
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    stage = st; phase = ph;
 #ifdef QB_EPOCH_TRACE
                     if (prog.trace && lane == 0) prog.trace[tile * 32 + 28] = (unsigned long long)(clock64() - c_tma0);
 #endif
                     kb = pre;
                 }
+                uint32_t eready = kb < kb_total ? mbar_test(empty_bar(stage), phase ^ 1) : 0u;
                 for (; kb < kb_total; kb++) {
                     const int p = kb < kb_first ? 0 : 1, kk = kb < kb_first ? kb : kb - kb_first;
-                    mbar_wait(empty_bar(stage), phase ^ 1);
-                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-                    if (issuer) {
-                        mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                        tma_load_2d(sa, &maps.m[S.a_map[p]], full_bar(stage), kk * BK, m_blk * BM + mb * S.a_row_mb[p]);
-                        tma_load_2d(sb, &maps.m[S.b_map[p]], full_bar(stage), kk * BK, n_blk * BN + mb * S.b_row_mb[p]);
-                    }
-                    __syncwarp();
+                    if (!eready) mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES, fb = full_bar(stage);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    eready = (kb + 1 < kb_total) ? mbar_test(empty_bar(stage), phase ^ 1) : 0u;
+                    mbar_expect_tx_if(issue, fb, C::STAGE_BYTES);
+                    tma_load_2d_if(issue, sa, &maps.m[S.a_map[p]], fb, kk * BK, m_blk * BM + mb * S.a_row_mb[p]);
+                    tma_load_2d_if(issue, sb, &maps.m[S.b_map[p]], fb, kk * BK, n_blk * BN + mb * S.b_row_mb[p]);
                 }
             }
         }
@@ -278,7 +269,7 @@ gibbs_epoch_kernel(const __grid_constant__ EpochMaps maps, const __grid_constant
         // ===== MMA issuer: warp-uniform loop, one elected lane issues; the next k-step's barrier is tested while this one's
         // MMAs are issued (see mbar_test)
         {
-            const bool issuer = elect_one();
+            const uint32_t issue = elect_one() ? 1u : 0u;
             constexpr uint32_t idesc_pos = make_idesc(BN, false), idesc_neg = make_idesc(BN, true);
             int stage = 0; uint32_t phase = 0;
             long long it = 0;
@@ -308,14 +299,11 @@ gibbs_epoch_kernel(const __grid_constant__ EpochMaps maps, const __grid_constant
                     const int cur = stage;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     ready = (kb + 1 < kb_total) ? mbar_test(full_bar(stage), phase) : 0u;
-                    if (issuer) {
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; k++)
-                            umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                        umma_commit(empty_bar(cur));
-                        if (kb == kb_total - 1) umma_commit(tfull_bar(as));
-                    }
-                    __syncwarp();
+                    for (int k = 0; k < BK / UMMA_K; k++)
+                        umma_bf16_if(issue, tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    umma_commit_if(issue, empty_bar(cur));
+                    umma_commit_if(kb == kb_total - 1 ? issue : 0u, tfull_bar(as));
 #ifdef QB_EPOCH_TRACE
                     if (prog.trace && lane == 0 && kb < 20)   // low words: (clock after the MMAs were issued, clock when the operands had landed)
                         prog.trace[tile * 32 + 8 + kb] = ((unsigned long long)(uint32_t)clock64() << 32) | (unsigned long long)(uint32_t)c_issue0;

@@ -153,6 +153,29 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// Predicated forms for the warp-uniform issue loops: `issue` is 1 in the elected lane and 0 elsewhere, and the predicate sits
+// INSIDE the asm, so there is no branch (no divergent region to enter and leave) around the tcgen05 / TMA instruction.  With a
+// C++ `if (issuer)` around four MMAs a k-step costs 256 clocks whatever the tile width; predicated, it runs at the rate the
+// MMAs execute (tools/mma_issue_probe.cu, patterns 8 / 11: N = 32: 256 -> 165 clocks, N = 64: 256 -> 191, N = 128: 256 -> 253).
+// Used by the single-CTA kernels (this file's gibbs_gemm_kernel, sm100_epoch.cuh), whose tiles are narrow.  The CTA-pair
+// kernels keep the `if (issuer)` form: their operands depend on the CTA's rank in the pair, which the compiler cannot prove
+// warp-uniform, so every predicated instruction drags a row of R2UR.BROADCAST with it -- A/B on one box 4160 vs 3940 us per
+// cfg5 step, and their 256-wide tiles have the clocks to hide a branch anyway.
+__device__ __forceinline__ void mbar_expect_tx_if(uint32_t issue, uint32_t bar, uint32_t bytes) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %2, 0;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes), "r"(issue)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_if(uint32_t issue, uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(issue)
+        : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -174,6 +197,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t issue, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(issue)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_if(uint32_t issue, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -712,43 +751,41 @@ gibbs_gemm_kernel(const __grid_constant__ Phases ph, const EpiParams ep) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
-        // ===== TMA producer: the whole warp runs the loop (uniform control flow), one elected lane issues (see elect_one)
+        // ===== TMA producer: the whole warp runs the loop (uniform control flow), the instructions are predicated on one elected
+        // lane (see elect_one, *_if); the next stage's `empty` barrier is tested before this stage's loads are issued
         {
-            const bool issuer = elect_one();
+            const uint32_t issue = elect_one() ? 1u : 0u;
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_blk = tile % tiles_m, n_blk = tile / tiles_m;
+                uint32_t eready = mbar_test(empty_bar(stage), phase ^ 1);
                 if (KIND != K_GRAD_LONG) {   // constant tensor-map indices on the production paths (see gibbs_gemm_kernel_2cta)
                     const int kb1 = ph.kb_end[0];
                     for (int kb = 0; kb < kb_total; kb++) {
-                        mbar_wait(empty_bar(stage), phase ^ 1);
-                        const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-                        if (issuer) {
-                            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                            if (kb < kb1) {
-                                tma_load_2d(sa, &ph.A[0], full_bar(stage), kb * BK, m_blk * BM);
-                                tma_load_2d(sb, &ph.B[0], full_bar(stage), kb * BK, n_blk * BN);
-                            } else {
-                                tma_load_2d(sa, &ph.A[1], full_bar(stage), (kb - kb1) * BK, m_blk * BM);
-                                tma_load_2d(sb, &ph.B[1], full_bar(stage), (kb - kb1) * BK, n_blk * BN);
-                            }
-                        }
-                        __syncwarp();
+                        if (!eready) mbar_wait(empty_bar(stage), phase ^ 1);
+                        const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES, fb = full_bar(stage);
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                        eready = (kb + 1 < kb_total) ? mbar_test(empty_bar(stage), phase ^ 1) : 0u;
+                        mbar_expect_tx_if(issue, fb, C::STAGE_BYTES);
+                        if (kb < kb1) {
+                            tma_load_2d_if(issue, sa, &ph.A[0], fb, kb * BK, m_blk * BM);
+                            tma_load_2d_if(issue, sb, &ph.B[0], fb, kb * BK, n_blk * BN);
+                        } else {
+                            tma_load_2d_if(issue, sa, &ph.A[1], fb, (kb - kb1) * BK, m_blk * BM);
+                            tma_load_2d_if(issue, sb, &ph.B[1], fb, (kb - kb1) * BK, n_blk * BN);
+                        }
                     }
                 } else {
                     int p = 0, kb0 = 0;
                     for (int kb = 0; kb < kb_total; kb++) {
                         while (kb >= ph.kb_end[p]) kb0 = ph.kb_end[p++];
-                        mbar_wait(empty_bar(stage), phase ^ 1);
-                        const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-                        if (issuer) {
-                            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                            tma_load_2d(sa, &ph.A[p], full_bar(stage), (kb - kb0) * BK, m_blk * BM);
-                            tma_load_2d(sb, &ph.B[p], full_bar(stage), (kb - kb0) * BK, n_blk * BN);
-                        }
-                        __syncwarp();
+                        if (!eready) mbar_wait(empty_bar(stage), phase ^ 1);
+                        const uint32_t sa = smem_base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES, fb = full_bar(stage);
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                        eready = (kb + 1 < kb_total) ? mbar_test(empty_bar(stage), phase ^ 1) : 0u;
+                        mbar_expect_tx_if(issue, fb, C::STAGE_BYTES);
+                        tma_load_2d_if(issue, sa, &ph.A[p], fb, (kb - kb0) * BK, m_blk * BM);
+                        tma_load_2d_if(issue, sb, &ph.B[p], fb, (kb - kb0) * BK, n_blk * BN);
                     }
                 }
             }
@@ -757,7 +794,7 @@ gibbs_gemm_kernel(const __grid_constant__ Phases ph, const EpiParams ep) {
         // ===== MMA issuer: warp-uniform loop, one elected lane issues; the next k-step's barrier is tested while this one's
         // MMAs are issued (see mbar_test)
         {
-            const bool issuer = elect_one();
+            const uint32_t issue = elect_one() ? 1u : 0u;
             constexpr uint32_t idesc_pos = make_idesc(BN, false), idesc_neg = make_idesc(BN, true);
             int stage = 0; uint32_t phase = 0;
             int iter = 0;
@@ -781,16 +818,13 @@ gibbs_gemm_kernel(const __grid_constant__ Phases ph, const EpiParams ep) {
                     const int cur = stage;
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     ready = (kb + 1 < kb_total) ? mbar_test(full_bar(stage), phase) : 0u;
-                    if (issuer) {
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; k++) {
-                            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-                            umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                        }
-                        umma_commit(empty_bar(cur));  // frees the smem slot once these MMAs retire
-                        if (kb == kb_total - 1) umma_commit(tfull_bar(as));
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                        umma_bf16_if(issue, tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                     }
-                    __syncwarp();
+                    umma_commit_if(issue, empty_bar(cur));  // frees the smem slot once these MMAs retire
+                    umma_commit_if(kb == kb_total - 1 ? issue : 0u, tfull_bar(as));
                 }
             }
         }

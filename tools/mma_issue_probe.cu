@@ -16,6 +16,8 @@
 //   8  6 + 7
 //   9  8 without the __syncwarp at the end of the step
 //  10  9 with 8 MMAs per step
+//  11  8 with the MMAs and the commit predicated inside the asm (no branch around them)
+//  12  11 with the barrier of step i + 2 tested (two steps of look-ahead)
 #include <cstdio>
 #include <cuda_runtime.h>
 
@@ -35,6 +37,23 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     return ok;
+}
+
+__device__ __forceinline__ void umma_bf16_if(uint32_t issue, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(issue)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t issue, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(issue)
+        : "memory");
 }
 
 template <int N, int PATTERN>
@@ -77,6 +96,23 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(long long *out) {
                 mbar_wait(done_bar, 0);
                 t2 = clock64();
             }
+        } else if (PATTERN >= 11) {
+            const uint32_t issue = elect_one() ? 1u : 0u;
+            t0 = clock64();
+            uint32_t ready = mbar_try(bar, 0), ready2 = (PATTERN == 12) ? mbar_try(bar, 0) : 0u;
+            for (int it = 0; it < R; it++) {
+                if (!ready) mbar_wait(bar, 0);
+                const uint64_t adesc = make_kmajor_sw128_desc(sa + (it & 1) * 16384), bdesc = make_kmajor_sw128_desc(sb + (it & 1) * 32768);
+                if (PATTERN == 12) { ready = ready2; ready2 = mbar_try(bar, 0); }
+                else ready = mbar_try(bar, 0);
+#pragma unroll
+                for (int k = 0; k < 4; k++) umma_bf16_if(issue, tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+                umma_commit_if(issue, ring + 8 * (it & 15));
+            }
+            t1 = clock64();
+            if (elect_one()) umma_commit(done_bar);
+            mbar_wait(done_bar, 0);
+            t2 = clock64();
         } else if (PATTERN >= 6) {
             const bool leader = elect_one();
             t0 = clock64();
@@ -144,7 +180,7 @@ void run(long long *d_out) {
 
 template <int N>
 void run_all(long long *d_out) {
-    run<N, 0>(d_out); run<N, 1>(d_out); run<N, 2>(d_out); run<N, 3>(d_out); run<N, 4>(d_out); run<N, 5>(d_out); run<N, 6>(d_out); run<N, 7>(d_out); run<N, 8>(d_out); run<N, 9>(d_out); run<N, 10>(d_out);
+    run<N, 0>(d_out); run<N, 1>(d_out); run<N, 2>(d_out); run<N, 3>(d_out); run<N, 4>(d_out); run<N, 5>(d_out); run<N, 6>(d_out); run<N, 7>(d_out); run<N, 8>(d_out); run<N, 9>(d_out); run<N, 10>(d_out); run<N, 11>(d_out); run<N, 12>(d_out);
 }
 
 int main() {
