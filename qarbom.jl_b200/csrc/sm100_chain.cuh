@@ -53,9 +53,6 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_gpu_add(unsigned int *p, unsigned int v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // after a gpu-scope fence by every contributing lane and a warp barrier, the relaxed add completes a release pattern
 // (fence.acq_rel + relaxed atomic); red.release would run a second fence of ~0.7 us behind the first one
 __device__ __forceinline__ void red_relaxed_gpu_add(unsigned int *p, unsigned int v) {
