@@ -56,3 +56,21 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src, f
+
+
+def test_bench_roofline_traffic_reads_the_committed_ncu_summaries():
+    """bench.py's roofline.traffic comes from the `ncu --set full` summaries committed under profiles/ (tools/ncu_summary.py):
+    the files it names must exist and parse to a per-launch byte count for the kernels of the timed region."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for name in (bench.NCU_GEMM_SUMMARY, bench.NCU_UPDATE_SUMMARY):
+        assert os.path.exists(os.path.join(root, "profiles", name)), name
+    gemm = bench.ncu_traffic(bench.NCU_GEMM_SUMMARY, "gibbs_", mix=bench.gemm_mix(bench.WORKLOADS["cfg5"]))
+    upd = bench.ncu_traffic(bench.NCU_UPDATE_SUMMARY, "update_w_kernel")
+    # algorithmic bytes: a chain launch streams >= 21 x 2 x 67 MB of states, the update 268 MB (DESIGN.md 3.2)
+    assert gemm is not None and 1e9 < gemm < 2e10, gemm
+    assert upd is not None and 1e8 < upd < 1e9, upd
